@@ -1,0 +1,332 @@
+"""ORACLE (test infrastructure only) -- object-graph-literal Python transliteration.
+
+A second, independent restatement of the reference's aligners, written to follow the Rust
+source *structurally* (heap cells holding parent lists, a LIFO `Vec` stack that copies the
+partial strings, recursion for the linear aligner) instead of the flat-array formulation in
+oracle/nw_affine.c.  It is slow (small inputs only) and exists to cross-check the C oracle:
+the Rust reference cannot be executed in this image (no cargo/rustc), so two independent
+restatements agreeing on thousands of random pairs is the strongest pin available
+("parity unpinned" by the reference's own tests for both NW aligners -- they are empty).
+
+Rust panics are modelled as `RefPanic`; Rust `usize` index underflow (`v[0 - 1]`) panics in
+both debug (overflow check) and release (index out of bounds), so it is raised explicitly.
+
+Only tests/ and scripts under tests/golden/ may import this module.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+I16_MIN = -32768
+
+
+class RefPanic(Exception):
+    """The reference process would abort here (exit code 101)."""
+
+    def __init__(self, site: str):
+        super().__init__(site)
+        self.site = site
+
+
+def _idx(seq: bytes, i: int, site: str) -> int:
+    if i < 0 or i >= len(seq):
+        raise RefPanic(site)
+    return seq[i]
+
+
+# ----------------------------------------------------------------------------------------
+# needleman_wunsch_affine.rs
+# ----------------------------------------------------------------------------------------
+IN_M, IN_D, IN_I = "InM", "InD", "InI"  # enum State :366-371
+
+
+@dataclass
+class AffineScheme:  # :15-20
+    gap_opening: int = -8
+    gap_extension: int = -6
+    mismatch: int = -4
+    match_: int = 5
+
+
+class ArrayElement:  # :22-39
+    __slots__ = ("score", "parents", "state")
+
+    def __init__(self, score: int = 0, parents: Optional[list] = None, state: str = IN_M):
+        self.score = score
+        self.parents = parents if parents is not None else []
+        self.state = state
+
+
+class AffineScoreMatrix:  # :59-154
+    def __init__(self, x: int, y: int, scheme: AffineScheme):
+        default = ArrayElement()  # Rc::default() shared by every slot (:420-422)
+        self.m_scores = [[default] * (y + 1) for _ in range(x + 1)]
+        self.i_scores = [[default] * (y + 1) for _ in range(x + 1)]
+        self.d_scores = [[default] * (y + 1) for _ in range(x + 1)]
+        self.s = scheme
+
+    def m_score(self, x, y, is_match):  # :76-86
+        return max(
+            self.m_scores[x - 1][y - 1].score,
+            self.i_scores[x - 1][y - 1].score,
+            self.d_scores[x - 1][y - 1].score,
+        ) + (self.s.match_ if is_match else self.s.mismatch)
+
+    def d_score(self, x, y):  # :87-90
+        return max(self.m_scores[x - 1][y].score + self.s.gap_opening, self.d_scores[x - 1][y].score) + self.s.gap_extension
+
+    def i_score(self, x, y):  # :91-94
+        return max(self.m_scores[x][y - 1].score + self.s.gap_opening, self.i_scores[x][y - 1].score) + self.s.gap_extension
+
+    def d_pointer(self, x, y):  # :96-107
+        p = []
+        if self.d_score(x, y) == self.d_scores[x - 1][y].score + self.s.gap_extension:
+            p.append(self.d_scores[x - 1][y])
+        if self.d_score(x, y) == self.m_scores[x - 1][y].score + self.s.gap_opening + self.s.gap_extension:
+            p.append(self.m_scores[x - 1][y])
+        return p
+
+    def i_pointer(self, x, y):  # :108-119
+        p = []
+        if self.i_score(x, y) == self.i_scores[x][y - 1].score + self.s.gap_extension:
+            p.append(self.i_scores[x][y - 1])
+        if self.i_score(x, y) == self.m_scores[x][y - 1].score + self.s.gap_opening + self.s.gap_extension:
+            p.append(self.m_scores[x][y - 1])
+        return p
+
+    def m_pointer(self, x, y, is_match):  # :120-153
+        p = []
+        sub = self.s.match_ if is_match else self.s.mismatch
+        if self.m_score(x, y, is_match) == self.m_scores[x - 1][y - 1].score + sub:
+            p.append(self.m_scores[x - 1][y - 1])
+        if self.m_score(x, y, is_match) == self.i_scores[x - 1][y - 1].score + sub:
+            p.append(self.i_scores[x - 1][y - 1])
+        if self.m_score(x, y, is_match) == self.d_scores[x - 1][y - 1].score + sub:
+            p.append(self.d_scores[x - 1][y - 1])
+        return p
+
+
+def affine_fill(seq1: bytes, seq2: bytes, scheme: AffineScheme) -> AffineScoreMatrix:  # :169-237
+    mat = AffineScoreMatrix(len(seq2), len(seq1), scheme)
+    s = scheme
+    mat.m_scores[0][0] = ArrayElement(0, [], IN_M)
+    mat.d_scores[0][0] = ArrayElement(I16_MIN, [], IN_D)
+    mat.i_scores[0][0] = ArrayElement(I16_MIN, [], IN_I)
+    for i in range(1, len(seq1) + 1):
+        mat.m_scores[0][i] = ArrayElement(I16_MIN, [], IN_M)
+        mat.i_scores[0][i] = ArrayElement(I16_MIN, [], IN_I)
+        mat.d_scores[0][i] = ArrayElement((i + 1) * s.gap_extension + s.gap_opening, [mat.d_scores[0][i - 1]], IN_D)
+    for i in range(1, len(seq2) + 1):
+        mat.m_scores[i][0] = ArrayElement(I16_MIN, [], IN_M)
+        mat.i_scores[i][0] = ArrayElement(s.gap_opening + (i + 1) * s.gap_extension, [mat.i_scores[i - 1][0]], IN_I)
+        mat.d_scores[i][0] = ArrayElement(I16_MIN, [], IN_D)
+    for i in range(1, len(seq2) + 1):
+        for j in range(1, len(seq1) + 1):
+            eq = seq1[j - 1] == seq2[i - 1]
+            mat.m_scores[i][j] = ArrayElement(mat.m_score(i, j, eq), mat.m_pointer(i, j, eq), IN_M)
+            mat.i_scores[i][j] = ArrayElement(mat.i_score(i, j), mat.i_pointer(i, j), IN_I)
+            mat.d_scores[i][j] = ArrayElement(mat.d_score(i, j), mat.d_pointer(i, j), IN_D)
+    return mat
+
+
+@dataclass
+class TraceBackInfo:  # :373-380
+    seq1: bytes
+    seq2: bytes
+    current_cell: ArrayElement
+    current_state: str
+    x: int
+    y: int
+
+    def display(self) -> str:  # :390-411
+        bars = "".join("|" if a == b else " " for a, b in zip(self.seq1, self.seq2))
+        return "\nseq1: %s\n      %s\nseq2: %s" % (self.seq1.decode("latin1"), bars, self.seq2.decode("latin1"))
+
+
+@dataclass
+class AffineOutcome:
+    score: int
+    alignments: List[Tuple[bytes, bytes]] = field(default_factory=list)  # printed, in order
+    stdout: str = ""
+    panicked: bool = False
+    panic_site: str = ""
+    truncated: bool = False  # enumeration budget hit (outcome beyond it unknown)
+
+
+def affine_traceback(mat: AffineScoreMatrix, seq1: bytes, seq2: bytes, max_pops: int = 2_000_000) -> AffineOutcome:  # :242-334
+    n1, n2 = len(seq1), len(seq2)
+    queue: List[TraceBackInfo] = []
+    max_val = max(mat.i_scores[n2][n1].score, mat.d_scores[n2][n1].score, mat.m_scores[n2][n1].score)
+    out = AffineOutcome(score=max_val)
+    if max_val == mat.i_scores[n2][n1].score:
+        queue.append(TraceBackInfo(b"", b"", mat.i_scores[n2][n1], IN_I, n2, n1))
+    if max_val == mat.m_scores[n2][n1].score:
+        queue.append(TraceBackInfo(b"", b"", mat.m_scores[n2][n1], IN_M, n2, n1))
+    if max_val == mat.d_scores[n2][n1].score:
+        queue.append(TraceBackInfo(b"", b"", mat.d_scores[n2][n1], IN_D, n2, n1))
+    pops = 0
+    text = []
+    try:
+        while queue:
+            element = queue.pop()
+            pops += 1
+            if pops > max_pops:
+                out.truncated = True
+                break
+            if element.x == 0 and element.y == 0:
+                text.append("alignment found\n")
+                text.append(element.display() + "\n")
+                out.alignments.append((element.seq1, element.seq2))
+            for parent in element.current_cell.parents:
+                x, y = element.x, element.y
+                if element.current_state == IN_M:
+                    s1 = bytes([_idx(seq1, element.y - 1, "nw_affine:293")]) + element.seq1
+                    s2 = bytes([_idx(seq2, element.x - 1, "nw_affine:294")]) + element.seq2
+                elif element.current_state == IN_D:
+                    s1 = b"-" + element.seq1
+                    s2 = bytes([_idx(seq2, element.x - 1, "nw_affine:299")]) + element.seq2
+                else:
+                    s1 = bytes([_idx(seq1, element.y - 1, "nw_affine:303")]) + element.seq1
+                    s2 = b"-" + element.seq2
+                if element.current_state == IN_M:
+                    x -= 1
+                    y -= 1
+                elif element.current_state == IN_D:
+                    x -= 1
+                else:
+                    y -= 1
+                queue.append(TraceBackInfo(s1, s2, parent, parent.state, x, y))
+    except RefPanic as e:
+        out.panicked = True
+        out.panic_site = e.site
+    out.stdout = "".join(text)
+    return out
+
+
+def affine_align(seq1: bytes, seq2: bytes, scheme: Optional[AffineScheme] = None, max_pops: int = 2_000_000) -> AffineOutcome:
+    """n_w_align, Mode::Global (:424-432) minus the Duration line."""
+    scheme = scheme or AffineScheme()
+    mat = affine_fill(seq1, seq2, scheme)
+    return affine_traceback(mat, seq1, seq2, max_pops)
+
+
+def columns_to_cigar(row1: bytes, row2: bytes) -> List[int]:
+    """Run-length (len<<2|op) with op 0=M (diag), 1=I (seq1 vs '-'), 2=D ('-' vs seq2)."""
+    out: List[int] = []
+    for a, b in zip(row1, row2):
+        op = 2 if a == 0x2D else (1 if b == 0x2D else 0)
+        if out and (out[-1] & 3) == op:
+            out[-1] += 4
+        else:
+            out.append(4 | op)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# needleman_wunsch.rs  (dead code at the reference commit: main.rs:4,14)
+# ----------------------------------------------------------------------------------------
+DOWN, RIGHT, DIAG = "Down", "Right", "Diag"  # enum Move :16-20
+
+
+@dataclass
+class LinearOutcome:
+    score: int  # scores[n1][n2] (global) -- never printed by the reference
+    hits: List[Tuple[str, str, int, int]] = field(default_factory=list)  # (query row, db row, start1, start2)
+    scores: Optional[List[List[int]]] = None
+    truncated: bool = False
+
+
+def linear_align(seq1: bytes, seq2: bytes, local: bool = False, max_hits: int = 100_000) -> LinearOutcome:
+    s1 = seq1.decode("latin1")  # vec_u8_to_str (:189-190)
+    s2 = seq2.decode("latin1")
+    gap_opening, gap_extension, mismatch, match_ = -8, -6, -4, 5  # :181-186
+    n1, n2 = len(s1), len(s2)
+    scores = [[0] * (n2 + 1) for _ in range(n1 + 1)]  # :38
+    paths: List[List[List[str]]] = [[[] for _ in range(n2 + 1)] for _ in range(n1 + 1)]
+    gaps = [[False] * (n2 + 1) for _ in range(n1 + 1)]
+    if not local:  # :44-65
+        for i in range(n2 + 1):
+            scores[0][i] += i * gap_extension + gap_opening
+            paths[0][i].append(RIGHT)
+            gaps[0][i] = True
+        for i in range(n1 + 1):
+            scores[i][0] += i * gap_extension + gap_opening
+            paths[i][0].append(DOWN)
+            gaps[i][0] = True
+    for i in range(1, n1 + 1):  # :66-103
+        for j in range(1, n2 + 1):
+            if s1[i - 1] == s2[j - 1]:
+                diag_score = scores[i - 1][j - 1] + match_
+            else:
+                diag_score = scores[i - 1][j - 1] + mismatch
+            down_score = scores[i - 1][j] + (gap_extension if gaps[i - 1][j] else gap_opening)
+            right_score = scores[i][j - 1] + (gap_extension if gaps[i][j - 1] else gap_opening)
+            max_score = max(down_score, right_score, diag_score)
+            if max_score == down_score or max_score == right_score:
+                gaps[i][j] = True
+            if local and max_score < 0:
+                paths[i][j] = []
+            else:
+                scores[i][j] = max_score
+                if max_score == down_score:
+                    paths[i][j].append(DOWN)
+                if max_score == right_score:
+                    paths[i][j].append(RIGHT)
+                if max_score == diag_score:
+                    paths[i][j].append(DIAG)
+    out = LinearOutcome(score=scores[n1][n2], scores=scores)
+    if local:  # argmax :256-272
+        best, starts = None, []
+        for i in range(n1 + 1):
+            for j in range(n2 + 1):
+                if best is None or scores[i][j] > best:
+                    best, starts = scores[i][j], [(i, j)]
+                elif scores[i][j] == best:
+                    starts.append((i, j))
+    else:
+        starts = [(n1, n2)]
+
+    import sys
+
+    sys.setrecursionlimit(max(10000, 4 * (n1 + n2) + 1000))
+
+    class _Stop(Exception):
+        pass
+
+    def get_next(current, hit):  # :205-254
+        if current == (0, 0) or not paths[current[0]][current[1]]:
+            if len(out.hits) >= max_hits:
+                out.truncated = True
+                raise _Stop()
+            out.hits.append((hit["query"][::-1], hit["db"][::-1], hit["sq"], hit["sd"]))
+            return
+        for p in paths[current[0]][current[1]]:
+            hit["sq"] = max(current[0], 1) - 1
+            hit["sd"] = max(current[1], 1) - 1
+            if p == DOWN:
+                if current[0] - 1 < 0:
+                    raise RefPanic("needleman_wunsch:220")
+                hit["query"] += s1[current[0] - 1]
+                hit["db"] += "-"
+                nxt = (current[0] - 1, current[1])
+            elif p == RIGHT:
+                if current[1] - 1 < 0:
+                    raise RefPanic("needleman_wunsch:230")
+                hit["query"] += "-"
+                hit["db"] += s2[current[1] - 1]
+                nxt = (current[0], current[1] - 1)
+            else:
+                hit["query"] += s1[current[0] - 1]
+                hit["db"] += s2[current[1] - 1]
+                nxt = (current[0] - 1, current[1] - 1)
+            get_next(nxt, hit)
+            hit["query"] = hit["query"][:-1]
+            hit["db"] = hit["db"][:-1]
+
+    try:
+        for st in starts:  # :112-115
+            get_next(st, {"query": "", "db": "", "sq": 0, "sd": 0})
+    except _Stop:
+        pass
+    return out
