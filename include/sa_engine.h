@@ -1,0 +1,170 @@
+/*
+ * sa_engine.h -- C ABI of the B200-native batched pairwise-alignment engine.
+ *
+ * Drop-in boundary for the data-parallel hot path of Qw11111111111/SequenceAligning
+ * (crate a_star_align): the `for d in db { for q in query { match algo {..} } }` loop of
+ * src/main.rs:61-79, i.e. the calls
+ *     n_w_align(q, d, verbose, mode)   src/needleman_wunsch_affine.rs:424   (SA_ALGO_NW_AFFINE)
+ *     n_w_align(q, d, verbose, local)  src/needleman_wunsch.rs:180          (SA_ALGO_NW_LINEAR)
+ *     wfa_align(q, d, mode)            src/wfa.rs:23                        (SA_ALGO_WFA)
+ * batched over many independent (query, db) pairs.  The reference returns nothing (results
+ * exist only as stdout text); this ABI returns, per pair, what that text is made of: a
+ * status, the score, and the FIRST alignment the reference prints (as a run-length CIGAR).
+ *
+ * Plain C: opaque handle, plain pointers and sizes, no C++/torch types, no exceptions.
+ * A Rust `extern "C"` block / bindgen, cgo, or ctypes binds exactly these symbols; see
+ * INTEGRATION.md for the Rust shim a maintainer of the reference would add.
+ *
+ * There is NO CPU fallback: every entry point that computes requires a CUDA device of
+ * compute capability 10.0 (B200) and fails with SA_E_CUDA otherwise.
+ *
+ * Conventions (src/main.rs:61-66): seq1 = QUERY record, seq2 = DB record,
+ * n1 = len(seq1), n2 = len(seq2).  Residues are raw bytes compared with `==`
+ * (needleman_wunsch_affine.rs:220), so 'N' == 'N' matches and 'N' != 'A'.
+ */
+#ifndef SA_ENGINE_H
+#define SA_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SA_ABI_VERSION 1
+
+typedef struct sa_engine sa_engine_t; /* opaque; one per (process, device) */
+
+/* parse.rs:36-42 `enum Algo` (A* is out of scope for the GPU path) */
+typedef enum { SA_ALGO_NW_AFFINE = 0, SA_ALGO_NW_LINEAR = 1, SA_ALGO_WFA = 2 } sa_algo_t;
+/* parse.rs:44-50 `enum Mode` */
+typedef enum { SA_MODE_GLOBAL = 0, SA_MODE_LOCAL = 1, SA_MODE_SEMIGLOBAL = 2 } sa_mode_t;
+
+/* Per-pair status (>= 0, stored in sa_result_t.status) and per-call errors (< 0). */
+typedef enum {
+  SA_OK = 0,                 /* the reference completes; score and alignment valid            */
+  SA_REF_PANIC = 1,          /* the reference prints >= 1 alignment, then panics
+                                (index 0-1 at nw_affine:299/:303); score and alignment valid  */
+  SA_REF_NO_CONVERGENCE = 2, /* WFA: `while is_converged().is_none()` never ends (wfa.rs:28)  */
+  SA_NOT_IMPLEMENTED = 3,    /* Err(AlignmentError("not implemented")) nw_affine:433-434,
+                                wfa.rs:26 -- non-global modes                                 */
+  SA_REF_PANIC_EARLY = 4,    /* the reference panics before printing anything: the first
+                                alignment in DFS order starts with a gap; score valid,
+                                alignment empty                                               */
+  SA_REF_NO_OUTPUT = 5,      /* completes but prints no alignment (only possible once the
+                                finite -32768 sentinel leaks, n1+n2 >~ 5.4k)                  */
+  SA_E_CUDA = -1,            /* CUDA failure (sa_last_error has the string)                   */
+  SA_E_ARG = -2,             /* bad argument                                                  */
+  SA_E_NOMEM = -3,           /* host or device allocation failed                              */
+  SA_E_CIGAR_CAPACITY = -4,  /* cigar_capacity too small; sa_result_t.cigar_used = needed     */
+  SA_E_UNSUPPORTED = -5      /* pair shape/scheme outside what the kernels implement          */
+} sa_status_t;
+
+/* Scoring scheme; defaults are the reference's compile-time consts
+ * (needleman_wunsch_affine.rs:15-20, needleman_wunsch.rs:181-186): 5, -4, -8, -6.
+ * For SA_ALGO_WFA the fields are penalties mismatch=4, gap_open=2, gap_ext=6, match=0
+ * (wfa.rs:17-21). Pass NULL for the reference's constants. */
+typedef struct {
+  int32_t match, mismatch, gap_open, gap_ext;
+} sa_scheme_t;
+
+/* CIGAR: 32-bit words (len << 2) | op in alignment order (first column first).
+ *   SA_OP_M  diagonal column  seq1[y-1] / seq2[x-1]   (match or mismatch; state InM)
+ *   SA_OP_I  seq1[y-1] / '-'   consumes a QUERY residue (state InI, nw_affine:302-306)
+ *   SA_OP_D  '-' / seq2[x-1]   consumes a DB residue    (state InD, nw_affine:297-301) */
+enum { SA_OP_M = 0, SA_OP_I = 1, SA_OP_D = 2 };
+
+/* One batch of pairs, caller-owned HOST memory (pinned via sa_alloc_pinned for overlap;
+ * pageable works but copies synchronously).  Pair p aligns
+ *   seq1 = residues[q_off[p] .. q_off[p]+q_len[p])   (query)
+ *   seq2 = residues[d_off[p] .. d_off[p]+d_len[p])   (db)
+ * Offsets may alias (1 query x N db) and need not be ordered; throughput is best when
+ * consecutive pairs have similar lengths (length-bucketed, which sa_pack_* produce). */
+typedef struct {
+  const uint8_t* residues;
+  uint64_t residues_len;
+  const uint64_t* q_off;
+  const uint32_t* q_len;
+  const uint64_t* d_off;
+  const uint32_t* d_len;
+  uint64_t n_pairs;
+  uint32_t packing; /* 0 = byte per residue (the only format in ABI v1) */
+} sa_batch_t;
+
+/* Results, caller-allocated HOST memory, engine fills.  Arrays have n_pairs entries. */
+typedef struct {
+  int32_t* score;      /* affine: max(I,D,M)[n2][n1] (nw_affine:247-250); linear: scores[n1][n2];
+                          wfa: the printed `converged with score` value (wfa.rs:31-36)      */
+  uint8_t* status;     /* sa_status_t >= 0                                                   */
+  uint64_t* cigar_off; /* offset (words) of pair p's CIGAR in `cigar`; monotone in p         */
+  uint32_t* cigar_len; /* words; 0 when the reference prints no alignment                    */
+  uint32_t* cigar;     /* pool of run-length words; may be NULL with cigar_capacity = 0 to
+                          skip traceback (score + status only)                               */
+  uint64_t cigar_capacity; /* words available in `cigar`                                     */
+  uint64_t cigar_used;     /* OUT: words written (or needed, on SA_E_CIGAR_CAPACITY)         */
+} sa_result_t;
+
+/* Kernel-time breakdown of the last call (device milliseconds from CUDA events). */
+typedef struct {
+  double h2d_ms, fill_ms, walk_ms, d2h_ms, total_ms;
+  uint64_t cells;         /* sum over pairs of n1*n2                                          */
+  uint64_t kernel_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t pairs_rerun;   /* pairs re-filled without the panic-detection bonus                */
+} sa_timing_t;
+
+/* -- lifecycle ------------------------------------------------------------------------ */
+sa_status_t sa_engine_create(int device_id, sa_engine_t** out);
+sa_status_t sa_engine_destroy(sa_engine_t* e);
+const char* sa_last_error(const sa_engine_t* e); /* never NULL; "" when none */
+int sa_abi_version(void);
+
+/* -- the hot path --------------------------------------------------------------------- */
+/* Align every pair of `batch` (host buffers in, host buffers out).  Blocking.  Shards
+ * nothing: one engine drives one GPU; multi-GPU callers create one engine per device (one
+ * process or thread each) and split the pair list (see sa_partition_lpt). */
+sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
+                           const sa_scheme_t* scheme, const sa_batch_t* batch,
+                           sa_result_t* result);
+
+/* Device-resident variant: upload once, align many times (benchmarks, repeated scoring). */
+typedef struct sa_resident sa_resident_t;
+sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* batch, sa_resident_t** out);
+sa_status_t sa_batch_free(sa_engine_t* e, sa_resident_t* r);
+/* Runs the kernels on the resident batch; results stay on the device until
+ * sa_resident_download.  Asynchronous w.r.t. the host: returns after enqueueing. */
+sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
+                              const sa_scheme_t* scheme, sa_resident_t* r, int want_cigar);
+sa_status_t sa_resident_download(sa_engine_t* e, sa_resident_t* r, sa_result_t* result);
+sa_status_t sa_engine_synchronize(sa_engine_t* e);
+/* cudaStream_t the engine launches on, as void* (for CUDA-event timing by the caller). */
+void* sa_engine_stream(sa_engine_t* e);
+
+sa_status_t sa_last_timing(const sa_engine_t* e, sa_timing_t* out);
+
+/* -- host helpers --------------------------------------------------------------------- */
+void* sa_alloc_pinned(size_t bytes);
+void sa_free_pinned(void* p);
+
+/* Greedy longest-processing-time partition of pairs over n_parts GPUs by n1*n2 cells
+ * (SURVEY 8e).  part[p] in [0, n_parts).  Deterministic.  Pure host code. */
+sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint64_t n_pairs,
+                             int n_parts, int32_t* part);
+
+/* parse_fasta (src/parse.rs:54-99), byte-for-byte semantics incl. the quirks pinned by
+ * parse.rs:166-251.  Returns #records (>= 0) or SA_E_ARG for the reference's FastaError.
+ * index holds (name_off, name_len, seq_off, seq_len) per record into `out`. */
+int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t* index,
+                       size_t index_cap, uint8_t* err_chars, size_t err_cap, size_t* n_err);
+
+/* The text the reference prints for one alignment (needleman_wunsch_affine.rs:283-286 and
+ * Display :390-411): "alignment found\n\nseq1: ..\n      ..\nseq2: ..\n".  snprintf-style:
+ * returns the bytes needed; SA_E_ARG if the CIGAR does not fit the sequences. */
+int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                         const uint32_t* cigar, uint32_t cigar_len, char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_ENGINE_H */

@@ -1,0 +1,16 @@
+"""sequencealigning_b200 -- B200-native batched pairwise alignment (affine NW hot path).
+
+Host side of the drop-in boundary; all compute lives in _lib/libsa_engine.so (CUDA, sm_100a).
+"""
+from ._capi import (ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
+                    NOT_IMPLEMENTED, OK, OP_D, OP_I, OP_M, REF_NO_CONVERGENCE, REF_NO_OUTPUT, REF_PANIC,
+                    REF_PANIC_EARLY)
+from .engine import (AlignResult, Engine, EngineError, PairBatch, Record, ResidentBatch, parse_fasta,
+                     render_affine)
+
+__all__ = [
+    "Engine", "EngineError", "PairBatch", "Record", "AlignResult", "ResidentBatch", "parse_fasta",
+    "render_affine", "ALGO_NW_AFFINE", "ALGO_NW_LINEAR", "ALGO_WFA", "MODE_GLOBAL", "MODE_LOCAL",
+    "MODE_SEMIGLOBAL", "OK", "REF_PANIC", "REF_NO_CONVERGENCE", "NOT_IMPLEMENTED", "REF_PANIC_EARLY",
+    "REF_NO_OUTPUT", "OP_M", "OP_I", "OP_D",
+]

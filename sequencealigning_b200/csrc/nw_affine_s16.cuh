@@ -1,0 +1,294 @@
+// nw_affine_s16.cuh -- affine-gap global NW fill for short pairs, packed u16x2, sm_100a.
+//
+// Computes what ScoreTensor::fill (Global) computes in the reference
+// (/root/reference/src/needleman_wunsch_affine.rs:169-237): the three-state M/I/D recurrences
+//     M[x][y] = max(M,I,D)[x-1][y-1] + (seq1[y-1]==seq2[x-1] ? match : mismatch)      :76-86
+//     I[x][y] = max(M[x][y-1] + open, I[x][y-1]) + ext                                :91-94
+//     D[x][y] = max(M[x-1][y] + open, D[x-1][y]) + ext                                :87-90
+// with the reference's boundary rows (:183-216: the boundary gap costs one extra extension)
+// and, per cell, the four tie bits that determine the FIRST alignment the reference's LIFO
+// DFS prints (:246-329).  x in [0,n2] walks seq2 (db), y in [0,n1] walks seq1 (query).
+//
+// Mapping to the hardware (see DESIGN.md section 4 for the derivation and the roofline):
+//   * Two pairs per register: every 32-bit register holds the same quantity for pair A (low
+//     half) and pair B (high half) as biased unsigned 16-bit numbers, so one VIMNMX.U16x2
+//     does two max operations and returns BOTH "a >= b" predicates, which are exactly the
+//     traceback tie bits.  Plain 32-bit IADD does two subtractions because no half can
+//     borrow (range proven below).
+//   * Scores are stored as V' = 2*V - match*(x+y) + BIAS.  Every comparison in the
+//     recurrence is between values of the same cell, so the per-cell offset cancels; the
+//     diagonal step then costs 0 for a match and 2*(match-mismatch) for a mismatch, which
+//     makes the substitution score one XOR + one VIMNMX.U16x2 (min(q^d, penalty)).
+//   * The factor 2 leaves the low bit free: boundary-chain cells get +1 ("panic bonus"),
+//     the bonus can only break ties, and it survives to the end cell iff some co-optimal
+//     path starts with a gap -- the condition under which the reference panics
+//     (nw_affine:299/:303).  Status is therefore exact with zero extra instructions.
+//   * G lanes share one pair-of-pairs: lane j owns column strips j, j+G, j+2G.. (K columns
+//     each, in registers) and runs one row behind lane j-1; the strip's right-edge H and E
+//     go to lane j+1 by __shfl_up_sync and from the last lane of the group to shared memory
+//     for the next pass.  Sequence words are staged once per tile in shared memory.
+//   * Traceback bits (4 per cell) leave the SM as one coalesced 8-byte store per lane per
+//     row-strip: [strip][row][group] uint2 = {pair A's 8 cells, pair B's 8 cells}.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sa {
+
+constexpr uint32_t kBias = 0xFF00u;  // stored = V' + kBias; V' <= 1 always
+// Largest n1pad + n2 for which no 16-bit half can underflow: the most negative V' is a path
+// of gaps only, 2*(open+ext) + ext'*(n1+n2) with ext' = 2*ext - match, plus one mismatch,
+// one open and one extension of look-ahead.  The engine checks the bound with the scheme.
+__host__ __device__ inline uint32_t s16_min_value_bound(int match, int mismatch, int open, int ext,
+                                                        uint32_t n1pad, uint32_t n2) {
+  const int extp = match - 2 * ext;                  // > 0 magnitude per boundary step
+  const int openp = -2 * open;                       // > 0
+  const int pen = 2 * (match - mismatch);            // > 0
+  // worst case: every step is the costliest of (ext', pen/2 per unit of x+y)
+  const int per_step = extp > (pen + 1) / 2 ? extp : (pen + 1) / 2;
+  return (uint32_t)(2 * (openp + extp) + per_step * (int)(n1pad + n2 + 2) + pen + openp + extp);
+}
+
+struct AffineS16Params {
+  const uint8_t* __restrict__ residues;
+  const uint64_t* __restrict__ q_off;
+  const uint32_t* __restrict__ q_len;
+  const uint64_t* __restrict__ d_off;
+  const uint32_t* __restrict__ d_len;
+  const uint32_t* __restrict__ pair_ids;  // launch index -> pair id, or nullptr for identity+base
+  uint32_t pair_base;
+  uint32_t n_launch_pairs;
+  uint2* __restrict__ tb;        // traceback scratch, tile-major
+  uint64_t tb_tile_stride;       // uint2 per tile
+  uint32_t tb_rows;              // row stride (launch-wide max n2)
+  uint32_t* __restrict__ end;    // per launch index: H'(16) | start_state << 16 | valid << 31
+  uint32_t smem_q_words, smem_d_words;  // per-warp panel sizes (words), multiples of 32/G
+  // scheme in transformed units (all positive magnitudes)
+  uint32_t pen2;    // 2*(match-mismatch), packed in both halves
+  uint32_t open2;   // -2*open, packed
+  uint32_t ext2;    // match - 2*ext, packed
+  uint32_t row0;    // kBias - 2*(-(open+ext)) + bonus, packed: H'[0][y] = row0 - y*ext2
+  uint32_t origin;  // kBias packed: H'[0][0]
+};
+
+// max of two packed u16 pairs that also records, per half, whether the FIRST operand won or
+// tied: bit BIT of acc_lo (low half = pair A) / acc_hi (high half = pair B) is set when
+// a >= b.  ptxas folds the setp.eq pair into the predicate outputs of one VIMNMX.U16x2, and
+// each conditional add becomes one predicated integer add (either integer pipe), so a tie
+// bit costs one issue slot instead of a SEL plus a merge.
+template <uint32_t BIT>
+__device__ __forceinline__ uint32_t vmax_tie(uint32_t a, uint32_t b, uint32_t& acc_lo,
+                                             uint32_t& acc_hi) {
+  uint32_t r;
+  asm("{\n\t"
+      ".reg .pred ph, pl;\n\t"
+      ".reg .u16 r0, r1, a0, a1;\n\t"
+      "max.u16x2 %0, %3, %4;\n\t"
+      "mov.b32 {r0, r1}, %0;\n\t"
+      "mov.b32 {a0, a1}, %3;\n\t"
+      "setp.eq.u16 pl, r0, a0;\n\t"
+      "setp.eq.u16 ph, r1, a1;\n\t"
+      "@pl add.u32 %1, %1, %5;\n\t"
+      "@ph add.u32 %2, %2, %5;\n\t"
+      "}"
+      : "=r"(r), "+r"(acc_lo), "+r"(acc_hi)
+      : "r"(a), "r"(b), "n"(BIT));
+  return r;
+}
+
+template <int K, int C>
+struct StripCells {
+  template <bool CAPTURE>
+  static __device__ __forceinline__ void run(uint32_t (&Hrow)[K], uint32_t (&F)[K],
+                                             const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
+                                             uint32_t& E, uint32_t pen2, uint32_t open2,
+                                             uint32_t ext2, uint32_t& acc_a, uint32_t& acc_b,
+                                             uint32_t (&capM)[K], uint32_t (&capE)[K],
+                                             uint32_t (&capF)[K]) {
+    constexpr int c = C;
+    const uint32_t hup = Hrow[c];
+    const uint32_t m = __vminu2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
+    const uint32_t M = hdiag - m;                 // M'[x][y]; no borrow (range bound)
+    if (CAPTURE) {
+      capM[c] = M;
+      capE[c] = E;
+      capF[c] = F[c];
+    }
+    const uint32_t t = vmax_tie<(1u << (4 * c))>(E, M, acc_a, acc_b);     // I >= M here
+    const uint32_t H = vmax_tie<(2u << (4 * c))>(F[c], t, acc_a, acc_b);  // D >= max(I,M)
+    const uint32_t Mo = M - open2;
+    const uint32_t En = vmax_tie<(4u << (4 * c))>(Mo, E, acc_a, acc_b);     // open ties/wins: I[x][y+1]
+    const uint32_t Fn = vmax_tie<(8u << (4 * c))>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D[x+1][y]
+    E = En - ext2;
+    F[c] = Fn - ext2;
+    Hrow[c] = H;
+    StripCells<K, C + 1>::template run<CAPTURE>(Hrow, F, q, d, hup, E, pen2, open2, ext2, acc_a,
+                                                acc_b, capM, capE, capF);
+  }
+};
+template <int K>
+struct StripCells<K, K> {
+  template <bool CAPTURE>
+  static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K],
+                                             uint32_t, uint32_t, uint32_t&, uint32_t, uint32_t,
+                                             uint32_t, uint32_t&, uint32_t&, uint32_t (&)[K],
+                                             uint32_t (&)[K], uint32_t (&)[K]) {}
+};
+
+// One row of one K-column strip for two packed pairs.
+template <int K, bool CAPTURE>
+__device__ __forceinline__ void strip_row(uint32_t (&Hrow)[K], uint32_t (&F)[K],
+                                          const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
+                                          uint32_t& E, uint32_t pen2, uint32_t open2,
+                                          uint32_t ext2, uint32_t& acc_a, uint32_t& acc_b,
+                                          uint32_t (&capM)[K], uint32_t (&capE)[K],
+                                          uint32_t (&capF)[K]) {
+  acc_a = 0;
+  acc_b = 0;
+  StripCells<K, 0>::template run<CAPTURE>(Hrow, F, q, d, hdiag, E, pen2, open2, ext2, acc_a, acc_b,
+                                          capM, capE, capF);
+}
+
+// start state of the traceback at the end cell (nw_affine:251-280: pushed I, M, D; popped
+// D, M, I): D if D == max, else M if M == max, else I.   codes: 0 = M, 1 = I, 2 = D
+__device__ __forceinline__ uint32_t end_word(uint32_t M, uint32_t E, uint32_t F) {
+  const uint32_t me = M > E ? M : E;
+  const uint32_t h = F > me ? F : me;
+  const uint32_t st = (F >= me) ? 2u : (M >= E ? 0u : 1u);
+  return h | (st << 16) | 0x80000000u;
+}
+
+template <int K, int G>
+__global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p) {
+  static_assert(K == 8, "traceback word layout assumes 8 cells x 4 bits");
+  constexpr int NG = 32 / G;       // pair-of-pairs per warp tile
+  constexpr int PPT = 2 * NG;      // pairs per tile
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x;
+  const int grp = lane / G, j = lane % G;
+  const uint32_t tile = blockIdx.x;
+
+  // ---- this lane's two pairs -------------------------------------------------------------
+  const uint32_t la = tile * PPT + 2 * grp, lb = la + 1;  // launch indices
+  uint32_t n1a = 0, n2a = 0, n1b = 0, n2b = 0;
+  uint64_t qoa = 0, doa = 0, qob = 0, dob = 0;
+  if (la < p.n_launch_pairs) {
+    const uint32_t id = p.pair_ids ? p.pair_ids[la] : p.pair_base + la;
+    n1a = p.q_len[id]; n2a = p.d_len[id]; qoa = p.q_off[id]; doa = p.d_off[id];
+  }
+  if (lb < p.n_launch_pairs) {
+    const uint32_t id = p.pair_ids ? p.pair_ids[lb] : p.pair_base + lb;
+    n1b = p.q_len[id]; n2b = p.d_len[id]; qob = p.q_off[id]; dob = p.d_off[id];
+  }
+  // pairs with an empty side have no interior cells; the walk kernel handles them in closed form
+  if (n1a == 0 || n2a == 0) n1a = n2a = 0;
+  if (n1b == 0 || n2b == 0) n1b = n2b = 0;
+  uint32_t n1t = max(n1a, n1b), n2t = max(n2a, n2b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n1t = max(n1t, __shfl_xor_sync(0xffffffffu, n1t, o));
+    n2t = max(n2t, __shfl_xor_sync(0xffffffffu, n2t, o));
+  }
+  if (n1t == 0 || n2t == 0) return;
+  const uint32_t nstrips = (n1t + K - 1) / K;
+  const uint32_t npass = (nstrips + G - 1) / G;
+  const uint32_t n1pad = npass * G * K;
+
+  uint32_t* qp = smem;                          // [n1pad][NG]
+  uint32_t* dp = qp + p.smem_q_words;           // [n2t][NG]
+  uint2* bnd = reinterpret_cast<uint2*>(dp + p.smem_d_words);  // [n2t][NG]
+
+  // ---- stage the sequence words: (byte << 7) in each half; XOR of two different residues
+  //      is then >= 128 >= pen2, XOR of equal residues is 0 ---------------------------------
+  for (uint32_t y = j; y < n1pad; y += G) {
+    const uint32_t a = (y < n1a) ? (uint32_t)p.residues[qoa + y] : 0u;
+    const uint32_t b = (y < n1b) ? (uint32_t)p.residues[qob + y] : 0u;
+    qp[y * NG + grp] = (a << 7) | (b << 23);
+  }
+  for (uint32_t x = j; x < n2t; x += G) {
+    const uint32_t a = (x < n2a) ? (uint32_t)p.residues[doa + x] : 0u;
+    const uint32_t b = (x < n2b) ? (uint32_t)p.residues[dob + x] : 0u;
+    dp[x * NG + grp] = (a << 7) | (b << 23);
+  }
+  __syncwarp();
+
+  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2;
+  // end-cell capture coordinates (strip, column-in-strip) per half
+  const uint32_t sa_ = n1a ? (n1a - 1) / K : 0xffffffffu, ca_ = n1a ? (n1a - 1) % K : 0;
+  const uint32_t sb_ = n1b ? (n1b - 1) / K : 0xffffffffu, cb_ = n1b ? (n1b - 1) % K : 0;
+
+  uint2* tb_tile = p.tb + (uint64_t)tile * p.tb_tile_stride;
+
+  for (uint32_t pass = 0; pass < npass; ++pass) {
+    const uint32_t s = pass * G + j;  // this lane's strip
+    const uint32_t y0 = s * K;        // columns to the left of the strip
+    uint32_t Hrow[K], F[K], q[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const uint32_t y = y0 + c + 1;
+      Hrow[c] = p.row0 - y * ext2;  // H'[0][y] = D'[0][y]  (nw_affine:194-198)
+      F[c] = Hrow[c] - ext2;        // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
+      q[c] = qp[(y - 1) * NG + grp];
+    }
+    uint32_t hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * ext2;  // H'[x-1][y0]
+    uint32_t colh = p.row0 - ext2;                                 // H'[1][0] = I'[1][0]
+    uint32_t out_h = 0, out_e = 0;
+    const bool cap_a_strip = (s == sa_), cap_b_strip = (s == sb_);
+    uint2* tb_strip = tb_tile + ((uint64_t)s * p.tb_rows) * NG + grp;
+
+    for (uint32_t t = 1; t < n2t + G; ++t) {
+      uint32_t rh = out_h, re = out_e;
+      if (G > 1) {
+        rh = __shfl_up_sync(0xffffffffu, out_h, 1);
+        re = __shfl_up_sync(0xffffffffu, out_e, 1);
+      }
+      const uint32_t x = t - j;  // wraps for t < j: fails the range test below
+      if (x >= 1 && x <= n2t) {
+        if (j == 0) {
+          if (pass == 0) {  // column 0: H'[x][0] = I'[x][0], and I'[x][1] extends it (:200-216)
+            rh = colh;
+            re = colh - ext2;
+            colh -= ext2;
+          } else {
+            const uint2 b = bnd[(x - 1) * NG + grp];
+            rh = b.x;
+            re = b.y;
+          }
+        }
+        const uint32_t d = dp[(x - 1) * NG + grp];
+        uint32_t E = re, acc_a, acc_b;
+        uint32_t capM[K], capE[K], capF[K];
+        const bool cap = (cap_a_strip && x == n2a) || (cap_b_strip && x == n2b);
+        if (!cap) {
+          strip_row<K, false>(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, capM,
+                              capE, capF);
+        } else {
+          strip_row<K, true>(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, capM,
+                             capE, capF);
+          if (cap_a_strip && x == n2a) {
+            uint32_t M = 0, Ei = 0, Fi = 0;
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+              if ((uint32_t)c == ca_) { M = capM[c] & 0xffffu; Ei = capE[c] & 0xffffu; Fi = capF[c] & 0xffffu; }
+            p.end[la] = end_word(M, Ei, Fi);
+          }
+          if (cap_b_strip && x == n2b) {
+            uint32_t M = 0, Ei = 0, Fi = 0;
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+              if ((uint32_t)c == cb_) { M = capM[c] >> 16; Ei = capE[c] >> 16; Fi = capF[c] >> 16; }
+            p.end[lb] = end_word(M, Ei, Fi);
+          }
+        }
+        hd_prev = rh;
+        out_h = Hrow[K - 1];
+        out_e = E;
+        if (j == G - 1) bnd[(x - 1) * NG + grp] = make_uint2(out_h, out_e);
+        tb_strip[(uint64_t)(x - 1) * NG] = make_uint2(acc_a, acc_b);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace sa

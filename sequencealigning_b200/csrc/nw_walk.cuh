@@ -1,0 +1,237 @@
+// nw_walk.cuh -- traceback ("first printed alignment") over the packed 4-bit matrix, and the
+// small scan that turns per-pair CIGAR lengths into pool offsets.
+//
+// The reference's traceback (/root/reference/src/needleman_wunsch_affine.rs:242-329) is a
+// LIFO depth-first enumeration of every co-optimal path.  The FIRST path it prints is the
+// greedy walk that always follows the LAST-pushed parent:
+//   end cell   : D if D == max, else M if M == max, else I            (:251-280 push I,M,D)
+//   from M     : the state of (x-1,y-1) with priority D > I > M       (:120-153 push M,I,D)
+//   from I     : M if opening ties/wins, else I                       (:108-119 push I,M)
+//   from D     : M if opening ties/wins, else D                       (:96-107  push D,M)
+// Reaching x == 0 with y > 0 (or y == 0 with x > 0) means the path runs into the boundary
+// chain D[0][y] / I[x][0], where the reference indexes seq2[0-1] / seq1[0-1] and panics
+// (:299/:303) -> SA_REF_PANIC_EARLY, no alignment.
+//
+// One thread walks one pair; lanes of a warp walk neighbouring pairs of the same tile, whose
+// paths stay close to each other, so the 8-byte traceback words they read share sectors.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nw_affine_s16.cuh"
+
+namespace sa {
+
+enum : uint8_t { kOk = 0, kRefPanic = 1, kRefNoConv = 2, kNotImpl = 3, kRefPanicEarly = 4, kRefNoOutput = 5 };
+
+struct WalkParams {
+  const uint32_t* __restrict__ q_len;
+  const uint32_t* __restrict__ d_len;
+  const uint32_t* __restrict__ pair_ids;  // launch index -> pair id (rerun list) or nullptr
+  uint32_t pair_base;
+  uint32_t n_launch_pairs;
+  const uint32_t* __restrict__ n_launch_dev;  // if non-null, overrides n_launch_pairs (device-side count)
+  const uint2* __restrict__ tb;
+  uint64_t tb_tile_stride;
+  uint32_t tb_rows;
+  uint32_t ng;           // pair-of-pairs per tile (32 / G)
+  const uint32_t* __restrict__ end;  // per launch index
+  int32_t match, open, ext;
+  // outputs, indexed by pair id
+  int32_t* __restrict__ score;
+  uint8_t* __restrict__ status;
+  uint32_t* __restrict__ cigar_len;
+  const uint64_t* __restrict__ cigar_off;
+  uint32_t* __restrict__ pool;
+  uint64_t pool_cap;
+  // first pass only: pairs whose end cell carries the panic bonus are queued for a clean refill
+  uint32_t* __restrict__ rerun_ids;
+  uint32_t* __restrict__ rerun_count;
+  int phase;  // 0: first fill (bonus on)  1: clean refill of queued pairs
+};
+
+__device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile_base, uint32_t grp,
+                                              uint32_t half, uint32_t x, uint32_t y) {
+  const uint32_t s = (y - 1) >> 3, c = (y - 1) & 7;
+  const uint2 w = __ldg(&p.tb[tile_base + ((uint64_t)s * p.tb_rows + (x - 1)) * p.ng + grp]);
+  return ((half ? w.y : w.x) >> (4 * c)) & 15u;
+}
+
+// MODE 0: classify + count runs (writes score/status/cigar_len, queues tainted pairs)
+// MODE 1: write runs into the pool (needs cigar_off)
+template <int MODE>
+__global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
+  const uint32_t n_launch = p.n_launch_dev ? *p.n_launch_dev : p.n_launch_pairs;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_launch) return;
+  const uint32_t id = p.pair_ids ? p.pair_ids[i] : p.pair_base + i;
+  const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
+  const uint32_t ppt = 2 * p.ng;
+  const uint32_t tile = i / ppt, grp = (i % ppt) >> 1, half = i & 1;
+  const uint64_t tile_base = (uint64_t)tile * p.tb_tile_stride;
+
+  if (n1 == 0 || n2 == 0) {
+    if (MODE == 0 && p.phase == 0) {
+      if (n1 == 0 && n2 == 0) {  // M[0][0] = 0 is popped at (0,0): one empty alignment (:283-286)
+        p.score[id] = 0;
+        p.status[id] = kOk;
+      } else {  // the end cell IS a boundary-chain cell (:183-216): expanding it panics
+        const int32_t n = (int32_t)(n1 + n2);
+        p.score[id] = p.open + (n + 1) * p.ext;
+        p.status[id] = kRefPanicEarly;
+      }
+      p.cigar_len[id] = 0;
+    }
+    return;
+  }
+
+  const uint32_t w = p.end[i];
+  uint32_t st = (w >> 16) & 3u;
+  if (MODE == 0) {
+    const int32_t t2 = (int32_t)(w & 0xffffu) - (int32_t)kBias + p.match * (int32_t)(n1 + n2);
+    const int32_t taint = t2 & 1;
+    if (p.phase == 0) {
+      p.score[id] = (t2 - taint) / 2;
+      if (taint) {  // some co-optimal path starts with a gap: the reference panics somewhere.
+        const uint32_t slot = atomicAdd(p.rerun_count, 1u);
+        p.rerun_ids[slot] = id;
+        p.cigar_len[id] = 0;
+        p.status[id] = kRefPanic;  // refined by the clean refill
+        return;
+      }
+    }
+  } else {
+    // write pass: skip pairs that have no alignment, and (phase 0) pairs owned by the refill
+    if (p.cigar_len[id] == 0) return;
+    if (p.phase == 0 && p.status[id] != kOk) return;
+  }
+
+  uint32_t x = n2, y = n1;
+  uint32_t nruns = 0, run_op = 3, run_len = 0;
+  uint64_t wpos = 0;
+  if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];  // runs are produced last-to-first
+  while (x > 0 && y > 0) {
+    if (st != run_op) {
+      if (MODE == 1 && run_len) {
+        --wpos;
+        if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
+      }
+      run_op = st;
+      run_len = 0;
+      ++nruns;
+    }
+    ++run_len;
+    if (st == 0) {  // InM: emit a diagonal column, the next state is the best state of (x-1,y-1)
+      --x;
+      --y;
+      if (x > 0 && y > 0) {
+        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
+        st = (nb & 2u) ? 2u : ((nb & 1u) ? 1u : 0u);
+      }
+    } else if (st == 1) {  // InI: seq1[y-1] against '-'
+      --y;
+      if (y > 0) {
+        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
+        st = (nb & 4u) ? 0u : 1u;
+      }
+    } else {  // InD: '-' against seq2[x-1]
+      --x;
+      if (x > 0) {
+        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
+        st = (nb & 8u) ? 0u : 2u;
+      }
+    }
+  }
+  const bool complete = (x == 0 && y == 0);
+  if (MODE == 0) {
+    if (p.phase == 0) {
+      // untainted pairs cannot run into the boundary chain (that path would carry the bonus)
+      p.status[id] = complete ? kOk : kRefPanicEarly;
+      p.cigar_len[id] = complete ? nruns : 0;
+    } else {
+      p.status[id] = complete ? kRefPanic : kRefPanicEarly;
+      p.cigar_len[id] = complete ? nruns : 0;
+    }
+  } else if (complete && run_len) {
+    --wpos;
+    if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
+  }
+}
+
+// ---- exclusive scan of cigar_len -> cigar_off (three small kernels, no library) -------------
+constexpr int kScanBlock = 1024;
+
+__global__ void __launch_bounds__(kScanBlock) scan_block_sums(const uint32_t* __restrict__ len,
+                                                              uint64_t* __restrict__ block_sums,
+                                                              uint32_t n) {
+  __shared__ uint64_t warp_sums[32];
+  const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+  uint64_t v = i < n ? len[i] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint64_t s = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+  }
+}
+
+// single block: exclusive scan of block sums in place, starting from *carry; updates *carry
+__global__ void __launch_bounds__(kScanBlock) scan_block_offsets(uint64_t* __restrict__ block_sums,
+                                                                 uint32_t n_blocks,
+                                                                 uint64_t* __restrict__ carry) {
+  __shared__ uint64_t sh[kScanBlock];
+  __shared__ uint64_t running;
+  if (threadIdx.x == 0) running = *carry;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += kScanBlock) {
+    const uint32_t i = base + threadIdx.x;
+    const uint64_t v = i < n_blocks ? block_sums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+      const uint64_t a = threadIdx.x >= (uint32_t)o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (i < n_blocks) block_sums[i] = running + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) running += sh[kScanBlock - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *carry = running;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply(const uint32_t* __restrict__ len,
+                                                         const uint64_t* __restrict__ block_sums,
+                                                         uint64_t* __restrict__ off, uint32_t n) {
+  __shared__ uint64_t warp_sums[32];
+  const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+  const uint64_t v = i < n ? len[i] : 0;
+  uint64_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t a = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= (uint32_t)o) incl += a;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint64_t w = warp_sums[threadIdx.x];
+    uint64_t s = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t a = __shfl_up_sync(0xffffffffu, s, o);
+      if (threadIdx.x >= (uint32_t)o) s += a;
+    }
+    warp_sums[threadIdx.x] = s - w;  // exclusive
+  }
+  __syncthreads();
+  if (i < n) off[i] = block_sums[blockIdx.x] + warp_sums[threadIdx.x >> 5] + incl - v;
+}
+
+}  // namespace sa

@@ -1,0 +1,291 @@
+"""Host-side mirror of the reference's aligner interface over the C ABI.
+
+The reference's only API is three functions called once per (query, db) pair from the loop in
+/root/reference/src/main.rs:61-79:
+    n_w_align(seq1: &Record, seq2: &Record, verbose, mode)   needleman_wunsch_affine.rs:424
+    wfa_align(seq1, seq2, mode)                              wfa.rs:23
+Here the same call is made once per BATCH of pairs.  `Record` keeps the reference's field
+names (parse.rs:135-139).  All computation happens in libsa_engine.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import (ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
+                    NOT_IMPLEMENTED, OK, REF_NO_CONVERGENCE, REF_NO_OUTPUT, REF_PANIC, REF_PANIC_EARLY)
+
+STATUS_NAMES = {
+    OK: "OK", REF_PANIC: "REF_PANIC", REF_NO_CONVERGENCE: "REF_NO_CONVERGENCE",
+    NOT_IMPLEMENTED: "NOT_IMPLEMENTED", REF_PANIC_EARLY: "REF_PANIC_EARLY", REF_NO_OUTPUT: "REF_NO_OUTPUT",
+}
+ALGOS = {"needleman-wunsch": ALGO_NW_AFFINE, "needleman-wunsch-linear": ALGO_NW_LINEAR, "wfa": ALGO_WFA}
+MODES = {"global": MODE_GLOBAL, "local": MODE_LOCAL, "semi-global": MODE_SEMIGLOBAL}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sa_engine error {code}: {msg}")
+        self.code = code
+
+
+@dataclass
+class Record:
+    """parse.rs:135-139.  `name` includes the leading '>'."""
+    seq: bytes
+    name: bytes = b""
+
+
+@dataclass
+class PairBatch:
+    """Pairs as (offset, length) views into one residue buffer -- the layout of sa_batch_t."""
+    residues: np.ndarray  # uint8
+    q_off: np.ndarray     # uint64
+    q_len: np.ndarray     # uint32
+    d_off: np.ndarray     # uint64
+    d_len: np.ndarray     # uint32
+
+    def __post_init__(self):
+        self.residues = np.ascontiguousarray(self.residues, np.uint8)
+        self.q_off = np.ascontiguousarray(self.q_off, np.uint64)
+        self.d_off = np.ascontiguousarray(self.d_off, np.uint64)
+        self.q_len = np.ascontiguousarray(self.q_len, np.uint32)
+        self.d_len = np.ascontiguousarray(self.d_len, np.uint32)
+        n = len(self.q_len)
+        if not (len(self.q_off) == len(self.d_off) == len(self.d_len) == n):
+            raise ValueError("offset/length arrays differ in length")
+
+    @property
+    def n_pairs(self) -> int:
+        return len(self.q_len)
+
+    @property
+    def cells(self) -> int:
+        return int((self.q_len.astype(np.uint64) * self.d_len.astype(np.uint64)).sum())
+
+    def query(self, p: int) -> bytes:
+        o, l = int(self.q_off[p]), int(self.q_len[p])
+        return self.residues[o:o + l].tobytes()
+
+    def db(self, p: int) -> bytes:
+        o, l = int(self.d_off[p]), int(self.d_len[p])
+        return self.residues[o:o + l].tobytes()
+
+    def select(self, idx: np.ndarray) -> "PairBatch":
+        return PairBatch(self.residues, self.q_off[idx], self.q_len[idx], self.d_off[idx], self.d_len[idx])
+
+    @staticmethod
+    def from_pairs(pairs: Iterable[Tuple[bytes, bytes]]) -> "PairBatch":
+        chunks, q_off, q_len, d_off, d_len, cur = [], [], [], [], [], 0
+        for q, d in pairs:
+            q_off.append(cur); q_len.append(len(q)); chunks.append(q); cur += len(q)
+            d_off.append(cur); d_len.append(len(d)); chunks.append(d); cur += len(d)
+        res = np.frombuffer(b"".join(chunks), np.uint8) if cur else np.zeros(0, np.uint8)
+        return PairBatch(res, np.array(q_off, np.uint64), np.array(q_len, np.uint32),
+                         np.array(d_off, np.uint64), np.array(d_len, np.uint32))
+
+    @staticmethod
+    def from_records(query: Sequence[Record], db: Sequence[Record]) -> "PairBatch":
+        """The db-major cross product of main.rs:61-62: for d in db { for q in query { .. } }."""
+        seqs = [r.seq for r in query] + [r.seq for r in db]
+        offs = np.zeros(len(seqs) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+        res = np.frombuffer(b"".join(seqs), np.uint8) if offs[-1] else np.zeros(0, np.uint8)
+        nq, nd = len(query), len(db)
+        qi = np.tile(np.arange(nq), nd)
+        di = np.repeat(np.arange(nd), nq) + nq
+        lens = np.array([len(s) for s in seqs], np.uint32)
+        return PairBatch(res, offs[qi], lens[qi], offs[di], lens[di])
+
+
+@dataclass
+class AlignResult:
+    score: np.ndarray      # int32
+    status: np.ndarray     # uint8 (sa_status_t)
+    cigar_off: np.ndarray  # uint64
+    cigar_len: np.ndarray  # uint32
+    cigar: np.ndarray      # uint32 pool
+
+    def cigar_of(self, p: int) -> List[int]:
+        o, l = int(self.cigar_off[p]), int(self.cigar_len[p])
+        return [int(v) for v in self.cigar[o:o + l]]
+
+    def cigar_string(self, p: int) -> str:
+        return "".join(f"{w >> 2}{'MID'[w & 3]}" for w in self.cigar_of(p))
+
+
+def _scheme(s) -> Optional[_capi.Scheme]:
+    if s is None:
+        return None
+    if isinstance(s, _capi.Scheme):
+        return s
+    return _capi.Scheme(*s)
+
+
+class Engine:
+    """One engine per (process, GPU).  Multi-GPU: one process per GPU, see shard.py."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        rc = self._lib.sa_engine_create(device, C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.sa_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                self._lib.sa_engine_destroy(self._h)
+                self._h = C.c_void_p()
+            raise EngineError(rc, msg)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sa_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise EngineError(rc, self._lib.sa_last_error(self._h).decode())
+
+    @staticmethod
+    def _c_batch(b: PairBatch) -> _capi.Batch:
+        return _capi.Batch(b.residues.ctypes.data, b.residues.size, b.q_off.ctypes.data, b.q_len.ctypes.data,
+                           b.d_off.ctypes.data, b.d_len.ctypes.data, b.n_pairs, 0)
+
+    @staticmethod
+    def _alloc_result(n: int, cigar_capacity: int):
+        score = np.zeros(n, np.int32)
+        status = np.zeros(n, np.uint8)
+        off = np.zeros(n, np.uint64)
+        ln = np.zeros(n, np.uint32)
+        pool = np.zeros(max(cigar_capacity, 0), np.uint32)
+        res = _capi.Result(score.ctypes.data, status.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                           pool.ctypes.data if cigar_capacity > 0 else None, max(cigar_capacity, 0), 0)
+        return res, (score, status, off, ln, pool)
+
+    def align(self, batch: PairBatch, algo: int = ALGO_NW_AFFINE, mode: int = MODE_GLOBAL, scheme=None,
+              cigar: bool = True, cigar_capacity: Optional[int] = None) -> AlignResult:
+        """sa_align_batch: host buffers in, host buffers out (the reference-facing call)."""
+        n = batch.n_pairs
+        cap = 0
+        if cigar:
+            cap = cigar_capacity if cigar_capacity is not None else max(64, 32 * n)
+        sc = _scheme(scheme)
+        cb = self._c_batch(batch)
+        while True:
+            res, arrs = self._alloc_result(n, cap)
+            rc = self._lib.sa_align_batch(self._h, algo, mode, C.byref(sc) if sc else None, C.byref(cb), C.byref(res))
+            if rc == _capi.E_CIGAR_CAPACITY and cigar_capacity is None:
+                cap = int(res.cigar_used) + 16
+                continue
+            self._check(rc)
+            break
+        score, status, off, ln, pool = arrs
+        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)] if cap else pool)
+
+    # ---- device-resident path (benchmarks: inputs already in HBM) -------------------------
+    def upload(self, batch: PairBatch) -> "ResidentBatch":
+        h = C.c_void_p()
+        cb = self._c_batch(batch)
+        self._check(self._lib.sa_batch_upload(self._h, C.byref(cb), C.byref(h)))
+        self._check(self._lib.sa_engine_synchronize(self._h))
+        return ResidentBatch(self, h, batch.n_pairs)
+
+    def synchronize(self):
+        self._check(self._lib.sa_engine_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.sa_engine_stream(self._h) or 0)
+
+    def timing(self) -> dict:
+        t = _capi.Timing()
+        self._lib.sa_last_timing(self._h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+
+class ResidentBatch:
+    def __init__(self, eng: Engine, handle, n_pairs: int):
+        self._eng, self._h, self.n_pairs = eng, handle, n_pairs
+
+    def align(self, algo: int = ALGO_NW_AFFINE, mode: int = MODE_GLOBAL, scheme=None, cigar: bool = True):
+        sc = _scheme(scheme)
+        e = self._eng
+        e._check(e._lib.sa_align_resident(e._h, algo, mode, C.byref(sc) if sc else None, self._h, int(cigar)))
+
+    def download(self, cigar_capacity: Optional[int] = None) -> AlignResult:
+        e = self._eng
+        n = self.n_pairs
+        cap = cigar_capacity if cigar_capacity is not None else max(64, 32 * n)
+        while True:
+            res, arrs = e._alloc_result(n, cap)
+            rc = e._lib.sa_resident_download(e._h, self._h, C.byref(res))
+            if rc == _capi.E_CIGAR_CAPACITY and cigar_capacity is None:
+                cap = int(res.cigar_used) + 16
+                continue
+            e._check(rc)
+            break
+        score, status, off, ln, pool = arrs
+        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)])
+
+    def free(self):
+        if self._h:
+            self._eng._lib.sa_batch_free(self._eng._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def render_affine(seq1: bytes, seq2: bytes, cigar: Sequence[int]) -> str:
+    """Reference stdout for one alignment (needleman_wunsch_affine.rs:283-286, :390-411)."""
+    l = _capi.lib()
+    arr = (C.c_uint32 * max(len(cigar), 1))(*cigar)
+    need = l.sa_render_affine(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), None, 0)
+    if need < 0:
+        raise ValueError("CIGAR does not fit the sequences")
+    buf = C.create_string_buffer(need + 1)
+    l.sa_render_affine(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), buf, need + 1)
+    return buf.value.decode("latin1")
+
+
+def parse_fasta(path: str):
+    """parse_fasta (parse.rs:54-99).  Returns (records, err_chars); raises ValueError for the
+    reference's FastaError.  Non-empty err_chars <=> the reference returns CharError carrying
+    these records (main.rs:29-35 then continues with them)."""
+    import os
+    l = _capi.lib()
+    size = os.path.getsize(path) if os.path.exists(path) else 0
+    out = np.zeros(max(size, 1), np.uint8)
+    with open(path, "rb") as f:
+        idx_cap = f.read().count(b">") + 1 if size else 1
+    idx = np.zeros(4 * idx_cap, np.uint64)
+    err = np.zeros(max(size, 1), np.uint8)
+    nerr = C.c_size_t()
+    n = l.sa_parse_fasta(path.encode(), out.ctypes.data, out.size, idx.ctypes.data, idx_cap, err.ctypes.data, err.size, C.byref(nerr))
+    if n < 0:
+        raise ValueError(f"FastaError: {path}")
+    raw = out.tobytes()
+    recs = []
+    for r in range(n):
+        no, nl, so, sl = (int(v) for v in idx[4 * r:4 * r + 4])
+        recs.append(Record(seq=raw[so:so + sl], name=raw[no:no + nl]))
+    return recs, err[: nerr.value].tobytes()

@@ -1,0 +1,138 @@
+"""GPU parity tests proper: the CUDA affine-NW path, called through the C ABI, against the
+literal oracle (oracle/nw_affine.c) on the same inputs.  Bit-exact: score, status, CIGAR.
+
+Reference path under test: /root/reference/src/needleman_wunsch_affine.rs:169-334.
+"""
+import numpy as np
+import pytest
+
+from tests.util import check_against_oracle, random_pair_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(pairs):
+    from sequencealigning_b200 import PairBatch
+    return PairBatch.from_pairs(pairs)
+
+
+def test_known_answers(engine, oracle):
+    # SURVEY.md 8c seed vectors (hand-checkable) -- (seq1, seq2, score, status, cigar string)
+    from sequencealigning_b200 import OK, REF_PANIC_EARLY
+    kats = [
+        (b"ACGT", b"ACGT", 20, OK, "4M"),
+        (b"ACGT", b"AGT", 1, OK, "1M1I2M"),
+        (b"AGT", b"ACGT", 1, OK, "1M1D2M"),
+        (b"ACGTT", b"ACGT", 6, OK, "3M1I1M"),
+        (b"AAAA", b"AAA", 1, OK, "2M1I1M"),
+        (b"ACGTACGT", b"ACGGT", -1, OK, "3M3I2M"),
+        (b"GACGT", b"ACGT", 0, REF_PANIC_EARLY, ""),
+        (b"ACGT", b"GACGT", 0, REF_PANIC_EARLY, ""),
+        (b"", b"", 0, OK, ""),
+        (b"ACG", b"", -8 - 6 * 4, REF_PANIC_EARLY, ""),
+        (b"", b"AC", -8 - 6 * 3, REF_PANIC_EARLY, ""),
+        (b"NNNN", b"NNNN", 20, OK, "4M"),
+    ]
+    b = _batch([(k[0], k[1]) for k in kats])
+    r = engine.align(b)
+    for i, (_, _, score, status, cig) in enumerate(kats):
+        assert r.score[i] == score, (i, kats[i], r.score[i])
+        assert r.status[i] == status, (i, kats[i], r.status[i])
+        assert r.cigar_string(i) == cig, (i, kats[i], r.cigar_string(i))
+    check_against_oracle(oracle, b, r, what="kats")
+
+
+@pytest.mark.parametrize("seed,n,lo,hi", [(1, 3000, 0, 40), (2, 2000, 1, 130), (3, 1500, 100, 300)])
+def test_random_ragged(engine, oracle, seed, n, lo, hi):
+    b = _batch(random_pair_list(seed, n, lo, hi))
+    r = engine.align(b)
+    ref = check_against_oracle(oracle, b, r, what=f"ragged seed {seed}")
+    # the set must exercise every status the short-pair path can produce
+    if seed == 1:
+        assert {0, 1, 4} <= set(np.unique(ref.status).tolist())
+
+
+@pytest.mark.parametrize("length,indels", [(150, False), (150, True), (250, True)])
+def test_config_shapes(engine, oracle, length, indels):
+    from sequencealigning_b200 import synth
+    b = synth.random_pairs(20000, length, 0.05, indels, seed=0x5A02 + length + indels)
+    r = engine.align(b)
+    ref = check_against_oracle(oracle, b, r, what=f"{length}bp indels={indels}")
+    if not indels:  # substitutions only: the reference prints exactly one alignment, never panics
+        assert (ref.status == 0).all()
+        assert (r.cigar_len == 1).all() and (r.cigar == (150 << 2)).all()
+
+
+@pytest.mark.parametrize("g", [1, 2, 4, 8, 16, 32])
+def test_every_lane_group_width(oracle, g, monkeypatch):
+    """Every instantiation of the fill kernel (lanes per pair-of-pairs) gives the same bits."""
+    from sequencealigning_b200 import Engine
+    monkeypatch.setenv("SA_FORCE_G", str(g))
+    with Engine(0) as eng:
+        b = _batch(random_pair_list(40 + g, 700, 1, 220))
+        r = eng.align(b)
+        check_against_oracle(oracle, b, r, what=f"G={g}")
+
+
+def test_chunked_and_refill_slices(oracle, monkeypatch):
+    """A tiny traceback budget forces many chunks and several refill slices per chunk."""
+    from sequencealigning_b200 import Engine
+    monkeypatch.setenv("SA_TB_BUDGET_MB", "2")
+    with Engine(0) as eng:
+        b = _batch(random_pair_list(77, 4000, 0, 60, rates=(0.3, 0.5)))
+        r = eng.align(b)
+        ref = check_against_oracle(oracle, b, r, what="chunked")
+        assert (ref.status != 0).sum() > 100
+
+
+def test_score_only_and_capacity(engine, oracle):
+    from sequencealigning_b200 import EngineError
+    b = _batch(random_pair_list(5, 500, 20, 80))
+    r = engine.align(b, cigar=False)
+    ref = oracle.affine_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len)
+    assert np.array_equal(r.score, ref.score) and np.array_equal(r.status, ref.status)
+    with pytest.raises(EngineError) as ei:
+        engine.align(b, cigar_capacity=3)
+    assert ei.value.code == -4
+
+
+def test_non_global_modes_not_implemented(engine):
+    from sequencealigning_b200 import MODE_LOCAL, MODE_SEMIGLOBAL, NOT_IMPLEMENTED
+    b = _batch([(b"ACGT", b"ACGT"), (b"AC", b"A")])
+    for mode in (MODE_LOCAL, MODE_SEMIGLOBAL):  # nw_affine:433-434
+        r = engine.align(b, mode=mode)
+        assert (r.status == NOT_IMPLEMENTED).all() and (r.cigar_len == 0).all()
+
+
+def test_one_query_many_db_aliasing(engine, oracle):
+    """main.rs:61-62 cross product: every pair shares the same query bytes."""
+    from sequencealigning_b200 import PairBatch, Record, synth
+    b0 = synth.random_pairs(300, 150, 0.05, True, seed=9)
+    query = [Record(b0.query(0), b">q")]
+    db = [Record(b0.db(i), b">d%d" % i) for i in range(300)]
+    b = PairBatch.from_records(query, db)
+    assert (b.q_off == b.q_off[0]).all()
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, what="1xN")
+
+
+def test_resident_path_matches_host_path(engine):
+    from sequencealigning_b200 import synth
+    b = synth.random_pairs(5000, 150, 0.05, True, seed=11)
+    r1 = engine.align(b)
+    rb = engine.upload(b)
+    rb.align()
+    rb.align()  # idempotent
+    r2 = rb.download()
+    rb.free()
+    for a, c in ((r1.score, r2.score), (r1.status, r2.status), (r1.cigar_len, r2.cigar_len), (r1.cigar, r2.cigar)):
+        assert np.array_equal(a, c)
+
+
+def test_render_matches_reference_text(engine, oracle):
+    from sequencealigning_b200 import render_affine
+    for q, d in [(b"ACGT", b"AGT"), (b"ACGTACGT", b"ACGGT"), (b"AAAA", b"AAA")]:
+        b = _batch([(q, d)])
+        r = engine.align(b)
+        text, n, pan = oracle.affine_print_all(q, d, max_alignments=1)
+        assert render_affine(q, d, r.cigar_of(0)) == text
