@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: batched affine-gap NW (score + traceback), GCUPS.
+
+Workload (BASELINE.json configs[1]): synthetic 150 bp read pairs at 5 % divergence
+(sub:ins:del = 2:1:1), 1,000,000 pairs PER GPU; a "step" is one pass of the hot path over
+the whole batch.  GCUPS = sum(n1*n2) / seconds / 1e9.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # this engine
+    python bench.py --impl reference ...                      # CPU oracle of the reference
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, no collective
+                                                              # on the data path (weak scaling)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GCUPS, batched affine-gap NW score+traceback (alignments/s in config)"
+OPS_PER_CELL_ISSUED = 9.0     # SASS lane-instructions per DP cell in the fill (18 per packed pair of cells)
+OPS_PER_CELL_S32_EQUIV = 16.0  # SURVEY.md 8d / BASELINE.md figure for score + 4-bit traceback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
+    ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--divergence", type=float, default=0.05)
+    ap.add_argument("--no-indels", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batch(args, rank: int):
+    from sequencealigning_b200 import synth
+    return synth.random_pairs(args.pairs, args.length, args.divergence, not args.no_indels,
+                              seed=synth.SEEDS["config2"] + 7919 * rank)
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    return {
+        "workload": f"affine NW score+traceback, {args.pairs} synthetic {args.length} bp read pairs per GPU at "
+                    f"{args.divergence:.0%} divergence ({'sub:ins:del 2:1:1' if not args.no_indels else 'substitutions only'}) "
+                    f"(BASELINE.json configs[1])",
+        "pairs_per_gpu": args.pairs, "length": args.length, "n_gpus": n_gpus,
+        "scheme": "match 5 / mismatch -4 / open -8 / ext -6 (nw_affine.rs:15-20)",
+        "sharding": "independent shards per rank, no collective on the data path",
+        "l2": "inputs (~%.0f MB) + traceback scratch (GBs) exceed the 126 MB L2; no flush needed" % (args.pairs * args.length * 2 / 1e6),
+    }
+
+
+def cpu_baseline(batch, n_sample: int, n_threads: int, min_seconds: float = 0.0) -> dict:
+    """Times the CPU oracle (literal restatement of the reference) on a bounded sample."""
+    from oracle import binding as ob
+    ob.build()
+    n_sample = min(n_sample, batch.n_pairs)
+    idx = np.arange(n_sample)
+    sub = batch.select(idx)
+    stride = int((sub.q_len.astype(np.int64) + sub.d_len).max()) + 1
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        ob.affine_batch(sub.residues, sub.q_off, sub.q_len, sub.d_off, sub.d_len, cigar_stride=stride, n_threads=n_threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    cells = sub.cells * reps
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": n_threads, "kind": "port",
+            "alignments_per_s": n_sample * reps / dt, "seconds": dt,
+            "sample": f"first {n_sample} pairs of the workload x {reps} pass(es), oracle/nw_affine.c "
+                      f"(flat-array restatement; the Rust original allocates >=3 Rc per cell and is far slower)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (the oracle port; the Rust crate cannot
+    be built in this image) on the same workload, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = make_batch(args, 0)
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or min(args.pairs, 4000 * cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(batch, min(n_sample, 2000), cores)
+    vals = []
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(batch, n_sample, cores))
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "i32", "data": "synthetic", "config": workload_config(args, args.gpus), "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def int_peak() -> dict:
+    """Measured integer issue rate (own microbenchmark, sequencealigning_b200/csrc/microbench)."""
+    from sequencealigning_b200.build import INT_PEAK_PATH
+    try:
+        r = subprocess.run([INT_PEAK_PATH], capture_output=True, text=True, timeout=120)
+        d = json.loads(r.stdout)["results"]
+        return {"issue_lane_ops_per_s": max(d["iadd"]["lane_ops_per_s"], d["mix_lop3_imad"]["lane_ops_per_s"]),
+                "alu_pipe_lane_ops_per_s": d["viaddmnmx_s16x2"]["lane_ops_per_s"], "source": "int_peak microbenchmark, this run"}
+    except Exception as ex:  # nominal: 32 lanes/clk/SMSP * 4 * 148 * 1.965 GHz
+        return {"issue_lane_ops_per_s": 32 * 4 * 148 * 1.965e9, "alu_pipe_lane_ops_per_s": 16 * 4 * 148 * 1.965e9,
+                "source": f"nominal (microbenchmark failed: {ex})"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from sequencealigning_b200 import Engine
+    from sequencealigning_b200.build import build_all
+    build_all()
+    eng = Engine(local)
+    batch = make_batch(args, rank)
+    cells = batch.cells
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg: `value` ------------------------------------------
+    rb = eng.upload(batch)
+    for _ in range(args.warmup):
+        rb.align()
+    eng.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    launches = 0
+    reruns = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        rb.align()
+        t = eng.timing()
+        launches += t["kernel_launches"]
+        reruns = t["pairs_rerun"]
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        ct = torch.tensor([float(cells)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ct, op=dist.ReduceOp.SUM)
+        cells_all = float(ct.item())
+    else:
+        cells_all = float(cells)
+    ms_step = ms_total / args.steps
+    gcups = cells_all / (ms_step * 1e-3) / 1e9
+    res_dev = rb.download()
+    rb.free()
+
+    # ---------------- end-to-end leg through the reference-facing call: `e2e` ----------------
+    e2e = None
+    if not args.skip_e2e:
+        def pinned(a):
+            t = torch.from_numpy(a.copy()).pin_memory()
+            return t, t.numpy()
+        keep = []
+        from sequencealigning_b200 import PairBatch
+        arrs = []
+        for a in (batch.residues, batch.q_off, batch.q_len, batch.d_off, batch.d_len):
+            t, v = pinned(a)
+            keep.append(t); arrs.append(v)
+        pb = PairBatch.__new__(PairBatch)
+        pb.residues, pb.q_off, pb.q_len, pb.d_off, pb.d_len = arrs
+        cap = int(res_dev.cigar.size) + 1024
+        for _ in range(2):
+            eng.align(pb, cigar_capacity=cap)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = eng.align(pb, cigar_capacity=cap)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        tim = eng.timing()
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(tim["h2d_bytes"]), "d2h_bytes_per_step": int(tim["d2h_bytes"]),
+               "alignments_per_s": args.pairs * world / dt,
+               "api": "sa_align_batch (C ABI) with pinned host buffers; host wall clock, max over ranks"}
+        assert np.array_equal(r.score, res_dev.score)
+
+    if rank == 0:
+        peak = int_peak()
+        issued = gcups * 1e9 * OPS_PER_CELL_ISSUED / world
+        tb_bytes = cells / 2.0
+        hbm_bytes = tb_bytes + batch.residues.size + batch.n_pairs * (24 + 17) + res_dev.cigar.size * 4
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        out = {
+            "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16x2 (packed pairs; exact integer)",
+            "data": "synthetic", "config": workload_config(args, world),
+            "alignments_per_s": args.pairs * world / (ms_step * 1e-3),
+            "gpu_launches": int(launches // max(args.steps, 1)), "pairs_rerun_per_step": int(reruns),
+            "clocks": clocks, "e2e": e2e,
+            "roofline": {
+                "bound": "int-issue", "achieved": issued / 1e12, "peak": peak["issue_lane_ops_per_s"] / 1e12, "unit": "T lane-ops/s",
+                "frac": issued / peak["issue_lane_ops_per_s"], "traffic": None,
+                "per_gpu": True, "ops_per_cell": OPS_PER_CELL_ISSUED,
+                "note": "whole step (fill + walks + scan) timed; achieved = cells/s x 9 issued lane-instructions per cell; peak = " + peak["source"],
+                "s32_equiv_frac": gcups * 1e9 / world * OPS_PER_CELL_S32_EQUIV / peak["issue_lane_ops_per_s"],
+                "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                        "bytes": "sequences + 0.5 B/cell traceback written + results"},
+            },
+        }
+        if not args.skip_cpu:
+            n_sample = args.cpu_sample or 20000
+            out["cpu_baseline"] = cpu_baseline(batch, n_sample, 1)
+            cores = os.cpu_count() or 1
+            allc = cpu_baseline(batch, n_sample * min(cores, 8), cores)
+            out["cpu_baseline"]["all_cores"] = {"value": allc["value"], "cores": cores, "unit": "GCUPS"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
