@@ -107,7 +107,7 @@ typedef struct {
 
 /* Kernel-time breakdown of the last call (device milliseconds from CUDA events). */
 typedef struct {
-  double h2d_ms, fill_ms, walk_ms, d2h_ms, total_ms;
+  double h2d_ms, fill_ms /* all kernels of the call */, walk_ms /* main fill kernel only */, d2h_ms, total_ms;
   uint64_t cells;         /* sum over pairs of n1*n2                                          */
   uint64_t kernel_launches;
   uint64_t h2d_bytes, d2h_bytes;

@@ -63,6 +63,7 @@ struct sa_engine {
   int sm_count = 0;
   size_t smem_optin = 0;
   int force_g = 0;
+  uint32_t ormask = 0x0F;
   size_t tb_budget = 0;
 };
 
@@ -105,7 +106,7 @@ struct Geometry {
   uint32_t ng = 8, ppt = 16;
   uint32_t nstrips_pad = 0, n1pad = 0, tb_rows = 0;
   uint64_t tile_stride = 0;  // uint2 per tile
-  uint32_t q_words = 0, d_words = 0;
+  uint32_t d_halfs = 0, q_halfs = 0;
   size_t smem_bytes = 0;
 };
 
@@ -120,10 +121,10 @@ Geometry make_geometry(int G, uint32_t n1max, uint32_t n2max) {
   g.n1pad = g.nstrips_pad * kK;
   g.tb_rows = std::max(1u, n2max);
   g.tile_stride = (uint64_t)g.nstrips_pad * g.tb_rows * g.ng;
-  g.q_words = g.n1pad * g.ng;
-  g.d_words = g.tb_rows * g.ng;
-  if ((g.q_words + g.d_words) & 1) g.d_words += 1;  // keep the uint2 boundary array 8-byte aligned
-  g.smem_bytes = (size_t)(g.q_words + g.d_words) * 4 + (size_t)g.tb_rows * g.ng * 8;
+  g.d_halfs = g.tb_rows * g.ng;  // one u16 (two residues) per row per pair-of-pairs
+  g.q_halfs = g.n1pad * g.ng;
+  g.smem_bytes = (size_t)g.tb_rows * g.ng * 8 + (size_t)(g.d_halfs + g.q_halfs) * 2;
+  g.smem_bytes = (g.smem_bytes + 15) & ~(size_t)15;
   return g;
 }
 
@@ -151,16 +152,30 @@ int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
   return best;
 }
 
-template <int G>
-sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                        uint32_t n_tiles) {
-  auto kern = sa::nw_affine_fill_s16<kK, G>;
+template <int G, uint32_t ORMASK>
+sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
+                          uint32_t n_tiles) {
+  auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK>;
   CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)g.smem_bytes));
   kern<<<n_tiles, 32, g.smem_bytes, e->stream>>>(p);
   CUDA_TRY(e, cudaGetLastError());
   e->timing.kernel_launches++;
   return SA_OK;
+}
+
+template <int G>
+sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
+                        uint32_t n_tiles) {
+  switch (e->ormask) {
+    case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles);
+    case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles);
+    case 0x1F: return launch_fill_m<G, 0x1F>(e, p, g, n_tiles);
+    case 0x3F: return launch_fill_m<G, 0x3F>(e, p, g, n_tiles);
+    case 0x7F: return launch_fill_m<G, 0x7F>(e, p, g, n_tiles);
+    case 0xFF: return launch_fill_m<G, 0xFF>(e, p, g, n_tiles);
+  }
+  return fail(e, SA_E_ARG, "SA_ORMASK 0x%x has no instantiation", e->ormask);
 }
 
 sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
@@ -211,6 +226,7 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   for (auto& ev : e->ev) CUDA_TRY(e, cudaEventCreate(&ev));
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
+  if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   return SA_OK;
 }
@@ -344,6 +360,7 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   e->timing.cells = r->cells;
   e->timing.pairs_rerun = 0;
   e->timing.kernel_launches = 0;
+  e->timing.walk_ms = 0;
   if (n == 0) {
     r->aligned = true;
     return SA_OK;
@@ -422,8 +439,8 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   fp.d_len = r->d_len;
   fp.tb_tile_stride = g.tile_stride;
   fp.tb_rows = g.tb_rows;
-  fp.smem_q_words = g.q_words;
-  fp.smem_d_words = g.d_words;
+  fp.smem_bnd_rows = g.tb_rows;
+  fp.smem_d_halfs = g.d_halfs;
   fp.pen2 = pack2((uint32_t)pen);
   fp.open2 = pack2((uint32_t)openp);
   fp.ext2 = pack2((uint32_t)extp);
@@ -462,7 +479,9 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     fp.end = (uint32_t*)e->end.p;
     fp.row0 = pack2(row0_clean + 1);
     CUDA_TRY(e, cudaMemsetAsync(d_rerun_count, 0, 4, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev[6], e->stream));
     if ((st = launch_fill_g(e, fp, g, ctiles)) != SA_OK) return st;
+    CUDA_TRY(e, cudaEventRecord(e->ev[7], e->stream));
     // 2. classify + count
     wp.pair_ids = nullptr;
     wp.pair_base = (uint32_t)base;
@@ -479,6 +498,10 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     const uint32_t n_re = *e->h_count;
     e->timing.pairs_rerun += n_re;
+    {
+      float fms = 0;
+      if (cudaEventElapsedTime(&fms, e->ev[6], e->ev[7]) == cudaSuccess) e->timing.walk_ms += fms;
+    }
     const uint32_t re_chunk = (uint32_t)(tiles_re * g.ppt);
     struct ReLaunch { uint32_t off, cnt; };
     std::vector<ReLaunch> re_launches;

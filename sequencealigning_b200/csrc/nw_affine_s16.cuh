@@ -62,13 +62,14 @@ struct AffineS16Params {
   uint64_t tb_tile_stride;       // uint2 per tile
   uint32_t tb_rows;              // row stride (launch-wide max n2)
   uint32_t* __restrict__ end;    // per launch index: H'(16) | start_state << 16 | valid << 31
-  uint32_t smem_q_words, smem_d_words;  // per-warp panel sizes (words), multiples of 32/G
+  uint32_t smem_bnd_rows, smem_d_halfs;  // per-warp layout: boundary rows, then db panel (u16), then query panel
   // scheme in transformed units (all positive magnitudes)
   uint32_t pen2;    // 2*(match-mismatch), packed in both halves
   uint32_t open2;   // -2*open, packed
   uint32_t ext2;    // match - 2*ext, packed
   uint32_t row0;    // kBias - 2*(-(open+ext)) + bonus, packed: H'[0][y] = row0 - y*ext2
   uint32_t origin;  // kBias packed: H'[0][0]
+  uint32_t zero;    // always 0; opaque to ptxas so that `or` bit-sets stay LOP3 (alu pipe)
 };
 
 // max of two packed u16 pairs that also records, per half, whether the FIRST operand won or
@@ -76,89 +77,89 @@ struct AffineS16Params {
 // a >= b.  ptxas folds the setp.eq pair into the predicate outputs of one VIMNMX.U16x2, and
 // each conditional add becomes one predicated integer add (either integer pipe), so a tie
 // bit costs one issue slot instead of a SEL plus a merge.
-template <uint32_t BIT>
+template <uint32_t BIT, bool LO_OR, bool HI_OR>
 __device__ __forceinline__ uint32_t vmax_tie(uint32_t a, uint32_t b, uint32_t& acc_lo,
                                              uint32_t& acc_hi) {
   uint32_t r;
-  asm("{\n\t"
-      ".reg .pred ph, pl;\n\t"
-      ".reg .u16 r0, r1, a0, a1;\n\t"
-      "max.u16x2 %0, %3, %4;\n\t"
-      "mov.b32 {r0, r1}, %0;\n\t"
-      "mov.b32 {a0, a1}, %3;\n\t"
-      "setp.eq.u16 pl, r0, a0;\n\t"
-      "setp.eq.u16 ph, r1, a1;\n\t"
-      "@pl add.u32 %1, %1, %5;\n\t"
-      "@ph add.u32 %2, %2, %5;\n\t"
-      "}"
-      : "=r"(r), "+r"(acc_lo), "+r"(acc_hi)
-      : "r"(a), "r"(b), "n"(BIT));
+  // The two conditional bit-sets can issue on either integer pipe: `or` becomes a predicated
+  // LOP3 (alu pipe), `add` a predicated VIADD (fma-heavy pipe on sm_100).  Which of the eight
+  // bit-sets of a cell go where is a template mask so the pipes can be balanced against the
+  // VIMNMX (alu, half rate) and IMAD.IADD (fma-heavy) work of the recurrence.
+  if (LO_OR && HI_OR) {
+    asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, a0, a1;\n\t"
+        "max.u16x2 %0, %3, %4;\n\tmov.b32 {r0, r1}, %0;\n\tmov.b32 {a0, a1}, %3;\n\t"
+        "setp.eq.u16 pl, r0, a0;\n\tsetp.eq.u16 ph, r1, a1;\n\t"
+        "@pl or.b32 %1, %1, %5;\n\t@ph or.b32 %2, %2, %5;\n\t}"
+        : "=r"(r), "+r"(acc_lo), "+r"(acc_hi) : "r"(a), "r"(b), "n"(BIT));
+  } else if (LO_OR) {
+    asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, a0, a1;\n\t"
+        "max.u16x2 %0, %3, %4;\n\tmov.b32 {r0, r1}, %0;\n\tmov.b32 {a0, a1}, %3;\n\t"
+        "setp.eq.u16 pl, r0, a0;\n\tsetp.eq.u16 ph, r1, a1;\n\t"
+        "@pl or.b32 %1, %1, %5;\n\t@ph add.u32 %2, %2, %5;\n\t}"
+        : "=r"(r), "+r"(acc_lo), "+r"(acc_hi) : "r"(a), "r"(b), "n"(BIT));
+  } else if (HI_OR) {
+    asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, a0, a1;\n\t"
+        "max.u16x2 %0, %3, %4;\n\tmov.b32 {r0, r1}, %0;\n\tmov.b32 {a0, a1}, %3;\n\t"
+        "setp.eq.u16 pl, r0, a0;\n\tsetp.eq.u16 ph, r1, a1;\n\t"
+        "@pl add.u32 %1, %1, %5;\n\t@ph or.b32 %2, %2, %5;\n\t}"
+        : "=r"(r), "+r"(acc_lo), "+r"(acc_hi) : "r"(a), "r"(b), "n"(BIT));
+  } else {
+    asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, a0, a1;\n\t"
+        "max.u16x2 %0, %3, %4;\n\tmov.b32 {r0, r1}, %0;\n\tmov.b32 {a0, a1}, %3;\n\t"
+        "setp.eq.u16 pl, r0, a0;\n\tsetp.eq.u16 ph, r1, a1;\n\t"
+        "@pl add.u32 %1, %1, %5;\n\t@ph add.u32 %2, %2, %5;\n\t}"
+        : "=r"(r), "+r"(acc_lo), "+r"(acc_hi) : "r"(a), "r"(b), "n"(BIT));
+  }
   return r;
 }
 
-template <int K, int C>
+// ORMASK: bit (2*k + half) set -> the tie bit of comparison k (0 pI, 1 pD, 2 pE, 3 pF) for
+// that half is set with `or` (alu pipe), else with `add` (fma-heavy pipe).
+template <int K, int C, uint32_t ORMASK>
 struct StripCells {
-  template <bool CAPTURE>
   static __device__ __forceinline__ void run(uint32_t (&Hrow)[K], uint32_t (&F)[K],
                                              const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
                                              uint32_t& E, uint32_t pen2, uint32_t open2,
                                              uint32_t ext2, uint32_t& acc_a, uint32_t& acc_b,
-                                             uint32_t (&capM)[K], uint32_t (&capE)[K],
-                                             uint32_t (&capF)[K]) {
+                                             uint32_t (&Mv)[K], uint32_t (&Ev)[K]) {
     constexpr int c = C;
     const uint32_t hup = Hrow[c];
     const uint32_t m = __vminu2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
     const uint32_t M = hdiag - m;                 // M'[x][y]; no borrow (range bound)
-    if (CAPTURE) {
-      capM[c] = M;
-      capE[c] = E;
-      capF[c] = F[c];
-    }
-    const uint32_t t = vmax_tie<(1u << (4 * c))>(E, M, acc_a, acc_b);     // I >= M here
-    const uint32_t H = vmax_tie<(2u << (4 * c))>(F[c], t, acc_a, acc_b);  // D >= max(I,M)
+    Mv[c] = M;  // kept only for the end-cell capture (a rarely taken branch after the row)
+    Ev[c] = E;
+    const uint32_t t = vmax_tie<(1u << (4 * c)), (ORMASK >> 0) & 1, (ORMASK >> 1) & 1>(E, M, acc_a, acc_b);     // I >= M
+    const uint32_t H = vmax_tie<(2u << (4 * c)), (ORMASK >> 2) & 1, (ORMASK >> 3) & 1>(F[c], t, acc_a, acc_b);  // D >= max(I,M)
     const uint32_t Mo = M - open2;
-    const uint32_t En = vmax_tie<(4u << (4 * c))>(Mo, E, acc_a, acc_b);     // open ties/wins: I[x][y+1]
-    const uint32_t Fn = vmax_tie<(8u << (4 * c))>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D[x+1][y]
+    const uint32_t En = vmax_tie<(4u << (4 * c)), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a, acc_b);     // open ties/wins: I[x][y+1]
+    const uint32_t Fn = vmax_tie<(8u << (4 * c)), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D[x+1][y]
     E = En - ext2;
     F[c] = Fn - ext2;
     Hrow[c] = H;
-    StripCells<K, C + 1>::template run<CAPTURE>(Hrow, F, q, d, hup, E, pen2, open2, ext2, acc_a,
-                                                acc_b, capM, capE, capF);
+    StripCells<K, C + 1, ORMASK>::run(Hrow, F, q, d, hup, E, pen2, open2, ext2, acc_a, acc_b, Mv, Ev);
   }
 };
-template <int K>
-struct StripCells<K, K> {
-  template <bool CAPTURE>
+template <int K, uint32_t ORMASK>
+struct StripCells<K, K, ORMASK> {
   static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K],
                                              uint32_t, uint32_t, uint32_t&, uint32_t, uint32_t,
                                              uint32_t, uint32_t&, uint32_t&, uint32_t (&)[K],
-                                             uint32_t (&)[K], uint32_t (&)[K]) {}
+                                             uint32_t (&)[K]) {}
 };
 
-// One row of one K-column strip for two packed pairs.
-template <int K, bool CAPTURE>
-__device__ __forceinline__ void strip_row(uint32_t (&Hrow)[K], uint32_t (&F)[K],
-                                          const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
-                                          uint32_t& E, uint32_t pen2, uint32_t open2,
-                                          uint32_t ext2, uint32_t& acc_a, uint32_t& acc_b,
-                                          uint32_t (&capM)[K], uint32_t (&capE)[K],
-                                          uint32_t (&capF)[K]) {
-  acc_a = 0;
-  acc_b = 0;
-  StripCells<K, 0>::template run<CAPTURE>(Hrow, F, q, d, hdiag, E, pen2, open2, ext2, acc_a, acc_b,
-                                          capM, capE, capF);
+// one residue byte per pair -> (byte << 7) in each 16-bit half
+__device__ __forceinline__ uint32_t widen(uint32_t v) {
+  return ((v & 0xffu) << 7) | ((v & 0xff00u) << 15);
 }
 
 // start state of the traceback at the end cell (nw_affine:251-280: pushed I, M, D; popped
 // D, M, I): D if D == max, else M if M == max, else I.   codes: 0 = M, 1 = I, 2 = D
-__device__ __forceinline__ uint32_t end_word(uint32_t M, uint32_t E, uint32_t F) {
-  const uint32_t me = M > E ? M : E;
-  const uint32_t h = F > me ? F : me;
-  const uint32_t st = (F >= me) ? 2u : (M >= E ? 0u : 1u);
-  return h | (st << 16) | 0x80000000u;
+__device__ __forceinline__ uint32_t end_word(uint32_t H, uint32_t M, uint32_t E, bool d_wins) {
+  const uint32_t st = d_wins ? 2u : (M >= E ? 0u : 1u);
+  return H | (st << 16) | 0x80000000u;
 }
 
-template <int K, int G>
+template <int K, int G, uint32_t ORMASK>
 __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p) {
   static_assert(K == 8, "traceback word layout assumes 8 cells x 4 bits");
   constexpr int NG = 32 / G;       // pair-of-pairs per warp tile
@@ -194,25 +195,26 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   const uint32_t npass = (nstrips + G - 1) / G;
   const uint32_t n1pad = npass * G * K;
 
-  uint32_t* qp = smem;                          // [n1pad][NG]
-  uint32_t* dp = qp + p.smem_q_words;           // [n2t][NG]
-  uint2* bnd = reinterpret_cast<uint2*>(dp + p.smem_d_words);  // [n2t][NG]
+  // panels hold one byte per pair per position: low byte pair A, high byte pair B
+  uint2* bnd = reinterpret_cast<uint2*>(smem);                                     // [rows][NG]
+  uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (size_t)p.smem_bnd_rows * NG);  // [rows][NG]
+  uint16_t* qp = dp + p.smem_d_halfs;                                              // [n1pad][NG]
 
-  // ---- stage the sequence words: (byte << 7) in each half; XOR of two different residues
-  //      is then >= 128 >= pen2, XOR of equal residues is 0 ---------------------------------
+  // ---- stage the residues; they are widened to (byte << 7) per 16-bit half when read, so the
+  //      XOR of two different residues is >= 128 >= pen2 and the XOR of equal residues is 0 ----
   for (uint32_t y = j; y < n1pad; y += G) {
     const uint32_t a = (y < n1a) ? (uint32_t)p.residues[qoa + y] : 0u;
     const uint32_t b = (y < n1b) ? (uint32_t)p.residues[qob + y] : 0u;
-    qp[y * NG + grp] = (a << 7) | (b << 23);
+    qp[y * NG + grp] = (uint16_t)(a | (b << 8));
   }
   for (uint32_t x = j; x < n2t; x += G) {
     const uint32_t a = (x < n2a) ? (uint32_t)p.residues[doa + x] : 0u;
     const uint32_t b = (x < n2b) ? (uint32_t)p.residues[dob + x] : 0u;
-    dp[x * NG + grp] = (a << 7) | (b << 23);
+    dp[x * NG + grp] = (uint16_t)(a | (b << 8));
   }
   __syncwarp();
 
-  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2;
+  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2, zero = p.zero;
   // end-cell capture coordinates (strip, column-in-strip) per half
   const uint32_t sa_ = n1a ? (n1a - 1) / K : 0xffffffffu, ca_ = n1a ? (n1a - 1) % K : 0;
   const uint32_t sb_ = n1b ? (n1b - 1) / K : 0xffffffffu, cb_ = n1b ? (n1b - 1) % K : 0;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
       const uint32_t y = y0 + c + 1;
       Hrow[c] = p.row0 - y * ext2;  // H'[0][y] = D'[0][y]  (nw_affine:194-198)
       F[c] = Hrow[c] - ext2;        // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
-      q[c] = qp[(y - 1) * NG + grp];
+      q[c] = widen(qp[(y - 1) * NG + grp]);
     }
     uint32_t hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * ext2;  // H'[x-1][y0]
     uint32_t colh = p.row0 - ext2;                                 // H'[1][0] = I'[1][0]
@@ -255,29 +257,24 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
             re = b.y;
           }
         }
-        const uint32_t d = dp[(x - 1) * NG + grp];
-        uint32_t E = re, acc_a, acc_b;
-        uint32_t capM[K], capE[K], capF[K];
-        const bool cap = (cap_a_strip && x == n2a) || (cap_b_strip && x == n2b);
-        if (!cap) {
-          strip_row<K, false>(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, capM,
-                              capE, capF);
-        } else {
-          strip_row<K, true>(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, capM,
-                             capE, capF);
+        const uint32_t d = widen(dp[(x - 1) * NG + grp]);
+        uint32_t E = re, acc_a = zero, acc_b = zero;
+        uint32_t Mv[K], Ev[K];
+        StripCells<K, 0, ORMASK>::run(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, Mv, Ev);
+        if ((cap_a_strip && x == n2a) || (cap_b_strip && x == n2b)) {  // rare: a pair's end cell
           if (cap_a_strip && x == n2a) {
-            uint32_t M = 0, Ei = 0, Fi = 0;
+            uint32_t H = 0, M = 0, Ei = 0;
 #pragma unroll
             for (int c = 0; c < K; ++c)
-              if ((uint32_t)c == ca_) { M = capM[c] & 0xffffu; Ei = capE[c] & 0xffffu; Fi = capF[c] & 0xffffu; }
-            p.end[la] = end_word(M, Ei, Fi);
+              if ((uint32_t)c == ca_) { H = Hrow[c] & 0xffffu; M = Mv[c] & 0xffffu; Ei = Ev[c] & 0xffffu; }
+            p.end[la] = end_word(H, M, Ei, (acc_a >> (4 * ca_ + 1)) & 1u);
           }
           if (cap_b_strip && x == n2b) {
-            uint32_t M = 0, Ei = 0, Fi = 0;
+            uint32_t H = 0, M = 0, Ei = 0;
 #pragma unroll
             for (int c = 0; c < K; ++c)
-              if ((uint32_t)c == cb_) { M = capM[c] >> 16; Ei = capE[c] >> 16; Fi = capF[c] >> 16; }
-            p.end[lb] = end_word(M, Ei, Fi);
+              if ((uint32_t)c == cb_) { H = Hrow[c] >> 16; M = Mv[c] >> 16; Ei = Ev[c] >> 16; }
+            p.end[lb] = end_word(H, M, Ei, (acc_b >> (4 * cb_ + 1)) & 1u);
           }
         }
         hd_prev = rh;
