@@ -1,9 +1,16 @@
 // engine.cu -- C ABI (include/sa_engine.h) over the CUDA kernels.  sm_100a only, no CPU path.
 //
 // Replaces the reference's per-pair dispatch loop (/root/reference/src/main.rs:61-79) with
-// batched launches: the pair list is cut into chunks whose packed traceback matrices fit in
-// the device scratch, each chunk is filled (nw_affine_s16.cuh), walked (nw_walk.cuh) and its
-// CIGARs are gathered into one pool in pair order.
+// batched launches.  The pair list is cut into SEGMENTS (up to 512 Ki pairs, fewer when the
+// packed traceback matrices would not fit the scratch budget).  Per segment:
+//     copy-in stream : offsets/lengths of the segment + the residue ranges it touches
+//     compute stream : fill (panic bonus on) -> classify/count walk -> [host reads the number of
+//                      pairs whose end cell carries the bonus] -> clean refill + count walk of
+//                      those pairs -> scan of CIGAR lengths -> write walks
+//     copy-out stream: score / status / cigar_len / cigar_off of the segment
+// The copy-in of segment i+1 is enqueued before the host waits on segment i, so transfers,
+// kernels and result copies of neighbouring segments overlap; the CIGAR pool is copied once at
+// the end (its size is only known then).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -13,6 +20,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sa_engine.h"
@@ -28,36 +36,50 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-}  // namespace
-
-struct sa_resident {
-  uint64_t n_pairs = 0;
-  uint64_t residues_len = 0;
+// device views the kernels work on (either engine-owned staging or a resident batch)
+struct DeviceBatch {
   uint8_t* residues = nullptr;
   uint64_t *q_off = nullptr, *d_off = nullptr;
   uint32_t *q_len = nullptr, *d_len = nullptr;
-  // results (device)
   int32_t* score = nullptr;
   uint8_t* status = nullptr;
   uint32_t* cigar_len = nullptr;
   uint64_t* cigar_off = nullptr;
   uint32_t* pool = nullptr;
   uint64_t pool_cap = 0;
-  uint64_t* carry = nullptr;  // total words used (device)
-  // host-side shape summary
-  uint32_t n1max = 0, n2max = 0;
-  uint64_t cells = 0;
+  uint64_t* carry = nullptr;
+};
+
+}  // namespace
+
+struct sa_resident {
+  uint64_t n_pairs = 0;
+  uint64_t residues_len = 0;
+  DeviceBatch d;
   std::vector<uint32_t> h_q_len, h_d_len;
+  uint64_t cells = 0;
+  uint64_t used = 0;  // CIGAR words of the last alignment
   bool aligned = false;
   bool want_cigar = false;
 };
 
 struct sa_engine {
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_carry[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
   std::string err;
-  DevBuf tb, tb2, end, end2, rerun_ids, misc, block_sums;
+  // Two segments are in flight on the compute stream (the fill of segment i+1 is queued before
+  // the host reads segment i's refill count), so per-segment scratch is double-buffered.
+  struct Slot {
+    DevBuf tb, end, rerun_ids;
+    cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
+                                    // the next fill overlaps the tail of the previous one
+    cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
+  } slot[2];
+  // scratch (grow-only)
+  DevBuf tb2, end2, misc, block_sums;
+  // staging for sa_align_batch (grow-only)
+  DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry;
   uint32_t* h_count = nullptr;  // pinned
   sa_timing_t timing = {};
   int sm_count = 0;
@@ -65,6 +87,9 @@ struct sa_engine {
   int force_g = 0;
   uint32_t ormask = 0x0F;
   size_t tb_budget = 0;
+  size_t budget_cached = 0;
+  uint32_t seg_pairs = 524288;
+  bool seg_pairs_forced = false;
 };
 
 namespace {
@@ -88,10 +113,14 @@ sa_status_t fail(sa_engine* e, sa_status_t st, const char* fmt, ...) {
   } while (0)
 
 sa_status_t ensure(sa_engine* e, DevBuf& b, size_t bytes) {
-  if (b.cap >= bytes) return SA_OK;
-  if (b.p) CUDA_TRY(e, cudaFree(b.p));
+  if (b.cap >= bytes && b.p) return SA_OK;
+  if (b.p) {
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    CUDA_TRY(e, cudaFree(b.p));
+  }
   b.p = nullptr;
   b.cap = 0;
+  bytes = std::max<size_t>(bytes, 256);
   cudaError_t err = cudaMalloc(&b.p, bytes);
   if (err != cudaSuccess) {
     cudaGetLastError();
@@ -128,8 +157,9 @@ Geometry make_geometry(int G, uint32_t n1max, uint32_t n2max) {
   return g;
 }
 
-// Pick lanes-per-pair-of-pairs: least padded work among the configurations that leave at
-// least 8 resident warps per SM; ties go to the smaller G (fewer shuffles, fewer ramp steps).
+// Lanes per pair-of-pairs: least padded work (passes x rows incl. the G-1 ramp rows, per pair),
+// discounted when fewer than 12 warps fit one SM's shared memory (the fill is latency-bound
+// below that: ncu shows "wait" stalls dominating at 10 warps/SM).
 int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
   if (e->force_g) return e->force_g;
   int best = 0;
@@ -137,13 +167,12 @@ int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
   for (int G : {1, 2, 4, 8, 16, 32}) {
     const Geometry g = make_geometry(G, n1max, n2max);
     if (g.smem_bytes > e->smem_optin) continue;
-    const double warps = std::min(32.0, std::floor(227.0 * 1024 / (double)(g.smem_bytes + 1024)));
+    const double warps = std::min(24.0, std::floor(227.0 * 1024 / (double)(g.smem_bytes + 1024)));
     if (warps < 1) continue;
     const double npass = g.nstrips_pad / G;
-    // steps per tile / pairs per tile, discounted when occupancy cannot cover latencies
     double cost = npass * (n2max + G - 1) / (double)g.ppt;
-    const double occ = std::min(1.0, warps / 8.0);
-    cost /= (0.55 + 0.45 * occ);
+    const double occ = std::min(1.0, warps / 12.0);
+    cost /= (0.45 + 0.55 * occ);
     if (cost < best_cost - 1e-12) {
       best_cost = cost;
       best = G;
@@ -154,11 +183,15 @@ int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
 
 template <int G, uint32_t ORMASK>
 sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                          uint32_t n_tiles) {
+                          uint32_t n_tiles, cudaStream_t stream) {
   auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK>;
-  CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)g.smem_bytes));
-  kern<<<n_tiles, 32, g.smem_bytes, e->stream>>>(p);
+  static size_t configured = 0;  // per instantiation; smem opt-in only grows
+  if (g.smem_bytes > configured) {
+    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)std::min(e->smem_optin, std::max<size_t>(g.smem_bytes, 48 * 1024))));
+    configured = std::max<size_t>(g.smem_bytes, 48 * 1024);
+  }
+  kern<<<n_tiles, 32, g.smem_bytes, stream>>>(p);
   CUDA_TRY(e, cudaGetLastError());
   e->timing.kernel_launches++;
   return SA_OK;
@@ -166,32 +199,457 @@ sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geom
 
 template <int G>
 sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                        uint32_t n_tiles) {
+                        uint32_t n_tiles, cudaStream_t stream) {
   switch (e->ormask) {
-    case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles);
-    case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles);
-    case 0x1F: return launch_fill_m<G, 0x1F>(e, p, g, n_tiles);
-    case 0x3F: return launch_fill_m<G, 0x3F>(e, p, g, n_tiles);
-    case 0x7F: return launch_fill_m<G, 0x7F>(e, p, g, n_tiles);
-    case 0xFF: return launch_fill_m<G, 0xFF>(e, p, g, n_tiles);
+    case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles, stream);
+    case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles, stream);
+    case 0x3F: return launch_fill_m<G, 0x3F>(e, p, g, n_tiles, stream);
+    case 0xFF: return launch_fill_m<G, 0xFF>(e, p, g, n_tiles, stream);
   }
   return fail(e, SA_E_ARG, "SA_ORMASK 0x%x has no instantiation", e->ormask);
 }
 
 sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                          uint32_t n_tiles) {
+                          uint32_t n_tiles, cudaStream_t stream) {
   switch (g.G) {
-    case 1: return launch_fill<1>(e, p, g, n_tiles);
-    case 2: return launch_fill<2>(e, p, g, n_tiles);
-    case 4: return launch_fill<4>(e, p, g, n_tiles);
-    case 8: return launch_fill<8>(e, p, g, n_tiles);
-    case 16: return launch_fill<16>(e, p, g, n_tiles);
-    case 32: return launch_fill<32>(e, p, g, n_tiles);
+    case 1: return launch_fill<1>(e, p, g, n_tiles, stream);
+    case 2: return launch_fill<2>(e, p, g, n_tiles, stream);
+    case 4: return launch_fill<4>(e, p, g, n_tiles, stream);
+    case 8: return launch_fill<8>(e, p, g, n_tiles, stream);
+    case 16: return launch_fill<16>(e, p, g, n_tiles, stream);
+    case 32: return launch_fill<32>(e, p, g, n_tiles, stream);
   }
   return fail(e, SA_E_ARG, "bad G %d", g.G);
 }
 
 uint32_t pack2(uint32_t v) { return v | (v << 16); }
+
+// Byte ranges of the residue buffer already resident on the device (sorted, disjoint).
+struct Coverage {
+  std::vector<std::pair<uint64_t, uint64_t>> iv;
+  // calls f(lo, hi) for every missing sub-range of [lo, hi) and marks it covered
+  template <class F>
+  void request(uint64_t lo, uint64_t hi, F&& f) {
+    if (lo >= hi) return;
+    std::vector<std::pair<uint64_t, uint64_t>> out;
+    uint64_t cur = lo;
+    uint64_t nlo = lo, nhi = hi;
+    for (auto& p : iv) {
+      if (p.second < lo || p.first > hi) {
+        out.push_back(p);
+        continue;
+      }
+      if (p.first > cur) f(cur, std::min(p.first, hi));
+      cur = std::max(cur, p.second);
+      nlo = std::min(nlo, p.first);
+      nhi = std::max(nhi, p.second);
+    }
+    if (cur < hi) f(cur, hi);
+    out.emplace_back(nlo, nhi);
+    std::sort(out.begin(), out.end());
+    iv.swap(out);
+  }
+};
+
+struct Scheme2 {
+  sa_scheme_t sc;
+  int pen, openp, extp;
+};
+
+struct Segment {
+  uint64_t base = 0;
+  uint32_t n = 0;
+  uint32_t n1max = 0, n2max = 0;
+  uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
+  Geometry g;
+};
+
+// The whole affine path over device views.  `in`/`out` non-null: stream inputs from / results
+// to host buffers segment by segment; null: everything is already resident / stays resident.
+sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h_q_len,
+                       const uint32_t* h_d_len, const Scheme2& s2, bool want_cigar,
+                       const sa_batch_t* in, sa_result_t* out, uint64_t* used_out,
+                       uint64_t* pool_sent_out) {
+  const sa_scheme_t& sc = s2.sc;
+  sa_status_t st;
+  *used_out = 0;
+  *pool_sent_out = 0;
+
+  // ---- scratch budget ---------------------------------------------------------------------
+  size_t budget = e->tb_budget;
+  if (!budget) {
+    // cudaMemGetInfo is slow enough to show up per call; look once and keep the figure while
+    // the scratch already held covers it
+    const size_t held = e->slot[0].tb.cap + e->slot[1].tb.cap + e->tb2.cap;
+    if (!e->budget_cached || held > e->budget_cached) {
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(e, cudaMemGetInfo(&free_b, &total_b));
+      e->budget_cached = std::min<size_t>((size_t)((double)(free_b + held) * 0.6), (size_t)32 << 30);
+    }
+    budget = e->budget_cached;
+  }
+  // two segment buffers and one refill region
+  const size_t budget_main = budget * 2 / 5, budget_re = budget / 5;
+  if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
+  uint32_t* d_counts = (uint32_t*)e->misc.p;  // [2] refill queue lengths
+
+  sa::AffineS16Params fp{};
+  fp.residues = db.residues;
+  fp.q_off = db.q_off;
+  fp.q_len = db.q_len;
+  fp.d_off = db.d_off;
+  fp.d_len = db.d_len;
+  fp.pen2 = pack2((uint32_t)s2.pen);
+  fp.open2 = pack2((uint32_t)s2.openp);
+  fp.ext2 = pack2((uint32_t)s2.extp);
+  fp.origin = pack2(sa::kBias);
+  fp.zero = 0;
+  const uint32_t row0_clean = sa::kBias - (uint32_t)(s2.openp + (-2 * sc.gap_ext));
+
+  sa::WalkParams wp{};
+  wp.q_len = db.q_len;
+  wp.d_len = db.d_len;
+  wp.match = sc.match;
+  wp.open = sc.gap_open;
+  wp.ext = sc.gap_ext;
+  wp.score = db.score;
+  wp.status = db.status;
+  wp.cigar_len = db.cigar_len;
+  wp.cigar_off = db.cigar_off;
+  wp.pool = db.pool;
+  wp.pool_cap = db.pool_cap;
+
+  // Segment size: at least two segments (alternate streams overlap each other's tails), at
+  // most seg_pairs; when inputs stream from the host the first segment is small.
+  const uint64_t seg_max = e->seg_pairs_forced ? e->seg_pairs
+                                                : std::min<uint64_t>(e->seg_pairs, std::max<uint64_t>(32768, (n + 1) / 2));
+  uint64_t seg_target = (in && !e->seg_pairs_forced) ? std::min<uint64_t>(seg_max, 65536) : seg_max;
+
+  Coverage cov;
+  // Scans the next segment on the host: extent, shape maxima, residue ranges, geometry.
+  auto prepare = [&](uint64_t base, Segment& sg) -> sa_status_t {
+    sg = Segment{};
+    sg.base = base;
+    uint32_t cn = (uint32_t)std::min<uint64_t>(seg_target, n - base);
+    // streaming from the host: ramp the segment size up so the first copy-in is short
+    if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
+    for (uint32_t i = 0; i < cn; ++i) {
+      const uint32_t a = h_q_len[base + i], b = h_d_len[base + i];
+      sg.n1max = std::max(sg.n1max, a);
+      sg.n2max = std::max(sg.n2max, b);
+    }
+    const int G = choose_g(e, sg.n1max, sg.n2max);
+    if (!G)
+      return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u needs more shared memory than one SM has",
+                  sg.n1max, sg.n2max);
+    sg.g = make_geometry(G, sg.n1max, sg.n2max);
+    const uint32_t need = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext,
+                                                  sg.g.n1pad, sg.n2max);
+    if (need + 64 > sa::kBias)
+      return fail(e, SA_E_UNSUPPORTED,
+                  "pair shape %u x %u exceeds the 16-bit packed range (long-pair kernel not built yet)",
+                  sg.n1max, sg.n2max);
+    const size_t tile_bytes = (size_t)sg.g.tile_stride * 8;
+    const uint64_t tiles_fit = std::max<uint64_t>(1, budget_main / tile_bytes);
+    cn = (uint32_t)std::min<uint64_t>(cn, tiles_fit * sg.g.ppt);
+    sg.n = cn;
+    if (in) {
+      for (uint32_t i = 0; i < cn; ++i) {
+        const uint64_t p = base + i;
+        if (h_q_len[p]) {
+          sg.qlo = std::min(sg.qlo, in->q_off[p]);
+          sg.qhi = std::max(sg.qhi, in->q_off[p] + h_q_len[p]);
+        }
+        if (h_d_len[p]) {
+          sg.dlo = std::min(sg.dlo, in->d_off[p]);
+          sg.dhi = std::max(sg.dhi, in->d_off[p] + h_d_len[p]);
+        }
+        e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
+      }
+      if (sg.qhi > in->residues_len || sg.dhi > in->residues_len)
+        return fail(e, SA_E_ARG, "a pair in [%llu, %llu) reaches past residues_len",
+                    (unsigned long long)base, (unsigned long long)(base + cn));
+    }
+    return SA_OK;
+  };
+  // Enqueues the segment's inputs on the copy-in stream.
+  auto upload = [&](const Segment& sg) -> sa_status_t {
+    if (!in) return SA_OK;
+    cudaError_t err = cudaSuccess;
+    auto cp = [&](void* dst, const void* src, size_t bytes) {
+      if (err == cudaSuccess && bytes) {
+        err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->s_in);
+        e->timing.h2d_bytes += bytes;
+      }
+    };
+    cp(db.q_off + sg.base, in->q_off + sg.base, (size_t)sg.n * 8);
+    cp(db.d_off + sg.base, in->d_off + sg.base, (size_t)sg.n * 8);
+    cp(db.q_len + sg.base, in->q_len + sg.base, (size_t)sg.n * 4);
+    cp(db.d_len + sg.base, in->d_len + sg.base, (size_t)sg.n * 4);
+    auto range = [&](uint64_t lo, uint64_t hi) { cp(db.residues + lo, in->residues + lo, hi - lo); };
+    if (sg.qlo < sg.qhi) cov.request(sg.qlo, sg.qhi, range);
+    if (sg.dlo < sg.dhi) cov.request(sg.dlo, sg.dhi, range);
+    if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(err));
+    CUDA_TRY(e, cudaEventRecord(e->ev_in, e->s_in));
+    return SA_OK;
+  };
+  auto set_geometry = [&](const Geometry& g) {
+    fp.tb_tile_stride = g.tile_stride;
+    fp.tb_rows = g.tb_rows;
+    fp.smem_bnd_rows = g.tb_rows;
+    fp.smem_d_halfs = g.d_halfs;
+    wp.tb_tile_stride = g.tile_stride;
+    wp.tb_rows = g.tb_rows;
+    wp.ng = g.ng;
+  };
+  // Streams the CIGAR pool to the host as segments finish.  After segment i's write walks a
+  // copy of the running total is queued (slot i&1); one segment later the host reads it (by then
+  // the walks are complete) and queues pool[pool_sent, total) on the copy-out stream.
+  uint64_t pool_sent = 0;
+  int seg_index = 0;
+  auto send_pool_upto = [&](int slot) -> cudaError_t {
+    cudaError_t er = cudaEventSynchronize(e->ev_carry[slot]);
+    if (er != cudaSuccess) return er;
+    uint64_t total;
+    memcpy(&total, e->h_count + 8 + 2 * slot, 8);
+    const uint64_t hi = std::min<uint64_t>(std::min<uint64_t>(total, db.pool_cap), out->cigar_capacity);
+    if (hi > pool_sent) {
+      er = cudaMemcpyAsync(out->cigar + pool_sent, db.pool + pool_sent, (hi - pool_sent) * 4,
+                           cudaMemcpyDeviceToHost, e->s_out);
+      e->timing.d2h_bytes += (hi - pool_sent) * 4;
+      pool_sent = hi;
+    }
+    return er;
+  };
+  // Stage A of a segment: fill with the panic bonus on, classify + count walk, queue length.
+  auto stage_a = [&](const Segment& sg, int k) -> sa_status_t {
+    sa_engine::Slot& sl = e->slot[k];
+    const Geometry& g = sg.g;
+    const uint32_t cn = sg.n;
+    const size_t tile_bytes = (size_t)g.tile_stride * 8;
+    const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
+    sa_status_t r;
+    if ((r = ensure(e, sl.tb, (size_t)ctiles * tile_bytes)) != SA_OK) return r;
+    if ((r = ensure(e, sl.end, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
+    if ((r = ensure(e, sl.rerun_ids, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
+    set_geometry(g);
+    cudaStream_t sx = sl.stream;
+    CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_bdone, 0));  // the slot's previous user is done
+    if (in) CUDA_TRY(e, cudaStreamWaitEvent(sx, e->ev_in, 0));
+    fp.pair_ids = nullptr;
+    fp.pair_base = (uint32_t)sg.base;
+    fp.n_launch_pairs = cn;
+    fp.tb = (uint2*)sl.tb.p;
+    fp.end = (uint32_t*)sl.end.p;
+    fp.row0 = pack2(row0_clean + 1);
+    CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
+    CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
+    if ((r = launch_fill_g(e, fp, g, ctiles, sx)) != SA_OK) return r;
+    CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sx));
+    wp.pair_ids = nullptr;
+    wp.pair_base = (uint32_t)sg.base;
+    wp.n_launch_pairs = cn;
+    wp.n_launch_dev = nullptr;
+    wp.tb = (const uint2*)sl.tb.p;
+    wp.end = (const uint32_t*)sl.end.p;
+    wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
+    wp.rerun_count = d_counts + k;
+    wp.phase = 0;
+    sa::nw_affine_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
+    CUDA_TRY(e, cudaGetLastError());
+    e->timing.kernel_launches++;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
+    CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));
+    return SA_OK;
+  };
+  // Stage B: clean refill of the queued pairs, scan of the lengths, write walks, results out.
+  auto stage_b = [&](const Segment& sg, int k) -> sa_status_t {
+    sa_engine::Slot& sl = e->slot[k];
+    const Geometry& g = sg.g;
+    const uint32_t cn = sg.n;
+    const size_t tile_bytes = (size_t)g.tile_stride * 8;
+    const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
+    sa_status_t r;
+    CUDA_TRY(e, cudaEventSynchronize(sl.ev_count));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sl.ev_count, 0));
+    const uint32_t n_re = e->h_count[4 + k];
+    e->timing.pairs_rerun += n_re;
+    float fms = 0;
+    if (cudaEventElapsedTime(&fms, sl.ev_f0, sl.ev_f1) == cudaSuccess) e->timing.walk_ms += fms;
+    const uint64_t tiles_re = std::max<uint64_t>(1, std::min<uint64_t>(ctiles, std::max<uint64_t>(1, budget_re / tile_bytes)));
+    const uint32_t sb = (cn + sa::kScanBlock - 1) / sa::kScanBlock;
+    if (n_re) {
+      if ((r = ensure(e, e->tb2, (size_t)tiles_re * tile_bytes)) != SA_OK) return r;
+      if ((r = ensure(e, e->end2, (size_t)tiles_re * g.ppt * 4)) != SA_OK) return r;
+    }
+    if ((r = ensure(e, e->block_sums, (size_t)sb * 8)) != SA_OK) return r;
+    set_geometry(g);
+    const uint32_t re_chunk = (uint32_t)(tiles_re * g.ppt);
+    struct ReLaunch {
+      uint32_t off, cnt;
+    };
+    std::vector<ReLaunch> re_launches;
+    for (uint32_t off = 0; off < n_re; off += re_chunk)
+      re_launches.push_back({off, std::min(re_chunk, n_re - off)});
+    // The refill region may be smaller than the queue: refill and count in slices; the write
+    // pass (after the scan, which needs every length of the segment) repeats the fill of a
+    // slice unless there was only one.
+    auto refill = [&](const ReLaunch& rl, bool do_fill) -> sa_status_t {
+      fp.pair_ids = (const uint32_t*)sl.rerun_ids.p + rl.off;
+      fp.pair_base = 0;
+      fp.n_launch_pairs = rl.cnt;
+      fp.tb = (uint2*)e->tb2.p;
+      fp.end = (uint32_t*)e->end2.p;
+      fp.row0 = pack2(row0_clean);
+      if (do_fill) {
+        sa_status_t r2 = launch_fill_g(e, fp, g, (rl.cnt + g.ppt - 1) / g.ppt, e->stream);
+        if (r2 != SA_OK) return r2;
+      }
+      wp.pair_ids = fp.pair_ids;
+      wp.pair_base = 0;
+      wp.n_launch_pairs = rl.cnt;
+      wp.n_launch_dev = nullptr;
+      wp.tb = (const uint2*)e->tb2.p;
+      wp.end = (const uint32_t*)e->end2.p;
+      wp.rerun_ids = nullptr;
+      wp.rerun_count = nullptr;
+      wp.phase = 1;
+      return SA_OK;
+    };
+    for (const ReLaunch& rl : re_launches) {
+      if ((r = refill(rl, true)) != SA_OK) return r;
+      sa::nw_affine_walk<0><<<(rl.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+    }
+    // offsets of this segment (continuing from the previous segments' total)
+    sa::scan_block_sums<<<sb, sa::kScanBlock, 0, e->stream>>>(db.cigar_len + sg.base, (uint64_t*)e->block_sums.p, cn);
+    sa::scan_block_offsets<<<1, sa::kScanBlock, 0, e->stream>>>((uint64_t*)e->block_sums.p, sb, db.carry);
+    sa::scan_apply<<<sb, sa::kScanBlock, 0, e->stream>>>(db.cigar_len + sg.base, (const uint64_t*)e->block_sums.p, db.cigar_off + sg.base, cn);
+    CUDA_TRY(e, cudaGetLastError());
+    e->timing.kernel_launches += 3;
+    if (want_cigar) {
+      // write pass: main region, then each refill slice.  Writes past pool_cap are dropped and
+      // detected by the caller from the final total.
+      wp.pair_ids = nullptr;
+      wp.pair_base = (uint32_t)sg.base;
+      wp.n_launch_pairs = cn;
+      wp.tb = (const uint2*)sl.tb.p;
+      wp.end = (const uint32_t*)sl.end.p;
+      wp.phase = 0;
+      sa::nw_affine_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+      for (const ReLaunch& rl : re_launches) {
+        if ((r = refill(rl, re_launches.size() > 1)) != SA_OK) return r;
+        sa::nw_affine_walk<1><<<(rl.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
+        CUDA_TRY(e, cudaGetLastError());
+        e->timing.kernel_launches++;
+      }
+    }
+    CUDA_TRY(e, cudaEventRecord(sl.ev_bdone, e->stream));  // the slot's scratch is free again
+    if (out && want_cigar) {
+      const int cs = seg_index & 1;
+      CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 8 + 2 * cs, db.carry, 8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(e, cudaEventRecord(e->ev_carry[cs], e->stream));
+      if (seg_index > 0) CUDA_TRY(e, send_pool_upto(cs ^ 1));  // the previous segment's words
+    }
+    ++seg_index;
+    if (out) {  // results of this segment to the host
+      CUDA_TRY(e, cudaEventRecord(e->ev_done, e->stream));
+      CUDA_TRY(e, cudaStreamWaitEvent(e->s_out, e->ev_done, 0));
+      cudaError_t err = cudaSuccess;
+      auto cp = [&](void* dst, const void* src, size_t bytes) {
+        if (err == cudaSuccess && dst && bytes) {
+          err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->s_out);
+          e->timing.d2h_bytes += bytes;
+        }
+      };
+      cp(out->score ? out->score + sg.base : nullptr, db.score + sg.base, (size_t)cn * 4);
+      cp(out->status ? out->status + sg.base : nullptr, db.status + sg.base, (size_t)cn);
+      cp(out->cigar_len ? out->cigar_len + sg.base : nullptr, db.cigar_len + sg.base, (size_t)cn * 4);
+      cp(out->cigar_off ? out->cigar_off + sg.base : nullptr, db.cigar_off + sg.base, (size_t)cn * 8);
+      if (err != cudaSuccess) return fail(e, SA_E_CUDA, "D2H copy failed: %s", cudaGetErrorString(err));
+    }
+    return SA_OK;
+  };
+
+  CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev_t0, e->stream));
+  for (int k = 0; k < 2; ++k) {  // order the slot streams after everything queued so far
+    CUDA_TRY(e, cudaEventRecord(e->slot[k].ev_bdone, e->stream));
+  }
+
+  // Software pipeline over segments: A(0); then for each i: A(i+1) is queued BEFORE the host
+  // waits for segment i's refill count, so the GPU never idles across the host round trip.
+  Segment seg[2];
+  if ((st = prepare(0, seg[0])) != SA_OK) return st;
+  if ((st = upload(seg[0])) != SA_OK) return st;
+  if ((st = stage_a(seg[0], 0)) != SA_OK) return st;
+  for (int k = 0;; k ^= 1) {
+    const uint64_t next_base = seg[k].base + seg[k].n;
+    const bool have_next = next_base < n;
+    if (have_next) {
+      if ((st = prepare(next_base, seg[k ^ 1])) != SA_OK) return st;
+      if ((st = upload(seg[k ^ 1])) != SA_OK) return st;
+      if ((st = stage_a(seg[k ^ 1], k ^ 1)) != SA_OK) return st;
+    }
+    if ((st = stage_b(seg[k], k)) != SA_OK) return st;
+    if (!have_next) break;
+  }
+  CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->stream));
+  if (out || want_cigar) {
+    // total CIGAR words (also the overflow check)
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 2, db.carry, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    memcpy(used_out, e->h_count + 2, 8);
+    if (out && want_cigar) {
+      CUDA_TRY(e, send_pool_upto((seg_index - 1) & 1));  // the last segment's words
+      *pool_sent_out = pool_sent;
+    }
+  }
+  return SA_OK;
+}
+
+sa_status_t resolve_scheme(sa_engine* e, const sa_scheme_t* scheme, Scheme2& s2) {
+  s2.sc = sa_scheme_t{5, -4, -8, -6};  // nw_affine.rs:15-20
+  if (scheme) s2.sc = *scheme;
+  const sa_scheme_t& sc = s2.sc;
+  if (!(sc.match > sc.mismatch) || sc.gap_open > 0 || sc.gap_ext > 0 || sc.match < 0)
+    return fail(e, SA_E_UNSUPPORTED, "scheme (%d,%d,%d,%d) outside the packed kernel's domain",
+                sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
+  s2.pen = 2 * (sc.match - sc.mismatch);
+  s2.openp = -2 * sc.gap_open;
+  s2.extp = sc.match - 2 * sc.gap_ext;
+  if (s2.pen > 128 || s2.extp <= 0)
+    return fail(e, SA_E_UNSUPPORTED, "scheme magnitudes exceed the packed kernel's range");
+  return SA_OK;
+}
+
+// nw_affine:433-434, wfa.rs:26: every pair returns Err("not implemented") in non-global modes.
+sa_status_t fill_not_implemented(sa_engine* e, DeviceBatch& db, uint64_t n) {
+  CUDA_TRY(e, cudaMemsetAsync(db.status, SA_NOT_IMPLEMENTED, n, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.score, 0, n * 4, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.cigar_len, 0, n * 4, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.cigar_off, 0, n * 8, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, e->stream));
+  return SA_OK;
+}
+
+sa_status_t check_algo(sa_engine* e, sa_algo_t algo, sa_mode_t mode, bool* not_impl) {
+  *not_impl = false;
+  if (mode != SA_MODE_GLOBAL && mode != SA_MODE_LOCAL && mode != SA_MODE_SEMIGLOBAL)
+    return fail(e, SA_E_ARG, "mode %d", (int)mode);
+  if (mode != SA_MODE_GLOBAL) {
+    if (algo == SA_ALGO_NW_AFFINE || algo == SA_ALGO_WFA) {
+      *not_impl = true;
+      return SA_OK;
+    }
+    return fail(e, SA_E_UNSUPPORTED, "mode %d for algo %d is not built yet", (int)mode, (int)algo);
+  }
+  if (algo != SA_ALGO_NW_AFFINE) return fail(e, SA_E_UNSUPPORTED, "algo %d is not built yet", (int)algo);
+  return SA_OK;
+}
 
 }  // namespace
 
@@ -223,11 +681,23 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  for (auto& ev : e->ev) CUDA_TRY(e, cudaEventCreate(&ev));
+  CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->slot[k].stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* ev : {&e->ev_in, &e->ev_done, &e->ev_carry[0], &e->ev_carry[1], &e->slot[0].ev_count, &e->slot[1].ev_count,
+                          &e->slot[0].ev_bdone, &e->slot[1].ev_bdone})
+    CUDA_TRY(e, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  for (cudaEvent_t* ev : {&e->ev_t0, &e->ev_t1, &e->slot[0].ev_f0, &e->slot[0].ev_f1, &e->slot[1].ev_f0,
+                          &e->slot[1].ev_f1})
+    CUDA_TRY(e, cudaEventCreate(ev));
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
+  if (const char* s = getenv("SA_SEG_PAIRS")) {
+    e->seg_pairs = std::max(1, atoi(s));
+    e->seg_pairs_forced = true;
+  }
   return SA_OK;
 }
 
@@ -235,13 +705,22 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
   if (!e) return SA_OK;
   if (e->stream) {
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->tb, &e->tb2, &e->end, &e->end2, &e->rerun_ids, &e->misc, &e->block_sums})
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
+                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc,
+                      &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
+                      &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})
       if (b->p) cudaFree(b->p);
-    for (auto& ev : e->ev)
+    for (cudaEvent_t ev : {e->ev_in, e->ev_done, e->ev_carry[0], e->ev_carry[1], e->ev_t0, e->ev_t1, e->slot[0].ev_count,
+                           e->slot[0].ev_f0, e->slot[0].ev_f1, e->slot[1].ev_count, e->slot[1].ev_f0,
+                           e->slot[1].ev_f1, e->slot[0].ev_bdone, e->slot[1].ev_bdone})
       if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     cudaStreamDestroy(e->stream);
+    for (int k = 0; k < 2; ++k)
+      if (e->slot[k].stream) cudaStreamDestroy(e->slot[k].stream);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
   }
   delete e;
   return SA_OK;
@@ -251,7 +730,10 @@ void* sa_engine_stream(sa_engine_t* e) { return e ? (void*)e->stream : nullptr; 
 
 sa_status_t sa_engine_synchronize(sa_engine_t* e) {
   if (!e) return SA_E_ARG;
+  for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaStreamSynchronize(e->slot[k].stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->s_in));
+  CUDA_TRY(e, cudaStreamSynchronize(e->s_out));
   return SA_OK;
 }
 
@@ -280,9 +762,9 @@ sa_status_t sa_batch_free(sa_engine_t* e, sa_resident_t* r) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
   }
-  for (void* p : {(void*)r->residues, (void*)r->q_off, (void*)r->d_off, (void*)r->q_len,
-                  (void*)r->d_len, (void*)r->score, (void*)r->status, (void*)r->cigar_len,
-                  (void*)r->cigar_off, (void*)r->pool, (void*)r->carry})
+  for (void* p : {(void*)r->d.residues, (void*)r->d.q_off, (void*)r->d.d_off, (void*)r->d.q_len,
+                  (void*)r->d.d_len, (void*)r->d.score, (void*)r->d.status, (void*)r->d.cigar_len,
+                  (void*)r->d.cigar_off, (void*)r->d.pool, (void*)r->d.carry})
     if (p) cudaFree(p);
   delete r;
   return SA_OK;
@@ -308,45 +790,39 @@ sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t**
       delete r;
       return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
     }
-    r->n1max = std::max(r->n1max, b->q_len[i]);
-    r->n2max = std::max(r->n2max, b->d_len[i]);
     r->cells += (uint64_t)b->q_len[i] * b->d_len[i];
   }
   const size_t n1 = std::max<uint64_t>(n, 1);
   auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)); };
   cudaError_t err = cudaSuccess;
-  if (err == cudaSuccess) err = alloc((void**)&r->residues, b->residues_len);
-  if (err == cudaSuccess) err = alloc((void**)&r->q_off, n1 * 8);
-  if (err == cudaSuccess) err = alloc((void**)&r->d_off, n1 * 8);
-  if (err == cudaSuccess) err = alloc((void**)&r->q_len, n1 * 4);
-  if (err == cudaSuccess) err = alloc((void**)&r->d_len, n1 * 4);
-  if (err == cudaSuccess) err = alloc((void**)&r->score, n1 * 4);
-  if (err == cudaSuccess) err = alloc((void**)&r->status, n1);
-  if (err == cudaSuccess) err = alloc((void**)&r->cigar_len, n1 * 4);
-  if (err == cudaSuccess) err = alloc((void**)&r->cigar_off, n1 * 8);
-  if (err == cudaSuccess) err = alloc((void**)&r->carry, 16);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.residues, b->residues_len);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.q_off, n1 * 8);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.d_off, n1 * 8);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.q_len, n1 * 4);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.d_len, n1 * 4);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.score, n1 * 4);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.status, n1);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.cigar_len, n1 * 4);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.cigar_off, n1 * 8);
+  if (err == cudaSuccess) err = alloc((void**)&r->d.carry, 16);
   if (err != cudaSuccess) {
     cudaGetLastError();
     sa_batch_free(e, r);
     return fail(e, SA_E_NOMEM, "device allocation for the batch failed: %s", cudaGetErrorString(err));
   }
-  cudaEventRecord(e->ev[0], e->stream);
   if (b->residues_len)
-    cudaMemcpyAsync(r->residues, b->residues, b->residues_len, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(r->d.residues, b->residues, b->residues_len, cudaMemcpyHostToDevice, e->stream);
   if (n) {
-    cudaMemcpyAsync(r->q_off, b->q_off, n * 8, cudaMemcpyHostToDevice, e->stream);
-    cudaMemcpyAsync(r->d_off, b->d_off, n * 8, cudaMemcpyHostToDevice, e->stream);
-    cudaMemcpyAsync(r->q_len, b->q_len, n * 4, cudaMemcpyHostToDevice, e->stream);
-    cudaMemcpyAsync(r->d_len, b->d_len, n * 4, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(r->d.q_off, b->q_off, n * 8, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(r->d.d_off, b->d_off, n * 8, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(r->d.q_len, b->q_len, n * 4, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(r->d.d_len, b->d_len, n * 4, cudaMemcpyHostToDevice, e->stream);
   }
-  cudaEventRecord(e->ev[1], e->stream);
-  cudaError_t last = cudaGetLastError();
+  cudaError_t last = cudaStreamSynchronize(e->stream);
   if (last != cudaSuccess) {
     sa_batch_free(e, r);
     return fail(e, SA_E_CUDA, "upload failed: %s", cudaGetErrorString(last));
   }
-  e->timing = sa_timing_t{};
-  e->timing.h2d_bytes = b->residues_len + n * 24;
   *out = r;
   return SA_OK;
 }
@@ -357,240 +833,45 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   CUDA_TRY(e, cudaSetDevice(e->device));
   const uint64_t n = r->n_pairs;
   r->want_cigar = want_cigar != 0;
+  r->used = 0;
+  e->timing = sa_timing_t{};
   e->timing.cells = r->cells;
-  e->timing.pairs_rerun = 0;
-  e->timing.kernel_launches = 0;
-  e->timing.walk_ms = 0;
+  bool not_impl = false;
+  sa_status_t st = check_algo(e, algo, mode, &not_impl);
+  if (st != SA_OK) return st;
   if (n == 0) {
     r->aligned = true;
     return SA_OK;
   }
-  if (mode != SA_MODE_GLOBAL) {
-    // nw_affine:433-434, wfa.rs:26: every pair returns Err("not implemented")
-    if (algo == SA_ALGO_NW_AFFINE || algo == SA_ALGO_WFA) {
-      CUDA_TRY(e, cudaMemsetAsync(r->status, SA_NOT_IMPLEMENTED, n, e->stream));
-      CUDA_TRY(e, cudaMemsetAsync(r->score, 0, n * 4, e->stream));
-      CUDA_TRY(e, cudaMemsetAsync(r->cigar_len, 0, n * 4, e->stream));
-      CUDA_TRY(e, cudaMemsetAsync(r->cigar_off, 0, n * 8, e->stream));
-      CUDA_TRY(e, cudaMemsetAsync(r->carry, 0, 16, e->stream));
-      r->aligned = true;
-      return SA_OK;
-    }
-    return fail(e, SA_E_UNSUPPORTED, "mode %d for algo %d is not built yet", (int)mode, (int)algo);
+  if (not_impl) {
+    st = fill_not_implemented(e, r->d, n);
+    r->aligned = st == SA_OK;
+    return st;
   }
-  if (algo != SA_ALGO_NW_AFFINE)
-    return fail(e, SA_E_UNSUPPORTED, "algo %d is not built yet", (int)algo);
-
-  sa_scheme_t sc = {5, -4, -8, -6};  // nw_affine.rs:15-20
-  if (scheme) sc = *scheme;
-  if (!(sc.match > sc.mismatch) || sc.gap_open > 0 || sc.gap_ext > 0 || sc.match < 0)
-    return fail(e, SA_E_UNSUPPORTED, "scheme (%d,%d,%d,%d) outside the packed kernel's domain",
-                sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
-  const int pen = 2 * (sc.match - sc.mismatch), openp = -2 * sc.gap_open,
-            extp = sc.match - 2 * sc.gap_ext;
-  if (pen > 128 || extp <= 0)
-    return fail(e, SA_E_UNSUPPORTED, "scheme magnitudes exceed the packed kernel's range");
-
-  const int G = choose_g(e, r->n1max, r->n2max);
-  if (!G) return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u needs more shared memory than one SM has", r->n1max, r->n2max);
-  const Geometry g = make_geometry(G, r->n1max, r->n2max);
-  const uint32_t need = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, g.n1pad, r->n2max);
-  if (need + 64 > sa::kBias)
-    return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u exceeds the 16-bit packed range (long-pair kernel not built yet)", r->n1max, r->n2max);
-
-  // ---- chunking: traceback scratch for the main fill and for the clean refill ------------
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(e, cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = e->tb_budget ? e->tb_budget : (size_t)((double)(free_b + e->tb.cap + e->tb2.cap) * 0.70);
-  const size_t tile_bytes = (size_t)g.tile_stride * 8;
-  const uint64_t n_tiles_all = (n + g.ppt - 1) / g.ppt;
-  // main region gets 4/5 of the budget, refill region 1/5 (refills are a few % of pairs)
-  uint64_t tiles_main = std::max<uint64_t>(1, std::min<uint64_t>(n_tiles_all, budget * 4 / 5 / tile_bytes));
-  uint64_t tiles_re = std::max<uint64_t>(1, std::min<uint64_t>(tiles_main, std::max<uint64_t>(budget / 5 / tile_bytes, 1)));
-  tiles_re = std::min<uint64_t>(tiles_re, std::max<uint64_t>(1, (tiles_main + 3) / 4));
-  const uint64_t chunk_pairs = tiles_main * g.ppt;
-  sa_status_t st;
-  if ((st = ensure(e, e->tb, tiles_main * tile_bytes)) != SA_OK) return st;
-  if ((st = ensure(e, e->tb2, tiles_re * tile_bytes)) != SA_OK) return st;
-  if ((st = ensure(e, e->end, chunk_pairs * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->end2, tiles_re * g.ppt * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->rerun_ids, chunk_pairs * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
-  const uint32_t scan_blocks_max = (uint32_t)((chunk_pairs + sa::kScanBlock - 1) / sa::kScanBlock);
-  if ((st = ensure(e, e->block_sums, (size_t)scan_blocks_max * 8)) != SA_OK) return st;
-  uint32_t* d_rerun_count = (uint32_t*)e->misc.p;
-
-  if (want_cigar && !r->pool) {
-    // worst case is n1+n2 runs per pair; size for the common case and grow on demand
-    r->pool_cap = std::max<uint64_t>(1024, n * 24);
-    cudaError_t err = cudaMalloc((void**)&r->pool, r->pool_cap * 4);
-    if (err != cudaSuccess) {
-      cudaGetLastError();
-      r->pool = nullptr;
-      return fail(e, SA_E_NOMEM, "cigar pool allocation failed");
+  Scheme2 s2;
+  if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (want_cigar && !r->d.pool) {
+      r->d.pool_cap = std::max<uint64_t>(std::max<uint64_t>(1024, n * 24), r->used + 1024);
+      cudaError_t err = cudaMalloc((void**)&r->d.pool, r->d.pool_cap * 4);
+      if (err != cudaSuccess) {
+        cudaGetLastError();
+        r->d.pool = nullptr;
+        return fail(e, SA_E_NOMEM, "cigar pool allocation failed");
+      }
     }
-  }
-
-  sa::AffineS16Params fp{};
-  fp.residues = r->residues;
-  fp.q_off = r->q_off;
-  fp.q_len = r->q_len;
-  fp.d_off = r->d_off;
-  fp.d_len = r->d_len;
-  fp.tb_tile_stride = g.tile_stride;
-  fp.tb_rows = g.tb_rows;
-  fp.smem_bnd_rows = g.tb_rows;
-  fp.smem_d_halfs = g.d_halfs;
-  fp.pen2 = pack2((uint32_t)pen);
-  fp.open2 = pack2((uint32_t)openp);
-  fp.ext2 = pack2((uint32_t)extp);
-  fp.origin = pack2(sa::kBias);
-  const uint32_t row0_clean = sa::kBias - (uint32_t)(openp + (-2 * sc.gap_ext));
-
-  sa::WalkParams wp{};
-  wp.q_len = r->q_len;
-  wp.d_len = r->d_len;
-  wp.tb_tile_stride = g.tile_stride;
-  wp.tb_rows = g.tb_rows;
-  wp.ng = g.ng;
-  wp.match = sc.match;
-  wp.open = sc.gap_open;
-  wp.ext = sc.gap_ext;
-  wp.score = r->score;
-  wp.status = r->status;
-  wp.cigar_len = r->cigar_len;
-  wp.cigar_off = r->cigar_off;
-  wp.pool = r->pool;
-  wp.pool_cap = r->pool_cap;
-  wp.rerun_ids = (uint32_t*)e->rerun_ids.p;
-  wp.rerun_count = d_rerun_count;
-
-  CUDA_TRY(e, cudaMemsetAsync(r->carry, 0, 16, e->stream));
-  CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
-
-  for (uint64_t base = 0; base < n; base += chunk_pairs) {
-    const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_pairs, n - base);
-    const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
-    // 1. fill with the panic bonus on
-    fp.pair_ids = nullptr;
-    fp.pair_base = (uint32_t)base;
-    fp.n_launch_pairs = cn;
-    fp.tb = (uint2*)e->tb.p;
-    fp.end = (uint32_t*)e->end.p;
-    fp.row0 = pack2(row0_clean + 1);
-    CUDA_TRY(e, cudaMemsetAsync(d_rerun_count, 0, 4, e->stream));
-    CUDA_TRY(e, cudaEventRecord(e->ev[6], e->stream));
-    if ((st = launch_fill_g(e, fp, g, ctiles)) != SA_OK) return st;
-    CUDA_TRY(e, cudaEventRecord(e->ev[7], e->stream));
-    // 2. classify + count
-    wp.pair_ids = nullptr;
-    wp.pair_base = (uint32_t)base;
-    wp.n_launch_pairs = cn;
-    wp.n_launch_dev = nullptr;
-    wp.tb = (const uint2*)e->tb.p;
-    wp.end = (const uint32_t*)e->end.p;
-    wp.phase = 0;
-    sa::nw_affine_walk<0><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
-    CUDA_TRY(e, cudaGetLastError());
-    e->timing.kernel_launches++;
-    // 3. clean refill of the pairs whose end cell carries the bonus
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_count, d_rerun_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    uint64_t used = 0;
+    uint64_t sent = 0;
+    st = run_affine(e, r->d, n, r->h_q_len.data(), r->h_d_len.data(), s2, want_cigar != 0, nullptr,
+                    nullptr, &used, &sent);
+    if (st != SA_OK) return st;
+    r->used = used;
+    if (!want_cigar || used <= r->d.pool_cap) break;
+    // the pool was too small: writes past its end were dropped; grow to the exact size, redo
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    const uint32_t n_re = *e->h_count;
-    e->timing.pairs_rerun += n_re;
-    {
-      float fms = 0;
-      if (cudaEventElapsedTime(&fms, e->ev[6], e->ev[7]) == cudaSuccess) e->timing.walk_ms += fms;
-    }
-    const uint32_t re_chunk = (uint32_t)(tiles_re * g.ppt);
-    struct ReLaunch { uint32_t off, cnt; };
-    std::vector<ReLaunch> re_launches;
-    // The refill region may be smaller than the queue: refill, count and (after the scan)
-    // write in slices.  Writing needs the offsets of the whole chunk, so when more than one
-    // slice is needed the count pass runs per slice first and the fills are repeated for the
-    // write pass.
-    for (uint32_t off = 0; off < n_re; off += re_chunk)
-      re_launches.push_back({off, std::min(re_chunk, n_re - off)});
-    auto refill = [&](const ReLaunch& rl, bool do_fill) -> sa_status_t {
-      fp.pair_ids = (const uint32_t*)e->rerun_ids.p + rl.off;
-      fp.pair_base = 0;
-      fp.n_launch_pairs = rl.cnt;
-      fp.tb = (uint2*)e->tb2.p;
-      fp.end = (uint32_t*)e->end2.p;
-      fp.row0 = pack2(row0_clean);
-      if (do_fill) {
-        sa_status_t s2 = launch_fill_g(e, fp, g, (rl.cnt + g.ppt - 1) / g.ppt);
-        if (s2 != SA_OK) return s2;
-      }
-      wp.pair_ids = fp.pair_ids;
-      wp.pair_base = 0;
-      wp.n_launch_pairs = rl.cnt;
-      wp.tb = (const uint2*)e->tb2.p;
-      wp.end = (const uint32_t*)e->end2.p;
-      wp.phase = 1;
-      return SA_OK;
-    };
-    for (const ReLaunch& rl : re_launches) {
-      if ((st = refill(rl, true)) != SA_OK) return st;
-      sa::nw_affine_walk<0><<<(rl.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
-      CUDA_TRY(e, cudaGetLastError());
-      e->timing.kernel_launches++;
-    }
-    // 4. offsets for this chunk (continuing from the previous chunk's total)
-    const uint32_t sb = (cn + sa::kScanBlock - 1) / sa::kScanBlock;
-    sa::scan_block_sums<<<sb, sa::kScanBlock, 0, e->stream>>>(r->cigar_len + base, (uint64_t*)e->block_sums.p, cn);
-    sa::scan_block_offsets<<<1, sa::kScanBlock, 0, e->stream>>>((uint64_t*)e->block_sums.p, sb, r->carry);
-    sa::scan_apply<<<sb, sa::kScanBlock, 0, e->stream>>>(r->cigar_len + base, (const uint64_t*)e->block_sums.p, r->cigar_off + base, cn);
-    CUDA_TRY(e, cudaGetLastError());
-    e->timing.kernel_launches += 3;
-    if (want_cigar) {
-      // grow the pool if this chunk does not fit
-      CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 2, r->carry, 8, cudaMemcpyDeviceToHost, e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-      uint64_t used;
-      memcpy(&used, e->h_count + 2, 8);
-      if (used > r->pool_cap) {
-        const uint64_t remaining_pairs = n - (base + cn);
-        const uint64_t new_cap = used + remaining_pairs * 24 + 1024;
-        uint32_t* np = nullptr;
-        cudaError_t err = cudaMalloc((void**)&np, new_cap * 4);
-        if (err != cudaSuccess) {
-          cudaGetLastError();
-          return fail(e, SA_E_NOMEM, "cigar pool growth to %llu words failed", (unsigned long long)new_cap);
-        }
-        // only earlier chunks' words exist so far
-        uint64_t prev_used = 0;
-        if (base) {
-          CUDA_TRY(e, cudaMemcpy(&prev_used, r->cigar_off + base, 8, cudaMemcpyDeviceToHost));
-          CUDA_TRY(e, cudaMemcpyAsync(np, r->pool, prev_used * 4, cudaMemcpyDeviceToDevice, e->stream));
-          CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-        }
-        cudaFree(r->pool);
-        r->pool = np;
-        r->pool_cap = new_cap;
-      }
-      wp.pool = r->pool;
-      wp.pool_cap = r->pool_cap;
-      // 5. write pass: main region, then each refill slice
-      wp.pair_ids = nullptr;
-      wp.pair_base = (uint32_t)base;
-      wp.n_launch_pairs = cn;
-      wp.tb = (const uint2*)e->tb.p;
-      wp.end = (const uint32_t*)e->end.p;
-      wp.phase = 0;
-      sa::nw_affine_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
-      CUDA_TRY(e, cudaGetLastError());
-      e->timing.kernel_launches++;
-      for (const ReLaunch& rl : re_launches) {
-        // with a single slice the refill region still holds its traceback matrix
-        if ((st = refill(rl, re_launches.size() > 1)) != SA_OK) return st;
-        sa::nw_affine_walk<1><<<(rl.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
-        CUDA_TRY(e, cudaGetLastError());
-        e->timing.kernel_launches++;
-      }
-    }
+    cudaFree(r->d.pool);
+    r->d.pool = nullptr;
   }
-  CUDA_TRY(e, cudaEventRecord(e->ev[3], e->stream));
   r->aligned = true;
   return SA_OK;
 }
@@ -600,58 +881,121 @@ sa_status_t sa_resident_download(sa_engine_t* e, sa_resident_t* r, sa_result_t* 
   if (!r->aligned) return fail(e, SA_E_ARG, "sa_align_resident has not run on this batch");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const uint64_t n = r->n_pairs;
-  uint64_t used = 0;
-  CUDA_TRY(e, cudaEventRecord(e->ev[4], e->stream));
+  const uint64_t used = r->used;
   if (n) {
-    CUDA_TRY(e, cudaMemcpyAsync(&used, r->carry, 8, cudaMemcpyDeviceToHost, e->stream));
-    if (res->score) CUDA_TRY(e, cudaMemcpyAsync(res->score, r->score, n * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (res->status) CUDA_TRY(e, cudaMemcpyAsync(res->status, r->status, n, cudaMemcpyDeviceToHost, e->stream));
-    if (res->cigar_len) CUDA_TRY(e, cudaMemcpyAsync(res->cigar_len, r->cigar_len, n * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (res->cigar_off) CUDA_TRY(e, cudaMemcpyAsync(res->cigar_off, r->cigar_off, n * 8, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (res->score) CUDA_TRY(e, cudaMemcpyAsync(res->score, r->d.score, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (res->status) CUDA_TRY(e, cudaMemcpyAsync(res->status, r->d.status, n, cudaMemcpyDeviceToHost, e->stream));
+    if (res->cigar_len) CUDA_TRY(e, cudaMemcpyAsync(res->cigar_len, r->d.cigar_len, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (res->cigar_off) CUDA_TRY(e, cudaMemcpyAsync(res->cigar_off, r->d.cigar_off, n * 8, cudaMemcpyDeviceToHost, e->stream));
   }
   res->cigar_used = used;
-  uint64_t d2h = n * 17 + 8;
   sa_status_t rc = SA_OK;
   if (res->cigar && r->want_cigar && used) {
-    if (used > res->cigar_capacity) {
+    if (used > res->cigar_capacity)
       rc = fail(e, SA_E_CIGAR_CAPACITY, "cigar pool needs %llu words, capacity is %llu",
                 (unsigned long long)used, (unsigned long long)res->cigar_capacity);
-    } else {
-      CUDA_TRY(e, cudaMemcpyAsync(res->cigar, r->pool, used * 4, cudaMemcpyDeviceToHost, e->stream));
-      d2h += used * 4;
-    }
+    else
+      CUDA_TRY(e, cudaMemcpyAsync(res->cigar, r->d.pool, used * 4, cudaMemcpyDeviceToHost, e->stream));
   }
-  CUDA_TRY(e, cudaEventRecord(e->ev[5], e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]) == cudaSuccess) e->timing.fill_ms = ms;
-  if (cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]) == cudaSuccess) e->timing.d2h_ms = ms;
-  if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) e->timing.h2d_ms = ms;
-  cudaGetLastError();
-  e->timing.d2h_bytes = d2h;
-  e->timing.total_ms = e->timing.h2d_ms + e->timing.fill_ms + e->timing.d2h_ms;
   return rc;
 }
 
 sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
-                           const sa_scheme_t* scheme, const sa_batch_t* batch,
-                           sa_result_t* result) {
-  if (!e || !batch || !result) return SA_E_ARG;
-  sa_resident_t* r = nullptr;
-  sa_status_t st = sa_batch_upload(e, batch, &r);
+                           const sa_scheme_t* scheme, const sa_batch_t* b, sa_result_t* res) {
+  if (!e || !b || !res) return SA_E_ARG;
+  if (b->packing != 0) return fail(e, SA_E_UNSUPPORTED, "packing %u not supported in ABI v1", b->packing);
+  if (b->n_pairs >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)b->n_pairs);
+  if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len)))
+    return fail(e, SA_E_ARG, "null input array");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const uint64_t n = b->n_pairs;
+  e->timing = sa_timing_t{};
+  res->cigar_used = 0;
+  bool not_impl = false;
+  sa_status_t st = check_algo(e, algo, mode, &not_impl);
   if (st != SA_OK) return st;
-  st = sa_align_resident(e, algo, mode, scheme, r, result->cigar != nullptr && result->cigar_capacity > 0);
-  if (st == SA_OK) st = sa_resident_download(e, r, result);
-  sa_batch_free(e, r);
-  return st;
+  if (n == 0) return SA_OK;
+  if (not_impl) {
+    if (res->status) memset(res->status, SA_NOT_IMPLEMENTED, n);
+    if (res->score) memset(res->score, 0, n * 4);
+    if (res->cigar_len) memset(res->cigar_len, 0, n * 4);
+    if (res->cigar_off) memset(res->cigar_off, 0, n * 8);
+    return SA_OK;
+  }
+  Scheme2 s2;
+  if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
+  const bool want_cigar = res->cigar != nullptr && res->cigar_capacity > 0;
+
+  // engine-owned staging, grow-only: no allocation on the steady-state path
+  if ((st = ensure(e, e->b_res, b->residues_len)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_qoff, n * 8)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_doff, n * 8)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_qlen, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_dlen, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_score, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_status, n)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_clen, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_coff, n * 8)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_carry, 16)) != SA_OK) return st;
+  uint64_t want_pool = want_cigar ? std::max<uint64_t>(res->cigar_capacity, 1024) : 0;
+  uint64_t used = 0, sent = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (want_cigar && (st = ensure(e, e->b_pool, want_pool * 4)) != SA_OK) return st;
+    DeviceBatch db;
+    db.residues = (uint8_t*)e->b_res.p;
+    db.q_off = (uint64_t*)e->b_qoff.p;
+    db.d_off = (uint64_t*)e->b_doff.p;
+    db.q_len = (uint32_t*)e->b_qlen.p;
+    db.d_len = (uint32_t*)e->b_dlen.p;
+    db.score = (int32_t*)e->b_score.p;
+    db.status = (uint8_t*)e->b_status.p;
+    db.cigar_len = (uint32_t*)e->b_clen.p;
+    db.cigar_off = (uint64_t*)e->b_coff.p;
+    db.pool = want_cigar ? (uint32_t*)e->b_pool.p : nullptr;
+    db.pool_cap = want_cigar ? e->b_pool.cap / 4 : 0;
+    db.carry = (uint64_t*)e->b_carry.p;
+    e->timing.h2d_bytes = 0;
+    e->timing.d2h_bytes = 0;
+    e->timing.cells = 0;
+    st = run_affine(e, db, n, b->q_len, b->d_len, s2, want_cigar, b, res, &used, &sent);
+    if (st != SA_OK) {
+      cudaStreamSynchronize(e->s_in);
+      cudaStreamSynchronize(e->s_out);
+      cudaStreamSynchronize(e->stream);
+      return st;
+    }
+    if (!want_cigar || used <= db.pool_cap) break;
+    // The caller cannot take it either if it exceeds cigar_capacity; otherwise redo with room.
+    if (used > res->cigar_capacity) break;
+    want_pool = used + 1024;
+  }
+  res->cigar_used = used;
+  sa_status_t rc = SA_OK;
+  if (want_cigar && used) {
+    if (used > res->cigar_capacity) {
+      rc = fail(e, SA_E_CIGAR_CAPACITY, "cigar pool needs %llu words, capacity is %llu",
+                (unsigned long long)used, (unsigned long long)res->cigar_capacity);
+    } else if (sent < used) {  // (normally everything was streamed out already)
+      CUDA_TRY(e, cudaMemcpyAsync(res->cigar + sent, (uint32_t*)e->b_pool.p + sent, (used - sent) * 4,
+                                  cudaMemcpyDeviceToHost, e->s_out));
+      e->timing.d2h_bytes += (used - sent) * 4;
+    }
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(e->s_out));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.fill_ms = ms;
+  cudaGetLastError();
+  e->timing.total_ms = e->timing.fill_ms;
+  return rc;
 }
 
 sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint64_t n_pairs,
                              int n_parts, int32_t* part) {
   if (n_parts < 1 || (n_pairs && (!q_len || !d_len || !part))) return SA_E_ARG;
   // Greedy LPT on n1*n2.  Equal-cost pairs are dealt in index order, so the result is
-  // deterministic and, for uniform batches, contiguous-cyclic.
+  // deterministic and, for uniform batches, cyclic.
   std::vector<uint64_t> order(n_pairs);
   for (uint64_t i = 0; i < n_pairs; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {

@@ -118,6 +118,60 @@ class AlignResult:
         return "".join(f"{w >> 2}{'MID'[w & 3]}" for w in self.cigar_of(p))
 
 
+class PinnedBuffer:
+    """Page-locked host memory from sa_alloc_pinned, viewed as a numpy array."""
+
+    def __init__(self, n: int, dtype):
+        self._lib = _capi.lib()
+        self.nbytes = max(int(n) * np.dtype(dtype).itemsize, 1)
+        self.ptr = self._lib.sa_alloc_pinned(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"sa_alloc_pinned({self.nbytes}) failed")
+        raw = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=dtype, count=int(n))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._lib.sa_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedResult:
+    """Caller-owned pinned result buffers for Engine.align(..., out=...)."""
+
+    def __init__(self, n_pairs: int, cigar_capacity: int):
+        self.n_pairs, self.cigar_capacity = n_pairs, cigar_capacity
+        self._bufs = [PinnedBuffer(n_pairs, np.int32), PinnedBuffer(n_pairs, np.uint8), PinnedBuffer(n_pairs, np.uint64),
+                      PinnedBuffer(n_pairs, np.uint32), PinnedBuffer(max(cigar_capacity, 1), np.uint32)]
+        self.score, self.status, self.cigar_off, self.cigar_len, self.cigar = (b.array for b in self._bufs)
+
+    def free(self):
+        for b in self._bufs:
+            b.free()
+
+
+def pin_batch(batch: "PairBatch"):
+    """Copies a batch into pinned memory (what a packer would write into directly)."""
+    bufs = []
+    arrs = []
+    for a in (batch.residues, batch.q_off, batch.q_len, batch.d_off, batch.d_len):
+        pb = PinnedBuffer(a.size, a.dtype)
+        pb.array[:] = a
+        bufs.append(pb)
+        arrs.append(pb.array)
+    out = PairBatch.__new__(PairBatch)
+    out.residues, out.q_off, out.q_len, out.d_off, out.d_len = arrs
+    out._pinned = bufs
+    return out
+
+
 def _scheme(s) -> Optional[_capi.Scheme]:
     if s is None:
         return None
@@ -179,9 +233,17 @@ class Engine:
         return res, (score, status, off, ln, pool)
 
     def align(self, batch: PairBatch, algo: int = ALGO_NW_AFFINE, mode: int = MODE_GLOBAL, scheme=None,
-              cigar: bool = True, cigar_capacity: Optional[int] = None) -> AlignResult:
+              cigar: bool = True, cigar_capacity: Optional[int] = None, out: Optional["PinnedResult"] = None) -> AlignResult:
         """sa_align_batch: host buffers in, host buffers out (the reference-facing call)."""
         n = batch.n_pairs
+        if out is not None:
+            sc = _scheme(scheme)
+            cb = self._c_batch(batch)
+            res = _capi.Result(out.score.ctypes.data, out.status.ctypes.data, out.cigar_off.ctypes.data,
+                               out.cigar_len.ctypes.data, out.cigar.ctypes.data if cigar else None,
+                               out.cigar_capacity if cigar else 0, 0)
+            self._check(self._lib.sa_align_batch(self._h, algo, mode, C.byref(sc) if sc else None, C.byref(cb), C.byref(res)))
+            return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)])
         cap = 0
         if cigar:
             cap = cigar_capacity if cigar_capacity is not None else max(64, 32 * n)

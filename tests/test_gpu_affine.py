@@ -85,6 +85,21 @@ def test_chunked_and_refill_slices(oracle, monkeypatch):
         assert (ref.status != 0).sum() > 100
 
 
+def test_many_small_segments_stream_results(oracle, monkeypatch):
+    """Segments of 700 pairs: inputs, per-pair results and the CIGAR pool all stream in pieces."""
+    from sequencealigning_b200 import Engine
+    monkeypatch.setenv("SA_SEG_PAIRS", "700")
+    with Engine(0) as eng:
+        b = _batch(random_pair_list(78, 5000, 0, 90))
+        r = eng.align(b)
+        check_against_oracle(oracle, b, r, what="small segments")
+        rb = eng.upload(b)
+        rb.align()
+        r2 = rb.download()
+        rb.free()
+        assert np.array_equal(r.cigar, r2.cigar) and np.array_equal(r.score, r2.score)
+
+
 def test_score_only_and_capacity(engine, oracle):
     from sequencealigning_b200 import EngineError
     b = _batch(random_pair_list(5, 500, 20, 80))

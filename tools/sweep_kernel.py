@@ -16,7 +16,7 @@ def main():
     pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
     length = int(sys.argv[2]) if len(sys.argv) > 2 else 150
     gs = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["4"])]
-    masks = sys.argv[4].split(",") if len(sys.argv) > 4 else ["0x00", "0x0F", "0x1F", "0x3F", "0x7F", "0xFF"]
+    masks = sys.argv[4].split(",") if len(sys.argv) > 4 else ["0x0F"]
     batch = synth.random_pairs(pairs, length, 0.05, True, seed=0x5A02)
     ref = None
     for g in gs:
