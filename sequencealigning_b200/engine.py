@@ -335,7 +335,9 @@ def parse_fasta(path: str):
     these records (main.rs:29-35 then continues with them)."""
     import os
     l = _capi.lib()
-    size = os.path.getsize(path) if os.path.exists(path) else 0
+    if not os.path.isfile(path):
+        raise ValueError(f"FastaError: {path}")  # parse.rs:62 `read(path)?`
+    size = os.path.getsize(path)
     out = np.zeros(max(size, 1), np.uint8)
     with open(path, "rb") as f:
         idx_cap = f.read().count(b">") + 1 if size else 1
