@@ -181,10 +181,10 @@ int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
   return best;
 }
 
-template <int G, uint32_t ORMASK>
+template <int G, uint32_t ORMASK, int ALGO = sa::kAffine>
 sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
                           uint32_t n_tiles, cudaStream_t stream) {
-  auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK>;
+  auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK, ALGO>;
   static size_t configured = 0;  // per instantiation; smem opt-in only grows
   if (g.smem_bytes > configured) {
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -199,7 +199,8 @@ sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geom
 
 template <int G>
 sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                        uint32_t n_tiles, cudaStream_t stream) {
+                        uint32_t n_tiles, cudaStream_t stream, int algo) {
+  if (algo == SA_ALGO_NW_LINEAR) return launch_fill_m<G, 0x0F, sa::kLinear>(e, p, g, n_tiles, stream);
   switch (e->ormask) {
     case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles, stream);
     case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles, stream);
@@ -210,14 +211,14 @@ sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geomet
 }
 
 sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                          uint32_t n_tiles, cudaStream_t stream) {
+                          uint32_t n_tiles, cudaStream_t stream, int algo = SA_ALGO_NW_AFFINE) {
   switch (g.G) {
-    case 1: return launch_fill<1>(e, p, g, n_tiles, stream);
-    case 2: return launch_fill<2>(e, p, g, n_tiles, stream);
-    case 4: return launch_fill<4>(e, p, g, n_tiles, stream);
-    case 8: return launch_fill<8>(e, p, g, n_tiles, stream);
-    case 16: return launch_fill<16>(e, p, g, n_tiles, stream);
-    case 32: return launch_fill<32>(e, p, g, n_tiles, stream);
+    case 1: return launch_fill<1>(e, p, g, n_tiles, stream, algo);
+    case 2: return launch_fill<2>(e, p, g, n_tiles, stream, algo);
+    case 4: return launch_fill<4>(e, p, g, n_tiles, stream, algo);
+    case 8: return launch_fill<8>(e, p, g, n_tiles, stream, algo);
+    case 16: return launch_fill<16>(e, p, g, n_tiles, stream, algo);
+    case 32: return launch_fill<32>(e, p, g, n_tiles, stream, algo);
   }
   return fail(e, SA_E_ARG, "bad G %d", g.G);
 }
@@ -254,6 +255,7 @@ struct Coverage {
 struct Scheme2 {
   sa_scheme_t sc;
   int pen, openp, extp;
+  int algo = SA_ALGO_NW_AFFINE;
 };
 
 struct Segment {
@@ -293,18 +295,37 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
   uint32_t* d_counts = (uint32_t*)e->misc.p;  // [2] refill queue lengths
 
+  const bool linear = s2.algo == SA_ALGO_NW_LINEAR;
   sa::AffineS16Params fp{};
   fp.residues = db.residues;
-  fp.q_off = db.q_off;
-  fp.q_len = db.q_len;
-  fp.d_off = db.d_off;
-  fp.d_len = db.d_len;
   fp.pen2 = pack2((uint32_t)s2.pen);
-  fp.open2 = pack2((uint32_t)s2.openp);
-  fp.ext2 = pack2((uint32_t)s2.extp);
-  fp.origin = pack2(sa::kBias);
   fp.zero = 0;
-  const uint32_t row0_clean = sa::kBias - (uint32_t)(s2.openp + (-2 * sc.gap_ext));
+  uint32_t row0_clean;
+  if (linear) {
+    // needleman_wunsch.rs: rows walk seq1, columns walk seq2 -> swap the kernel's roles.
+    // S' = 2S - match*(i+j): a gap step costs match - 2*open (flag clear) or match - 2*ext.
+    fp.q_off = db.d_off;
+    fp.q_len = db.d_len;
+    fp.d_off = db.q_off;
+    fp.d_len = db.q_len;
+    fp.open2 = pack2((uint32_t)(sc.match - 2 * sc.gap_open));
+    fp.ext2 = pack2((uint32_t)(2 * (sc.gap_ext - sc.gap_open)));
+    fp.step2 = pack2((uint32_t)s2.extp);
+    fp.origin = pack2(sa::kBias - (uint32_t)(2 * s2.openp));  // S[0][0] = 2*open (:45-64)
+    row0_clean = sa::kBias - (uint32_t)s2.openp;               // S[0][j] = open + j*ext
+  } else {
+    fp.q_off = db.q_off;
+    fp.q_len = db.q_len;
+    fp.d_off = db.d_off;
+    fp.d_len = db.d_len;
+    fp.open2 = pack2((uint32_t)s2.openp);
+    fp.ext2 = pack2((uint32_t)s2.extp);
+    fp.origin = pack2(sa::kBias);
+    row0_clean = sa::kBias - (uint32_t)(s2.openp + (-2 * sc.gap_ext));
+  }
+  // kernel columns / rows: (seq1, seq2) for affine, (seq2, seq1) for linear
+  const uint32_t* h_cols = linear ? h_d_len : h_q_len;
+  const uint32_t* h_rows = linear ? h_q_len : h_d_len;
 
   sa::WalkParams wp{};
   wp.q_len = db.q_len;
@@ -334,7 +355,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     // streaming from the host: ramp the segment size up so the first copy-in is short
     if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
     for (uint32_t i = 0; i < cn; ++i) {
-      const uint32_t a = h_q_len[base + i], b = h_d_len[base + i];
+      const uint32_t a = h_cols[base + i], b = h_rows[base + i];
       sg.n1max = std::max(sg.n1max, a);
       sg.n2max = std::max(sg.n2max, b);
     }
@@ -441,10 +462,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     fp.n_launch_pairs = cn;
     fp.tb = (uint2*)sl.tb.p;
     fp.end = (uint32_t*)sl.end.p;
-    fp.row0 = pack2(row0_clean + 1);
+    fp.row0 = pack2(row0_clean + (linear ? 0u : 1u));  // affine: panic bonus on
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
-    if ((r = launch_fill_g(e, fp, g, ctiles, sx)) != SA_OK) return r;
+    if ((r = launch_fill_g(e, fp, g, ctiles, sx, s2.algo)) != SA_OK) return r;
     CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sx));
     wp.pair_ids = nullptr;
     wp.pair_base = (uint32_t)sg.base;
@@ -455,7 +476,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
     wp.rerun_count = d_counts + k;
     wp.phase = 0;
-    sa::nw_affine_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
+    if (linear)
+      sa::nw_linear_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
+    else
+      sa::nw_affine_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
     CUDA_TRY(e, cudaGetLastError());
     e->timing.kernel_launches++;
     CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
@@ -537,7 +561,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       wp.tb = (const uint2*)sl.tb.p;
       wp.end = (const uint32_t*)sl.end.p;
       wp.phase = 0;
-      sa::nw_affine_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
+      if (linear)
+        sa::nw_linear_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
+      else
+        sa::nw_affine_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
       for (const ReLaunch& rl : re_launches) {
@@ -647,7 +674,8 @@ sa_status_t check_algo(sa_engine* e, sa_algo_t algo, sa_mode_t mode, bool* not_i
     }
     return fail(e, SA_E_UNSUPPORTED, "mode %d for algo %d is not built yet", (int)mode, (int)algo);
   }
-  if (algo != SA_ALGO_NW_AFFINE) return fail(e, SA_E_UNSUPPORTED, "algo %d is not built yet", (int)algo);
+  if (algo != SA_ALGO_NW_AFFINE && algo != SA_ALGO_NW_LINEAR)
+    return fail(e, SA_E_UNSUPPORTED, "algo %d is not built yet", (int)algo);
   return SA_OK;
 }
 
@@ -850,6 +878,7 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   }
   Scheme2 s2;
   if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
+  s2.algo = (int)algo;
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (want_cigar && !r->d.pool) {
       r->d.pool_cap = std::max<uint64_t>(std::max<uint64_t>(1024, n * 24), r->used + 1024);
@@ -925,6 +954,7 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   }
   Scheme2 s2;
   if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
+  s2.algo = (int)algo;
   const bool want_cigar = res->cigar != nullptr && res->cigar_capacity > 0;
 
   // engine-owned staging, grow-only: no allocation on the steady-state path

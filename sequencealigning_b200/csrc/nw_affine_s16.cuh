@@ -70,6 +70,7 @@ struct AffineS16Params {
   uint32_t row0;    // kBias - 2*(-(open+ext)) + bonus, packed: H'[0][y] = row0 - y*ext2
   uint32_t origin;  // kBias packed: H'[0][0]
   uint32_t zero;    // always 0; opaque to ptxas so that `or` bit-sets stay LOP3 (alu pipe)
+  uint32_t step2;   // linear aligner: boundary step magnitude match - 2*ext, packed
 };
 
 // max of two packed u16 pairs that also records, per half, whether the FIRST operand won or
@@ -147,6 +148,70 @@ struct StripCells<K, K, ORMASK> {
                                              uint32_t (&)[K]) {}
 };
 
+// ---------------------------------------------------------------------------------------------
+// Single-matrix "linear / pseudo-affine" NW of /root/reference/src/needleman_wunsch.rs:66-103:
+//     diag  = S[i-1][j-1] + (eq ? match : mismatch)
+//     down  = S[i-1][j]   + (gaps[i-1][j] ? ext : open)        (consumes seq1[i-1])
+//     right = S[i][j-1]   + (gaps[i][j-1] ? ext : open)        (consumes seq2[j-1])
+//     S[i][j] = max3; gaps[i][j] = (S == down || S == right); moves pushed Down, Right, Diag
+// Rows walk seq1 and columns seq2 in the reference (:38); the kernel is launched with the
+// sequence roles swapped to match.  The first printed hit follows the FIRST stored move, i.e.
+// Down if S == down, else Right if S == right, else Diag -- which two predicates decide:
+//     p1 = down >= right,  p2 = max(down,right) >= diag   (p2 is also the gap flag)
+// so the traceback needs 2 bits per cell (kept in the low half of the affine nibble).
+// The per-cell gap cost is carried as a packed magnitude g = open' - p2*(open' - ext').
+// ---------------------------------------------------------------------------------------------
+enum { kAffine = 0, kLinear = 1 };
+
+// max that records the tie bit and, when the first operand wins or ties, also subtracts DELTA
+// from the matching half of g (the gap-cost magnitude of this cell)
+template <uint32_t BIT>
+__device__ __forceinline__ uint32_t vmax_tie_g(uint32_t a, uint32_t b, uint32_t& acc_lo,
+                                               uint32_t& acc_hi, uint32_t& g, uint32_t delta_lo,
+                                               uint32_t delta_hi) {
+  uint32_t r;
+  asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, a0, a1;\n\t"
+      "max.u16x2 %0, %4, %5;\n\tmov.b32 {r0, r1}, %0;\n\tmov.b32 {a0, a1}, %4;\n\t"
+      "setp.eq.u16 pl, r0, a0;\n\tsetp.eq.u16 ph, r1, a1;\n\t"
+      "@pl or.b32 %1, %1, %6;\n\t@ph or.b32 %2, %2, %6;\n\t"
+      "@pl sub.u32 %3, %3, %7;\n\t@ph sub.u32 %3, %3, %8;\n\t}"
+      : "=r"(r), "+r"(acc_lo), "+r"(acc_hi), "+r"(g)
+      : "r"(a), "r"(b), "n"(BIT), "r"(delta_lo), "r"(delta_hi));
+  return r;
+}
+
+template <int K, int C>
+struct LinearCells {
+  // Hrow: S' of the row above; Gm: gap-cost magnitude of the cell above; (sl, gl): S' and gap
+  // magnitude of the cell to the left (in: left boundary, out: last column of the strip)
+  static __device__ __forceinline__ void run(uint32_t (&Hrow)[K], uint32_t (&Gm)[K],
+                                             const uint32_t (&q)[K], uint32_t d, uint32_t sdiag,
+                                             uint32_t& sl, uint32_t& gl, uint32_t pen2,
+                                             uint32_t gopen2, uint32_t delta_lo, uint32_t delta_hi,
+                                             uint32_t& acc_a, uint32_t& acc_b) {
+    constexpr int c = C;
+    const uint32_t hup = Hrow[c];
+    const uint32_t m = __vminu2(q[c] ^ d, pen2);
+    const uint32_t diag = sdiag - m;
+    const uint32_t down = hup - Gm[c];
+    const uint32_t right = sl - gl;
+    const uint32_t t = vmax_tie<(1u << (4 * c)), true, true>(down, right, acc_a, acc_b);  // p1
+    uint32_t g = gopen2;
+    const uint32_t S = vmax_tie_g<(2u << (4 * c))>(t, diag, acc_a, acc_b, g, delta_lo, delta_hi);  // p2
+    Hrow[c] = S;
+    Gm[c] = g;
+    sl = S;
+    gl = g;
+    LinearCells<K, C + 1>::run(Hrow, Gm, q, d, hup, sl, gl, pen2, gopen2, delta_lo, delta_hi, acc_a, acc_b);
+  }
+};
+template <int K>
+struct LinearCells<K, K> {
+  static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K],
+                                             uint32_t, uint32_t, uint32_t&, uint32_t&, uint32_t,
+                                             uint32_t, uint32_t, uint32_t, uint32_t&, uint32_t&) {}
+};
+
 // one residue byte per pair -> (byte << 7) in each 16-bit half
 __device__ __forceinline__ uint32_t widen(uint32_t v) {
   return ((v & 0xffu) << 7) | ((v & 0xff00u) << 15);
@@ -159,7 +224,83 @@ __device__ __forceinline__ uint32_t end_word(uint32_t H, uint32_t M, uint32_t E,
   return H | (st << 16) | 0x80000000u;
 }
 
-template <int K, int G, uint32_t ORMASK>
+// Per-lane state of one pass over a strip (all in registers).
+template <int K>
+struct StripState {
+  uint32_t Hrow[K], F[K], q[K];
+  uint32_t hd_prev;      // H'[x-1][y0]: the diagonal input of the strip's first column
+  uint32_t out_h, out_e; // right boundary of the row just computed: H'[x][yK], E'[x][yK+1]
+  uint32_t x;            // row this lane computes next (1-based)
+  const uint16_t* dptr;  // shared: db residues of row x (both pairs)
+  uint2* bptr;           // shared: boundary column entry of row x
+  uint2* tptr;           // global: traceback word of (strip, row x)
+  uint32_t capx_a, capx_b;  // row of pair A's / B's end cell if it lies in this strip, else 0
+};
+
+// One row of the lane's strip.  CHECKED = the lane may be outside [1, n2t] (ramp rows of a
+// pass, where the G lanes of a group are not all active yet / any more).
+template <int K, int G, uint32_t ORMASK, bool CHECKED, int ALGO>
+__device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Params& p, int j,
+                                         uint32_t n2t, uint32_t pen2, uint32_t open2,
+                                         uint32_t ext2, uint32_t zero, uint32_t la, uint32_t lb,
+                                         uint32_t ca_, uint32_t cb_) {
+  constexpr int NG = 32 / G;
+  uint32_t rh = 0, re = 0;
+  if (G > 1) {
+    rh = __shfl_up_sync(0xffffffffu, st.out_h, 1);
+    re = __shfl_up_sync(0xffffffffu, st.out_e, 1);
+  }
+  const bool active = !CHECKED || (st.x >= 1 && st.x <= n2t);
+  if (active) {
+    if (j == 0) {  // left edge of the group: column 0 (pass 0, staged in the prologue) or the
+      const uint2 b = *st.bptr;  // previous pass's last strip
+      rh = b.x;
+      re = b.y;
+    }
+    const uint32_t d = widen(*st.dptr);
+    uint32_t E = re, acc_a = zero, acc_b = zero;
+    uint32_t Mv[K], Ev[K];
+    if (ALGO == kLinear) {
+      // open2 = open' magnitude, ext2 = open' - ext' (what a set gap flag saves), per half
+      uint32_t sl = rh;
+      LinearCells<K, 0>::run(st.Hrow, st.F, st.q, d, st.hd_prev, sl, E, pen2, open2, ext2 & 0xffffu,
+                             ext2 & 0xffff0000u, acc_a, acc_b);
+#pragma unroll
+      for (int c = 0; c < K; ++c) Mv[c] = Ev[c] = 0;
+    } else {
+      StripCells<K, 0, ORMASK>::run(st.Hrow, st.F, st.q, d, st.hd_prev, E, pen2, open2, ext2, acc_a,
+                                    acc_b, Mv, Ev);
+    }
+    if (st.x == st.capx_a || st.x == st.capx_b) {  // rare: this row holds a pair's end cell
+      if (st.x == st.capx_a) {
+        uint32_t H = 0, M = 0, Ei = 0;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if ((uint32_t)c == ca_) { H = st.Hrow[c] & 0xffffu; M = Mv[c] & 0xffffu; Ei = Ev[c] & 0xffffu; }
+        p.end[la] = end_word(H, M, Ei, (acc_a >> (4 * ca_ + 1)) & 1u);
+      }
+      if (st.x == st.capx_b) {
+        uint32_t H = 0, M = 0, Ei = 0;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if ((uint32_t)c == cb_) { H = st.Hrow[c] >> 16; M = Mv[c] >> 16; Ei = Ev[c] >> 16; }
+        p.end[lb] = end_word(H, M, Ei, (acc_b >> (4 * cb_ + 1)) & 1u);
+      }
+    }
+    st.hd_prev = rh;
+    st.out_h = st.Hrow[K - 1];
+    st.out_e = E;
+    if (j == G - 1) *st.bptr = make_uint2(st.out_h, st.out_e);
+    *st.tptr = make_uint2(acc_a, acc_b);
+  }
+  // the cursor advances whether or not the row was in range, so that x == t - j always
+  st.x += 1;
+  st.dptr += NG;
+  st.bptr += NG;
+  st.tptr += NG;
+}
+
+template <int K, int G, uint32_t ORMASK, int ALGO = kAffine>
 __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p) {
   static_assert(K == 8, "traceback word layout assumes 8 cells x 4 bits");
   constexpr int NG = 32 / G;       // pair-of-pairs per warp tile
@@ -200,6 +341,8 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (size_t)p.smem_bnd_rows * NG);  // [rows][NG]
   uint16_t* qp = dp + p.smem_d_halfs;                                              // [n1pad][NG]
 
+  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2, zero = p.zero;
+
   // ---- stage the residues; they are widened to (byte << 7) per 16-bit half when read, so the
   //      XOR of two different residues is >= 128 >= pen2 and the XOR of equal residues is 0 ----
   for (uint32_t y = j; y < n1pad; y += G) {
@@ -211,10 +354,18 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
     const uint32_t a = (x < n2a) ? (uint32_t)p.residues[doa + x] : 0u;
     const uint32_t b = (x < n2b) ? (uint32_t)p.residues[dob + x] : 0u;
     dp[x * NG + grp] = (uint16_t)(a | (b << 8));
+    // column 0 as the "previous pass" of pass 0.  Affine: H'[x][0] = I'[x][0] (:200-216), and
+    // I'[x][1] extends it (M[x][0] + open is the sentinel).  Linear: S'[i][0] with its gap flag
+    // set (needleman_wunsch.rs:55-64), i.e. the cell to its right pays an extension.
+    if (ALGO == kLinear) {
+      bnd[x * NG + grp] = make_uint2(p.row0 - (x + 1) * p.step2, open2 - ext2);
+    } else {
+      const uint32_t h = p.row0 - (x + 1) * ext2;
+      bnd[x * NG + grp] = make_uint2(h, h - ext2);
+    }
   }
   __syncwarp();
 
-  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2, zero = p.zero;
   // end-cell capture coordinates (strip, column-in-strip) per half
   const uint32_t sa_ = n1a ? (n1a - 1) / K : 0xffffffffu, ca_ = n1a ? (n1a - 1) % K : 0;
   const uint32_t sb_ = n1b ? (n1b - 1) / K : 0xffffffffu, cb_ = n1b ? (n1b - 1) % K : 0;
@@ -224,66 +375,44 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   for (uint32_t pass = 0; pass < npass; ++pass) {
     const uint32_t s = pass * G + j;  // this lane's strip
     const uint32_t y0 = s * K;        // columns to the left of the strip
-    uint32_t Hrow[K], F[K], q[K];
+    StripState<K> st;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       const uint32_t y = y0 + c + 1;
-      Hrow[c] = p.row0 - y * ext2;  // H'[0][y] = D'[0][y]  (nw_affine:194-198)
-      F[c] = Hrow[c] - ext2;        // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
-      q[c] = widen(qp[(y - 1) * NG + grp]);
+      if (ALGO == kLinear) {
+        st.Hrow[c] = p.row0 - y * p.step2;  // S'[0][j], gap flag set (needleman_wunsch.rs:45-54)
+        st.F[c] = open2 - ext2;             // -> the cell below pays an extension
+      } else {
+        st.Hrow[c] = p.row0 - y * ext2;  // H'[0][y] = D'[0][y]  (nw_affine:194-198)
+        st.F[c] = st.Hrow[c] - ext2;     // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
+      }
+      st.q[c] = widen(qp[(y - 1) * NG + grp]);
     }
-    uint32_t hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * ext2;  // H'[x-1][y0]
-    uint32_t colh = p.row0 - ext2;                                 // H'[1][0] = I'[1][0]
-    uint32_t out_h = 0, out_e = 0;
-    const bool cap_a_strip = (s == sa_), cap_b_strip = (s == sb_);
-    uint2* tb_strip = tb_tile + ((uint64_t)s * p.tb_rows) * NG + grp;
+    if (ALGO == kLinear)
+      st.hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * p.step2;  // S'[0][j0]; S[0][0] = 2*open
+    else
+      st.hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * ext2;  // H'[0][y0]
+    st.out_h = 0;
+    st.out_e = 0;
+    st.capx_a = (s == sa_) ? n2a : 0u;
+    st.capx_b = (s == sb_) ? n2b : 0u;
+    // lane j runs j rows behind lane 0: its cursor starts at row 1 - j
+    st.x = 1u - (uint32_t)j;
+    st.dptr = dp + grp - (ptrdiff_t)j * NG;
+    st.bptr = bnd + grp - (ptrdiff_t)j * NG;
+    st.tptr = tb_tile + ((uint64_t)s * p.tb_rows) * NG + grp - (ptrdiff_t)j * NG;
 
-    for (uint32_t t = 1; t < n2t + G; ++t) {
-      uint32_t rh = out_h, re = out_e;
-      if (G > 1) {
-        rh = __shfl_up_sync(0xffffffffu, out_h, 1);
-        re = __shfl_up_sync(0xffffffffu, out_e, 1);
-      }
-      const uint32_t x = t - j;  // wraps for t < j: fails the range test below
-      if (x >= 1 && x <= n2t) {
-        if (j == 0) {
-          if (pass == 0) {  // column 0: H'[x][0] = I'[x][0], and I'[x][1] extends it (:200-216)
-            rh = colh;
-            re = colh - ext2;
-            colh -= ext2;
-          } else {
-            const uint2 b = bnd[(x - 1) * NG + grp];
-            rh = b.x;
-            re = b.y;
-          }
-        }
-        const uint32_t d = widen(dp[(x - 1) * NG + grp]);
-        uint32_t E = re, acc_a = zero, acc_b = zero;
-        uint32_t Mv[K], Ev[K];
-        StripCells<K, 0, ORMASK>::run(Hrow, F, q, d, hd_prev, E, pen2, open2, ext2, acc_a, acc_b, Mv, Ev);
-        if ((cap_a_strip && x == n2a) || (cap_b_strip && x == n2b)) {  // rare: a pair's end cell
-          if (cap_a_strip && x == n2a) {
-            uint32_t H = 0, M = 0, Ei = 0;
-#pragma unroll
-            for (int c = 0; c < K; ++c)
-              if ((uint32_t)c == ca_) { H = Hrow[c] & 0xffffu; M = Mv[c] & 0xffffu; Ei = Ev[c] & 0xffffu; }
-            p.end[la] = end_word(H, M, Ei, (acc_a >> (4 * ca_ + 1)) & 1u);
-          }
-          if (cap_b_strip && x == n2b) {
-            uint32_t H = 0, M = 0, Ei = 0;
-#pragma unroll
-            for (int c = 0; c < K; ++c)
-              if ((uint32_t)c == cb_) { H = Hrow[c] >> 16; M = Mv[c] >> 16; Ei = Ev[c] >> 16; }
-            p.end[lb] = end_word(H, M, Ei, (acc_b >> (4 * cb_ + 1)) & 1u);
-          }
-        }
-        hd_prev = rh;
-        out_h = Hrow[K - 1];
-        out_e = E;
-        if (j == G - 1) bnd[(x - 1) * NG + grp] = make_uint2(out_h, out_e);
-        tb_strip[(uint64_t)(x - 1) * NG] = make_uint2(acc_a, acc_b);
-      }
-    }
+    uint32_t t = 1;
+    // ramp-up: lanes j >= t are not active yet
+    for (; t < (uint32_t)G && t <= n2t + G - 1; ++t)
+      row_step<K, G, ORMASK, true, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
+    // steady state: every lane is inside [1, n2t]
+#pragma unroll 2
+    for (; t <= n2t; ++t)
+      row_step<K, G, ORMASK, false, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
+    // ramp-down
+    for (; t <= n2t + G - 1; ++t)
+      row_step<K, G, ORMASK, true, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     __syncwarp();
   }
 }

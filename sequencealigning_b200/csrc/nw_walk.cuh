@@ -158,6 +158,80 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   }
 }
 
+// Linear ("pseudo-affine") NW walk: the first hit of get_next (needleman_wunsch.rs:205-254)
+// follows the first stored move of every cell, in push order Down, Right, Diag (:92-100).
+// The fill kernel ran with rows = seq1 (query) and columns = seq2 (db), like the reference.
+//   nibble bit0 = down >= right, bit1 = max(down,right) >= diag
+//   Down  (seq1[i-1] over '-') -> SA_OP_I      Right ('-' over seq2[j-1]) -> SA_OP_D
+// Row 0 holds [Right] and column 0 [Down] (:44-65), so the walk runs along the border to (0,0);
+// nothing can panic in global mode.
+template <int MODE>
+__global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
+  const uint32_t i_launch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i_launch >= p.n_launch_pairs) return;
+  const uint32_t id = p.pair_base + i_launch;
+  const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
+  const uint32_t ppt = 2 * p.ng;
+  const uint32_t tile = i_launch / ppt, grp = (i_launch % ppt) >> 1, half = i_launch & 1;
+  const uint64_t tile_base = (uint64_t)tile * p.tb_tile_stride;
+  if (MODE == 0) {
+    int32_t score;
+    if (n1 == 0 || n2 == 0) {  // border cells (:44-65); scores[0][0] gets both increments
+      score = (n1 == 0 && n2 == 0) ? 2 * p.open : p.open + (int32_t)(n1 + n2) * p.ext;
+    } else {
+      const int32_t t2 = (int32_t)(p.end[i_launch] & 0xffffu) - (int32_t)kBias + p.match * (int32_t)(n1 + n2);
+      score = t2 / 2;
+    }
+    p.score[id] = score;
+    p.status[id] = kOk;
+  } else if (p.cigar_len[id] == 0) {
+    return;
+  }
+  uint32_t i = n1, j = n2;  // rows walk seq1, columns walk seq2
+  uint32_t nruns = 0, run_op = 3, run_len = 0;
+  uint64_t wpos = 0;
+  if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];
+  while (i > 0 || j > 0) {
+    uint32_t op;
+    if (i == 0) {
+      op = 2;
+      --j;
+    } else if (j == 0) {
+      op = 1;
+      --i;
+    } else {
+      const uint32_t nb = tb_nibble(p, tile_base, grp, half, i, j);
+      if ((nb & 3u) == 3u) {
+        op = 1;
+        --i;
+      } else if (nb & 2u) {
+        op = 2;
+        --j;
+      } else {
+        op = 0;
+        --i;
+        --j;
+      }
+    }
+    if (op != run_op) {
+      if (MODE == 1 && run_len) {
+        --wpos;
+        if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
+      }
+      run_op = op;
+      run_len = 0;
+      ++nruns;
+    }
+    ++run_len;
+  }
+  if (MODE == 0) {
+    p.cigar_len[id] = nruns;
+  } else if (run_len) {
+    --wpos;
+    if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
+  }
+}
+
 // ---- exclusive scan of cigar_len -> cigar_off (three small kernels, no library) -------------
 constexpr int kScanBlock = 1024;
 
