@@ -102,6 +102,12 @@ def _bind_wfa(l):  # filled in by oracle/wfa.c's section below
     l.sao_wfa_gotoh_cost.restype = C.c_int64
     l.sao_wfa_standard.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32]
     l.sao_wfa_standard.restype = C.c_int64
+    l.sao_wfa_literal_ex.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(_WfaResult), i32p, C.c_uint32, u32p, i32p]
+    l.sao_wfa_literal_ex.restype = C.c_int
+    l.sao_wfa_literal_cap.argtypes = [C.c_uint32, C.c_uint32]
+    l.sao_wfa_literal_cap.restype = C.c_uint32
+    l.sao_wfa_literal_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    l.sao_wfa_literal_batch.restype = C.c_int
 
 
 class _WfaResult(C.Structure):
@@ -311,10 +317,45 @@ class WfaResult:
     n_wavefronts: int
 
 
-def wfa_literal(seq1: bytes, seq2: bytes, max_score: int = 4000) -> WfaResult:
+def wfa_literal_cap(n1: int, n2: int) -> int:
+    return lib().sao_wfa_literal_cap(n1, n2)
+
+
+def wfa_literal(seq1: bytes, seq2: bytes, max_score: Optional[int] = None) -> WfaResult:
     r = _WfaResult()
+    if max_score is None:
+        max_score = wfa_literal_cap(len(seq1), len(seq2))
     lib().sao_wfa_literal(seq1, len(seq1), seq2, len(seq2), max_score, C.byref(r))
     return WfaResult(r.status, r.printed_score, r.panic_line, r.n_wavefronts)
+
+
+def wfa_literal_ex(seq1: bytes, seq2: bytes, max_score: Optional[int] = None):
+    """(result, [(lo, hi) lines], converged element (offset, state, parents) or None)"""
+    r = _WfaResult()
+    if max_score is None:
+        max_score = wfa_literal_cap(len(seq1), len(seq2))
+    cap = max_score + 8
+    lohi = (C.c_int32 * (2 * cap))()
+    n = C.c_uint32()
+    conv = (C.c_int32 * 6)()
+    lib().sao_wfa_literal_ex(seq1, len(seq1), seq2, len(seq2), max_score, C.byref(r), lohi, cap, C.byref(n), conv)
+    lines = [(lohi[2 * k], lohi[2 * k + 1]) for k in range(min(n.value, cap))]
+    ce = None
+    if r.status == OK:
+        ce = (conv[0], "MDI"[conv[1]], tuple("MDI"[conv[3 + k]] for k in range(conv[2])))
+    return WfaResult(r.status, r.printed_score, r.panic_line, r.n_wavefronts), lines, ce
+
+
+def wfa_literal_batch(residues, q_off, q_len, d_off, d_len):
+    residues, q_off, q_len, d_off, d_len = _batch_args(residues, q_off, q_len, d_off, d_len)
+    n = len(q_len)
+    score = np.zeros(n, np.int32)
+    status = np.zeros(n, np.uint8)
+    rc = lib().sao_wfa_literal_batch(residues.ctypes.data, q_off.ctypes.data, q_len.ctypes.data, d_off.ctypes.data,
+                                     d_len.ctypes.data, n, score.ctypes.data, status.ctypes.data)
+    if rc != 0:
+        raise MemoryError("oracle wfa batch failed")
+    return score, status
 
 
 def wfa_gotoh_cost(seq1: bytes, seq2: bytes, x: int = 4, o: int = 2, e: int = 6) -> int:

@@ -330,3 +330,275 @@ def linear_align(seq1: bytes, seq2: bytes, local: bool = False, max_hits: int = 
     except _Stop:
         pass
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# wfa.rs  -- literal transliteration (release-profile integer semantics: `usize`/`i32`
+# arithmetic wraps, Vec::rotate_left(k > len) and slice indexing panic in both profiles)
+# ----------------------------------------------------------------------------------------
+W_M, W_D, W_I = "M", "D", "I"  # enum State :44-50
+WFA_MISMATCH, WFA_GAP_OPENING, WFA_GAP_EXTENSION = 4, 2, 6  # :17-21
+MINLENGTH, MAXDIFF = 5, 20  # :14-15
+_USIZE = 1 << 64
+
+
+def _as_usize(v: int) -> int:
+    return v % _USIZE
+
+
+class WfElement:  # :75-102
+    __slots__ = ("offset", "parents", "state")
+
+    def __init__(self, offset=0, parents=None, state=W_M):
+        self.offset, self.parents, self.state = offset, list(parents or []), state
+
+    def x(self, diag):
+        return _as_usize(self.offset - min(diag, 0))
+
+    def y(self, diag):
+        return _as_usize(self.offset + max(diag, 0))
+
+    def get_distance(self, n1, n2, diag):
+        return max(n1 - self.offset - diag, n2 - self.offset)
+
+    def clone(self):
+        return WfElement(self.offset, self.parents, self.state)
+
+    def key(self):
+        return (self.offset, tuple(self.parents), self.state)
+
+
+class WaveFront:  # :118-192
+    def __init__(self, hi=0, lo=0, elements=None):
+        self.hi, self.lo, self.elements = hi, lo, list(elements or [])
+
+    def get_element(self, idx):
+        k = _as_usize(idx - self.lo)
+        if k < len(self.elements):
+            return self.elements[k]
+        return None
+
+    def get_offset(self, idx):
+        e = self.get_element(idx)
+        return None if e is None else e.offset
+
+    def expand(self, seq1, seq2):  # :127-139
+        for i, e in enumerate(self.elements):
+            if e is None:
+                continue
+            d = self.lo + i
+            while e.y(d) < len(seq1) and e.x(d) < len(seq2) and seq1[e.y(d)] == seq2[e.x(d)]:
+                e.offset += 1
+
+    def is_converged(self, seq1, seq2):  # :180-191
+        tx, ty = _as_usize(len(seq2) - 1), _as_usize(len(seq1) - 1)
+        for i, e in enumerate(self.elements):
+            if e is not None and e.x(self.lo + i) == tx and e.y(self.lo + i) == ty:
+                return e
+        return None
+
+    def key(self):
+        return (self.hi, self.lo, tuple(None if e is None else e.key() for e in self.elements))
+
+
+class WfTensor:  # :211-440
+    def __init__(self, i=None, d=None, m=None):
+        self.i, self.d, self.m = i, d, m
+
+    def key(self):
+        return tuple(None if w is None else w.key() for w in (self.i, self.d, self.m))
+
+    def is_converged(self, seq1, seq2):  # :422-439  order I, D, M
+        for w in (self.i, self.d, self.m):
+            if w is not None:
+                e = w.is_converged(seq1, seq2)
+                if e is not None:
+                    return e
+        return None
+
+
+def _opt_max(vals):
+    """max over Option<i32> with None < Some (Rust's Ord for Option)."""
+    best = None
+    for v in vals:
+        if v is not None and (best is None or v > best):
+            best = v
+    return best
+
+
+def _rotate_left(v: list, k: int, site: str):
+    if k > len(v):
+        raise RefPanic(site)
+    v[:] = v[k:] + v[:k]
+
+
+def wf_tensor_new(open_, ext, mis, log: Optional[list] = None):  # WaveFrontTensor::new :225-420
+    his = [t.hi for t in (open_.m if open_ else None, mis.m if mis else None, ext.i if ext else None, ext.d if ext else None) if t is not None]
+    if not his:
+        return None
+    hi = max(his) + 1
+    los = [t.lo for t in (open_.m if open_ else None, mis.m if mis else None, ext.i if ext else None, ext.d if ext else None) if t is not None]
+    lo = min(los) - 1
+    if log is not None:
+        log.append((lo, hi))  # println!("lo: {}, hi: {}") :251
+    i, d, m = WaveFront(hi, lo), WaveFront(hi, lo), WaveFront(hi, lo)
+    trk = {k: [lo, hi, False] for k in "idm"}  # cur_lo, cur_hi, lo_set
+
+    def mark(k, idx):
+        trk[k][1] = idx
+        if not trk[k][2]:
+            trk[k][0] = idx
+            trk[k][2] = True
+
+    def parents(offset, els):
+        return [e.state for e in els if e is not None and e.offset == offset]
+
+    om = open_.m if open_ else None
+    ed = ext.d if ext else None
+    ei = ext.i if ext else None
+    mm = mis.m if mis else None
+    for idx in range(lo, hi + 1):
+        srcs = [om.get_element(idx + 1) if om else None, ed.get_element(idx + 1) if ed else None]
+        off = _opt_max([s.offset if s else None for s in srcs])
+        if off is not None:
+            d.elements.append(WfElement(off, parents(off, srcs), W_D))
+            mark("d", idx)
+        else:
+            d.elements.append(None)
+        srcs = [om.get_element(idx - 1) if om else None, ei.get_element(idx - 1) if ei else None]
+        off = _opt_max([s.offset if s else None for s in srcs])
+        if off is not None:
+            i.elements.append(WfElement(off + 1, parents(off, srcs), W_I))
+            mark("i", idx)
+        else:
+            i.elements.append(None)
+        me = mm.get_element(idx) if mm else None
+        tmp = WfElement(me.offset + 1, [], W_M) if me is not None else None
+        cand = [tmp, i.get_element(idx), d.get_element(idx)]
+        off = _opt_max([c.offset if c else None for c in cand])
+        if off is not None:
+            m.elements.append(WfElement(off, parents(off, cand), W_M))
+            mark("m", idx)
+        elif trk["m"][2]:
+            m.elements.append(None)
+    i.lo, i.hi = trk["i"][0], trk["i"][1]
+    d.lo, d.hi = trk["d"][0], trk["d"][1]
+    m.lo, m.hi = trk["m"][0], trk["m"][1]
+    _rotate_left(i.elements, abs(lo - i.lo), "wfa:405")
+    del i.elements[abs(i.hi - i.lo) + 1:]
+    _rotate_left(d.elements, abs(lo - d.lo), "wfa:407")
+    del d.elements[abs(d.hi - d.lo) + 1:]
+    del m.elements[abs(m.hi - m.lo) + 1:]
+    return WfTensor(i if trk["i"][2] else None, d if trk["d"][2] else None, m if trk["m"][2] else None)
+
+
+def _wfa_trim(cur: WfTensor, seq1, seq2):  # Ocean::trim :490-623
+    m = cur.m
+    if m is None:
+        return
+    if abs(m.lo - m.hi) <= MINLENGTH:
+        return
+    n1, n2 = len(seq1), len(seq2)
+    min_d = 0
+    for diag in range(m.lo, m.hi + 1):
+        e = m.get_element(diag)
+        if e is not None:
+            min_d = min(min_d, e.get_distance(n1, n2, diag))
+
+    def first():
+        if not m.elements or m.elements[0] is None:
+            raise RefPanic("wfa:519-524")
+        return m.elements[0]
+
+    def last():
+        if not m.elements or m.elements[-1] is None:
+            raise RefPanic("wfa:545-551")
+        return m.elements[-1]
+
+    next_d = first().get_distance(n1, n2, m.lo)
+    while m.lo < m.hi and abs(next_d - min_d) > MAXDIFF:
+        m.lo += 1
+        m.elements.pop(0)
+        while m.get_element(m.lo) is None:
+            if m.lo == m.hi:
+                break
+            m.lo += 1
+            m.elements.pop(0)
+        next_d = first().get_distance(n1, n2, m.lo)
+    next_d = last().get_distance(n1, n2, m.hi)
+    while m.hi > m.lo and abs(next_d - min_d) > MAXDIFF:
+        m.hi -= 1
+        m.elements.pop()
+        while m.get_element(m.hi) is None:
+            if m.lo == m.hi:
+                break
+            m.hi -= 1
+            m.elements.pop()
+        next_d = last().get_distance(n1, n2, m.hi)
+    for w, site in ((cur.i, "wfa:577"), (cur.d, "wfa:603")):
+        if w is None:
+            continue
+        if w.lo < m.lo:
+            _rotate_left(w.elements, abs(w.lo - m.lo), site)
+            t = abs(w.lo - m.lo) + (abs(w.hi - m.hi) if w.hi > m.hi else 0)
+        elif w.hi > m.hi:
+            t = abs(w.hi - m.hi)
+        else:
+            t = 0
+        new_len = _as_usize(len(w.elements) - t)  # release profile: wraps, truncate is then a no-op
+        if new_len < len(w.elements):
+            del w.elements[new_len:]
+        w.hi = min(w.hi, m.hi)
+        w.lo = max(w.lo, m.lo)
+
+
+@dataclass
+class WfaOutcome:
+    status: str            # "OK" | "PANIC" | "NO_CONVERGENCE"
+    printed_score: int = 0  # wfs.len() at convergence (:31-36) = index of the wavefront + 1
+    panic_site: str = ""
+    lo_hi: List[Tuple[int, int]] = field(default_factory=list)  # the `lo: .., hi: ..` lines (:251)
+    converged: Optional[Tuple[int, Tuple[str, ...], str]] = None  # (offset, parents, state)
+    m_offsets: dict = field(default_factory=dict)  # score -> (lo, [offsets or None]) after extend+trim
+
+
+def wfa_expand(wfs: list, seq1: bytes, seq2: bytes, log: Optional[list] = None):  # Ocean::expand :467-488
+    s = len(wfs)
+
+    def get(k):  # `(s - ..) as usize` wraps for negatives -> Vec::get returns None
+        return wfs[k] if 0 <= k < len(wfs) else None
+
+    wfs.append(wf_tensor_new(get(s - WFA_GAP_OPENING - WFA_GAP_EXTENSION), get(s - WFA_GAP_EXTENSION), get(s - WFA_MISMATCH), log))
+    cur = wfs[s]
+    if cur is not None:
+        if cur.m is not None:
+            cur.m.expand(seq1, seq2)
+        _wfa_trim(cur, seq1, seq2)
+
+
+def wfa_global_initial():  # Ocean::global :450-465
+    return [WfTensor(None, None, WaveFront(0, 0, [WfElement(0, [], W_M)]))]
+
+
+def wfa_align(seq1: bytes, seq2: bytes, max_score: int = 4000) -> WfaOutcome:  # wfa_align :23-42
+    wfs = wfa_global_initial()
+    out = WfaOutcome("OK")
+    try:
+        while True:
+            last = wfs[-1]
+            conv = last.is_converged(seq1, seq2) if last is not None else None
+            if conv is not None:
+                out.printed_score = len(wfs)
+                out.converged = (conv.offset, tuple(conv.parents), conv.state)
+                return out
+            if len(wfs) > max_score:
+                out.status = "NO_CONVERGENCE"
+                return out
+            wfa_expand(wfs, seq1, seq2, out.lo_hi)
+            cur = wfs[-1]
+            if cur is not None and cur.m is not None:
+                out.m_offsets[len(wfs) - 1] = (cur.m.lo, [None if e is None else e.offset for e in cur.m.elements])
+    except RefPanic as e:
+        out.status = "PANIC"
+        out.panic_site = e.site
+        return out
