@@ -37,7 +37,14 @@ extern "C" {
 typedef struct sa_engine sa_engine_t; /* opaque; one per (process, device) */
 
 /* parse.rs:36-42 `enum Algo` (A* is out of scope for the GPU path) */
-typedef enum { SA_ALGO_NW_AFFINE = 0, SA_ALGO_NW_LINEAR = 1, SA_ALGO_WFA = 2 } sa_algo_t;
+typedef enum {
+  SA_ALGO_NW_AFFINE = 0,
+  SA_ALGO_NW_LINEAR = 1,
+  SA_ALGO_WFA = 2,          /* wfa_align exactly as the reference executes it (score + status) */
+  SA_ALGO_WFA_STANDARD = 3  /* extension: textbook gap-affine WFA cost with the same penalties;
+                               the reference's own WFA panics or never converges on inputs
+                               beyond a few dozen residues (wfa.rs:189, :577, :603)            */
+} sa_algo_t;
 /* parse.rs:44-50 `enum Mode` */
 typedef enum { SA_MODE_GLOBAL = 0, SA_MODE_LOCAL = 1, SA_MODE_SEMIGLOBAL = 2 } sa_mode_t;
 

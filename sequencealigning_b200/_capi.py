@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "_lib", "libsa_engine.so")
 # sa_status_t
 OK, REF_PANIC, REF_NO_CONVERGENCE, NOT_IMPLEMENTED, REF_PANIC_EARLY, REF_NO_OUTPUT = range(6)
 E_CUDA, E_ARG, E_NOMEM, E_CIGAR_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4, -5
-ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA = 0, 1, 2
+ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD = 0, 1, 2, 3
 MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL = 0, 1, 2
 OP_M, OP_I, OP_D = 0, 1, 2
 

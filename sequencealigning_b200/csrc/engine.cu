@@ -26,6 +26,7 @@
 #include "../../include/sa_engine.h"
 #include "nw_affine_s16.cuh"
 #include "nw_walk.cuh"
+#include "wfa.cuh"
 
 namespace {
 
@@ -77,7 +78,7 @@ struct sa_engine {
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
   } slot[2];
   // scratch (grow-only)
-  DevBuf tb2, end2, misc, block_sums;
+  DevBuf tb2, end2, misc, block_sums, wfa_scratch;
   // staging for sa_align_batch (grow-only)
   DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry;
   uint32_t* h_count = nullptr;  // pinned
@@ -638,6 +639,110 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   return SA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// WFA (score only).  literal = the reference's wfa_align as it really behaves (status per
+// pair); standard = textbook gap-affine WFA.  Inputs are uploaded in one piece: the kernels are
+// orders of magnitude cheaper per residue than the traceback DP, so there is nothing to hide.
+// ---------------------------------------------------------------------------------------------
+sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h_q_len,
+                    const uint32_t* h_d_len, const sa_scheme_t* scheme, bool literal,
+                    const sa_batch_t* in, sa_result_t* out) {
+  sa_status_t st;
+  int32_t x = 4, o = 2, ex = 6;  // wfa.rs:17-21
+  if (scheme) {
+    x = scheme->mismatch;
+    o = scheme->gap_open;
+    ex = scheme->gap_ext;
+  }
+  if (x <= 0 || o < 0 || ex <= 0 || x >= sa::kWfRing || o + ex >= sa::kWfRing || (literal && (x > 8 || o + ex > 8)))
+    return fail(e, SA_E_UNSUPPORTED, "WFA penalties (x=%d, o=%d, e=%d) outside the kernel's ring", x, o, ex);
+  if (in) {
+    uint64_t max_end = 0;
+    for (uint64_t p = 0; p < n; ++p) {
+      max_end = std::max(max_end, std::max(in->q_off[p] + h_q_len[p], in->d_off[p] + h_d_len[p]));
+      e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
+    }
+    if (max_end > in->residues_len) return fail(e, SA_E_ARG, "a pair reaches past residues_len");
+    CUDA_TRY(e, cudaMemcpyAsync(db.residues, in->residues, in->residues_len, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(db.q_off, in->q_off, n * 8, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(db.d_off, in->d_off, n * 8, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(db.q_len, in->q_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(db.d_len, in->d_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    e->timing.h2d_bytes += in->residues_len + n * 24;
+  }
+  uint32_t nmax_sum = 0;
+  for (uint64_t p = 0; p < n; ++p) nmax_sum = std::max<uint32_t>(nmax_sum, h_q_len[p] + h_d_len[p]);
+  sa::WfaParams wp{};
+  wp.residues = db.residues;
+  wp.q_off = db.q_off;
+  wp.q_len = db.q_len;
+  wp.d_off = db.d_off;
+  wp.d_len = db.d_len;
+  wp.x = x;
+  wp.o = o;
+  wp.e = ex;
+  wp.score = db.score;
+  wp.status = db.status;
+  CUDA_TRY(e, cudaMemsetAsync(db.cigar_len, 0, n * 4, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.cigar_off, 0, n * 8, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev_t0, e->stream));
+  if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
+  if (literal) {
+    const uint64_t cap = std::min<uint64_t>(8ull * nmax_sum + 64, 2048);
+    const uint32_t wcap = (uint32_t)(2 * (cap / 4) + 16);
+    const uint64_t stride = (uint64_t)sa::kLitRing * 3 * wcap;
+    size_t budget = e->tb_budget ? e->tb_budget : (size_t)4 << 30;
+    const uint64_t chunk = std::max<uint64_t>(64, std::min<uint64_t>(n, budget / (stride * 4)));
+    if ((st = ensure(e, e->wfa_scratch, chunk * stride * 4)) != SA_OK) return st;
+    wp.scratch = (int32_t*)e->wfa_scratch.p;
+    wp.scratch_stride = stride;
+    wp.lit_wcap = wcap;
+    for (uint64_t base = 0; base < n; base += chunk) {
+      wp.pair_base = (uint32_t)base;
+      wp.n_launch_pairs = (uint32_t)std::min<uint64_t>(chunk, n - base);
+      sa::wfa_literal_kernel<<<(wp.n_launch_pairs + 63) / 64, 64, 0, e->stream>>>(wp);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+    }
+  } else {
+    const uint32_t width = nmax_sum + 1;
+    const uint32_t warps_per_block = 4;
+    const uint32_t smem_seq = 24 * 1024;  // per warp: both sequences up to ~24 kB stay on chip
+    const size_t smem = (size_t)warps_per_block * smem_seq;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(e, cudaFuncSetAttribute(sa::wfa_standard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const uint64_t stride = (uint64_t)sa::kWfRing * 3 * width + (nmax_sum + 32) / 4 + 8;
+    uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 2);
+    if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4)) != SA_OK) return st;
+    uint32_t* d_next = (uint32_t*)e->misc.p + 8;
+    CUDA_TRY(e, cudaMemsetAsync(d_next, 0, 4, e->stream));
+    wp.scratch = (int32_t*)e->wfa_scratch.p;
+    wp.scratch_stride = stride;
+    wp.width = width;
+    wp.next_pair = d_next;
+    wp.smem_seq_bytes = smem_seq;
+    wp.pair_base = 0;
+    wp.n_launch_pairs = (uint32_t)n;
+    sa::wfa_standard_kernel<<<blocks, warps_per_block * 32, smem, e->stream>>>(wp);
+    CUDA_TRY(e, cudaGetLastError());
+    e->timing.kernel_launches++;
+  }
+  CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->stream));
+  if (out) {
+    if (out->score) CUDA_TRY(e, cudaMemcpyAsync(out->score, db.score, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (out->status) CUDA_TRY(e, cudaMemcpyAsync(out->status, db.status, n, cudaMemcpyDeviceToHost, e->stream));
+    if (out->cigar_len) memset(out->cigar_len, 0, n * 4);
+    if (out->cigar_off) memset(out->cigar_off, 0, n * 8);
+    e->timing.d2h_bytes += n * 5;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  }
+  return SA_OK;
+}
+
 sa_status_t resolve_scheme(sa_engine* e, const sa_scheme_t* scheme, Scheme2& s2) {
   s2.sc = sa_scheme_t{5, -4, -8, -6};  // nw_affine.rs:15-20
   if (scheme) s2.sc = *scheme;
@@ -668,14 +773,15 @@ sa_status_t check_algo(sa_engine* e, sa_algo_t algo, sa_mode_t mode, bool* not_i
   if (mode != SA_MODE_GLOBAL && mode != SA_MODE_LOCAL && mode != SA_MODE_SEMIGLOBAL)
     return fail(e, SA_E_ARG, "mode %d", (int)mode);
   if (mode != SA_MODE_GLOBAL) {
-    if (algo == SA_ALGO_NW_AFFINE || algo == SA_ALGO_WFA) {
+    if (algo == SA_ALGO_NW_AFFINE || algo == SA_ALGO_WFA || algo == SA_ALGO_WFA_STANDARD) {
       *not_impl = true;
       return SA_OK;
     }
     return fail(e, SA_E_UNSUPPORTED, "mode %d for algo %d is not built yet", (int)mode, (int)algo);
   }
-  if (algo != SA_ALGO_NW_AFFINE && algo != SA_ALGO_NW_LINEAR)
-    return fail(e, SA_E_UNSUPPORTED, "algo %d is not built yet", (int)algo);
+  if (algo != SA_ALGO_NW_AFFINE && algo != SA_ALGO_NW_LINEAR && algo != SA_ALGO_WFA &&
+      algo != SA_ALGO_WFA_STANDARD)
+    return fail(e, SA_E_ARG, "algo %d", (int)algo);
   return SA_OK;
 }
 
@@ -735,7 +841,7 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
-                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc,
+                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch,
                       &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
                       &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})
       if (b->p) cudaFree(b->p);
@@ -876,6 +982,12 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     r->aligned = st == SA_OK;
     return st;
   }
+  if (algo == SA_ALGO_WFA || algo == SA_ALGO_WFA_STANDARD) {
+    st = run_wfa(e, r->d, n, r->h_q_len.data(), r->h_d_len.data(), scheme, algo == SA_ALGO_WFA, nullptr, nullptr);
+    r->aligned = st == SA_OK;
+    r->want_cigar = false;
+    return st;
+  }
   Scheme2 s2;
   if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
   s2.algo = (int)algo;
@@ -952,10 +1064,11 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     if (res->cigar_off) memset(res->cigar_off, 0, n * 8);
     return SA_OK;
   }
+  const bool is_wfa = algo == SA_ALGO_WFA || algo == SA_ALGO_WFA_STANDARD;
   Scheme2 s2;
-  if ((st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
+  if (!is_wfa && (st = resolve_scheme(e, scheme, s2)) != SA_OK) return st;
   s2.algo = (int)algo;
-  const bool want_cigar = res->cigar != nullptr && res->cigar_capacity > 0;
+  const bool want_cigar = !is_wfa && res->cigar != nullptr && res->cigar_capacity > 0;
 
   // engine-owned staging, grow-only: no allocation on the steady-state path
   if ((st = ensure(e, e->b_res, b->residues_len)) != SA_OK) return st;
@@ -968,6 +1081,24 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   if ((st = ensure(e, e->b_clen, n * 4)) != SA_OK) return st;
   if ((st = ensure(e, e->b_coff, n * 8)) != SA_OK) return st;
   if ((st = ensure(e, e->b_carry, 16)) != SA_OK) return st;
+  if (is_wfa) {
+    DeviceBatch db;
+    db.residues = (uint8_t*)e->b_res.p;
+    db.q_off = (uint64_t*)e->b_qoff.p;
+    db.d_off = (uint64_t*)e->b_doff.p;
+    db.q_len = (uint32_t*)e->b_qlen.p;
+    db.d_len = (uint32_t*)e->b_dlen.p;
+    db.score = (int32_t*)e->b_score.p;
+    db.status = (uint8_t*)e->b_status.p;
+    db.cigar_len = (uint32_t*)e->b_clen.p;
+    db.cigar_off = (uint64_t*)e->b_coff.p;
+    db.carry = (uint64_t*)e->b_carry.p;
+    st = run_wfa(e, db, n, b->q_len, b->d_len, scheme, algo == SA_ALGO_WFA, b, res);
+    float ms = 0;
+    if (st == SA_OK && cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.fill_ms = ms;
+    cudaGetLastError();
+    return st;
+  }
   uint64_t want_pool = want_cigar ? std::max<uint64_t>(res->cigar_capacity, 1024) : 0;
   uint64_t used = 0, sent = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {

@@ -22,7 +22,10 @@
 
 namespace sa {
 
+#ifndef SA_STATUS_CODES
+#define SA_STATUS_CODES
 enum : uint8_t { kOk = 0, kRefPanic = 1, kRefNoConv = 2, kNotImpl = 3, kRefPanicEarly = 4, kRefNoOutput = 5 };
+#endif
 
 struct WalkParams {
   const uint32_t* __restrict__ q_len;

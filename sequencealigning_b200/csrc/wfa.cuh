@@ -1,0 +1,469 @@
+// wfa.cuh -- gap-affine wavefront alignment on the GPU (score only), two modes.
+//
+// STANDARD mode  (wfa_standard_kernel): the textbook gap-affine WFA recurrences the reference's
+//   wfa.rs is modelled on (WaveFrontTensor::new :225-420 is the "next" step, WaveFront::expand
+//   :127-139 the "extend" step), with the reference's penalties x=4, o=2, e=6 (:17-21) as
+//   defaults, WITHOUT the reference's defects.  One warp per pair: lanes own diagonals, the
+//   extend step compares 4 residues per iteration on word-packed sequences staged in shared
+//   memory, wavefronts of the last max(x, o+e)+1 scores live in a per-warp ring in global
+//   memory (L2 resident).  Result = optimal gap-affine cost; validated against a Gotoh cost DP.
+//   This is what BASELINE.json configs[3] (1-10 kbp pairs) can actually exercise, because the
+//   reference itself panics or never converges on inputs of that size.
+//
+// LITERAL mode (wfa_literal_kernel): wfa_align (:23-42) exactly as the reference executes it,
+//   defects included -- wavefront 0 never extended (:467-483), the x()/y() geometry of :85-90,
+//   convergence tested at (n2-1, n1-1) (:189), the trim heuristic (:490-623) and its
+//   Vec::rotate_left panics (:577/:603) -- one thread per pair, reported as per-pair status
+//   OK (score = wfs.len(), :31-36) / REF_PANIC / REF_NO_CONVERGENCE.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sa {
+
+#ifndef SA_STATUS_CODES
+#define SA_STATUS_CODES
+enum : uint8_t { kOk = 0, kRefPanic = 1, kRefNoConv = 2, kNotImpl = 3, kRefPanicEarly = 4, kRefNoOutput = 5 };
+#endif
+
+constexpr int32_t kWfNone = -(1 << 29);
+
+struct WfaParams {
+  const uint8_t* __restrict__ residues;
+  const uint64_t* __restrict__ q_off;
+  const uint32_t* __restrict__ q_len;
+  const uint64_t* __restrict__ d_off;
+  const uint32_t* __restrict__ d_len;
+  uint32_t pair_base, n_launch_pairs;
+  int32_t x, o, e;        // penalties
+  int32_t* __restrict__ score;
+  uint8_t* __restrict__ status;
+  int32_t* __restrict__ scratch;   // per warp (standard) / per thread (literal) wavefront storage
+  uint64_t scratch_stride;         // int32 per warp / thread
+  uint32_t width;                  // standard: diagonals per component array (max n1+n2+1)
+  uint32_t* __restrict__ next_pair;  // standard: dynamic work counter
+  uint32_t smem_seq_bytes;         // standard: bytes available per warp for staged sequences
+  uint32_t lit_wcap;               // literal: element capacity per component
+};
+
+// ---------------------------------------------------------------------------------------------
+// STANDARD MODE
+// ---------------------------------------------------------------------------------------------
+constexpr int kWfRing = 16;  // >= max(x, o+e) + 1, power of two
+
+// residues a[v..], b[h..] compared 4 at a time on 32-bit words (any byte alphabet).
+// `sa`, `sb` point to 4-byte aligned copies with at least 4 bytes of padding after the end.
+__device__ __forceinline__ int32_t wf_extend(const uint32_t* sa, const uint32_t* sb, int32_t v,
+                                             int32_t h, int32_t n1, int32_t n2) {
+  for (;;) {
+    const int32_t room = min(n1 - v, n2 - h);
+    if (room <= 0) return v;
+    const uint32_t a0 = sa[v >> 2], a1 = sa[(v >> 2) + 1];
+    const uint32_t b0 = sb[h >> 2], b1 = sb[(h >> 2) + 1];
+    const uint32_t wa = __funnelshift_r(a0, a1, (v & 3) * 8);
+    const uint32_t wb = __funnelshift_r(b0, b1, (h & 3) * 8);
+    const uint32_t x = wa ^ wb;
+    const int32_t same = x ? ((__ffs(x) - 1) >> 3) : 4;  // matching leading residues
+    const int32_t adv = min(same, room);
+    v += adv;
+    h += adv;
+    if (adv < 4) return v;
+  }
+}
+
+// One warp per pair, pairs handed out dynamically.  blockDim.x = 32 * warps.
+__global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
+  extern __shared__ uint32_t smem_w[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+  uint32_t* sq = smem_w + (size_t)warp * (p.smem_seq_bytes >> 2);
+  int32_t* ring = p.scratch + (uint64_t)gwarp * p.scratch_stride;  // [kWfRing][3][width]
+  const int32_t W = (int32_t)p.width;
+  // per-slot diagonal range, kept in shared memory (uniform per warp)
+  __shared__ int32_t s_lo[4][kWfRing], s_hi[4][kWfRing];
+  int32_t* lo_ = s_lo[warp];
+  int32_t* hi_ = s_hi[warp];
+
+  for (;;) {
+    uint32_t li = 0;
+    if (lane == 0) li = atomicAdd(p.next_pair, 1u);
+    li = __shfl_sync(0xffffffffu, li, 0);
+    if (li >= p.n_launch_pairs) break;
+    const uint32_t id = p.pair_base + li;
+    const int32_t n1 = (int32_t)p.q_len[id], n2 = (int32_t)p.d_len[id];
+    const uint8_t* g1 = p.residues + p.q_off[id];
+    const uint8_t* g2 = p.residues + p.d_off[id];
+    // stage both sequences as words (padding zeroed); fall back to global scratch copies
+    // appended after the ring when they do not fit
+    const uint32_t w1 = (uint32_t)(n1 + 8) >> 2, w2 = (uint32_t)(n2 + 8) >> 2;
+    uint32_t* s1w;
+    uint32_t* s2w;
+    if ((w1 + w2) * 4 <= p.smem_seq_bytes) {
+      s1w = sq;
+      s2w = sq + w1;
+    } else {
+      s1w = reinterpret_cast<uint32_t*>(ring + (size_t)kWfRing * 3 * W);
+      s2w = s1w + w1;
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < w1; k += 32) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; ++b) {
+        const int32_t pos = (int32_t)(k * 4 + b);
+        if (pos < n1) v |= (uint32_t)g1[pos] << (8 * b);
+      }
+      s1w[k] = v;
+    }
+    for (uint32_t k = lane; k < w2; k += 32) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; ++b) {
+        const int32_t pos = (int32_t)(k * 4 + b);
+        if (pos < n2) v |= (uint32_t)g2[pos] << (8 * b);
+      }
+      s2w[k] = v;
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    const int32_t kend = n1 - n2;
+    const int32_t koff = n2;  // array index = k + n2
+    int32_t result = -1;
+    // score 0
+    if (lane < kWfRing) {
+      lo_[lane] = 1;
+      hi_[lane] = 0;  // empty
+    }
+    __syncwarp();
+    {
+      const int32_t v0 = wf_extend(s1w, s2w, 0, 0, n1, n2);
+      if (lane == 0) {
+        ring[(0 * 3 + 0) * W + koff] = v0;
+        ring[(0 * 3 + 1) * W + koff] = kWfNone;
+        ring[(0 * 3 + 2) * W + koff] = kWfNone;
+        lo_[0] = 0;
+        hi_[0] = 0;
+      }
+      if (kend == 0 && v0 == n1) result = 0;
+    }
+    __syncwarp();
+    const int32_t max_s = 2 * p.o + p.e * (n1 + n2) + p.x + 8;
+    for (int32_t s = 1; result < 0 && s <= max_s; ++s) {
+      const int slot = s & (kWfRing - 1);
+      const int sx = (s - p.x) & (kWfRing - 1), so = (s - p.o - p.e) & (kWfRing - 1),
+                se = (s - p.e) & (kWfRing - 1);
+      const bool hx = s - p.x >= 0 && lo_[sx] <= hi_[sx];
+      const bool ho = s - p.o - p.e >= 0 && lo_[so] <= hi_[so];
+      const bool he = s - p.e >= 0 && lo_[se] <= hi_[se];
+      int32_t lo = 1 << 30, hi = -(1 << 30);
+      if (hx) { lo = min(lo, lo_[sx]); hi = max(hi, hi_[sx]); }
+      if (ho) { lo = min(lo, lo_[so] - 1); hi = max(hi, hi_[so] + 1); }
+      if (he) { lo = min(lo, lo_[se] - 1); hi = max(hi, hi_[se] + 1); }
+      __syncwarp();
+      if (lo > hi) {
+        if (lane == 0) { lo_[slot] = 1; hi_[slot] = 0; }
+        __syncwarp();
+        continue;
+      }
+      lo = max(lo, -n2);
+      hi = min(hi, n1);
+      int32_t* Mc = ring + (slot * 3 + 0) * W + koff;
+      int32_t* Ic = ring + (slot * 3 + 1) * W + koff;
+      int32_t* Dc = ring + (slot * 3 + 2) * W + koff;
+      const int32_t* Mx = ring + (sx * 3 + 0) * W + koff;
+      const int32_t* Mo = ring + (so * 3 + 0) * W + koff;
+      const int32_t* Ie = ring + (se * 3 + 1) * W + koff;
+      const int32_t* De = ring + (se * 3 + 2) * W + koff;
+      const int32_t xlo = hx ? lo_[sx] : 1, xhi = hx ? hi_[sx] : 0;
+      const int32_t olo = ho ? lo_[so] : 1, ohi = ho ? hi_[so] : 0;
+      const int32_t elo = he ? lo_[se] : 1, ehi = he ? hi_[se] : 0;
+      bool found = false;
+      for (int32_t k = lo + lane; k <= hi; k += 32) {
+        int32_t iv = kWfNone, dv = kWfNone, mv = kWfNone;
+        {  // insertion: consumes a seq1 residue: (k-1) -> k, v + 1
+          int32_t a = (k - 1 >= olo && k - 1 <= ohi) ? Mo[k - 1] : kWfNone;
+          int32_t b = (k - 1 >= elo && k - 1 <= ehi) ? Ie[k - 1] : kWfNone;
+          const int32_t best = max(a, b);
+          if (best > kWfNone) iv = best + 1;
+        }
+        {  // deletion: consumes a seq2 residue: (k+1) -> k, v unchanged
+          int32_t a = (k + 1 >= olo && k + 1 <= ohi) ? Mo[k + 1] : kWfNone;
+          int32_t b = (k + 1 >= elo && k + 1 <= ehi) ? De[k + 1] : kWfNone;
+          dv = max(a, b);
+        }
+        if (k >= xlo && k <= xhi && Mx[k] > kWfNone) mv = Mx[k] + 1;
+        // cells outside the matrix do not exist
+        if (iv > kWfNone && (iv > n1 || iv - k > n2 || iv - k < 0)) iv = kWfNone;
+        if (dv > kWfNone && (dv > n1 || dv - k > n2 || dv < 0)) dv = kWfNone;
+        if (mv > kWfNone && (mv > n1 || mv - k > n2)) mv = kWfNone;
+        mv = max(mv, max(iv, dv));
+        if (mv > kWfNone) mv = wf_extend(s1w, s2w, mv, mv - k, n1, n2);
+        Mc[k] = mv;
+        Ic[k] = iv;
+        Dc[k] = dv;
+        if (k == kend && mv == n1) found = true;
+      }
+      if (lane == 0) { lo_[slot] = lo; hi_[slot] = hi; }
+      __syncwarp();
+      if (__any_sync(0xffffffffu, found)) result = s;
+    }
+    if (lane == 0) {
+      p.score[id] = result;
+      p.status[id] = 0;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LITERAL MODE: one thread per pair, the reference's algorithm step by step.
+// A wavefront component is a Vec<Option<element>> (:118-124); only the offsets matter for
+// status and score, so an element is an int32 offset (kWfNone = None).  Each component keeps
+// (present, lo, hi, len) and its elements at data[0..len) with element k on diagonal lo + k
+// -- exactly the indexing of get_element (:159-163), including its behaviour once trim has
+// made lo/hi inconsistent with the vector.
+// ---------------------------------------------------------------------------------------------
+struct LitComp {
+  int32_t present, lo, hi, len;
+  int32_t* data;
+};
+constexpr int kLitRing = 9;  // scores s-8 .. s
+
+__device__ __forceinline__ int32_t lit_get(const LitComp* w, int32_t idx) {  // get_offset :165-171
+  if (!w || !w->present) return kWfNone;
+  const int64_t k = (int64_t)idx - w->lo;
+  if (k < 0 || k >= w->len) return kWfNone;
+  return w->data[k];
+}
+__device__ __forceinline__ uint64_t lit_x(int32_t off, int32_t diag) {  // :85-87, `as usize`
+  return (uint64_t)(int64_t)(off - min(diag, 0));
+}
+__device__ __forceinline__ uint64_t lit_y(int32_t off, int32_t diag) {  // :88-90
+  return (uint64_t)(int64_t)(off + max(diag, 0));
+}
+__device__ __forceinline__ int32_t lit_distance(int32_t off, int32_t n1, int32_t n2, int32_t diag) {
+  return max(n1 - off - diag, n2 - off);  // get_distance :96-101
+}
+__device__ __forceinline__ uint32_t lit_absdiff(int32_t a, int32_t b) {
+  return a > b ? (uint32_t)(a - b) : (uint32_t)(b - a);
+}
+// Vec::rotate_left; false where Rust panics (k > len)
+__device__ bool lit_rotate_left(LitComp* w, uint32_t k) {
+  if (k > (uint32_t)w->len) return false;
+  if (k == 0 || k == (uint32_t)w->len) return true;
+  // reverse three times (in place)
+  auto rev = [&](int a, int b) {
+    for (; a < b; ++a, --b) {
+      const int32_t t = w->data[a];
+      w->data[a] = w->data[b];
+      w->data[b] = t;
+    }
+  };
+  rev(0, (int)k - 1);
+  rev((int)k, w->len - 1);
+  rev(0, w->len - 1);
+  return true;
+}
+__device__ __forceinline__ void lit_remove_front(LitComp* w) {
+  if (w->len) {
+    w->data += 1;  // the slot's buffer has room: data only ever moves forward within one score
+    w->len -= 1;
+  }
+}
+
+__global__ void __launch_bounds__(64) wfa_literal_kernel(const WfaParams p) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= p.n_launch_pairs) return;
+  const uint32_t id = p.pair_base + li;
+  const int32_t n1 = (int32_t)p.q_len[id], n2 = (int32_t)p.d_len[id];
+  const uint8_t* s1 = p.residues + p.q_off[id];
+  const uint8_t* s2 = p.residues + p.d_off[id];
+  const int32_t wcap = (int32_t)p.lit_wcap;
+  int32_t* base = p.scratch + (uint64_t)li * p.scratch_stride;  // [kLitRing][3][wcap]
+  LitComp ring[kLitRing][3];  // 0 = I, 1 = D, 2 = M
+  int32_t tensor_present[kLitRing];
+  for (int r = 0; r < kLitRing; ++r) {
+    tensor_present[r] = 0;
+    for (int c = 0; c < 3; ++c) ring[r][c] = LitComp{0, 0, 0, 0, base + ((size_t)r * 3 + c) * wcap};
+  }
+  const uint64_t cap64 = 8ull * ((uint64_t)n1 + (uint64_t)n2) + 64;
+  const int32_t max_score = (int32_t)(cap64 < 2048 ? cap64 : 2048);
+  // Ocean::global :450-465: wavefront 0 = M{lo=hi=0, offset 0}; it is NOT extended
+  tensor_present[0] = 1;
+  ring[0][2].present = 1;
+  ring[0][2].lo = ring[0][2].hi = 0;
+  ring[0][2].len = 1;
+  ring[0][2].data[0] = 0;
+  int32_t len = 1;  // wfs.len()
+  int32_t status = -1, score = 0;
+  const uint64_t tx = (uint64_t)(int64_t)n2 - 1, ty = (uint64_t)(int64_t)n1 - 1;  // :189 (usize)
+  while (status < 0) {
+    // is_converged on the last tensor, components in order I, D, M (:422-439)
+    const int cur = (len - 1) % kLitRing;
+    if (tensor_present[cur]) {
+      for (int c = 0; c < 3 && status < 0; ++c) {
+        const LitComp& w = ring[cur][c];
+        if (!w.present) continue;
+        for (int32_t k = 0; k < w.len; ++k) {
+          const int32_t off = w.data[k];
+          if (off == kWfNone) continue;
+          const int32_t diag = w.lo + k;
+          if (lit_x(off, diag) == tx && lit_y(off, diag) == ty) {
+            status = kOk;
+            score = len;  // printed `converged with score {wfs.len()}` (:31-36)
+            break;
+          }
+        }
+      }
+      if (status >= 0) break;
+    }
+    if (len > max_score) {
+      status = kRefNoConv;
+      break;
+    }
+    // Ocean::expand :467-488
+    const int32_t s = len;
+    const int slot = s % kLitRing;
+    const LitComp* om = (s - p.o - p.e >= 0 && tensor_present[(s - p.o - p.e) % kLitRing]) ? &ring[(s - p.o - p.e) % kLitRing][2] : nullptr;
+    const LitComp* mm = (s - p.x >= 0 && tensor_present[(s - p.x) % kLitRing]) ? &ring[(s - p.x) % kLitRing][2] : nullptr;
+    const LitComp* ei = (s - p.e >= 0 && tensor_present[(s - p.e) % kLitRing]) ? &ring[(s - p.e) % kLitRing][0] : nullptr;
+    const LitComp* ed = (s - p.e >= 0 && tensor_present[(s - p.e) % kLitRing]) ? &ring[(s - p.e) % kLitRing][1] : nullptr;
+    if (om && !om->present) om = nullptr;
+    if (mm && !mm->present) mm = nullptr;
+    if (ei && !ei->present) ei = nullptr;
+    if (ed && !ed->present) ed = nullptr;
+    LitComp* ci = &ring[slot][0];
+    LitComp* cd = &ring[slot][1];
+    LitComp* cm = &ring[slot][2];
+    for (int c = 0; c < 3; ++c) {
+      ring[slot][c].present = 0;
+      ring[slot][c].len = 0;
+      ring[slot][c].data = base + ((size_t)slot * 3 + c) * wcap;
+    }
+    tensor_present[slot] = 0;
+    ++len;
+    // WaveFrontTensor::new :225-420
+    bool any = false;
+    int32_t hi = 0, lo = 0;
+    const LitComp* srcs[4] = {om, mm, ei, ed};
+    for (int k = 0; k < 4; ++k)
+      if (srcs[k]) {
+        if (!any || srcs[k]->hi > hi) hi = srcs[k]->hi;
+        if (!any || srcs[k]->lo < lo) lo = srcs[k]->lo;
+        any = true;
+      }
+    if (!any) continue;  // the tensor is None (:238)
+    hi += 1;
+    lo -= 1;
+    if ((int64_t)hi - lo + 1 > wcap) {  // cannot happen below max_score; defensive
+      status = kRefNoConv;
+      break;
+    }
+    int32_t i_lo = lo, i_hi = hi, d_lo = lo, d_hi = hi, m_lo = lo, m_hi = hi;
+    bool i_set = false, d_set = false, m_set = false;
+    // every component is first built over [lo, hi] (element k on diagonal lo + k), M without
+    // its leading Nones (:396-398)
+    ci->lo = lo; cd->lo = lo;
+    int32_t m_first = 0;
+    for (int32_t idx = lo; idx <= hi; ++idx) {
+      const int32_t k = idx - lo;
+      const int32_t dv = max(lit_get(om, idx + 1), lit_get(ed, idx + 1));  // :272-311
+      cd->data[k] = dv;
+      if (dv != kWfNone) { d_hi = idx; if (!d_set) { d_lo = idx; d_set = true; } }
+      const int32_t ib = max(lit_get(om, idx - 1), lit_get(ei, idx - 1));  // :313-352
+      const int32_t iv = ib != kWfNone ? ib + 1 : kWfNone;
+      ci->data[k] = iv;
+      if (iv != kWfNone) { i_hi = idx; if (!i_set) { i_lo = idx; i_set = true; } }
+      const int32_t mb = lit_get(mm, idx);                                 // :353-398
+      int32_t mv = mb != kWfNone ? mb + 1 : kWfNone;
+      mv = max(mv, max(iv, dv));
+      if (mv != kWfNone) {
+        if (!m_set) { m_lo = idx; m_set = true; m_first = k; }
+        m_hi = idx;
+      }
+      cm->data[k] = mv;
+    }
+    // rotate_left + truncate of :401-409 leave each component's own [lo, hi] window
+    ci->data += (i_lo - lo); ci->lo = i_lo; ci->hi = i_hi; ci->len = (int32_t)lit_absdiff(i_hi, i_lo) + 1; ci->present = i_set;
+    cd->data += (d_lo - lo); cd->lo = d_lo; cd->hi = d_hi; cd->len = (int32_t)lit_absdiff(d_hi, d_lo) + 1; cd->present = d_set;
+    cm->data += m_first;     cm->lo = m_lo; cm->hi = m_hi; cm->len = (int32_t)lit_absdiff(m_hi, m_lo) + 1; cm->present = m_set;
+    if (!m_set) cm->len = 0;
+    tensor_present[slot] = 1;
+    // WaveFrontTensor::expand: extend M only (:219-223, :127-139)
+    if (cm->present) {
+      for (int32_t k = 0; k < cm->len; ++k) {
+        int32_t off = cm->data[k];
+        if (off == kWfNone) continue;
+        const int32_t diag = cm->lo + k;
+        for (;;) {
+          const uint64_t y = lit_y(off, diag), x = lit_x(off, diag);
+          if (!(y < (uint64_t)n1 && x < (uint64_t)n2 && s1[y] == s2[x])) break;
+          ++off;
+        }
+        cm->data[k] = off;
+      }
+    }
+    // Ocean::trim :490-623
+    if (cm->present && lit_absdiff(cm->lo, cm->hi) > 5) {
+      int32_t min_d = 0;  // :511
+      for (int32_t diag = cm->lo; diag <= cm->hi; ++diag) {
+        const int32_t off = lit_get(cm, diag);
+        if (off != kWfNone) min_d = min(min_d, lit_distance(off, n1, n2, diag));
+      }
+      bool panic = false;
+      if (!cm->len || cm->data[0] == kWfNone) panic = true;
+      if (!panic) {
+        int32_t next_d = lit_distance(cm->data[0], n1, n2, cm->lo);
+        while (cm->lo < cm->hi && lit_absdiff(next_d, min_d) > 20) {
+          cm->lo += 1;
+          lit_remove_front(cm);
+          while (lit_get(cm, cm->lo) == kWfNone) {
+            if (cm->lo == cm->hi) break;
+            cm->lo += 1;
+            lit_remove_front(cm);
+          }
+          if (!cm->len || cm->data[0] == kWfNone) { panic = true; break; }
+          next_d = lit_distance(cm->data[0], n1, n2, cm->lo);
+        }
+      }
+      if (!panic && (!cm->len || cm->data[cm->len - 1] == kWfNone)) panic = true;
+      if (!panic) {
+        int32_t next_d = lit_distance(cm->data[cm->len - 1], n1, n2, cm->hi);
+        while (cm->hi > cm->lo && lit_absdiff(next_d, min_d) > 20) {
+          cm->hi -= 1;
+          if (cm->len) cm->len -= 1;
+          while (lit_get(cm, cm->hi) == kWfNone) {
+            if (cm->lo == cm->hi) break;
+            cm->hi -= 1;
+            if (cm->len) cm->len -= 1;
+          }
+          if (!cm->len || cm->data[cm->len - 1] == kWfNone) { panic = true; break; }
+          next_d = lit_distance(cm->data[cm->len - 1], n1, n2, cm->hi);
+        }
+      }
+      for (int c = 0; c < 2 && !panic; ++c) {  // clip I then D to M's range (:574-622)
+        LitComp* w = &ring[slot][c];
+        if (!w->present) continue;
+        uint64_t t;
+        if (w->lo < cm->lo) {
+          if (!lit_rotate_left(w, lit_absdiff(w->lo, cm->lo))) { panic = true; break; }  // :577 / :603
+          t = (uint64_t)lit_absdiff(w->lo, cm->lo) + (w->hi > cm->hi ? lit_absdiff(w->hi, cm->hi) : 0);
+        } else if (w->hi > cm->hi) {
+          t = lit_absdiff(w->hi, cm->hi);
+        } else {
+          t = 0;
+        }
+        if (t <= (uint64_t)w->len) w->len -= (int32_t)t;  // else `len - t` wraps (release): no-op
+        w->hi = min(w->hi, cm->hi);
+        w->lo = max(w->lo, cm->lo);
+      }
+      if (panic) {
+        status = kRefPanic;
+        break;
+      }
+    }
+  }
+  p.score[id] = status == kOk ? score : 0;
+  p.status[id] = (uint8_t)status;
+}
+
+}  // namespace sa

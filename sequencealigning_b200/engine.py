@@ -16,14 +16,15 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
-from ._capi import (ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
+from ._capi import (ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
                     NOT_IMPLEMENTED, OK, REF_NO_CONVERGENCE, REF_NO_OUTPUT, REF_PANIC, REF_PANIC_EARLY)
 
 STATUS_NAMES = {
     OK: "OK", REF_PANIC: "REF_PANIC", REF_NO_CONVERGENCE: "REF_NO_CONVERGENCE",
     NOT_IMPLEMENTED: "NOT_IMPLEMENTED", REF_PANIC_EARLY: "REF_PANIC_EARLY", REF_NO_OUTPUT: "REF_NO_OUTPUT",
 }
-ALGOS = {"needleman-wunsch": ALGO_NW_AFFINE, "needleman-wunsch-linear": ALGO_NW_LINEAR, "wfa": ALGO_WFA}
+ALGOS = {"needleman-wunsch": ALGO_NW_AFFINE, "needleman-wunsch-linear": ALGO_NW_LINEAR, "wfa": ALGO_WFA,
+         "wfa-standard": ALGO_WFA_STANDARD}
 MODES = {"global": MODE_GLOBAL, "local": MODE_LOCAL, "semi-global": MODE_SEMIGLOBAL}
 
 
