@@ -189,6 +189,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from sequencealigning_b200 import Engine
