@@ -1,0 +1,214 @@
+// sa_align -- command line with the reference's flags (/root/reference/src/parse.rs:8-34) over
+// the C ABI.  It replaces the `for d in db { for q in query { .. } }` loop of
+// /root/reference/src/main.rs:61-79 by ONE batched call and prints, per pair and in the same
+// db-major order, the text the reference prints for the FIRST alignment
+// (needleman_wunsch_affine.rs:283-286, Display :390-411).
+//
+//   sa_align -q <query.fa> -d <db.fa> [-o PATH] [-v] [-m global|local|semi-global]
+//            [-a a-star|needleman-wunsch|needleman-wunsch-linear|wfa|wfa-standard] [--strict]
+//
+// Differences from the reference binary, all deliberate and printed on stderr when they apply:
+//   * only the first co-optimal alignment of a pair is printed (the reference prints all);
+//   * where the reference process would panic (nw_affine:299/:303, wfa.rs:577/:603) this tool
+//     reports it on stderr and goes on; with --strict it exits with status 101 like a Rust panic;
+//   * a-star (the reference's default algorithm) is not part of the GPU path.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sa_engine.h"
+
+struct Rec {
+  std::string name, seq;
+};
+
+static bool load_fasta(const char* what, const std::string& path, std::vector<Rec>& recs) {
+  FILE* f = fopen(path.c_str(), "rb");
+  size_t size = 0;
+  if (f) {
+    fseek(f, 0, SEEK_END);
+    size = (size_t)ftell(f);
+    fclose(f);
+  }
+  std::vector<uint8_t> out(size + 1), err(size + 1);
+  std::vector<uint64_t> index(4 * (size / 2 + 2));
+  size_t nerr = 0;
+  const int64_t n = sa_parse_fasta(path.c_str(), out.data(), out.size(), index.data(), index.size() / 4,
+                                   err.data(), err.size(), &nerr);
+  if (n < 0) {  // main.rs:24-28 / :44-48
+    fprintf(stderr, "%s fasta could not be opened: invalid input parameter\naborting\n", what);
+    return false;
+  }
+  if (nerr) {  // main.rs:29-35: continue with the partial records
+    std::string chars;
+    for (size_t k = 0; k < nerr && k < err.size(); ++k) {
+      if (k) chars += ", ";
+      chars += "'";
+      chars += (char)err[k];
+      chars += "'";
+    }
+    fprintf(stderr, "Invalid character '[%s]' detected in %s fasta; continuing by ignoring it\n", chars.c_str(),
+            strcmp(what, "DB") == 0 ? "db" : "query");
+  }
+  for (int64_t r = 0; r < n; ++r) {
+    Rec rec;
+    rec.name.assign((const char*)out.data() + index[4 * r], index[4 * r + 1]);
+    rec.seq.assign((const char*)out.data() + index[4 * r + 2], index[4 * r + 3]);
+    recs.push_back(std::move(rec));
+  }
+  return true;
+}
+
+static void usage() {
+  fprintf(stderr,
+          "Usage: sa_align --query-file <QUERY_FILE> --db-file <DB_FILE> [OPTIONS]\n\n"
+          "Options:\n  -q, --query-file <QUERY_FILE>  Path to query sequence\n"
+          "  -d, --db-file <DB_FILE>        path to db sequence\n"
+          "  -o, --out-path <OUT_PATH>      out path [default: ./results]\n"
+          "  -v, --verbose                  verbose\n"
+          "  -m, --mode <MODE>              modus [default: global] [possible values: global, local, semi-global]\n"
+          "  -a, --algo <ALGO>              algo [default: needleman-wunsch] [possible values: a-star, needleman-wunsch,\n"
+          "                                 needleman-wunsch-linear, wfa, wfa-standard]\n"
+          "      --strict                   exit 101 where the reference would panic\n"
+          "      --device <N>               CUDA device [default: 0]\n"
+          "  -h, --help                     Print help\n  -V, --version                  Print version\n");
+}
+
+// Rust's `{:#?}` of a Duration, close enough for the line the reference prints per pair
+static std::string duration_debug(double seconds) {
+  char buf[64];
+  if (seconds >= 1.0) snprintf(buf, sizeof(buf), "%.9gs", seconds);
+  else if (seconds >= 1e-3) snprintf(buf, sizeof(buf), "%.6gms", seconds * 1e3);
+  else if (seconds >= 1e-6) snprintf(buf, sizeof(buf), "%.3f\xC2\xB5s", seconds * 1e6);
+  else snprintf(buf, sizeof(buf), "%.0fns", seconds * 1e9);
+  return buf;
+}
+
+int main(int argc, char** argv) {
+  std::string qpath, dpath, mode = "global", algo = "needleman-wunsch";
+  bool verbose = false, strict = false;
+  int device = 0;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto val = [&](const char* s, const char* l) -> const char* {
+      if (a == s || a == l) {
+        if (i + 1 >= argc) { usage(); exit(2); }
+        return argv[++i];
+      }
+      const std::string pre = std::string(l) + "=";
+      if (a.rfind(pre, 0) == 0) return argv[i] + pre.size();
+      return nullptr;
+    };
+    if (const char* v = val("-q", "--query-file")) qpath = v;
+    else if (const char* v = val("-d", "--db-file")) dpath = v;
+    else if (const char* v = val("-o", "--out-path")) (void)v;  // parsed and unused, as in the reference
+    else if (const char* v = val("-m", "--mode")) mode = v;
+    else if (const char* v = val("-a", "--algo")) algo = v;
+    else if (const char* v = val("--device", "--device")) device = atoi(v);
+    else if (a == "-v" || a == "--verbose") verbose = true;
+    else if (a == "--strict") strict = true;
+    else if (a == "-h" || a == "--help") { usage(); return 0; }
+    else if (a == "-V" || a == "--version") { printf("sa_align 0.1.0 (ABI %d)\n", sa_abi_version()); return 0; }
+    else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
+  }
+  if (qpath.empty() || dpath.empty()) { usage(); return 2; }
+  sa_mode_t m;
+  if (mode == "global") m = SA_MODE_GLOBAL;
+  else if (mode == "local") m = SA_MODE_LOCAL;
+  else if (mode == "semi-global") m = SA_MODE_SEMIGLOBAL;
+  else { fprintf(stderr, "error: invalid value '%s' for '--mode <MODE>'\n", mode.c_str()); return 2; }
+  sa_algo_t al;
+  if (algo == "needleman-wunsch") al = SA_ALGO_NW_AFFINE;
+  else if (algo == "needleman-wunsch-linear") al = SA_ALGO_NW_LINEAR;
+  else if (algo == "wfa") al = SA_ALGO_WFA;
+  else if (algo == "wfa-standard") al = SA_ALGO_WFA_STANDARD;
+  else if (algo == "a-star") { fprintf(stderr, "a-star is not part of the GPU path (see DESIGN.md); use the reference binary\n"); return 2; }
+  else { fprintf(stderr, "error: invalid value '%s' for '--algo <ALGO>'\n", algo.c_str()); return 2; }
+
+  std::vector<Rec> db, query;
+  if (!load_fasta("DB", dpath, db)) return 0;       // the reference returns from main, status 0
+  if (!load_fasta("Query", qpath, query)) return 0;
+
+  // pack: every record once, pairs in the db-major order of main.rs:61-62
+  std::string residues;
+  std::vector<uint64_t> off;
+  for (auto& r : query) { off.push_back(residues.size()); residues += r.seq; }
+  for (auto& r : db) { off.push_back(residues.size()); residues += r.seq; }
+  const size_t nq = query.size(), nd = db.size(), n = nq * nd;
+  std::vector<uint64_t> q_off(n), d_off(n);
+  std::vector<uint32_t> q_len(n), d_len(n);
+  for (size_t d = 0, p = 0; d < nd; ++d)
+    for (size_t q = 0; q < nq; ++q, ++p) {
+      q_off[p] = off[q]; q_len[p] = (uint32_t)query[q].seq.size();
+      d_off[p] = off[nq + d]; d_len[p] = (uint32_t)db[d].seq.size();
+    }
+  sa_engine_t* eng = nullptr;
+  if (sa_engine_create(device, &eng) != SA_OK) {
+    fprintf(stderr, "sa_engine_create: %s\n", sa_last_error(eng));
+    sa_engine_destroy(eng);
+    return 1;
+  }
+  sa_batch_t batch{(const uint8_t*)residues.data(), residues.size(), q_off.data(), q_len.data(), d_off.data(), d_len.data(), n, 0};
+  std::vector<int32_t> score(n);
+  std::vector<uint8_t> status(n);
+  std::vector<uint64_t> coff(n);
+  std::vector<uint32_t> clen(n), pool(64 * n + 1024);
+  sa_result_t res{score.data(), status.data(), coff.data(), clen.data(), pool.data(), pool.size(), 0};
+  const auto t0 = std::chrono::steady_clock::now();
+  sa_status_t rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
+  if (rc == SA_E_CIGAR_CAPACITY) {
+    pool.resize(res.cigar_used + 16);
+    res.cigar = pool.data();
+    res.cigar_capacity = pool.size();
+    rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
+  }
+  const double per_pair = n ? std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (double)n : 0;
+  if (rc != SA_OK) {
+    fprintf(stderr, "sa_align_batch: %s\n", sa_last_error(eng));
+    sa_engine_destroy(eng);
+    return 1;
+  }
+  int exit_code = 0;
+  for (size_t d = 0, p = 0; d < nd && !exit_code; ++d)
+    for (size_t q = 0; q < nq; ++q, ++p) {
+      const Rec &Q = query[q], &D = db[d];
+      if (status[p] == SA_NOT_IMPLEMENTED) {  // main.rs:68-74 + errors.rs:11-12
+        fprintf(stderr, "An error occured during alignment of %s and %s\nError in alignment: not implemented\n",
+                Q.name.c_str(), D.name.c_str());
+        continue;
+      }
+      if (al == SA_ALGO_WFA || al == SA_ALGO_WFA_STANDARD) {
+        if (status[p] == SA_OK) printf("converged with score %d: \n", score[p]);  // wfa.rs:36
+        else {
+          fprintf(stderr, "%s vs %s: the reference %s here\n", Q.name.c_str(), D.name.c_str(),
+                  status[p] == SA_REF_PANIC ? "panics in trim (wfa.rs:577/603)" : "never converges (wfa.rs:189)");
+          if (strict && status[p] == SA_REF_PANIC) { exit_code = 101; break; }
+        }
+        continue;
+      }
+      if (al == SA_ALGO_NW_LINEAR)  // needleman_wunsch.rs:196-200
+        printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
+      const bool has_alignment = clen[p] > 0 || (Q.seq.empty() && D.seq.empty());
+      if (has_alignment) {
+        const int64_t need = sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                              (uint32_t)D.seq.size(), pool.data() + coff[p], clen[p], nullptr, 0);
+        std::string text((size_t)need + 1, '\0');
+        sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
+                         pool.data() + coff[p], clen[p], &text[0], text.size());
+        text.resize((size_t)need);
+        fputs(text.c_str(), stdout);
+      }
+      if (verbose) printf("score: %d\n", score[p]);
+      if (status[p] == SA_REF_PANIC || status[p] == SA_REF_PANIC_EARLY) {
+        fprintf(stderr, "%s vs %s: the reference panics here (index out of bounds, needleman_wunsch_affine.rs:299/303)%s\n",
+                Q.name.c_str(), D.name.c_str(), status[p] == SA_REF_PANIC ? " after printing" : " before printing anything");
+        if (strict) { exit_code = 101; break; }
+      }
+      if (al == SA_ALGO_NW_AFFINE) printf("%s\n", duration_debug(per_pair).c_str());  // nw_affine:431
+    }
+  sa_engine_destroy(eng);
+  return exit_code;
+}
