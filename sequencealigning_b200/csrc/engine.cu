@@ -72,7 +72,7 @@ struct sa_engine {
   // Two segments are in flight on the compute stream (the fill of segment i+1 is queued before
   // the host reads segment i's refill count), so per-segment scratch is double-buffered.
   struct Slot {
-    DevBuf tb, end, rerun_ids;
+    DevBuf tb, end, rerun_ids, tmp_runs;
     cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
                                     // the next fill overlaps the tail of the previous one
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
@@ -454,6 +454,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if ((r = ensure(e, sl.tb, (size_t)ctiles * tile_bytes)) != SA_OK) return r;
     if ((r = ensure(e, sl.end, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
     if ((r = ensure(e, sl.rerun_ids, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
+    if (want_cigar && (r = ensure(e, sl.tmp_runs, (size_t)cn * sa::kTmpRuns * 4)) != SA_OK) return r;
     set_geometry(g);
     cudaStream_t sx = sl.stream;
     CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_bdone, 0));  // the slot's previous user is done
@@ -477,6 +478,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
     wp.rerun_count = d_counts + k;
     wp.phase = 0;
+    wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
+    wp.tmp_base = (uint32_t)sg.base;
     if (linear)
       sa::nw_linear_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
     else
@@ -539,6 +542,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       wp.rerun_ids = nullptr;
       wp.rerun_count = nullptr;
       wp.phase = 1;
+      wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
+      wp.tmp_base = (uint32_t)sg.base;
       return SA_OK;
     };
     for (const ReLaunch& rl : re_launches) {
@@ -554,8 +559,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     CUDA_TRY(e, cudaGetLastError());
     e->timing.kernel_launches += 3;
     if (want_cigar) {
-      // write pass: main region, then each refill slice.  Writes past pool_cap are dropped and
-      // detected by the caller from the final total.
+      // pool fill: a gather from the runs parked by the count passes, then a second walk for
+      // the (rare) pairs with more than kTmpRuns runs: main region, then each refill slice.
+      // Writes past pool_cap are dropped and detected by the caller from the final total.
+      sa::cigar_gather<<<(cn * 8 + 255) / 256, 256, 0, e->stream>>>(
+          (const uint32_t*)sl.tmp_runs.p, db.cigar_len, db.cigar_off, db.pool, db.pool_cap, (uint32_t)sg.base, cn);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+      wp.tmp_runs = nullptr;
       wp.pair_ids = nullptr;
       wp.pair_base = (uint32_t)sg.base;
       wp.n_launch_pairs = cn;
@@ -840,7 +851,7 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
   if (e->stream) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
+    for (DevBuf* b : {&e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
                       &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch,
                       &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
                       &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})

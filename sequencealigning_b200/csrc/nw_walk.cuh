@@ -51,7 +51,14 @@ struct WalkParams {
   uint32_t* __restrict__ rerun_ids;
   uint32_t* __restrict__ rerun_count;
   int phase;  // 0: first fill (bonus on)  1: clean refill of queued pairs
+  // The count pass already sees every run: it parks up to kTmpRuns of them per pair (back to
+  // front, like the pool) so that the pool can be filled by a plain gather after the scan;
+  // only pairs with more runs are walked a second time.
+  uint32_t* __restrict__ tmp_runs;  // [segment pairs][kTmpRuns], indexed by (id - tmp_base)
+  uint32_t tmp_base;
 };
+
+constexpr uint32_t kTmpRuns = 24;
 
 __device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile_base, uint32_t grp,
                                               uint32_t half, uint32_t x, uint32_t y) {
@@ -104,8 +111,9 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
       }
     }
   } else {
-    // write pass: skip pairs that have no alignment, and (phase 0) pairs owned by the refill
-    if (p.cigar_len[id] == 0) return;
+    // write pass: only pairs whose runs did not fit the temp slot; skip pairs that have no
+    // alignment, and (phase 0) pairs owned by the refill
+    if (p.cigar_len[id] <= kTmpRuns) return;
     if (p.phase == 0 && p.status[id] != kOk) return;
   }
 
@@ -113,12 +121,14 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   uint32_t nruns = 0, run_op = 3, run_len = 0;
   uint64_t wpos = 0;
   if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];  // runs are produced last-to-first
+  uint32_t* tmp = (MODE == 0 && p.tmp_runs) ? p.tmp_runs + (uint64_t)(id - p.tmp_base) * kTmpRuns : nullptr;
   while (x > 0 && y > 0) {
     if (st != run_op) {
       if (MODE == 1 && run_len) {
         --wpos;
         if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
       }
+      if (MODE == 0 && run_len && tmp && nruns <= kTmpRuns) tmp[kTmpRuns - nruns] = (run_len << 2) | run_op;
       run_op = st;
       run_len = 0;
       ++nruns;
@@ -147,6 +157,7 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   }
   const bool complete = (x == 0 && y == 0);
   if (MODE == 0) {
+    if (complete && run_len && tmp && nruns <= kTmpRuns) tmp[kTmpRuns - nruns] = (run_len << 2) | run_op;
     if (p.phase == 0) {
       // untainted pairs cannot run into the boundary chain (that path would carry the bonus)
       p.status[id] = complete ? kOk : kRefPanicEarly;
@@ -187,13 +198,14 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
     }
     p.score[id] = score;
     p.status[id] = kOk;
-  } else if (p.cigar_len[id] == 0) {
+  } else if (p.cigar_len[id] <= kTmpRuns) {
     return;
   }
   uint32_t i = n1, j = n2;  // rows walk seq1, columns walk seq2
   uint32_t nruns = 0, run_op = 3, run_len = 0;
   uint64_t wpos = 0;
   if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];
+  uint32_t* tmp = (MODE == 0 && p.tmp_runs) ? p.tmp_runs + (uint64_t)(id - p.tmp_base) * kTmpRuns : nullptr;
   while (i > 0 || j > 0) {
     uint32_t op;
     if (i == 0) {
@@ -221,6 +233,7 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
         --wpos;
         if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
       }
+      if (MODE == 0 && run_len && tmp && nruns <= kTmpRuns) tmp[kTmpRuns - nruns] = (run_len << 2) | run_op;
       run_op = op;
       run_len = 0;
       ++nruns;
@@ -228,11 +241,31 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
     ++run_len;
   }
   if (MODE == 0) {
+    if (run_len && tmp && nruns <= kTmpRuns) tmp[kTmpRuns - nruns] = (run_len << 2) | run_op;
     p.cigar_len[id] = nruns;
   } else if (run_len) {
     --wpos;
     if (wpos < p.pool_cap) p.pool[wpos] = (run_len << 2) | run_op;
   }
+}
+
+// Pool fill for the common case: the count pass left pair p's runs at the END of its temp slot
+// (tmp[kTmpRuns - len .. kTmpRuns)); copy them to pool[cigar_off[p] ..].
+__global__ void __launch_bounds__(256) cigar_gather(const uint32_t* __restrict__ tmp_runs,
+                                                    const uint32_t* __restrict__ cigar_len,
+                                                    const uint64_t* __restrict__ cigar_off,
+                                                    uint32_t* __restrict__ pool, uint64_t pool_cap,
+                                                    uint32_t base, uint32_t n) {
+  // 8 lanes per pair: each lane copies runs k, k+8, ..
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t >> 3, sub = t & 7;
+  if (i >= n) return;
+  const uint32_t len = cigar_len[base + i];
+  if (len == 0 || len > kTmpRuns) return;
+  const uint64_t off = cigar_off[base + i];
+  const uint32_t* src = tmp_runs + (uint64_t)i * kTmpRuns + (kTmpRuns - len);
+  for (uint32_t k = sub; k < len; k += 8)
+    if (off + k < pool_cap) pool[off + k] = src[k];
 }
 
 // ---- exclusive scan of cigar_len -> cigar_off (three small kernels, no library) -------------
