@@ -37,8 +37,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
-    ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
+                    help="config2 (default, the headline): 150 bp affine NW; config3: 250 bp affine NW; "
+                         "config4: WFA (standard mode) on 1-10 kbp pairs at 1-15 %% error")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (0 = the workload's default)")
+    ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--divergence", type=float, default=0.05)
     ap.add_argument("--no-indels", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
@@ -96,22 +99,58 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+WORKLOADS = {  # name -> (default pairs per GPU, length, BASELINE.json index)
+    "config2": (1_000_000, 150, 1),
+    "config3": (1_000_000, 250, 2),
+    "config4": (20_000, 0, 3),
+}
+
+
+def resolve_workload(args):
+    pairs, length, _ = WORKLOADS[args.workload]
+    args.pairs = args.pairs or pairs
+    args.length = args.length or length
+
+
 def make_batch(args, rank: int):
     from sequencealigning_b200 import synth
+    if args.workload == "config4":
+        return synth.config4(args.pairs, seed=synth.SEEDS["config4"] + 7919 * rank)
     return synth.random_pairs(args.pairs, args.length, args.divergence, not args.no_indels,
-                              seed=synth.SEEDS["config2"] + 7919 * rank)
+                              seed=synth.SEEDS[args.workload] + 7919 * rank)
 
 
 def workload_config(args, n_gpus: int) -> dict:
+    if args.workload == "config4":
+        return {"workload": f"gap-affine WFA (standard mode, x=4 o=2 e=6), {args.pairs} synthetic pairs per GPU of 1-10 kbp "
+                            f"(log-uniform) at 1-15 % error (BASELINE.json configs[3]); GCUPS is EQUIVALENT cells n1*n2/s",
+                "pairs_per_gpu": args.pairs, "n_gpus": n_gpus,
+                "note": "the reference's own WFA panics (wfa.rs:577/603) or never converges (wfa.rs:189) on inputs of this size"}
     return {
         "workload": f"affine NW score+traceback, {args.pairs} synthetic {args.length} bp read pairs per GPU at "
                     f"{args.divergence:.0%} divergence ({'sub:ins:del 2:1:1' if not args.no_indels else 'substitutions only'}) "
-                    f"(BASELINE.json configs[1])",
+                    f"(BASELINE.json configs[{WORKLOADS[args.workload][2]}])",
         "pairs_per_gpu": args.pairs, "length": args.length, "n_gpus": n_gpus,
         "scheme": "match 5 / mismatch -4 / open -8 / ext -6 (nw_affine.rs:15-20)",
         "sharding": "independent shards per rank, no collective on the data path",
         "l2": "inputs (~%.0f MB) + traceback scratch (GBs) exceed the 126 MB L2; no flush needed" % (args.pairs * args.length * 2 / 1e6),
     }
+
+
+def cpu_baseline_wfa(batch, n_sample: int) -> dict:
+    """config4: textbook gap-affine WFA on the CPU (oracle/wfa.c), 1 core, a bounded sample."""
+    from oracle import binding as ob
+    ob.build()
+    n_sample = min(n_sample, batch.n_pairs)
+    t0 = time.perf_counter()
+    cells = 0
+    for p in range(n_sample):
+        ob.wfa_standard(batch.query(p), batch.db(p))
+        cells += int(batch.q_len[p]) * int(batch.d_len[p])
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt / 1e9, "unit": "GCUPS (equivalent cells)", "cores": 1, "kind": "port",
+            "alignments_per_s": n_sample / dt, "seconds": dt,
+            "sample": f"first {n_sample} pairs, oracle/wfa.c sao_wfa_standard (the reference's own wfa.rs produces no result on these inputs)"}
 
 
 def cpu_baseline(batch, n_sample: int, n_threads: int, min_seconds: float = 0.0) -> dict:
@@ -145,6 +184,14 @@ def run_reference(args):
         return
     batch = make_batch(args, 0)
     cores = os.cpu_count() or 1
+    if args.workload == "config4":
+        cb = cpu_baseline_wfa(batch, args.cpu_sample or 64)
+        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GCUPS", "n_gpus": args.gpus, "steps": 1,
+               "warmup": 0, "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "i32", "data": "synthetic", "config": workload_config(args, args.gpus), "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(out), flush=True)
+        return
     n_sample = args.cpu_sample or min(args.pairs, 4000 * cores)
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(batch, min(n_sample, 2000), cores)
@@ -176,6 +223,7 @@ def int_peak() -> dict:
 
 def main():
     args = parse_args()
+    resolve_workload(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -206,13 +254,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg: `value` ------------------------------------------
+    from sequencealigning_b200 import ALGO_NW_AFFINE, ALGO_WFA_STANDARD
+    algo = ALGO_WFA_STANDARD if args.workload == "config4" else ALGO_NW_AFFINE
     rb = eng.upload(batch)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # nvidia-smi start-up happens during warm-up, not in the timed region
         time.sleep(0.5)
     for _ in range(args.warmup):
-        rb.align()
+        rb.align(algo=algo)
     eng.synchronize()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -221,7 +271,7 @@ def main():
     reruns = 0
     e0.record(stream)
     for _ in range(args.steps):
-        rb.align()
+        rb.align(algo=algo)
         t = eng.timing()
         launches += t["kernel_launches"]
         reruns = t["pairs_rerun"]
@@ -254,11 +304,11 @@ def main():
         cap = int(res_dev.cigar.size) + 1024
         pres = PinnedResult(batch.n_pairs, cap)
         for _ in range(2):
-            eng.align(pb, out=pres)
+            eng.align(pb, algo=algo, out=pres)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            r = eng.align(pb, out=pres)
+            r = eng.align(pb, algo=algo, out=pres)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.steps
         tim = eng.timing()
@@ -302,7 +352,13 @@ def main():
                         "bytes": "sequences + 0.5 B/cell traceback written + results"},
             },
         }
-        if not args.skip_cpu:
+        if args.workload == "config4":
+            out["roofline"] = {"bound": "latency (wavefront dependency chain)", "achieved": None, "peak": None, "unit": None,
+                               "frac": None, "traffic": None,
+                               "note": "WFA does O(s^2) work, not n1*n2: GCUPS here is equivalent cells; no roofline is claimed this round"}
+            if not args.skip_cpu:
+                out["cpu_baseline"] = cpu_baseline_wfa(batch, args.cpu_sample or 64)
+        elif not args.skip_cpu:
             n_sample = args.cpu_sample or 20000
             out["cpu_baseline"] = cpu_baseline(batch, n_sample, 1)
             cores = os.cpu_count() or 1

@@ -72,7 +72,7 @@ struct sa_engine {
   // Two segments are in flight on the compute stream (the fill of segment i+1 is queued before
   // the host reads segment i's refill count), so per-segment scratch is double-buffered.
   struct Slot {
-    DevBuf tb, end, rerun_ids, tmp_runs;
+    DevBuf tb, end, rerun_ids, tmp_runs, order;
     cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
                                     // the next fill overlaps the tail of the previous one
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
@@ -90,6 +90,7 @@ struct sa_engine {
   size_t tb_budget = 0;
   size_t budget_cached = 0;
   uint32_t seg_pairs = 524288;
+  int sort_mode = 0;  // 0 auto, 1 always, 2 never (SA_SORT)
   bool seg_pairs_forced = false;
 };
 
@@ -263,6 +264,7 @@ struct Segment {
   uint64_t base = 0;
   uint32_t n = 0;
   uint32_t n1max = 0, n2max = 0;
+  std::vector<uint32_t> order;  // launch index -> pair id, sorted by shape; empty = identity
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
   Geometry g;
 };
@@ -352,7 +354,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   auto prepare = [&](uint64_t base, Segment& sg) -> sa_status_t {
     sg = Segment{};
     sg.base = base;
-    uint32_t cn = (uint32_t)std::min<uint64_t>(seg_target, n - base);
+    uint32_t cn = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(seg_target, 1u << 24), n - base);
     // streaming from the host: ramp the segment size up so the first copy-in is short
     if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
     for (uint32_t i = 0; i < cn; ++i) {
@@ -375,6 +377,39 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     const uint64_t tiles_fit = std::max<uint64_t>(1, budget_main / tile_bytes);
     cn = (uint32_t)std::min<uint64_t>(cn, tiles_fit * sg.g.ppt);
     sg.n = cn;
+    {
+      // Ragged segment: the 16-64 pairs of a warp tile all run to the tile's largest shape, so
+      // bucket pairs by (rows, columns) when the padded work of the given order exceeds the real
+      // work by more than ~15 % (uniform read sets skip this; the sort is host time).
+      uint64_t real = 0, padded = 0;
+      const uint32_t ppt = sg.g.ppt;
+      for (uint32_t t0 = 0; t0 < cn; t0 += ppt) {
+        uint32_t a = 0, b = 0;
+        const uint32_t t1 = std::min(cn, t0 + ppt);
+        for (uint32_t i = t0; i < t1; ++i) {
+          a = std::max(a, h_cols[base + i]);
+          b = std::max(b, h_rows[base + i]);
+          real += (uint64_t)h_cols[base + i] * h_rows[base + i];
+        }
+        padded += (uint64_t)a * b * (t1 - t0);
+      }
+      if (e->sort_mode == 1 || (e->sort_mode == 0 && padded > real + real / 7 && cn > ppt)) {
+        // stable counting sort by columns, then by rows (LSD): O(n + longest sequence)
+        std::vector<uint32_t> tmp(cn), cnt;
+        sg.order.resize(cn);
+        cnt.assign((size_t)sg.n1max + 2, 0);
+        for (uint32_t i = 0; i < cn; ++i) cnt[h_cols[base + i] + 1]++;
+        for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+        for (uint32_t i = 0; i < cn; ++i) tmp[cnt[h_cols[base + i]]++] = i;
+        cnt.assign((size_t)sg.n2max + 2, 0);
+        for (uint32_t i = 0; i < cn; ++i) cnt[h_rows[base + i] + 1]++;
+        for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+        for (uint32_t i = 0; i < cn; ++i) {
+          const uint32_t src = tmp[i];
+          sg.order[cnt[h_rows[base + src]]++] = (uint32_t)(base + src);
+        }
+      }
+    }
     if (in) {
       for (uint32_t i = 0; i < cn; ++i) {
         const uint64_t p = base + i;
@@ -459,7 +494,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     cudaStream_t sx = sl.stream;
     CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_bdone, 0));  // the slot's previous user is done
     if (in) CUDA_TRY(e, cudaStreamWaitEvent(sx, e->ev_in, 0));
-    fp.pair_ids = nullptr;
+    const uint32_t* d_order = nullptr;
+    if (!sg.order.empty()) {
+      if ((r = ensure(e, sl.order, (size_t)cn * 4)) != SA_OK) return r;
+      // pageable source: the copy is staged by the runtime before the call returns
+      CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), (size_t)cn * 4, cudaMemcpyHostToDevice, sx));
+      d_order = (const uint32_t*)sl.order.p;
+    }
+    fp.pair_ids = d_order;
     fp.pair_base = (uint32_t)sg.base;
     fp.n_launch_pairs = cn;
     fp.tb = (uint2*)sl.tb.p;
@@ -469,7 +511,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
     if ((r = launch_fill_g(e, fp, g, ctiles, sx, s2.algo)) != SA_OK) return r;
     CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sx));
-    wp.pair_ids = nullptr;
+    wp.pair_ids = d_order;
     wp.pair_base = (uint32_t)sg.base;
     wp.n_launch_pairs = cn;
     wp.n_launch_dev = nullptr;
@@ -567,7 +609,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
       wp.tmp_runs = nullptr;
-      wp.pair_ids = nullptr;
+      wp.pair_ids = sg.order.empty() ? nullptr : (const uint32_t*)sl.order.p;
       wp.pair_base = (uint32_t)sg.base;
       wp.n_launch_pairs = cn;
       wp.tb = (const uint2*)sl.tb.p;
@@ -839,6 +881,7 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
+  if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);
   if (const char* s = getenv("SA_SEG_PAIRS")) {
     e->seg_pairs = std::max(1, atoi(s));
     e->seg_pairs_forced = true;
@@ -851,7 +894,7 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
   if (e->stream) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
+    for (DevBuf* b : {&e->slot[0].order, &e->slot[1].order, &e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
                       &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch,
                       &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
                       &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})

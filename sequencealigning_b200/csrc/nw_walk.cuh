@@ -183,7 +183,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
   const uint32_t i_launch = blockIdx.x * blockDim.x + threadIdx.x;
   if (i_launch >= p.n_launch_pairs) return;
-  const uint32_t id = p.pair_base + i_launch;
+  const uint32_t id = p.pair_ids ? p.pair_ids[i_launch] : p.pair_base + i_launch;
   const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
   const uint32_t ppt = 2 * p.ng;
   const uint32_t tile = i_launch / ppt, grp = (i_launch % ppt) >> 1, half = i_launch & 1;

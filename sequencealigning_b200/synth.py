@@ -86,3 +86,36 @@ def config1(n_db: int = 1000, seed: int = SEEDS["config1"]) -> PairBatch:
     residues = np.concatenate([ALPHABET[q]] + [ALPHABET[x] for x in dbs])
     d_off = np.uint64(150) + (np.cumsum(d_len, dtype=np.uint64) - d_len)
     return PairBatch(residues, np.zeros(n_db, np.uint64), np.full(n_db, 150, np.uint32), d_off.astype(np.uint64), d_len)
+
+
+def config4(n_pairs: int = 100_000, seed: int = SEEDS["config4"], min_len: int = 1000, max_len: int = 10000) -> PairBatch:
+    """WFA workload (BASELINE.json configs[3]): query length log-uniform in [1, 10] kbp, per-pair
+    error rate uniform in [1 %, 15 %], sub:ins:del = 2:1:1."""
+    rng = np.random.default_rng(seed)
+    lens = np.round(10 ** rng.uniform(np.log10(min_len), np.log10(max_len), n_pairs)).astype(np.int64)
+    err = rng.uniform(0.01, 0.15, n_pairs)
+    total = int(lens.sum())
+    q = rng.integers(0, 4, size=total, dtype=np.uint8)
+    pair_of = np.repeat(np.arange(n_pairs), lens)
+    u = rng.random(total, dtype=np.float32)
+    mutated = u < err[pair_of].astype(np.float32)
+    kind = rng.random(total, dtype=np.float32)
+    sub = mutated & (kind < 0.5)
+    ins = mutated & (kind >= 0.5) & (kind < 0.75)
+    dele = mutated & (kind >= 0.75)
+    shift = rng.integers(1, 4, size=total, dtype=np.uint8)
+    first = np.where(sub, (q + shift) & 3, q)
+    count = np.ones(total, np.int64)
+    count[ins] = 2
+    count[dele] = 0
+    starts = np.cumsum(count) - count
+    d = np.empty(int(count.sum()), np.uint8)
+    keep = count >= 1
+    d[starts[keep]] = first[keep]
+    two = count == 2
+    d[starts[two] + 1] = rng.integers(0, 4, size=int(two.sum()), dtype=np.uint8)
+    q_off = np.cumsum(lens) - lens
+    d_len = np.add.reduceat(count, q_off).astype(np.uint32)
+    d_off = total + (np.cumsum(d_len, dtype=np.uint64) - d_len)
+    residues = np.concatenate([ALPHABET[q], ALPHABET[d]])
+    return PairBatch(residues, q_off.astype(np.uint64), lens.astype(np.uint32), d_off.astype(np.uint64), d_len)

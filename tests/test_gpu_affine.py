@@ -100,6 +100,21 @@ def test_many_small_segments_stream_results(oracle, monkeypatch):
         assert np.array_equal(r.cigar, r2.cigar) and np.array_equal(r.score, r2.score)
 
 
+@pytest.mark.parametrize("sort_mode", ["1", "2"])
+def test_shape_bucketing_does_not_change_results(oracle, sort_mode, monkeypatch):
+    """SA_SORT=1 forces the per-segment (rows, columns) bucketing, 2 disables it."""
+    from sequencealigning_b200 import ALGO_NW_LINEAR, Engine
+    monkeypatch.setenv("SA_SORT", sort_mode)
+    monkeypatch.setenv("SA_SEG_PAIRS", "1500")
+    with Engine(0) as eng:
+        b = _batch(random_pair_list(91, 4000, 0, 200))
+        r = eng.align(b)
+        check_against_oracle(oracle, b, r, what=f"SA_SORT={sort_mode}")
+        rl = eng.align(b, algo=ALGO_NW_LINEAR)
+        ref = oracle.linear_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=401, n_threads=8)
+        assert np.array_equal(ref.score, rl.score) and np.array_equal(ref.cigar_len, rl.cigar_len)
+
+
 def test_score_only_and_capacity(engine, oracle):
     from sequencealigning_b200 import EngineError
     b = _batch(random_pair_list(5, 500, 20, 80))
