@@ -208,6 +208,32 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA
+    node its GPU hangs off, so that N ranks do not share one socket's memory controllers."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa node {node} ({len(allowed)} cpus)"
+        return f"numa node {node}: no allowed cpus, not bound"
+    except Exception as ex:  # containers often hide sysfs; binding is an optimisation only
+        return f"numa: not bound ({type(ex).__name__})"
+
+
 def int_peak() -> dict:
     """Measured integer issue rate (own microbenchmark, sequencealigning_b200/csrc/microbench)."""
     from sequencealigning_b200.build import INT_PEAK_PATH
@@ -240,6 +266,7 @@ def main():
         os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank"
     from sequencealigning_b200 import Engine
     from sequencealigning_b200.build import build_all
     build_all()
@@ -320,7 +347,8 @@ def main():
         e2e = {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(tim["h2d_bytes"]), "d2h_bytes_per_step": int(tim["d2h_bytes"]),
                "alignments_per_s": args.pairs * world / dt,
-               "api": "sa_align_batch (C ABI) with pinned host buffers; host wall clock, max over ranks"}
+               "api": "sa_align_batch (C ABI) with pinned host buffers; host wall clock, max over ranks",
+               "host_binding": numa}
         assert np.array_equal(r.score, res_dev.score)
 
     if rank == 0:

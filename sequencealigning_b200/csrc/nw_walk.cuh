@@ -12,6 +12,17 @@
 // chain D[0][y] / I[x][0], where the reference indexes seq2[0-1] / seq1[0-1] and panics
 // (:299/:303) -> SA_REF_PANIC_EARLY, no alignment.
 //
+// Why the "panic bonus" of the first fill cannot corrupt these bits for the pairs that keep
+// them: the bonus (+1 on boundary-chain cells, scores doubled) only ever changes the outcome
+// of a comparison between two candidates of EQUAL score, in favour of the one whose value
+// descends from a boundary-chain cell.  Suppose a tie bit read by this walk were polluted.
+// The walk only reads bits of cells on a co-optimal path (it starts at an optimal end state
+// and every step follows a tie parent), and the polluted comparison's tainted candidate is
+// then itself a tie parent of that cell, so a co-optimal path runs through a boundary-chain
+// cell and the bonus propagates, along maxima, to the end cell.  Contrapositive: an end cell
+// WITHOUT the bonus means every bit on every co-optimal path is clean.  Pairs WITH the bonus
+// are re-filled without it (phase 1) before they are walked.
+//
 // One thread walks one pair; lanes of a warp walk neighbouring pairs of the same tile, whose
 // paths stay close to each other, so the 8-byte traceback words they read share sectors.
 #pragma once

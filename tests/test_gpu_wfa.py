@@ -118,6 +118,17 @@ def test_standard_config4_shaped_pairs(engine, oracle):
     assert np.array_equal(exp2, r2.score[:12])
 
 
+def test_standard_long_pairs(engine, oracle):
+    """Pairs beyond what fits the on-chip staging (sequences read through L2): 30 kbp at 5 %."""
+    from sequencealigning_b200 import ALGO_WFA_STANDARD
+    rng = random.Random(6)
+    pairs = [_related(rng, 30000, 0.05), _related(rng, 24000, 0.02)]
+    b = _batch(pairs)
+    r = engine.align(b, algo=ALGO_WFA_STANDARD)
+    exp = [oracle.wfa_gotoh_cost(q, d) for q, d in pairs]
+    assert r.score.tolist() == exp
+
+
 def test_wfa_non_global_not_implemented(engine):
     from sequencealigning_b200 import ALGO_WFA, MODE_LOCAL, NOT_IMPLEMENTED
     r = engine.align(_batch([(b"ACGT", b"ACGA")]), algo=ALGO_WFA, mode=MODE_LOCAL)  # wfa.rs:26
