@@ -96,7 +96,10 @@ typedef struct {
   const uint64_t* d_off;
   const uint32_t* d_len;
   uint64_t n_pairs;
-  uint32_t packing; /* 0 = byte per residue (the only format in ABI v1) */
+  uint32_t packing; /* 0 = one byte per residue, offsets in bytes (raw bytes are compared, so
+                       'N' == 'N').  1 = 2-bit codes A=0 C=1 G=2 T=3, four per byte, residue i of
+                       the buffer at bits 2*(i&3) of byte i>>2; q_off/d_off count RESIDUES,
+                       residues_len counts BYTES (see sa_pack_2bit).  A/C/G/T only.           */
 } sa_batch_t;
 
 /* Results, caller-allocated HOST memory, engine fills.  Arrays have n_pairs entries. */
@@ -164,6 +167,10 @@ sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint6
  * index holds (name_off, name_len, seq_off, seq_len) per record into `out`. */
 int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t* index,
                        size_t index_cap, uint8_t* err_chars, size_t err_cap, size_t* n_err);
+
+/* Packer for packing = 1: appends n residues (A/C/G/T) to dst starting at residue index dst_pos.
+ * SA_E_ARG at the first other byte.  Pure host code. */
+sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_pos);
 
 /* The text the reference prints for one alignment (needleman_wunsch_affine.rs:283-286 and
  * Display :390-411): "alignment found\n\nseq1: ..\n      ..\nseq2: ..\n".  snprintf-style:

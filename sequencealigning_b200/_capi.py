@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "sa_abi_version", "sa_engine_create", "sa_engine_destroy", "sa_last_error", "sa_align_batch",
     "sa_batch_upload", "sa_batch_free", "sa_align_resident", "sa_resident_download",
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
-    "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine",
+    "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit",
 ]
 
 
@@ -101,5 +101,7 @@ def lib() -> C.CDLL:
     l.sa_parse_fasta.restype = C.c_int64
     l.sa_render_affine.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32, C.c_char_p, C.c_size_t]
     l.sa_render_affine.restype = C.c_int64
+    l.sa_pack_2bit.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
+    l.sa_pack_2bit.restype = C.c_int
     _lib = l
     return l

@@ -49,6 +49,7 @@ struct DeviceBatch {
   uint32_t* pool = nullptr;
   uint64_t pool_cap = 0;
   uint64_t* carry = nullptr;
+  uint32_t packing = 0;
 };
 
 }  // namespace
@@ -301,6 +302,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const bool linear = s2.algo == SA_ALGO_NW_LINEAR;
   sa::AffineS16Params fp{};
   fp.residues = db.residues;
+  fp.packing = db.packing;
   fp.pen2 = pack2((uint32_t)s2.pen);
   fp.zero = 0;
   uint32_t row0_clean;
@@ -423,7 +425,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         }
         e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
       }
-      if (sg.qhi > in->residues_len || sg.dhi > in->residues_len)
+      const uint64_t limit = in->packing ? in->residues_len * 4 : in->residues_len;
+      if (sg.qhi > limit || sg.dhi > limit)
         return fail(e, SA_E_ARG, "a pair in [%llu, %llu) reaches past residues_len",
                     (unsigned long long)base, (unsigned long long)(base + cn));
     }
@@ -444,8 +447,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     cp(db.q_len + sg.base, in->q_len + sg.base, (size_t)sg.n * 4);
     cp(db.d_len + sg.base, in->d_len + sg.base, (size_t)sg.n * 4);
     auto range = [&](uint64_t lo, uint64_t hi) { cp(db.residues + lo, in->residues + lo, hi - lo); };
-    if (sg.qlo < sg.qhi) cov.request(sg.qlo, sg.qhi, range);
-    if (sg.dlo < sg.dhi) cov.request(sg.dlo, sg.dhi, range);
+    const int sh = in->packing ? 2 : 0;  // residue index -> byte index
+    if (sg.qlo < sg.qhi) cov.request(sg.qlo >> sh, (sg.qhi + (sh ? 3 : 0)) >> sh, range);
+    if (sg.dlo < sg.dhi) cov.request(sg.dlo >> sh, (sg.dhi + (sh ? 3 : 0)) >> sh, range);
     if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(err));
     CUDA_TRY(e, cudaEventRecord(e->ev_in, e->s_in));
     return SA_OK;
@@ -715,7 +719,8 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
       max_end = std::max(max_end, std::max(in->q_off[p] + h_q_len[p], in->d_off[p] + h_d_len[p]));
       e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
     }
-    if (max_end > in->residues_len) return fail(e, SA_E_ARG, "a pair reaches past residues_len");
+    if (max_end > (in->packing ? in->residues_len * 4 : in->residues_len))
+      return fail(e, SA_E_ARG, "a pair reaches past residues_len");
     CUDA_TRY(e, cudaMemcpyAsync(db.residues, in->residues, in->residues_len, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(db.q_off, in->q_off, n * 8, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(db.d_off, in->d_off, n * 8, cudaMemcpyHostToDevice, e->stream));
@@ -727,6 +732,7 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
   for (uint64_t p = 0; p < n; ++p) nmax_sum = std::max<uint32_t>(nmax_sum, h_q_len[p] + h_d_len[p]);
   sa::WfaParams wp{};
   wp.residues = db.residues;
+  wp.packing = db.packing;
   wp.q_off = db.q_off;
   wp.q_len = db.q_len;
   wp.d_off = db.d_off;
@@ -961,7 +967,7 @@ sa_status_t sa_batch_free(sa_engine_t* e, sa_resident_t* r) {
 sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t** out) {
   if (!e || !b || !out) return SA_E_ARG;
   *out = nullptr;
-  if (b->packing != 0) return fail(e, SA_E_UNSUPPORTED, "packing %u not supported in ABI v1", b->packing);
+  if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
   if (b->n_pairs >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)b->n_pairs);
   if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len))
     return fail(e, SA_E_ARG, "null offset/length array");
@@ -971,10 +977,12 @@ sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t**
   const uint64_t n = b->n_pairs;
   r->n_pairs = n;
   r->residues_len = b->residues_len;
+  r->d.packing = b->packing;
   r->h_q_len.assign(b->q_len, b->q_len + n);
   r->h_d_len.assign(b->d_len, b->d_len + n);
   for (uint64_t i = 0; i < n; ++i) {
-    if (b->q_off[i] + b->q_len[i] > b->residues_len || b->d_off[i] + b->d_len[i] > b->residues_len) {
+    const uint64_t limit = b->packing ? b->residues_len * 4 : b->residues_len;
+    if (b->q_off[i] + b->q_len[i] > limit || b->d_off[i] + b->d_len[i] > limit) {
       delete r;
       return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
     }
@@ -1099,7 +1107,7 @@ sa_status_t sa_resident_download(sa_engine_t* e, sa_resident_t* r, sa_result_t* 
 sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
                            const sa_scheme_t* scheme, const sa_batch_t* b, sa_result_t* res) {
   if (!e || !b || !res) return SA_E_ARG;
-  if (b->packing != 0) return fail(e, SA_E_UNSUPPORTED, "packing %u not supported in ABI v1", b->packing);
+  if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
   if (b->n_pairs >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)b->n_pairs);
   if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len)))
     return fail(e, SA_E_ARG, "null input array");
@@ -1147,6 +1155,7 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     db.cigar_len = (uint32_t*)e->b_clen.p;
     db.cigar_off = (uint64_t*)e->b_coff.p;
     db.carry = (uint64_t*)e->b_carry.p;
+    db.packing = b->packing;
     st = run_wfa(e, db, n, b->q_len, b->d_len, scheme, algo == SA_ALGO_WFA, b, res);
     float ms = 0;
     if (st == SA_OK && cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.fill_ms = ms;
@@ -1170,6 +1179,7 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     db.pool = want_cigar ? (uint32_t*)e->b_pool.p : nullptr;
     db.pool_cap = want_cigar ? e->b_pool.cap / 4 : 0;
     db.carry = (uint64_t*)e->b_carry.p;
+    db.packing = b->packing;
     e->timing.h2d_bytes = 0;
     e->timing.d2h_bytes = 0;
     e->timing.cells = 0;

@@ -99,6 +99,34 @@ int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t*
   return nrec + 1;
 }
 
+// 2-bit packer for sa_batch_t.packing = 1: appends n residues (A, C, G, T only) to `dst`
+// starting at residue index dst_pos.  Returns SA_OK, or SA_E_ARG at the first other byte
+// (e.g. 'N': such inputs stay in the byte format, where raw bytes are compared).
+sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_pos) {
+  static const int8_t code[256] = {
+#define X -1
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, 0, X, 1, X, X, X, 2, X, X, X, X, X, X, X, X, X, X, X, X, 3, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X
+#undef X
+  };
+  if (n && (!src || !dst)) return SA_E_ARG;
+  for (uint64_t k = 0; k < n; ++k) {
+    const int c = code[src[k]];
+    if (c < 0) return SA_E_ARG;
+    const uint64_t pos = dst_pos + k;
+    uint8_t& b = dst[pos >> 2];
+    const int sh = 2 * (int)(pos & 3);
+    b = (uint8_t)((b & ~(3 << sh)) | (c << sh));
+  }
+  return SA_OK;
+}
+
 // Renders "alignment found\n\nseq1: ..\n      ..\nseq2: ..\n" for one CIGAR.
 // Returns the number of bytes needed (snprintf style).
 int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,

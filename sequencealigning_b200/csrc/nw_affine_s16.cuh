@@ -49,6 +49,15 @@ __host__ __device__ inline uint32_t s16_min_value_bound(int match, int mismatch,
   return (uint32_t)(2 * (openp + extp) + per_step * (int)(n1pad + n2 + 2) + pen + openp + extp);
 }
 
+// Residue access for both input formats of sa_batch_t: packing 0 = one byte per residue, offsets
+// in bytes; packing 1 = 2-bit codes (A=0 C=1 G=2 T=3), four per byte, residue i of the buffer at
+// bits 2*(i&3) of byte i>>2, offsets in RESIDUES.  Only equality of residues is ever used.
+__device__ __forceinline__ uint32_t load_residue(const uint8_t* __restrict__ residues, uint64_t pos,
+                                                 uint32_t packing) {
+  if (packing == 0) return residues[pos];
+  return ((uint32_t)residues[pos >> 2] >> (2 * (uint32_t)(pos & 3))) & 3u;
+}
+
 struct AffineS16Params {
   const uint8_t* __restrict__ residues;
   const uint64_t* __restrict__ q_off;
@@ -71,6 +80,7 @@ struct AffineS16Params {
   uint32_t origin;  // kBias packed: H'[0][0]
   uint32_t zero;    // always 0; opaque to ptxas so that `or` bit-sets stay LOP3 (alu pipe)
   uint32_t step2;   // linear aligner: boundary step magnitude match - 2*ext, packed
+  uint32_t packing; // input format (see load_residue)
 };
 
 // max of two packed u16 pairs that also records, per half, whether the FIRST operand won or
@@ -346,13 +356,13 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   // ---- stage the residues; they are widened to (byte << 7) per 16-bit half when read, so the
   //      XOR of two different residues is >= 128 >= pen2 and the XOR of equal residues is 0 ----
   for (uint32_t y = j; y < n1pad; y += G) {
-    const uint32_t a = (y < n1a) ? (uint32_t)p.residues[qoa + y] : 0u;
-    const uint32_t b = (y < n1b) ? (uint32_t)p.residues[qob + y] : 0u;
+    const uint32_t a = (y < n1a) ? load_residue(p.residues, qoa + y, p.packing) : 0u;
+    const uint32_t b = (y < n1b) ? load_residue(p.residues, qob + y, p.packing) : 0u;
     qp[y * NG + grp] = (uint16_t)(a | (b << 8));
   }
   for (uint32_t x = j; x < n2t; x += G) {
-    const uint32_t a = (x < n2a) ? (uint32_t)p.residues[doa + x] : 0u;
-    const uint32_t b = (x < n2b) ? (uint32_t)p.residues[dob + x] : 0u;
+    const uint32_t a = (x < n2a) ? load_residue(p.residues, doa + x, p.packing) : 0u;
+    const uint32_t b = (x < n2b) ? load_residue(p.residues, dob + x, p.packing) : 0u;
     dp[x * NG + grp] = (uint16_t)(a | (b << 8));
     // column 0 as the "previous pass" of pass 0.  Affine: H'[x][0] = I'[x][0] (:200-216), and
     // I'[x][1] extends it (M[x][0] + open is the sentinel).  Linear: S'[i][0] with its gap flag

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nw_affine_s16.cuh"
+
 namespace sa {
 
 #ifndef SA_STATUS_CODES
@@ -44,6 +46,7 @@ struct WfaParams {
   uint32_t* __restrict__ next_pair;  // standard: dynamic work counter
   uint32_t smem_seq_bytes;         // standard: bytes available per warp for staged sequences
   uint32_t lit_wcap;               // literal: element capacity per component
+  uint32_t packing;                // input format (see load_residue)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -91,8 +94,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     if (li >= p.n_launch_pairs) break;
     const uint32_t id = p.pair_base + li;
     const int32_t n1 = (int32_t)p.q_len[id], n2 = (int32_t)p.d_len[id];
-    const uint8_t* g1 = p.residues + p.q_off[id];
-    const uint8_t* g2 = p.residues + p.d_off[id];
+    const uint64_t o1 = p.q_off[id], o2 = p.d_off[id];
     // stage both sequences as words (padding zeroed); fall back to global scratch copies
     // appended after the ring when they do not fit
     const uint32_t w1 = (uint32_t)(n1 + 8) >> 2, w2 = (uint32_t)(n2 + 8) >> 2;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       uint32_t v = 0;
       for (int b = 0; b < 4; ++b) {
         const int32_t pos = (int32_t)(k * 4 + b);
-        if (pos < n1) v |= (uint32_t)g1[pos] << (8 * b);
+        if (pos < n1) v |= load_residue(p.residues, o1 + pos, p.packing) << (8 * b);
       }
       s1w[k] = v;
     }
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       uint32_t v = 0;
       for (int b = 0; b < 4; ++b) {
         const int32_t pos = (int32_t)(k * 4 + b);
-        if (pos < n2) v |= (uint32_t)g2[pos] << (8 * b);
+        if (pos < n2) v |= load_residue(p.residues, o2 + pos, p.packing) << (8 * b);
       }
       s2w[k] = v;
     }
@@ -275,8 +277,7 @@ __global__ void __launch_bounds__(64) wfa_literal_kernel(const WfaParams p) {
   if (li >= p.n_launch_pairs) return;
   const uint32_t id = p.pair_base + li;
   const int32_t n1 = (int32_t)p.q_len[id], n2 = (int32_t)p.d_len[id];
-  const uint8_t* s1 = p.residues + p.q_off[id];
-  const uint8_t* s2 = p.residues + p.d_off[id];
+  const uint64_t o1 = p.q_off[id], o2 = p.d_off[id];
   const int32_t wcap = (int32_t)p.lit_wcap;
   int32_t* base = p.scratch + (uint64_t)li * p.scratch_stride;  // [kLitRing][3][wcap]
   LitComp ring[kLitRing][3];  // 0 = I, 1 = D, 2 = M
@@ -396,7 +397,9 @@ __global__ void __launch_bounds__(64) wfa_literal_kernel(const WfaParams p) {
         const int32_t diag = cm->lo + k;
         for (;;) {
           const uint64_t y = lit_y(off, diag), x = lit_x(off, diag);
-          if (!(y < (uint64_t)n1 && x < (uint64_t)n2 && s1[y] == s2[x])) break;
+          if (!(y < (uint64_t)n1 && x < (uint64_t)n2 &&
+                load_residue(p.residues, o1 + y, p.packing) == load_residue(p.residues, o2 + x, p.packing)))
+            break;
           ++off;
         }
         cm->data[k] = off;

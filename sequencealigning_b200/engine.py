@@ -49,6 +49,7 @@ class PairBatch:
     q_len: np.ndarray     # uint32
     d_off: np.ndarray     # uint64
     d_len: np.ndarray     # uint32
+    packing: int = 0      # 0 = bytes, 1 = 2-bit codes (offsets then count residues)
 
     def __post_init__(self):
         self.residues = np.ascontiguousarray(self.residues, np.uint8)
@@ -68,16 +69,33 @@ class PairBatch:
     def cells(self) -> int:
         return int((self.q_len.astype(np.uint64) * self.d_len.astype(np.uint64)).sum())
 
+    def _seq(self, o: int, l: int) -> bytes:
+        if getattr(self, "packing", 0) == 0:
+            return self.residues[o:o + l].tobytes()
+        idx = np.arange(o, o + l)
+        codes = (self.residues[idx >> 2] >> (2 * (idx & 3)).astype(np.uint8)) & 3
+        return np.frombuffer(b"ACGT", np.uint8)[codes].tobytes()
+
     def query(self, p: int) -> bytes:
-        o, l = int(self.q_off[p]), int(self.q_len[p])
-        return self.residues[o:o + l].tobytes()
+        return self._seq(int(self.q_off[p]), int(self.q_len[p]))
 
     def db(self, p: int) -> bytes:
-        o, l = int(self.d_off[p]), int(self.d_len[p])
-        return self.residues[o:o + l].tobytes()
+        return self._seq(int(self.d_off[p]), int(self.d_len[p]))
 
     def select(self, idx: np.ndarray) -> "PairBatch":
-        return PairBatch(self.residues, self.q_off[idx], self.q_len[idx], self.d_off[idx], self.d_len[idx])
+        return PairBatch(self.residues, self.q_off[idx], self.q_len[idx], self.d_off[idx], self.d_len[idx],
+                         getattr(self, "packing", 0))
+
+    def packed(self) -> "PairBatch":
+        """The same pairs in the 2-bit format (sa_pack_2bit); raises ValueError on non-ACGT bytes."""
+        if getattr(self, "packing", 0) == 1:
+            return self
+        n = int(self.residues.size)
+        out = np.zeros((n + 3) // 4 + 1, np.uint8)
+        rc = _capi.lib().sa_pack_2bit(self.residues.ctypes.data, n, out.ctypes.data, 0)
+        if rc != 0:
+            raise ValueError("2-bit packing needs A/C/G/T only")
+        return PairBatch(out, self.q_off, self.q_len, self.d_off, self.d_len, 1)
 
     @staticmethod
     def from_pairs(pairs: Iterable[Tuple[bytes, bytes]]) -> "PairBatch":
@@ -169,6 +187,7 @@ def pin_batch(batch: "PairBatch"):
         arrs.append(pb.array)
     out = PairBatch.__new__(PairBatch)
     out.residues, out.q_off, out.q_len, out.d_off, out.d_len = arrs
+    out.packing = getattr(batch, "packing", 0)
     out._pinned = bufs
     return out
 
@@ -220,7 +239,7 @@ class Engine:
     @staticmethod
     def _c_batch(b: PairBatch) -> _capi.Batch:
         return _capi.Batch(b.residues.ctypes.data, b.residues.size, b.q_off.ctypes.data, b.q_len.ctypes.data,
-                           b.d_off.ctypes.data, b.d_len.ctypes.data, b.n_pairs, 0)
+                           b.d_off.ctypes.data, b.d_len.ctypes.data, b.n_pairs, getattr(b, "packing", 0))
 
     @staticmethod
     def _alloc_result(n: int, cigar_capacity: int):

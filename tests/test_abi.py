@@ -81,3 +81,13 @@ def test_pair_batch_cross_product_is_db_major():
     b = PairBatch.from_records([Record(b"AA"), Record(b"CCC")], [Record(b"G"), Record(b"TTTT"), Record(b"AC")])
     assert [(b.query(p), b.db(p)) for p in range(b.n_pairs)] == [
         (b"AA", b"G"), (b"CCC", b"G"), (b"AA", b"TTTT"), (b"CCC", b"TTTT"), (b"AA", b"AC"), (b"CCC", b"AC")]
+
+
+def test_pack_2bit(lib):
+    from sequencealigning_b200 import PairBatch
+    b = PairBatch.from_pairs([(b"ACGTTGCA", b"GATTACA"), (b"T", b"")])
+    pb = b.packed()
+    assert pb.packing == 1 and [pb.query(0), pb.db(0), pb.query(1), pb.db(1)] == [b"ACGTTGCA", b"GATTACA", b"T", b""]
+    assert pb.residues[0] == 0b11100100 and pb.residues[1] == 0b00011011   # A=0 C=1 G=2 T=3, little-endian pairs of bits
+    with pytest.raises(ValueError):
+        PairBatch.from_pairs([(b"ACGN", b"A")]).packed()

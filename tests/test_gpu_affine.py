@@ -115,6 +115,25 @@ def test_shape_bucketing_does_not_change_results(oracle, sort_mode, monkeypatch)
         assert np.array_equal(ref.score, rl.score) and np.array_equal(ref.cigar_len, rl.cigar_len)
 
 
+def test_two_bit_packed_input_gives_identical_results(engine, oracle):
+    """sa_batch_t.packing = 1 (2-bit codes, offsets in residues) vs the byte format."""
+    from sequencealigning_b200 import ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD, synth
+    b = synth.random_pairs(6000, 150, 0.08, True, seed=21)
+    b.q_len[::7] = 97          # ragged, and unaligned starts inside bytes
+    pb = b.packed()
+    assert pb.residues.size * 4 >= b.residues.size > pb.residues.size * 3
+    for algo in (0, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD):
+        r0, r1 = engine.align(b, algo=algo), engine.align(pb, algo=algo)
+        for a, c in ((r0.score, r1.score), (r0.status, r1.status), (r0.cigar_len, r1.cigar_len), (r0.cigar, r1.cigar)):
+            assert np.array_equal(a, c), algo
+    check_against_oracle(oracle, b, engine.align(pb), what="packed")
+    rb = engine.upload(pb)
+    rb.align()
+    r2 = rb.download()
+    rb.free()
+    assert np.array_equal(r2.cigar, engine.align(b).cigar)
+
+
 def test_score_only_and_capacity(engine, oracle):
     from sequencealigning_b200 import EngineError
     b = _batch(random_pair_list(5, 500, 20, 80))
