@@ -767,7 +767,7 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
   } else {
     const uint32_t width = nmax_sum + 1;
     const uint32_t warps_per_block = 4;
-    const uint32_t smem_seq = 24 * 1024;  // per warp: both sequences up to ~24 kB stay on chip
+    const uint32_t smem_seq = 6 * 1024;  // per warp: two 2-bit packed sequences of up to ~12 kbp stay on chip
     const size_t smem = (size_t)warps_per_block * smem_seq;
     static bool configured = false;
     if (!configured) {
@@ -775,8 +775,8 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
       configured = true;
     }
     const uint64_t stride = (uint64_t)sa::kWfRing * 3 * width + (nmax_sum + 32) / 4 + 8;
-    uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 2);
-    if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4)) != SA_OK) return st;
+    uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 8);
+    if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4 + n * 4)) != SA_OK) return st;
     uint32_t* d_next = (uint32_t*)e->misc.p + 8;
     CUDA_TRY(e, cudaMemsetAsync(d_next, 0, 4, e->stream));
     wp.scratch = (int32_t*)e->wfa_scratch.p;
@@ -786,6 +786,21 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     wp.smem_seq_bytes = smem_seq;
     wp.pair_base = 0;
     wp.n_launch_pairs = (uint32_t)n;
+    {
+      // all penalties share a factor (2 for the reference's 4/2/6): other scores stay empty
+      auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+      wp.s_step = std::max(1, gcd(gcd(x, o + ex), ex));
+      // longest pairs first: one warp per pair, so the long ones must not start last
+      std::vector<uint32_t> order(n);
+      for (uint64_t p = 0; p < n; ++p) order[p] = (uint32_t)p;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return (uint64_t)h_q_len[a] + h_d_len[a] > (uint64_t)h_q_len[b] + h_d_len[b];
+      });
+      uint32_t* d_order = (uint32_t*)((int32_t*)e->wfa_scratch.p + (size_t)blocks * warps_per_block * stride);
+      CUDA_TRY(e, cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // `order` is a local
+      wp.order = d_order;
+    }
     sa::wfa_standard_kernel<<<blocks, warps_per_block * 32, smem, e->stream>>>(wp);
     CUDA_TRY(e, cudaGetLastError());
     e->timing.kernel_launches++;

@@ -47,6 +47,8 @@ struct WfaParams {
   uint32_t smem_seq_bytes;         // standard: bytes available per warp for staged sequences
   uint32_t lit_wcap;               // literal: element capacity per component
   uint32_t packing;                // input format (see load_residue)
+  const uint32_t* __restrict__ order;  // standard: hand-out order (longest pairs first), or nullptr
+  int32_t s_step;                  // standard: gcd of the penalties -- only these scores can hold a wavefront
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -54,23 +56,27 @@ struct WfaParams {
 // ---------------------------------------------------------------------------------------------
 constexpr int kWfRing = 16;  // >= max(x, o+e) + 1, power of two
 
-// residues a[v..], b[h..] compared 4 at a time on 32-bit words (any byte alphabet).
-// `sa`, `sb` point to 4-byte aligned copies with at least 4 bytes of padding after the end.
+// Extend along a diagonal on word-packed sequences: BITS = 8 (any byte alphabet, 4 residues per
+// comparison) or BITS = 2 (A/C/G/T codes, 16 residues per comparison).  `sa`, `sb` are 4-byte
+// aligned copies with at least one zero word of padding after the end.
+template <int BITS>
 __device__ __forceinline__ int32_t wf_extend(const uint32_t* sa, const uint32_t* sb, int32_t v,
                                              int32_t h, int32_t n1, int32_t n2) {
+  constexpr int PER = 32 / BITS;          // residues per word
+  constexpr int SH = BITS == 8 ? 2 : 4;   // log2(PER)
   for (;;) {
     const int32_t room = min(n1 - v, n2 - h);
     if (room <= 0) return v;
-    const uint32_t a0 = sa[v >> 2], a1 = sa[(v >> 2) + 1];
-    const uint32_t b0 = sb[h >> 2], b1 = sb[(h >> 2) + 1];
-    const uint32_t wa = __funnelshift_r(a0, a1, (v & 3) * 8);
-    const uint32_t wb = __funnelshift_r(b0, b1, (h & 3) * 8);
+    const uint32_t a0 = sa[v >> SH], a1 = sa[(v >> SH) + 1];
+    const uint32_t b0 = sb[h >> SH], b1 = sb[(h >> SH) + 1];
+    const uint32_t wa = __funnelshift_r(a0, a1, (v & (PER - 1)) * BITS);
+    const uint32_t wb = __funnelshift_r(b0, b1, (h & (PER - 1)) * BITS);
     const uint32_t x = wa ^ wb;
-    const int32_t same = x ? ((__ffs(x) - 1) >> 3) : 4;  // matching leading residues
+    const int32_t same = x ? ((__ffs(x) - 1) / BITS) : PER;  // matching leading residues
     const int32_t adv = min(same, room);
     v += adv;
     h += adv;
-    if (adv < 4) return v;
+    if (adv < PER) return v;
   }
 }
 
@@ -92,12 +98,26 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     if (lane == 0) li = atomicAdd(p.next_pair, 1u);
     li = __shfl_sync(0xffffffffu, li, 0);
     if (li >= p.n_launch_pairs) break;
-    const uint32_t id = p.pair_base + li;
+    const uint32_t id = p.order ? p.order[li] : p.pair_base + li;
     const int32_t n1 = (int32_t)p.q_len[id], n2 = (int32_t)p.d_len[id];
     const uint64_t o1 = p.q_off[id], o2 = p.d_off[id];
-    // stage both sequences as words (padding zeroed); fall back to global scratch copies
-    // appended after the ring when they do not fit
-    const uint32_t w1 = (uint32_t)(n1 + 8) >> 2, w2 = (uint32_t)(n2 + 8) >> 2;
+    // Stage both sequences as words: 2-bit codes (16 residues per word) when every residue is
+    // A/C/G/T -- always true for packing 1 -- else bytes (4 per word).  They stay in shared
+    // memory when they fit, else in a global scratch area behind the ring.
+    bool wide = false;
+    if (p.packing == 0) {
+      for (int32_t pos = lane; pos < n1; pos += 32) {
+        const uint32_t c = p.residues[o1 + pos];
+        wide |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+      }
+      for (int32_t pos = lane; pos < n2; pos += 32) {
+        const uint32_t c = p.residues[o2 + pos];
+        wide |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+      }
+      wide = __any_sync(0xffffffffu, wide);
+    }
+    const int per = wide ? 4 : 16;
+    const uint32_t w1 = (uint32_t)(n1 + 2 * per) / per, w2 = (uint32_t)(n2 + 2 * per) / per;
     uint32_t* s1w;
     uint32_t* s2w;
     if ((w1 + w2) * 4 <= p.smem_seq_bytes) {
@@ -108,21 +128,23 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       s2w = s1w + w1;
     }
     __syncwarp();
-    for (uint32_t k = lane; k < w1; k += 32) {
-      uint32_t v = 0;
-      for (int b = 0; b < 4; ++b) {
-        const int32_t pos = (int32_t)(k * 4 + b);
-        if (pos < n1) v |= load_residue(p.residues, o1 + pos, p.packing) << (8 * b);
+    for (int which = 0; which < 2; ++which) {
+      uint32_t* dst = which ? s2w : s1w;
+      const uint32_t nw = which ? w2 : w1;
+      const int32_t len = which ? n2 : n1;
+      const uint64_t off = which ? o2 : o1;
+      for (uint32_t k = lane; k < nw; k += 32) {
+        uint32_t v = 0;
+        for (int b = 0; b < per; ++b) {
+          const int32_t pos = (int32_t)(k * per + b);
+          if (pos < len) {
+            uint32_t c = load_residue(p.residues, off + pos, p.packing);
+            if (!wide && p.packing == 0) c = (c >> 1) & 3u;  // 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54 -> 0,1,3,2
+            v |= c << (wide ? 8 * b : 2 * b);
+          }
+        }
+        dst[k] = v;
       }
-      s1w[k] = v;
-    }
-    for (uint32_t k = lane; k < w2; k += 32) {
-      uint32_t v = 0;
-      for (int b = 0; b < 4; ++b) {
-        const int32_t pos = (int32_t)(k * 4 + b);
-        if (pos < n2) v |= load_residue(p.residues, o2 + pos, p.packing) << (8 * b);
-      }
-      s2w[k] = v;
     }
     __syncwarp();
     __threadfence_block();
@@ -137,7 +159,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     }
     __syncwarp();
     {
-      const int32_t v0 = wf_extend(s1w, s2w, 0, 0, n1, n2);
+      const int32_t v0 = wide ? wf_extend<8>(s1w, s2w, 0, 0, n1, n2) : wf_extend<2>(s1w, s2w, 0, 0, n1, n2);
       if (lane == 0) {
         ring[(0 * 3 + 0) * W + koff] = v0;
         ring[(0 * 3 + 1) * W + koff] = kWfNone;
@@ -149,7 +171,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     }
     __syncwarp();
     const int32_t max_s = 2 * p.o + p.e * (n1 + n2) + p.x + 8;
-    for (int32_t s = 1; result < 0 && s <= max_s; ++s) {
+    for (int32_t s = p.s_step; result < 0 && s <= max_s; s += p.s_step) {
       const int slot = s & (kWfRing - 1);
       const int sx = (s - p.x) & (kWfRing - 1), so = (s - p.o - p.e) & (kWfRing - 1),
                 se = (s - p.e) & (kWfRing - 1);
@@ -179,30 +201,41 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       const int32_t olo = ho ? lo_[so] : 1, ohi = ho ? hi_[so] : 0;
       const int32_t elo = he ? lo_[se] : 1, ehi = he ? hi_[se] : 0;
       bool found = false;
-      for (int32_t k = lo + lane; k <= hi; k += 32) {
-        int32_t iv = kWfNone, dv = kWfNone, mv = kWfNone;
-        {  // insertion: consumes a seq1 residue: (k-1) -> k, v + 1
-          int32_t a = (k - 1 >= olo && k - 1 <= ohi) ? Mo[k - 1] : kWfNone;
-          int32_t b = (k - 1 >= elo && k - 1 <= ehi) ? Ie[k - 1] : kWfNone;
-          const int32_t best = max(a, b);
+      // kUnroll diagonals per lane per trip: all source loads of the trip are issued before
+      // the first use, so one L2 round trip covers kUnroll cells instead of one
+      constexpr int kUnroll = 8;
+      for (int32_t k0 = lo + lane; k0 <= hi; k0 += 32 * kUnroll) {
+        int32_t am[kUnroll], bi[kUnroll], ap[kUnroll], bd[kUnroll], mx[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int32_t k = k0 + 32 * u;
+          am[u] = (k <= hi && k - 1 >= olo && k - 1 <= ohi) ? Mo[k - 1] : kWfNone;
+          bi[u] = (k <= hi && k - 1 >= elo && k - 1 <= ehi) ? Ie[k - 1] : kWfNone;
+          ap[u] = (k <= hi && k + 1 >= olo && k + 1 <= ohi) ? Mo[k + 1] : kWfNone;
+          bd[u] = (k <= hi && k + 1 >= elo && k + 1 <= ehi) ? De[k + 1] : kWfNone;
+          mx[u] = (k <= hi && k >= xlo && k <= xhi) ? Mx[k] : kWfNone;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int32_t k = k0 + 32 * u;
+          if (k > hi) break;
+          int32_t iv = kWfNone, dv, mv = kWfNone;
+          const int32_t best = max(am[u], bi[u]);  // insertion: consumes a seq1 residue: (k-1) -> k, v + 1
           if (best > kWfNone) iv = best + 1;
+          dv = max(ap[u], bd[u]);                  // deletion: consumes a seq2 residue: (k+1) -> k, v unchanged
+          if (mx[u] > kWfNone) mv = mx[u] + 1;
+          // cells outside the matrix do not exist
+          if (iv > kWfNone && (iv > n1 || iv - k > n2 || iv - k < 0)) iv = kWfNone;
+          if (dv > kWfNone && (dv > n1 || dv - k > n2 || dv < 0)) dv = kWfNone;
+          if (mv > kWfNone && (mv > n1 || mv - k > n2)) mv = kWfNone;
+          mv = max(mv, max(iv, dv));
+          if (mv > kWfNone)
+            mv = wide ? wf_extend<8>(s1w, s2w, mv, mv - k, n1, n2) : wf_extend<2>(s1w, s2w, mv, mv - k, n1, n2);
+          Mc[k] = mv;
+          Ic[k] = iv;
+          Dc[k] = dv;
+          if (k == kend && mv == n1) found = true;
         }
-        {  // deletion: consumes a seq2 residue: (k+1) -> k, v unchanged
-          int32_t a = (k + 1 >= olo && k + 1 <= ohi) ? Mo[k + 1] : kWfNone;
-          int32_t b = (k + 1 >= elo && k + 1 <= ehi) ? De[k + 1] : kWfNone;
-          dv = max(a, b);
-        }
-        if (k >= xlo && k <= xhi && Mx[k] > kWfNone) mv = Mx[k] + 1;
-        // cells outside the matrix do not exist
-        if (iv > kWfNone && (iv > n1 || iv - k > n2 || iv - k < 0)) iv = kWfNone;
-        if (dv > kWfNone && (dv > n1 || dv - k > n2 || dv < 0)) dv = kWfNone;
-        if (mv > kWfNone && (mv > n1 || mv - k > n2)) mv = kWfNone;
-        mv = max(mv, max(iv, dv));
-        if (mv > kWfNone) mv = wf_extend(s1w, s2w, mv, mv - k, n1, n2);
-        Mc[k] = mv;
-        Ic[k] = iv;
-        Dc[k] = dv;
-        if (k == kend && mv == n1) found = true;
       }
       if (lane == 0) { lo_[slot] = lo; hi_[slot] = hi; }
       __syncwarp();
