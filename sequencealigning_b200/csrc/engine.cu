@@ -266,6 +266,15 @@ struct Segment {
   uint32_t n = 0;
   uint32_t n1max = 0, n2max = 0;
   std::vector<uint32_t> order;  // launch index -> pair id, sorted by shape; empty = identity
+  // A ragged (hence sorted) segment is launched as a few shape classes, each with its own
+  // lane-group width, tile size and traceback stride; a uniform segment is one class.
+  struct Sub {
+    uint32_t off = 0, cnt = 0;  // range of launch indices
+    Geometry g;
+    uint64_t tb_off = 0;        // uint2 offset of the class's first tile in the slot's scratch
+  };
+  std::vector<Sub> subs;
+  uint64_t tb_total = 0;        // uint2 for the whole segment
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
   Geometry g;
 };
@@ -412,6 +421,46 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         }
       }
     }
+    {
+      sg.subs.clear();
+      auto add_class = [&](uint32_t off, uint32_t cnt, uint32_t cmax, uint32_t rmax) -> sa_status_t {
+        Segment::Sub sub;
+        sub.off = off;
+        sub.cnt = cnt;
+        const int Gc = choose_g(e, cmax, rmax);
+        if (!Gc) return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u needs more shared memory than one SM has", cmax, rmax);
+        sub.g = make_geometry(Gc, cmax, rmax);
+        sub.tb_off = sg.tb_total;
+        sg.tb_total += (uint64_t)((cnt + sub.g.ppt - 1) / sub.g.ppt) * sub.g.tile_stride;
+        sg.subs.push_back(sub);
+        return SA_OK;
+      };
+      if (sg.order.empty()) {
+        sa_status_t rr = add_class(0, cn, sg.n1max, sg.n2max);
+        if (rr != SA_OK) return rr;
+      } else {
+        // sorted by rows, then columns: cut where either dimension has grown by more than a
+        // quarter since the class began (at most 8 classes, at least 2048 pairs each)
+        uint32_t start = 0, c_lo = ~0u, r_lo = ~0u, c_hi = 0, r_hi = 0;
+        for (uint32_t i = 0; i < cn; ++i) {
+          const uint32_t id = sg.order[i];
+          const uint32_t c = h_cols[id], r = h_rows[id];
+          const bool grow = i - start >= 2048 && sg.subs.size() < 7 &&
+                            ((uint64_t)std::max(r_hi, r) * 4 > (uint64_t)std::max(r_lo, 16u) * 5 + 32);
+          if (grow) {
+            sa_status_t rr = add_class(start, i - start, c_hi, r_hi);
+            if (rr != SA_OK) return rr;
+            start = i;
+            c_lo = r_lo = ~0u;
+            c_hi = r_hi = 0;
+          }
+          c_lo = std::min(c_lo, c); r_lo = std::min(r_lo, r);
+          c_hi = std::max(c_hi, c); r_hi = std::max(r_hi, r);
+        }
+        sa_status_t rr = add_class(start, cn - start, c_hi, r_hi);
+        if (rr != SA_OK) return rr;
+      }
+    }
     if (in) {
       for (uint32_t i = 0; i < cn; ++i) {
         const uint64_t p = base + i;
@@ -485,16 +534,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   // Stage A of a segment: fill with the panic bonus on, classify + count walk, queue length.
   auto stage_a = [&](const Segment& sg, int k) -> sa_status_t {
     sa_engine::Slot& sl = e->slot[k];
-    const Geometry& g = sg.g;
     const uint32_t cn = sg.n;
-    const size_t tile_bytes = (size_t)g.tile_stride * 8;
-    const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
     sa_status_t r;
-    if ((r = ensure(e, sl.tb, (size_t)ctiles * tile_bytes)) != SA_OK) return r;
-    if ((r = ensure(e, sl.end, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
-    if ((r = ensure(e, sl.rerun_ids, (size_t)ctiles * g.ppt * 4)) != SA_OK) return r;
+    if ((r = ensure(e, sl.tb, (size_t)sg.tb_total * 8)) != SA_OK) return r;
+    if ((r = ensure(e, sl.end, (size_t)cn * 4 + 256)) != SA_OK) return r;
+    if ((r = ensure(e, sl.rerun_ids, (size_t)cn * 4 + 256)) != SA_OK) return r;
     if (want_cigar && (r = ensure(e, sl.tmp_runs, (size_t)cn * sa::kTmpRuns * 4)) != SA_OK) return r;
-    set_geometry(g);
     cudaStream_t sx = sl.stream;
     CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_bdone, 0));  // the slot's previous user is done
     if (in) CUDA_TRY(e, cudaStreamWaitEvent(sx, e->ev_in, 0));
@@ -505,33 +550,39 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), (size_t)cn * 4, cudaMemcpyHostToDevice, sx));
       d_order = (const uint32_t*)sl.order.p;
     }
-    fp.pair_ids = d_order;
-    fp.pair_base = (uint32_t)sg.base;
-    fp.n_launch_pairs = cn;
-    fp.tb = (uint2*)sl.tb.p;
-    fp.end = (uint32_t*)sl.end.p;
-    fp.row0 = pack2(row0_clean + (linear ? 0u : 1u));  // affine: panic bonus on
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
-    if ((r = launch_fill_g(e, fp, g, ctiles, sx, s2.algo)) != SA_OK) return r;
+    for (const Segment::Sub& sub : sg.subs) {
+      set_geometry(sub.g);
+      fp.pair_ids = d_order ? d_order + sub.off : nullptr;
+      fp.pair_base = (uint32_t)sg.base + sub.off;
+      fp.n_launch_pairs = sub.cnt;
+      fp.tb = (uint2*)sl.tb.p + sub.tb_off;
+      fp.end = (uint32_t*)sl.end.p + sub.off;
+      fp.row0 = pack2(row0_clean + (linear ? 0u : 1u));  // affine: panic bonus on
+      if ((r = launch_fill_g(e, fp, sub.g, (sub.cnt + sub.g.ppt - 1) / sub.g.ppt, sx, s2.algo)) != SA_OK) return r;
+    }
     CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sx));
-    wp.pair_ids = d_order;
-    wp.pair_base = (uint32_t)sg.base;
-    wp.n_launch_pairs = cn;
-    wp.n_launch_dev = nullptr;
-    wp.tb = (const uint2*)sl.tb.p;
-    wp.end = (const uint32_t*)sl.end.p;
-    wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
-    wp.rerun_count = d_counts + k;
-    wp.phase = 0;
-    wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
-    wp.tmp_base = (uint32_t)sg.base;
-    if (linear)
-      sa::nw_linear_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
-    else
-      sa::nw_affine_walk<0><<<(cn + 127) / 128, 128, 0, sx>>>(wp);
-    CUDA_TRY(e, cudaGetLastError());
-    e->timing.kernel_launches++;
+    for (const Segment::Sub& sub : sg.subs) {
+      set_geometry(sub.g);
+      wp.pair_ids = d_order ? d_order + sub.off : nullptr;
+      wp.pair_base = (uint32_t)sg.base + sub.off;
+      wp.n_launch_pairs = sub.cnt;
+      wp.n_launch_dev = nullptr;
+      wp.tb = (const uint2*)sl.tb.p + sub.tb_off;
+      wp.end = (const uint32_t*)sl.end.p + sub.off;
+      wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
+      wp.rerun_count = d_counts + k;
+      wp.phase = 0;
+      wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
+      wp.tmp_base = (uint32_t)sg.base;
+      if (linear)
+        sa::nw_linear_walk<0><<<(sub.cnt + 127) / 128, 128, 0, sx>>>(wp);
+      else
+        sa::nw_affine_walk<0><<<(sub.cnt + 127) / 128, 128, 0, sx>>>(wp);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+    }
     CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));
     return SA_OK;
@@ -613,18 +664,22 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
       wp.tmp_runs = nullptr;
-      wp.pair_ids = sg.order.empty() ? nullptr : (const uint32_t*)sl.order.p;
-      wp.pair_base = (uint32_t)sg.base;
-      wp.n_launch_pairs = cn;
-      wp.tb = (const uint2*)sl.tb.p;
-      wp.end = (const uint32_t*)sl.end.p;
-      wp.phase = 0;
-      if (linear)
-        sa::nw_linear_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
-      else
-        sa::nw_affine_walk<1><<<(cn + 127) / 128, 128, 0, e->stream>>>(wp);
-      CUDA_TRY(e, cudaGetLastError());
-      e->timing.kernel_launches++;
+      for (const Segment::Sub& sub : sg.subs) {
+        set_geometry(sub.g);
+        wp.pair_ids = sg.order.empty() ? nullptr : (const uint32_t*)sl.order.p + sub.off;
+        wp.pair_base = (uint32_t)sg.base + sub.off;
+        wp.n_launch_pairs = sub.cnt;
+        wp.tb = (const uint2*)sl.tb.p + sub.tb_off;
+        wp.end = (const uint32_t*)sl.end.p + sub.off;
+        wp.phase = 0;
+        if (linear)
+          sa::nw_linear_walk<1><<<(sub.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
+        else
+          sa::nw_affine_walk<1><<<(sub.cnt + 127) / 128, 128, 0, e->stream>>>(wp);
+        CUDA_TRY(e, cudaGetLastError());
+        e->timing.kernel_launches++;
+      }
+      set_geometry(g);
       for (const ReLaunch& rl : re_launches) {
         if ((r = refill(rl, re_launches.size() > 1)) != SA_OK) return r;
         sa::nw_affine_walk<1><<<(rl.cnt + 127) / 128, 128, 0, e->stream>>>(wp);

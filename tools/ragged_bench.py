@@ -17,9 +17,12 @@ b = PairBatch(res, qo, ql, do, dl)
 for mode in ("2", "0"):
     os.environ["SA_SORT"] = mode
     with Engine(0) as eng:
-        eng.align(b); eng.align(b)
+        rb = eng.upload(b)
+        rb.align(); rb.align()
         t0 = time.perf_counter()
-        for _ in range(3):
-            r = eng.align(b)
-        dt = (time.perf_counter() - t0) / 3
+        for _ in range(5):
+            rb.align()
+        eng.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+        rb.free()
     print("SA_SORT", mode, "ms", round(dt * 1e3, 2), "GCUPS", round(b.cells / dt / 1e9, 1))
