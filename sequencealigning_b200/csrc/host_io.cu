@@ -116,14 +116,28 @@ sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t 
 #undef X
   };
   if (n && (!src || !dst)) return SA_E_ARG;
-  for (uint64_t k = 0; k < n; ++k) {
-    const int c = code[src[k]];
-    if (c < 0) return SA_E_ARG;
-    const uint64_t pos = dst_pos + k;
+  uint64_t k = 0;
+  auto put_one = [&](uint64_t i) -> bool {
+    const int c = code[src[i]];
+    if (c < 0) return false;
+    const uint64_t pos = dst_pos + i;
     uint8_t& b = dst[pos >> 2];
     const int sh = 2 * (int)(pos & 3);
     b = (uint8_t)((b & ~(3 << sh)) | (c << sh));
+    return true;
+  };
+  // head: up to the next output byte boundary
+  for (; k < n && ((dst_pos + k) & 3); ++k)
+    if (!put_one(k)) return SA_E_ARG;
+  // body: four residues -> one byte
+  uint8_t* out = dst + ((dst_pos + k) >> 2);
+  for (; k + 4 <= n; k += 4) {
+    const int c0 = code[src[k]], c1 = code[src[k + 1]], c2 = code[src[k + 2]], c3 = code[src[k + 3]];
+    if ((c0 | c1 | c2 | c3) < 0) return SA_E_ARG;
+    *out++ = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
   }
+  for (; k < n; ++k)
+    if (!put_one(k)) return SA_E_ARG;
   return SA_OK;
 }
 

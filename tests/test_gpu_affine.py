@@ -134,6 +134,31 @@ def test_two_bit_packed_input_gives_identical_results(engine, oracle):
     assert np.array_equal(r2.cigar, engine.align(b).cigar)
 
 
+def test_maximum_packed_size_and_range_extremes(engine, oracle):
+    """Pairs at the edge of the 16-bit packed range (n1pad + n2 ~ 3.6 k), including the most
+    negative scores the range bound has to cover (nothing matches) and the most positive."""
+    import random
+    from sequencealigning_b200 import ALGO_NW_LINEAR, EngineError
+    rng = random.Random(9)
+    q = bytes(rng.choice(b"ACGT") for _ in range(1740))
+    d = bytearray(q)
+    for _ in range(80):
+        d[rng.randrange(len(d))] = rng.choice(b"ACGT")
+    del d[500:520]
+    pairs = [(q, bytes(d)), (b"A" * 1700, b"C" * 1760), (b"A" * 1760, b"A" * 1760), (b"ACGT" * 430, b"TGCA" * 440),
+             (b"A" * 1750, b"C" * 3), (b"G" * 5, b"T" * 1700)]
+    b = _batch(pairs)
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, what="max size")
+    rl = engine.align(b, algo=ALGO_NW_LINEAR)
+    ref = oracle.linear_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=3600, n_threads=6)
+    assert np.array_equal(ref.score, rl.score) and np.array_equal(ref.cigar_len, rl.cigar_len)
+    # one residue beyond the range: a clean per-call error, not a wrong answer
+    with pytest.raises(EngineError) as ei:
+        engine.align(_batch([(b"A" * 2000, b"C" * 2000)]))
+    assert ei.value.code == -5
+
+
 def test_score_only_and_capacity(engine, oracle):
     from sequencealigning_b200 import EngineError
     b = _batch(random_pair_list(5, 500, 20, 80))
