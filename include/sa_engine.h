@@ -168,6 +168,15 @@ sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint6
 int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t* index,
                        size_t index_cap, uint8_t* err_chars, size_t err_cap, size_t* n_err);
 
+/* EVERY co-optimal alignment of one pair, in the reference's order and text: the LIFO DFS of
+ * needleman_wunsch_affine.rs:246-329 over the per-cell parent lists (:96-153), which the device
+ * computes (7 bits per cell); "alignment found\n\nseq1: ..\n      ..\nseq2: ..\n" per path.
+ * Stops after max_alignments, or where the reference panics (*panicked = 1; the text so far is
+ * what the reference had printed).  snprintf-style: returns the bytes needed, < 0 on error. */
+int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2,
+                                 uint32_t n2, const sa_scheme_t* scheme, uint64_t max_alignments,
+                                 char* buf, size_t cap, uint64_t* n_printed, int32_t* panicked);
+
 /* Packer for packing = 1: appends n residues (A/C/G/T) to dst starting at residue index dst_pos.
  * SA_E_ARG at the first other byte.  Pure host code. */
 sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_pos);

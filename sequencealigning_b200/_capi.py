@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "sa_abi_version", "sa_engine_create", "sa_engine_destroy", "sa_last_error", "sa_align_batch",
     "sa_batch_upload", "sa_batch_free", "sa_align_resident", "sa_resident_download",
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
-    "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit",
+    "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
 ]
 
 
@@ -103,5 +103,8 @@ def lib() -> C.CDLL:
     l.sa_render_affine.restype = C.c_int64
     l.sa_pack_2bit.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     l.sa_pack_2bit.restype = C.c_int
+    l.sa_affine_all_alignments.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(Scheme), C.c_uint64,
+                                           C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    l.sa_affine_all_alignments.restype = C.c_int64
     _lib = l
     return l

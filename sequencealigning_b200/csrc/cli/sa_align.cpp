@@ -73,6 +73,7 @@ static void usage() {
           "  -a, --algo <ALGO>              algo [default: needleman-wunsch] [possible values: a-star, needleman-wunsch,\n"
           "                                 needleman-wunsch-linear, wfa, wfa-standard]\n"
           "      --strict                   exit 101 where the reference would panic\n"
+          "      --all                      needleman-wunsch: print EVERY co-optimal alignment, like the reference\n"
           "      --device <N>               CUDA device [default: 0]\n"
           "  -h, --help                     Print help\n  -V, --version                  Print version\n");
 }
@@ -89,7 +90,7 @@ static std::string duration_debug(double seconds) {
 
 int main(int argc, char** argv) {
   std::string qpath, dpath, mode = "global", algo = "needleman-wunsch";
-  bool verbose = false, strict = false;
+  bool verbose = false, strict = false, all = false;
   int device = 0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -110,6 +111,7 @@ int main(int argc, char** argv) {
     else if (const char* v = val("--device", "--device")) device = atoi(v);
     else if (a == "-v" || a == "--verbose") verbose = true;
     else if (a == "--strict") strict = true;
+    else if (a == "--all") all = true;
     else if (a == "-h" || a == "--help") { usage(); return 0; }
     else if (a == "-V" || a == "--version") { printf("sa_align 0.1.0 (ABI %d)\n", sa_abi_version()); return 0; }
     else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
@@ -192,6 +194,28 @@ int main(int argc, char** argv) {
       if (al == SA_ALGO_NW_LINEAR)  // needleman_wunsch.rs:196-200
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
       const bool has_alignment = clen[p] > 0 || (Q.seq.empty() && D.seq.empty());
+      if (all && al == SA_ALGO_NW_AFFINE) {
+        // the reference's full output for the pair: every co-optimal alignment in DFS order,
+        // up to the point where it would panic
+        uint64_t n_printed = 0;
+        int32_t panicked = 0;
+        const int64_t need = sa_affine_all_alignments(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(),
+                                                      (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(), nullptr,
+                                                      ~0ull, nullptr, 0, &n_printed, &panicked);
+        if (need < 0) { fprintf(stderr, "sa_affine_all_alignments: %s\n", sa_last_error(eng)); exit_code = 1; break; }
+        std::string text((size_t)need + 1, '\0');
+        sa_affine_all_alignments(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                 (uint32_t)D.seq.size(), nullptr, ~0ull, &text[0], text.size(), &n_printed, &panicked);
+        text.resize((size_t)need);
+        fputs(text.c_str(), stdout);
+        if (panicked) {
+          fprintf(stderr, "%s vs %s: the reference panics here (index out of bounds, needleman_wunsch_affine.rs:299/303) after %llu alignment(s)\n",
+                  Q.name.c_str(), D.name.c_str(), (unsigned long long)n_printed);
+          if (strict) { exit_code = 101; break; }
+        }
+        printf("%s\n", duration_debug(per_pair).c_str());
+        continue;
+      }
       if (has_alignment) {
         const int64_t need = sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
                                               (uint32_t)D.seq.size(), pool.data() + coff[p], clen[p], nullptr, 0);

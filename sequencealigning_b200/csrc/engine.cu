@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,7 @@
 #include "nw_affine_s16.cuh"
 #include "nw_walk.cuh"
 #include "wfa.cuh"
+#include "nw_parents.cuh"
 
 namespace {
 
@@ -79,7 +81,7 @@ struct sa_engine {
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
   } slot[2];
   // scratch (grow-only)
-  DevBuf tb2, end2, misc, block_sums, wfa_scratch;
+  DevBuf tb2, end2, misc, block_sums, wfa_scratch, par_bytes, par_rows, par_in;
   // staging for sa_align_batch (grow-only)
   DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry;
   uint32_t* h_count = nullptr;  // pinned
@@ -971,7 +973,7 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&e->slot[0].order, &e->slot[1].order, &e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
-                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch,
+                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch, &e->par_bytes, &e->par_rows, &e->par_in,
                       &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
                       &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})
       if (b->p) cudaFree(b->p);
@@ -1284,6 +1286,145 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   cudaGetLastError();
   e->timing.total_ms = e->timing.fill_ms;
   return rc;
+}
+
+// Every co-optimal alignment of one pair, in the order and text of the reference's traceback
+// (needleman_wunsch_affine.rs:246-329, Display :390-411): the device computes the parent sets,
+// the host walks them with the reference's LIFO stack.  snprintf-style return (bytes needed).
+int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2,
+                                 uint32_t n2, const sa_scheme_t* scheme, uint64_t max_alignments,
+                                 char* buf, size_t cap, uint64_t* n_printed, int32_t* panicked) {
+  if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
+  if (n_printed) *n_printed = 0;
+  if (panicked) *panicked = 0;
+  sa_scheme_t sc{5, -4, -8, -6};
+  if (scheme) sc = *scheme;
+  if (cudaSetDevice(e->device) != cudaSuccess) return fail(e, SA_E_CUDA, "cudaSetDevice failed");
+  const uint64_t cells = (uint64_t)n1 * n2;
+  if (cells > ((uint64_t)1 << 32)) return fail(e, SA_E_UNSUPPORTED, "pair too large for full parent sets");
+  sa_status_t st;
+  if ((st = ensure(e, e->par_bytes, cells + 16)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_rows, (size_t)6 * (n1 + 1) * 4 + 64)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_in, (size_t)n1 + n2 + 256)) != SA_OK) return st;
+  // layout of par_in: [meta 128 B][seq1][seq2]
+  struct Meta {
+    uint64_t q_off, d_off, par_off;
+    uint32_t q_len, d_len;
+    int32_t end[3];
+  } meta{0, n1, 0, n1, n2, {0, 0, 0}};
+  uint8_t* d_in = (uint8_t*)e->par_in.p;
+  cudaError_t err = cudaMemcpyAsync(d_in, &meta, sizeof(meta), cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && n1) err = cudaMemcpyAsync(d_in + 128, seq1, n1, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && n2) err = cudaMemcpyAsync(d_in + 128 + n1, seq2, n2, cudaMemcpyHostToDevice, e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D failed: %s", cudaGetErrorString(err));
+  sa::ParentsParams pp{};
+  pp.residues = d_in + 128;
+  pp.q_off = (const uint64_t*)(d_in + offsetof(Meta, q_off));
+  pp.d_off = (const uint64_t*)(d_in + offsetof(Meta, d_off));
+  pp.q_len = (const uint32_t*)(d_in + offsetof(Meta, q_len));
+  pp.d_len = (const uint32_t*)(d_in + offsetof(Meta, d_len));
+  pp.parents_off = (const uint64_t*)(d_in + offsetof(Meta, par_off));
+  pp.end_scores = (int32_t*)(d_in + offsetof(Meta, end));
+  pp.n_pairs = 1;
+  pp.packing = 0;
+  pp.match = sc.match;
+  pp.mismatch = sc.mismatch;
+  pp.open = sc.gap_open;
+  pp.ext = sc.gap_ext;
+  pp.parents = (uint8_t*)e->par_bytes.p;
+  pp.rows = (int32_t*)e->par_rows.p;
+  pp.row_stride = n1 + 1;
+  sa::nw_affine_parents_kernel<<<1, 64, 0, e->stream>>>(pp);
+  if ((err = cudaGetLastError()) != cudaSuccess) return fail(e, SA_E_CUDA, "launch failed: %s", cudaGetErrorString(err));
+  std::vector<uint8_t> par(cells);
+  int32_t end[3] = {0, 0, 0};
+  if (cells) err = cudaMemcpyAsync(par.data(), e->par_bytes.p, cells, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(end, d_in + offsetof(Meta, end), 12, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "parents kernel failed: %s", cudaGetErrorString(err));
+
+  // ---- the reference's traceback loop over the device-computed parent lists -------------------
+  enum { ST_M = 0, ST_D = 1, ST_I = 2 };
+  struct Col {
+    uint8_t c1, c2;
+    int64_t next;
+  };
+  struct Frame {
+    int st;
+    uint32_t x, y;
+    int64_t cols;
+  };
+  std::vector<Col> cols;
+  std::vector<Frame> stack;
+  std::string text;
+  const int32_t em = end[0], ei = end[1], ed = end[2];
+  const int32_t mx = std::max(std::max(ei, ed), em);  // :247-250
+  if (mx == ei) stack.push_back({ST_I, n2, n1, -1});  // push order I, M, D (:251-280)
+  if (mx == em) stack.push_back({ST_M, n2, n1, -1});
+  if (mx == ed) stack.push_back({ST_D, n2, n1, -1});
+  uint64_t printed = 0;
+  bool pan = false;
+  while (!stack.empty() && !pan) {
+    const Frame f = stack.back();
+    stack.pop_back();
+    if (f.x == 0 && f.y == 0) {  // :283-286
+      if (printed >= max_alignments) break;
+      std::string r1, r2;
+      for (int64_t k = f.cols; k >= 0; k = cols[k].next) {
+        r1.push_back((char)cols[k].c1);
+        r2.push_back((char)cols[k].c2);
+      }
+      std::string bars(r1.size(), ' ');
+      for (size_t k = 0; k < r1.size(); ++k)
+        if (r1[k] == r2[k]) bars[k] = '|';
+      text += "alignment found\n\nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\n";
+      ++printed;
+    }
+    // the popped cell's parent list, in push order
+    int pst[3], np = 0;
+    if (f.x >= 1 && f.y >= 1) {
+      const uint8_t b = par[(uint64_t)(f.x - 1) * n1 + (f.y - 1)];
+      if (f.st == ST_M) {
+        if (b & 1) pst[np++] = ST_M;
+        if (b & 2) pst[np++] = ST_I;
+        if (b & 4) pst[np++] = ST_D;
+      } else if (f.st == ST_I) {
+        if (b & 8) pst[np++] = ST_I;
+        if (b & 16) pst[np++] = ST_M;
+      } else {
+        if (b & 32) pst[np++] = ST_D;
+        if (b & 64) pst[np++] = ST_M;
+      }
+    } else if (f.x == 0 && f.y >= 1 && f.st == ST_D) {
+      pst[np++] = ST_D;  // boundary chain, parent d_scores[0][y-1] (:194-198)
+    } else if (f.y == 0 && f.x >= 1 && f.st == ST_I) {
+      pst[np++] = ST_I;  // parent i_scores[x-1][0] (:206-210)
+    }
+    for (int k = 0; k < np; ++k) {
+      // the loop body indexes seq1[y-1] (InM, InI) and seq2[x-1] (InM, InD): panic on 0-1
+      const bool bad = f.st == ST_M ? (f.x == 0 || f.y == 0) : (f.st == ST_D ? f.x == 0 : f.y == 0);
+      if (bad) {
+        pan = true;
+        break;
+      }
+      Col c;
+      c.next = f.cols;
+      uint32_t x = f.x, y = f.y;
+      if (f.st == ST_M) { c.c1 = seq1[y - 1]; c.c2 = seq2[x - 1]; --x; --y; }
+      else if (f.st == ST_D) { c.c1 = '-'; c.c2 = seq2[x - 1]; --x; }
+      else { c.c1 = seq1[y - 1]; c.c2 = '-'; --y; }
+      cols.push_back(c);
+      stack.push_back({pst[k], x, y, (int64_t)cols.size() - 1});
+    }
+  }
+  if (n_printed) *n_printed = printed;
+  if (panicked) *panicked = pan ? 1 : 0;
+  if (buf && cap) {
+    const size_t n = text.size() < cap - 1 ? text.size() : cap - 1;
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)text.size();
 }
 
 sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint64_t n_pairs,

@@ -280,6 +280,19 @@ class Engine:
         score, status, off, ln, pool = arrs
         return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)] if cap else pool)
 
+    def all_alignments(self, seq1: bytes, seq2: bytes, scheme=None, max_alignments: int = 1 << 20):
+        """Every co-optimal alignment of one pair as the reference prints them.
+        Returns (text, n_printed, panicked)."""
+        sc = _scheme(scheme)
+        n = C.c_uint64()
+        pan = C.c_int32()
+        args = (self._h, seq1, len(seq1), seq2, len(seq2), C.byref(sc) if sc else None, max_alignments)
+        need = self._lib.sa_affine_all_alignments(*args, None, 0, C.byref(n), C.byref(pan))
+        self._check(need)
+        buf = C.create_string_buffer(need + 1)
+        self._check(self._lib.sa_affine_all_alignments(*args, buf, need + 1, C.byref(n), C.byref(pan)))
+        return buf.value.decode("latin1"), n.value, bool(pan.value)
+
     # ---- device-resident path (benchmarks: inputs already in HBM) -------------------------
     def upload(self, batch: PairBatch) -> "ResidentBatch":
         h = C.c_void_p()

@@ -57,6 +57,11 @@ def test_affine_stdout_matches_reference_text(cli, tmp_path, oracle):
     assert out == exp
     assert r.stderr.count("the reference panics here") == n_panic and n_panic >= 1
     assert r.stdout.count("\n") - out.count("\n") == len(db) * len(query)  # one Duration line per pair
+    # --all: every co-optimal alignment, i.e. the reference's complete stdout for the pair
+    r4 = subprocess.run([cli, "-q", q, "-d", d, "--all"], capture_output=True, text=True)
+    out4 = re.sub(r"^[0-9.]+(ns|µs|ms|s)\n", "", r4.stdout, flags=re.M)
+    exp4 = "".join(oracle.affine_print_all(qs, ds)[0] for dn, ds in db for qn, qs in query)
+    assert out4 == exp4 and out4.count("alignment found") > out.count("alignment found")
     # --strict: stop with exit status 101 at the first pair the reference dies on
     r2 = subprocess.run([cli, "-q", q, "-d", d, "--strict"], capture_output=True, text=True)
     assert r2.returncode == 101

@@ -210,3 +210,33 @@ def test_render_matches_reference_text(engine, oracle):
         r = engine.align(b)
         text, n, pan = oracle.affine_print_all(q, d, max_alignments=1)
         assert render_affine(q, d, r.cigar_of(0)) == text
+
+
+def test_all_cooptimal_alignments_match_reference_order(engine, oracle):
+    """every co-optimal alignment, in the reference's LIFO-DFS print order, and the
+    point where the reference panics (device-computed parent sets, host traversal)."""
+    import json, os, random
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "affine_golden.json")))["vectors"]
+    late = 0
+    for v in vec:
+        q, d = v["seq1"].encode(), v["seq2"].encode()
+        text, n, pan = engine.all_alignments(q, d)
+        exp_text, exp_n, exp_pan = oracle.affine_print_all(q, d)
+        assert (text, n, pan) == (exp_text, exp_n, exp_pan), v
+        assert n == v["n_printed"] and pan == v["panicked"]
+        late += pan and n > 0
+    assert late >= 4
+    rng = random.Random(12)
+    for _ in range(60):
+        q = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(20, 90)))
+        d = bytes((c if rng.random() > 0.1 else rng.choice(b"ACGT")) for c in q)
+        cut = rng.randrange(len(d))
+        d = d[:cut] + d[cut + rng.randint(0, 2):]
+        assert engine.all_alignments(q, d, max_alignments=500) == oracle.affine_print_all(q, d, max_alignments=500)
+    # custom scheme
+    assert engine.all_alignments(b"ACGTT", b"ACGT", scheme=(2, -3, -5, -2)) == oracle.affine_print_all(b"ACGTT", b"ACGT", (2, -3, -5, -2))
+    # the first printed alignment is the batched path's CIGAR
+    from sequencealigning_b200 import PairBatch, render_affine
+    q, d = b"AAAA", b"AAA"
+    r = engine.align(PairBatch.from_pairs([(q, d)]))
+    assert engine.all_alignments(q, d)[0].startswith(render_affine(q, d, r.cigar_of(0)))
