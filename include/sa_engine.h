@@ -61,6 +61,9 @@ typedef enum {
                                 alignment empty                                               */
   SA_REF_NO_OUTPUT = 5,      /* completes but prints no alignment (only possible once the
                                 finite -32768 sentinel leaks, n1+n2 >~ 5.4k)                  */
+  SA_ALIGNMENT_OMITTED = 0x80, /* flag ORed into a per-pair status: the pair went through the long-pair
+                                  kernel and its traceback matrix did not fit the scratch budget;
+                                  score and status are exact, cigar_len is 0                      */
   SA_E_CUDA = -1,            /* CUDA failure (sa_last_error has the string)                   */
   SA_E_ARG = -2,             /* bad argument                                                  */
   SA_E_NOMEM = -3,           /* host or device allocation failed                              */

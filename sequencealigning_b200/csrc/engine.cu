@@ -29,6 +29,7 @@
 #include "nw_walk.cuh"
 #include "wfa.cuh"
 #include "nw_parents.cuh"
+#include "nw_general.cuh"
 
 namespace {
 
@@ -65,6 +66,15 @@ struct sa_resident {
   uint64_t used = 0;  // CIGAR words of the last alignment
   bool aligned = false;
   bool want_cigar = false;
+  // segment plan of the last alignment (shapes do not change while the batch is resident):
+  // opaque here, owned through the deleter
+  void* plan = nullptr;
+  void (*plan_free)(void*) = nullptr;
+  uint64_t plan_key = 0;
+  size_t plan_budget = 0;
+  ~sa_resident() {
+    if (plan && plan_free) plan_free(plan);
+  }
 };
 
 struct sa_engine {
@@ -76,6 +86,7 @@ struct sa_engine {
   // the host reads segment i's refill count), so per-segment scratch is double-buffered.
   struct Slot {
     DevBuf tb, end, rerun_ids, tmp_runs, order;
+    DevBuf g_ids, g_meta, g_tb, g_rows, g_info, g_runs;  // long pairs (nw_general.cuh)
     cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
                                     // the next fill overlaps the tail of the previous one
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
@@ -277,16 +288,26 @@ struct Segment {
   };
   std::vector<Sub> subs;
   uint64_t tb_total = 0;        // uint2 for the whole segment
+  uint32_t n_short = 0;         // pairs handled by the packed kernel (= order.size() if explicit)
+  // pairs outside the packed 16-bit range go to the general 32-bit kernel (nw_general.cuh)
+  std::vector<uint32_t> long_ids;
+  std::vector<uint64_t> long_meta;  // per long pair: tb offset (uint16 units, ~0 = none), runs end
+  uint64_t long_tb_total = 0, long_runs_total = 0;
+  uint32_t long_n1max = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
   Geometry g;
 };
 
 // The whole affine path over device views.  `in`/`out` non-null: stream inputs from / results
 // to host buffers segment by segment; null: everything is already resident / stays resident.
+struct Plan {
+  std::vector<Segment> segs;
+};
+
 sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h_q_len,
                        const uint32_t* h_d_len, const Scheme2& s2, bool want_cigar,
                        const sa_batch_t* in, sa_result_t* out, uint64_t* used_out,
-                       uint64_t* pool_sent_out) {
+                       uint64_t* pool_sent_out, Plan* plan = nullptr, bool plan_valid = false) {
   const sa_scheme_t& sc = s2.sc;
   sa_status_t st;
   *used_out = 0;
@@ -364,73 +385,140 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
 
   Coverage cov;
   // Scans the next segment on the host: extent, shape maxima, residue ranges, geometry.
-  auto prepare = [&](uint64_t base, Segment& sg) -> sa_status_t {
+  auto fits_packed = [&](uint32_t cols, uint32_t rows, int G) {
+    const uint32_t n1pad = std::max(1u, ((cols + kK * G - 1) / (kK * G)) * (kK * G));
+    return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows) + 64 <= sa::kBias;
+  };
+  // lane-group width for a class: choose_g among the widths whose padded shape stays in range
+  auto pick_g = [&](uint32_t cols, uint32_t rows) -> int {
+    const int G = choose_g(e, cols, rows);
+    if (G && fits_packed(cols, rows, G)) return G;
+    for (int g : {1, 2, 4, 8, 16, 32}) {
+      const Geometry gg = make_geometry(g, cols, rows);
+      if (gg.smem_bytes <= e->smem_optin && fits_packed(cols, rows, g)) return g;
+    }
+    return 0;
+  };
+  // cheap per-pair test: no lane-group width keeps the pair inside the packed range and inside
+  // one SM's shared memory (same arithmetic as make_geometry / s16_min_value_bound, no structs)
+  const uint32_t bound0 = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, 0, 0) + 64;
+  const uint32_t per_step = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, 1, 0) + 64 - bound0;
+  const uint64_t max_sum = per_step ? (sa::kBias - std::min<uint32_t>(bound0, sa::kBias)) / per_step : 0;
+  auto is_long = [&](uint32_t cols, uint32_t rows) -> bool {
+    // fast path: with G = 32 (least shared memory, at most 255 columns of padding) the pair fits
+    if ((uint64_t)cols + rows + 256 <= max_sum && (uint64_t)rows * 10 + ((uint64_t)cols + 256) * 2 + 64 <= e->smem_optin)
+      return false;
+    if (!cols || !rows) return false;
+    for (uint32_t g = 1; g <= 32; g <<= 1) {
+      const uint64_t n1pad = ((uint64_t)cols + kK * g - 1) / (kK * g) * (kK * g);
+      const uint64_t ng = 32 / g;
+      const uint64_t smem = (((uint64_t)rows * ng * 8 + ((uint64_t)rows * ng + n1pad * ng) * 2) + 15) & ~(uint64_t)15;
+      if (smem <= e->smem_optin && bound0 + per_step * (n1pad + rows) <= sa::kBias) return false;
+    }
+    return true;
+  };
+  auto prepare_fresh = [&](uint64_t base, Segment& sg) -> sa_status_t {
     sg = Segment{};
     sg.base = base;
     uint32_t cn = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(seg_target, 1u << 24), n - base);
     // streaming from the host: ramp the segment size up so the first copy-in is short
     if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
+    // shape maxima over the pairs the packed kernel can take; the others are "long"
+    uint32_t n_long = 0;
     for (uint32_t i = 0; i < cn; ++i) {
       const uint32_t a = h_cols[base + i], b = h_rows[base + i];
+      if (is_long(a, b)) {
+        ++n_long;
+        continue;
+      }
       sg.n1max = std::max(sg.n1max, a);
       sg.n2max = std::max(sg.n2max, b);
     }
-    const int G = choose_g(e, sg.n1max, sg.n2max);
-    if (!G)
-      return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u needs more shared memory than one SM has",
-                  sg.n1max, sg.n2max);
+    if (n_long && linear)
+      return fail(e, SA_E_UNSUPPORTED, "linear NW: a pair exceeds the 16-bit packed range (no long-pair kernel for this aligner yet)");
+    int G = pick_g(sg.n1max, sg.n2max);
+    if (!G) G = 1;  // only possible when the segment has no short pair at all
     sg.g = make_geometry(G, sg.n1max, sg.n2max);
-    const uint32_t need = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext,
-                                                  sg.g.n1pad, sg.n2max);
-    if (need + 64 > sa::kBias)
-      return fail(e, SA_E_UNSUPPORTED,
-                  "pair shape %u x %u exceeds the 16-bit packed range (long-pair kernel not built yet)",
-                  sg.n1max, sg.n2max);
     const size_t tile_bytes = (size_t)sg.g.tile_stride * 8;
     const uint64_t tiles_fit = std::max<uint64_t>(1, budget_main / tile_bytes);
-    cn = (uint32_t)std::min<uint64_t>(cn, tiles_fit * sg.g.ppt);
+    if ((uint64_t)cn > tiles_fit * sg.g.ppt) {
+      cn = (uint32_t)(tiles_fit * sg.g.ppt);
+      n_long = 0;
+      for (uint32_t i = 0; i < cn; ++i) n_long += is_long(h_cols[base + i], h_rows[base + i]);
+    }
     sg.n = cn;
-    {
+    if (n_long) {
+      // explicit order without the long pairs; the long ones get their own launch
+      sg.order.reserve(cn - n_long);
+      uint64_t tb_room = budget_re;  // bytes of 16-bit traceback words the general kernel may use
+      for (uint32_t i = 0; i < cn; ++i) {
+        const uint32_t a = h_cols[base + i], b = h_rows[base + i];
+        if (is_long(a, b)) {
+          const uint64_t words = (uint64_t)a * b;
+          uint64_t off = ~0ull;
+          if (words * 2 <= tb_room) {
+            off = sg.long_tb_total;
+            sg.long_tb_total += words;
+            tb_room -= words * 2;
+          }
+          sg.long_runs_total += (uint64_t)a + b + 1;
+          sg.long_ids.push_back((uint32_t)(base + i));
+          sg.long_meta.push_back(off);
+          sg.long_meta.push_back(sg.long_runs_total);
+          sg.long_n1max = std::max(sg.long_n1max, a);
+        } else {
+          sg.order.push_back((uint32_t)(base + i));
+        }
+      }
+    }
+    const uint32_t ns = n_long ? (uint32_t)sg.order.size() : cn;
+    sg.n_short = ns;
+    auto id_at = [&](uint32_t i) -> uint32_t { return sg.order.empty() ? (uint32_t)(base + i) : sg.order[i]; };
+    if (ns) {
       // Ragged segment: the 16-64 pairs of a warp tile all run to the tile's largest shape, so
       // bucket pairs by (rows, columns) when the padded work of the given order exceeds the real
       // work by more than ~15 % (uniform read sets skip this; the sort is host time).
       uint64_t real = 0, padded = 0;
       const uint32_t ppt = sg.g.ppt;
-      for (uint32_t t0 = 0; t0 < cn; t0 += ppt) {
+      for (uint32_t t0 = 0; t0 < ns; t0 += ppt) {
         uint32_t a = 0, b = 0;
-        const uint32_t t1 = std::min(cn, t0 + ppt);
+        const uint32_t t1 = std::min(ns, t0 + ppt);
         for (uint32_t i = t0; i < t1; ++i) {
-          a = std::max(a, h_cols[base + i]);
-          b = std::max(b, h_rows[base + i]);
-          real += (uint64_t)h_cols[base + i] * h_rows[base + i];
+          const uint32_t id = id_at(i);
+          a = std::max(a, h_cols[id]);
+          b = std::max(b, h_rows[id]);
+          real += (uint64_t)h_cols[id] * h_rows[id];
         }
         padded += (uint64_t)a * b * (t1 - t0);
       }
-      if (e->sort_mode == 1 || (e->sort_mode == 0 && padded > real + real / 7 && cn > ppt)) {
+      if (e->sort_mode == 1 || (e->sort_mode == 0 && padded > real + real / 7 && ns > ppt)) {
         // stable counting sort by columns, then by rows (LSD): O(n + longest sequence)
-        std::vector<uint32_t> tmp(cn), cnt;
-        sg.order.resize(cn);
+        std::vector<uint32_t> src_ids(ns), tmp(ns), cnt;
+        for (uint32_t i = 0; i < ns; ++i) src_ids[i] = id_at(i);
+        sg.order.resize(ns);
         cnt.assign((size_t)sg.n1max + 2, 0);
-        for (uint32_t i = 0; i < cn; ++i) cnt[h_cols[base + i] + 1]++;
+        for (uint32_t i = 0; i < ns; ++i) cnt[h_cols[src_ids[i]] + 1]++;
         for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
-        for (uint32_t i = 0; i < cn; ++i) tmp[cnt[h_cols[base + i]]++] = i;
+        for (uint32_t i = 0; i < ns; ++i) tmp[cnt[h_cols[src_ids[i]]]++] = src_ids[i];
         cnt.assign((size_t)sg.n2max + 2, 0);
-        for (uint32_t i = 0; i < cn; ++i) cnt[h_rows[base + i] + 1]++;
+        for (uint32_t i = 0; i < ns; ++i) cnt[h_rows[tmp[i]] + 1]++;
         for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
-        for (uint32_t i = 0; i < cn; ++i) {
-          const uint32_t src = tmp[i];
-          sg.order[cnt[h_rows[base + src]]++] = (uint32_t)(base + src);
-        }
+        for (uint32_t i = 0; i < ns; ++i) sg.order[cnt[h_rows[tmp[i]]]++] = tmp[i];
       }
     }
     {
       sg.subs.clear();
       auto add_class = [&](uint32_t off, uint32_t cnt, uint32_t cmax, uint32_t rmax) -> sa_status_t {
+        if (!cnt) return SA_OK;
         Segment::Sub sub;
         sub.off = off;
         sub.cnt = cnt;
-        const int Gc = choose_g(e, cmax, rmax);
-        if (!Gc) return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u needs more shared memory than one SM has", cmax, rmax);
+        int Gc = pick_g(cmax, rmax);
+        if (!Gc) {
+          if (cmax && rmax)
+            return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u fits no packed-kernel configuration", cmax, rmax);
+          Gc = 1;  // a class of empty pairs: nothing to fill
+        }
         sub.g = make_geometry(Gc, cmax, rmax);
         sub.tb_off = sg.tb_total;
         sg.tb_total += (uint64_t)((cnt + sub.g.ppt - 1) / sub.g.ppt) * sub.g.tile_stride;
@@ -438,13 +526,13 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         return SA_OK;
       };
       if (sg.order.empty()) {
-        sa_status_t rr = add_class(0, cn, sg.n1max, sg.n2max);
+        sa_status_t rr = add_class(0, ns, sg.n1max, sg.n2max);
         if (rr != SA_OK) return rr;
       } else {
-        // sorted by rows, then columns: cut where either dimension has grown by more than a
+        // (possibly) sorted by rows, then columns: cut where the rows have grown by more than a
         // quarter since the class began (at most 8 classes, at least 2048 pairs each)
-        uint32_t start = 0, c_lo = ~0u, r_lo = ~0u, c_hi = 0, r_hi = 0;
-        for (uint32_t i = 0; i < cn; ++i) {
+        uint32_t start = 0, r_lo = ~0u, c_hi = 0, r_hi = 0;
+        for (uint32_t i = 0; i < ns; ++i) {
           const uint32_t id = sg.order[i];
           const uint32_t c = h_cols[id], r = h_rows[id];
           const bool grow = i - start >= 2048 && sg.subs.size() < 7 &&
@@ -453,13 +541,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
             sa_status_t rr = add_class(start, i - start, c_hi, r_hi);
             if (rr != SA_OK) return rr;
             start = i;
-            c_lo = r_lo = ~0u;
+            r_lo = ~0u;
             c_hi = r_hi = 0;
           }
-          c_lo = std::min(c_lo, c); r_lo = std::min(r_lo, r);
-          c_hi = std::max(c_hi, c); r_hi = std::max(r_hi, r);
+          r_lo = std::min(r_lo, r);
+          c_hi = std::max(c_hi, c);
+          r_hi = std::max(r_hi, r);
         }
-        sa_status_t rr = add_class(start, cn - start, c_hi, r_hi);
+        sa_status_t rr = add_class(start, ns - start, c_hi, r_hi);
         if (rr != SA_OK) return rr;
       }
     }
@@ -482,6 +571,17 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
                     (unsigned long long)base, (unsigned long long)(base + cn));
     }
     return SA_OK;
+  };
+  // Resident batches keep their segment plan between calls (the host scan is then skipped).
+  size_t plan_pos = 0;
+  auto prepare = [&](uint64_t base, Segment& sg) -> sa_status_t {
+    if (plan && plan_valid && plan_pos < plan->segs.size() && plan->segs[plan_pos].base == base) {
+      sg = plan->segs[plan_pos++];
+      return SA_OK;
+    }
+    const sa_status_t r = prepare_fresh(base, sg);
+    if (r == SA_OK && plan && !plan_valid) plan->segs.push_back(sg);
+    return r;
   };
   // Enqueues the segment's inputs on the copy-in stream.
   auto upload = [&](const Segment& sg) -> sa_status_t {
@@ -538,7 +638,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     sa_engine::Slot& sl = e->slot[k];
     const uint32_t cn = sg.n;
     sa_status_t r;
-    if ((r = ensure(e, sl.tb, (size_t)sg.tb_total * 8)) != SA_OK) return r;
+    if ((r = ensure(e, sl.tb, (size_t)sg.tb_total * 8 + 256)) != SA_OK) return r;
     if ((r = ensure(e, sl.end, (size_t)cn * 4 + 256)) != SA_OK) return r;
     if ((r = ensure(e, sl.rerun_ids, (size_t)cn * 4 + 256)) != SA_OK) return r;
     if (want_cigar && (r = ensure(e, sl.tmp_runs, (size_t)cn * sa::kTmpRuns * 4)) != SA_OK) return r;
@@ -547,10 +647,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if (in) CUDA_TRY(e, cudaStreamWaitEvent(sx, e->ev_in, 0));
     const uint32_t* d_order = nullptr;
     if (!sg.order.empty()) {
-      if ((r = ensure(e, sl.order, (size_t)cn * 4)) != SA_OK) return r;
+      if ((r = ensure(e, sl.order, sg.order.size() * 4)) != SA_OK) return r;
       // pageable source: the copy is staged by the runtime before the call returns
-      CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), (size_t)cn * 4, cudaMemcpyHostToDevice, sx));
+      CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), sg.order.size() * 4, cudaMemcpyHostToDevice, sx));
       d_order = (const uint32_t*)sl.order.p;
+    } else if (!sg.long_ids.empty()) {
+      d_order = (const uint32_t*)sl.order.p;  // every pair of the segment is long: nothing to launch
     }
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
@@ -582,6 +684,51 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         sa::nw_linear_walk<0><<<(sub.cnt + 127) / 128, 128, 0, sx>>>(wp);
       else
         sa::nw_affine_walk<0><<<(sub.cnt + 127) / 128, 128, 0, sx>>>(wp);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+    }
+    if (!sg.long_ids.empty()) {
+      // pairs outside the packed range: literal 32-bit kernel, one thread per pair
+      const uint32_t nl = (uint32_t)sg.long_ids.size();
+      const uint32_t stride = sg.long_n1max + 1;
+      if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_meta, (size_t)nl * 16)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total * 2 + 256)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_rows, (size_t)nl * 6 * stride * 4)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_info, (size_t)nl * 4 * stride)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_runs, (size_t)sg.long_runs_total * 4 + 256)) != SA_OK) return r;
+      std::vector<uint64_t> tb_off(nl), runs_end(nl);
+      for (uint32_t t = 0; t < nl; ++t) {
+        tb_off[t] = sg.long_meta[2 * t];
+        runs_end[t] = sg.long_meta[2 * t + 1];
+      }
+      CUDA_TRY(e, cudaMemcpyAsync(sl.g_ids.p, sg.long_ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, sx));
+      CUDA_TRY(e, cudaMemcpyAsync(sl.g_meta.p, tb_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+      CUDA_TRY(e, cudaMemcpyAsync((uint64_t*)sl.g_meta.p + nl, runs_end.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+      sa::GeneralParams gp{};
+      gp.residues = db.residues;
+      gp.q_off = db.q_off;
+      gp.q_len = db.q_len;
+      gp.d_off = db.d_off;
+      gp.d_len = db.d_len;
+      gp.ids = (const uint32_t*)sl.g_ids.p;
+      gp.n_ids = nl;
+      gp.packing = db.packing;
+      gp.match = sc.match;
+      gp.mismatch = sc.mismatch;
+      gp.open = sc.gap_open;
+      gp.ext = sc.gap_ext;
+      gp.tb = want_cigar ? (uint16_t*)sl.g_tb.p : nullptr;
+      gp.tb_off = (const uint64_t*)sl.g_meta.p;
+      gp.rows = (int32_t*)sl.g_rows.p;
+      gp.info = (uint8_t*)sl.g_info.p;
+      gp.row_stride = stride;
+      gp.runs = (uint32_t*)sl.g_runs.p;
+      gp.runs_end = (const uint64_t*)sl.g_meta.p + nl;
+      gp.score = db.score;
+      gp.status = db.status;
+      gp.cigar_len = db.cigar_len;
+      sa::nw_affine_general_kernel<<<(nl + 31) / 32, 32, 0, sx>>>(gp);
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
     }
@@ -665,6 +812,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           (const uint32_t*)sl.tmp_runs.p, db.cigar_len, db.cigar_off, db.pool, db.pool_cap, (uint32_t)sg.base, cn);
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
+      if (!sg.long_ids.empty()) {
+        const uint32_t nl = (uint32_t)sg.long_ids.size();
+        sa::general_runs_to_pool<<<nl, 128, 0, e->stream>>>((const uint32_t*)sl.g_ids.p, nl, (const uint32_t*)sl.g_runs.p,
+                                                            (const uint64_t*)sl.g_meta.p + nl, db.cigar_len, db.cigar_off,
+                                                            db.pool, db.pool_cap);
+        CUDA_TRY(e, cudaGetLastError());
+        e->timing.kernel_launches++;
+      }
       wp.tmp_runs = nullptr;
       for (const Segment::Sub& sub : sg.subs) {
         set_geometry(sub.g);
@@ -972,7 +1127,9 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
   if (e->stream) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->slot[0].order, &e->slot[1].order, &e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
+    for (DevBuf* b : {&e->slot[0].g_ids, &e->slot[0].g_meta, &e->slot[0].g_tb, &e->slot[0].g_rows, &e->slot[0].g_info,
+                      &e->slot[0].g_runs, &e->slot[1].g_ids, &e->slot[1].g_meta, &e->slot[1].g_tb, &e->slot[1].g_rows,
+                      &e->slot[1].g_info, &e->slot[1].g_runs, &e->slot[0].order, &e->slot[1].order, &e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
                       &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch, &e->par_bytes, &e->par_rows, &e->par_in,
                       &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
                       &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})
@@ -1137,8 +1294,24 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     }
     uint64_t used = 0;
     uint64_t sent = 0;
+    // plan key: everything the segment plan depends on besides the (immutable) lengths
+    const uint64_t key = 0x9e3779b97f4a7c15ull ^ ((uint64_t)algo << 56) ^ ((uint64_t)(uint32_t)s2.sc.match << 40) ^
+                         ((uint64_t)(uint32_t)(s2.sc.mismatch & 0xffff) << 24) ^ ((uint64_t)(uint32_t)(s2.sc.gap_open & 0xfff) << 12) ^
+                         (uint64_t)(uint32_t)(s2.sc.gap_ext & 0xfff) ^ ((uint64_t)e->tb_budget << 1) ^ ((uint64_t)e->seg_pairs << 20) ^
+                         ((uint64_t)e->force_g << 8) ^ ((uint64_t)e->sort_mode << 4);
+    Plan* plan = (Plan*)r->plan;
+    bool valid = plan && r->plan_key == key && e->budget_cached == r->plan_budget;
+    if (!valid) {
+      if (r->plan && r->plan_free) r->plan_free(r->plan);
+      plan = new (std::nothrow) Plan();
+      r->plan = plan;
+      r->plan_free = [](void* p) { delete (Plan*)p; };
+      r->plan_key = key;
+    }
     st = run_affine(e, r->d, n, r->h_q_len.data(), r->h_d_len.data(), s2, want_cigar != 0, nullptr,
-                    nullptr, &used, &sent);
+                    nullptr, &used, &sent, plan, valid);
+    r->plan_budget = e->budget_cached;
+    if (st != SA_OK && plan) plan->segs.clear(), r->plan_key = 0;
     if (st != SA_OK) return st;
     r->used = used;
     if (!want_cigar || used <= r->d.pool_cap) break;

@@ -153,9 +153,12 @@ def test_maximum_packed_size_and_range_extremes(engine, oracle):
     rl = engine.align(b, algo=ALGO_NW_LINEAR)
     ref = oracle.linear_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=3600, n_threads=6)
     assert np.array_equal(ref.score, rl.score) and np.array_equal(ref.cigar_len, rl.cigar_len)
-    # one residue beyond the range: a clean per-call error, not a wrong answer
+    # beyond the packed range the affine path switches to the general 32-bit kernel ...
+    big = _batch([(b"A" * 2000, b"C" * 2000)])
+    check_against_oracle(oracle, big, engine.align(big), what="beyond packed range")
+    # ... the linear aligner has no long-pair kernel yet: a clean per-call error, not a wrong answer
     with pytest.raises(EngineError) as ei:
-        engine.align(_batch([(b"A" * 2000, b"C" * 2000)]))
+        engine.align(big, algo=ALGO_NW_LINEAR)
     assert ei.value.code == -5
 
 
@@ -240,3 +243,51 @@ def test_all_cooptimal_alignments_match_reference_order(engine, oracle):
     q, d = b"AAAA", b"AAA"
     r = engine.align(PairBatch.from_pairs([(q, d)]))
     assert engine.all_alignments(q, d)[0].startswith(render_affine(q, d, r.cigar_of(0)))
+
+
+def test_long_pairs_take_the_general_kernel(engine, oracle):
+    """Pairs outside the packed 16-bit range (n1 + n2 above ~3.6 k) go through the literal
+    32-bit kernel (nw_general.cuh) inside the same batched call, mixed with short pairs."""
+    import random
+    rng = random.Random(31)
+
+    def related(n, err):
+        q = bytes(rng.choice(b"ACGT") for _ in range(n))
+        d = bytearray()
+        for c in q:
+            u = rng.random()
+            if u < err * 0.5:
+                d.append(rng.choice(b"ACGT"))
+            elif u < err * 0.75:
+                d.append(c); d.append(rng.choice(b"ACGT"))
+            elif u < err:
+                pass
+            else:
+                d.append(c)
+        return q, bytes(d)
+
+    pairs = random_pair_list(32, 300, 1, 200)
+    pairs[7] = related(2100, 0.05)
+    pairs[150] = related(2500, 0.02)
+    pairs[151] = (b"A" * 2000, b"C" * 2200)           # everything mismatches: deeply negative scores
+    pairs[299] = related(1900, 0.1)
+    b = _batch(pairs)
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, what="mixed long/short")
+    assert r.cigar_len[7] > 0 and r.cigar_len[150] > 0
+
+
+def test_sentinel_regime_long_pairs(engine, oracle):
+    """n1 + n2 > ~5.4 k: the reference's finite -32768 'minus infinity' leaks into the matrix
+    (SURVEY 7); the general kernel reproduces score, status and first alignment there too."""
+    import random
+    rng = random.Random(33)
+    q = bytes(rng.choice(b"ACGT") for _ in range(3000))
+    d = bytearray(q)
+    for _ in range(120):
+        d[rng.randrange(len(d))] = rng.choice(b"ACGT")
+    del d[1000:1010]
+    pairs = [(q, bytes(d)), (b"A" * 5600, b"C" * 3), (b"ACGT" * 700, b"TTGCA" * 600)]
+    b = _batch(pairs)
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, n_threads=3, what="sentinel regime")
