@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -104,6 +105,7 @@ struct sa_engine {
   size_t tb_budget = 0;
   size_t budget_cached = 0;
   uint32_t seg_pairs = 524288;
+  std::map<const void*, size_t> smem_configured;  // kernel -> opted-in dynamic smem ON THIS DEVICE
   int sort_mode = 0;  // 0 auto, 1 always, 2 never (SA_SORT)
   bool seg_pairs_forced = false;
 };
@@ -201,7 +203,7 @@ template <int G, uint32_t ORMASK, int ALGO = sa::kAffine>
 sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
                           uint32_t n_tiles, cudaStream_t stream) {
   auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK, ALGO>;
-  static size_t configured = 0;  // per instantiation; smem opt-in only grows
+  size_t& configured = e->smem_configured[(const void*)kern];  // per engine = per device; only grows
   if (g.smem_bytes > configured) {
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)std::min(e->smem_optin, std::max<size_t>(g.smem_bytes, 48 * 1024))));
@@ -981,10 +983,10 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     const uint32_t warps_per_block = 4;
     const uint32_t smem_seq = 6 * 1024;  // per warp: two 2-bit packed sequences of up to ~12 kbp stay on chip
     const size_t smem = (size_t)warps_per_block * smem_seq;
-    static bool configured = false;
-    if (!configured) {
+    size_t& configured = e->smem_configured[(const void*)sa::wfa_standard_kernel];
+    if (configured < smem) {
       CUDA_TRY(e, cudaFuncSetAttribute(sa::wfa_standard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+      configured = smem;
     }
     const uint64_t stride = (uint64_t)sa::kWfRing * 3 * width + (nmax_sum + 32) / 4 + 8;
     uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 8);

@@ -291,3 +291,30 @@ def test_sentinel_regime_long_pairs(engine, oracle):
     b = _batch(pairs)
     r = engine.align(b)
     check_against_oracle(oracle, b, r, n_threads=3, what="sentinel regime")
+
+
+def test_argument_errors_are_per_call_codes(engine):
+    """Bad inputs come back as SA_E_ARG / SA_E_UNSUPPORTED with a message, never as a crash."""
+    import ctypes as C
+    from sequencealigning_b200 import EngineError, PairBatch, _capi
+    b = PairBatch.from_pairs([(b"ACGT", b"ACGA"), (b"AC", b"A")])
+    bad = PairBatch(b.residues, b.q_off, b.q_len, b.d_off + np.uint64(1000), b.d_len)
+    with pytest.raises(EngineError) as ei:
+        engine.align(bad)
+    assert ei.value.code == -2 and "residues_len" in str(ei.value)
+    with pytest.raises(EngineError) as ei:
+        engine.align(b, scheme=(5, 6, -8, -6))   # mismatch above match
+    assert ei.value.code == -5
+    with pytest.raises(EngineError) as ei:
+        engine.align(b, algo=9)
+    assert ei.value.code == -2
+    lib = _capi.lib()
+    assert lib.sa_align_batch(None, 0, 0, None, None, None) == -2
+    empty = PairBatch.from_pairs([])
+    r = engine.align(empty)
+    assert r.score.size == 0 and r.cigar.size == 0
+    # two engines on the same device work side by side
+    from sequencealigning_b200 import Engine
+    with Engine(0) as e2:
+        r1, r2 = engine.align(b), e2.align(b)
+        assert np.array_equal(r1.score, r2.score) and np.array_equal(r1.cigar, r2.cigar)
