@@ -27,8 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "GCUPS, batched affine-gap NW score+traceback (alignments/s in config)"
-OPS_PER_CELL_ISSUED = 9.0     # SASS lane-instructions per DP cell in the fill (18 per packed pair of cells)
+OPS_PER_CELL_ISSUED = 8.0     # SASS lane-instructions per DP cell in the fill (16 per packed pair of cells)
 OPS_PER_CELL_S32_EQUIV = 16.0  # SURVEY.md 8d / BASELINE.md figure for score + 4-bit traceback
+PROBE_PAIRS = 262144          # one-segment launch used to time the fill kernel alone
 
 
 def parse_args():
@@ -247,6 +248,32 @@ def int_peak() -> dict:
                 "source": f"nominal (microbenchmark failed: {ex})"}
 
 
+def fill_kernel_probe(batch, device: int, reps: int = 7) -> dict:
+    """The fill kernel timed alone: a second engine whose segment size is forced to the probe size,
+    so the sub-batch is ONE fill launch; duration = CUDA events around that launch on its stream
+    (sa_last_timing.walk_ms), median of `reps` after 3 warm-ups."""
+    from sequencealigning_b200 import Engine
+    n = min(batch.n_pairs, PROBE_PAIRS)
+    sub = batch.select(np.arange(n, dtype=np.int64))
+    old = os.environ.get("SA_SEG_PAIRS")
+    os.environ["SA_SEG_PAIRS"] = str(n)
+    try:
+        with Engine(device) as eng:
+            rb = eng.upload(sub)
+            ms = []
+            for k in range(3 + reps):
+                rb.align()
+                if k >= 3:
+                    ms.append(eng.timing()["walk_ms"])
+            rb.free()
+    finally:
+        if old is None:
+            os.environ.pop("SA_SEG_PAIRS", None)
+        else:
+            os.environ["SA_SEG_PAIRS"] = old
+    return {"pairs": int(n), "cells": int(sub.cells), "residue_bytes": int(sub.q_len.sum()) + int(sub.d_len.sum()), "ms": float(np.median(ms))}
+
+
 def main():
     args = parse_args()
     resolve_workload(args)
@@ -296,12 +323,14 @@ def main():
     e1 = torch.cuda.Event(enable_timing=True)
     launches = 0
     reruns = 0
+    fill_ms = 0.0
     e0.record(stream)
     for _ in range(args.steps):
         rb.align(algo=algo)
         t = eng.timing()
         launches += t["kernel_launches"]
         reruns = t["pairs_rerun"]
+        fill_ms += t["walk_ms"]      # sum of the fill kernel's launch durations (CUDA events on its streams)
     e1.record(stream)
     e1.synchronize()
     barrier()
@@ -370,7 +399,8 @@ def main():
 
     if rank == 0:
         peak = int_peak()
-        issued = gcups * 1e9 * OPS_PER_CELL_ISSUED / world
+        step_issued = gcups * 1e9 * OPS_PER_CELL_ISSUED / world
+        fill_ms_step = fill_ms / max(args.steps, 1)
         tb_bytes = cells / 2.0
         hbm_bytes = tb_bytes + batch.residues.size + batch.n_pairs * (24 + 17) + res_dev.cigar.size * 4
         peaks = {}
@@ -379,6 +409,36 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ipeak = peak["issue_lane_ops_per_s"]
+        roof = None
+        if args.workload != "config4":
+            pr = fill_kernel_probe(batch, local)
+            k_cups = pr["cells"] / (pr["ms"] * 1e-3)
+            roof = {
+                "bound": "int-issue (integer max-plus DP: neither HBM nor tensor cores bind; DESIGN.md 4.1)",
+                "kernel": "nw_affine_fill_s16<8,G,0x00>",
+                "achieved": k_cups * OPS_PER_CELL_ISSUED / 1e12, "peak": ipeak / 1e12, "unit": "T lane-instr/s",
+                "frac": k_cups * OPS_PER_CELL_ISSUED / ipeak,
+                "lane_instr_per_cell": OPS_PER_CELL_ISSUED,
+                "launch": {"pairs": pr["pairs"], "cells": pr["cells"], "ms": pr["ms"], "gcups": k_cups / 1e9,
+                           "timed": "one fill launch alone, CUDA events on its stream, median of 7 after 3 warm-ups"},
+                "whole_step_frac": step_issued / ipeak,
+                # SURVEY.md 8d's algorithmic count (16 s32 ops per cell for score + 4-bit traceback); the packed
+                # u16x2 recurrence does that work in 8 issued instructions, so this ratio can pass 1
+                "s32_equivalent": {"ops_per_cell": OPS_PER_CELL_S32_EQUIV, "achieved": k_cups * OPS_PER_CELL_S32_EQUIV / 1e12,
+                                   "frac": k_cups * OPS_PER_CELL_S32_EQUIV / ipeak},
+                "traffic": (11743 + 324) * pr["pairs"] if args.length == 150 else None,
+                "traffic_detail": {"unit": "DRAM bytes per fill launch",
+                                   "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
+                                   "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 12067 B per 150 bp pair)"},
+                "per_gpu": True,
+                "fill_ms_per_step_summed": fill_ms_step,
+                "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
+                        "/ fill-kernel time, i.e. the share of all issue slots doing recurrence work; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",
+                "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                        "bytes": "sequences + 0.5 B/cell traceback written + results, whole step"},
+            }
         out = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16x2 (packed pairs; exact integer)",
@@ -386,16 +446,7 @@ def main():
             "alignments_per_s": args.pairs * world / (ms_step * 1e-3),
             "gpu_launches": int(launches // max(args.steps, 1)), "pairs_rerun_per_step": int(reruns),
             "clocks": clocks, "e2e": e2e,
-            "roofline": {
-                "bound": "int-issue", "achieved": issued / 1e12, "peak": peak["issue_lane_ops_per_s"] / 1e12, "unit": "T lane-ops/s",
-                "frac": issued / peak["issue_lane_ops_per_s"], "traffic": None,
-                "per_gpu": True, "ops_per_cell": OPS_PER_CELL_ISSUED,
-                "note": "whole step (fill + walks + scan) timed; achieved = cells/s x 9 issued lane-instructions per cell; peak = " + peak["source"],
-                "s32_equiv_frac": gcups * 1e9 / world * OPS_PER_CELL_S32_EQUIV / peak["issue_lane_ops_per_s"],
-                "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                        "bytes": "sequences + 0.5 B/cell traceback written + results"},
-            },
+            "roofline": roof,
         }
         if args.workload == "config4":
             out["roofline"] = {"bound": "latency (wavefront dependency chain)", "achieved": None, "peak": None, "unit": None,

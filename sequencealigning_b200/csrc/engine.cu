@@ -101,7 +101,7 @@ struct sa_engine {
   int sm_count = 0;
   size_t smem_optin = 0;
   int force_g = 0;
-  uint32_t ormask = 0x0F;
+  uint32_t ormask = 0x00;
   size_t tb_budget = 0;
   size_t budget_cached = 0;
   uint32_t seg_pairs = 524288;
@@ -221,6 +221,8 @@ sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geomet
   if (algo == SA_ALGO_NW_LINEAR) return launch_fill_m<G, 0x0F, sa::kLinear>(e, p, g, n_tiles, stream);
   switch (e->ormask) {
     case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles, stream);
+    case 0x03: return launch_fill_m<G, 0x03>(e, p, g, n_tiles, stream);
+    case 0x05: return launch_fill_m<G, 0x05>(e, p, g, n_tiles, stream);
     case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles, stream);
     case 0x3F: return launch_fill_m<G, 0x3F>(e, p, g, n_tiles, stream);
     case 0xFF: return launch_fill_m<G, 0xFF>(e, p, g, n_tiles, stream);
@@ -357,10 +359,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     fp.q_len = db.q_len;
     fp.d_off = db.d_off;
     fp.d_len = db.d_len;
+    // V' = 2V - 2*ext*(x+y) + bias: extensions free, diagonal +cm, boundaries constant
+    const uint32_t bias = sa::s16_affine_bias(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
     fp.open2 = pack2((uint32_t)s2.openp);
-    fp.ext2 = pack2((uint32_t)s2.extp);
-    fp.origin = pack2(sa::kBias);
-    row0_clean = sa::kBias - (uint32_t)(s2.openp + (-2 * sc.gap_ext));
+    fp.cm2 = pack2((uint32_t)(2 * sc.match - 4 * sc.gap_ext));
+    fp.origin = pack2(bias);
+    row0_clean = bias - (uint32_t)(s2.openp + (-2 * sc.gap_ext));  // 2*(open + (y+1)*ext) - 2*ext*y
   }
   // kernel columns / rows: (seq1, seq2) for affine, (seq2, seq1) for linear
   const uint32_t* h_cols = linear ? h_d_len : h_q_len;
@@ -370,6 +374,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   wp.q_len = db.q_len;
   wp.d_len = db.d_len;
   wp.match = sc.match;
+  wp.bias = linear ? (int32_t)sa::kBias : (int32_t)sa::s16_affine_bias(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
+  wp.diag2 = linear ? sc.match : 2 * sc.gap_ext;
   wp.open = sc.gap_open;
   wp.ext = sc.gap_ext;
   wp.score = db.score;
@@ -389,7 +395,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   // Scans the next segment on the host: extent, shape maxima, residue ranges, geometry.
   auto fits_packed = [&](uint32_t cols, uint32_t rows, int G) {
     const uint32_t n1pad = std::max(1u, ((cols + kK * G - 1) / (kK * G)) * (kK * G));
-    return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows) + 64 <= sa::kBias;
+    return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows) + 64 <= sa::kBias &&
+           (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows));
   };
   // lane-group width for a class: choose_g among the widths whose padded shape stays in range
   auto pick_g = [&](uint32_t cols, uint32_t rows) -> int {
@@ -408,14 +415,17 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const uint64_t max_sum = per_step ? (sa::kBias - std::min<uint32_t>(bound0, sa::kBias)) / per_step : 0;
   auto is_long = [&](uint32_t cols, uint32_t rows) -> bool {
     // fast path: with G = 32 (least shared memory, at most 255 columns of padding) the pair fits
-    if ((uint64_t)cols + rows + 256 <= max_sum && (uint64_t)rows * 10 + ((uint64_t)cols + 256) * 2 + 64 <= e->smem_optin)
+    if ((uint64_t)cols + rows + 256 <= max_sum && (uint64_t)rows * 10 + ((uint64_t)cols + 256) * 2 + 64 <= e->smem_optin &&
+        (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, cols + 256, rows)))
       return false;
     if (!cols || !rows) return false;
     for (uint32_t g = 1; g <= 32; g <<= 1) {
       const uint64_t n1pad = ((uint64_t)cols + kK * g - 1) / (kK * g) * (kK * g);
       const uint64_t ng = 32 / g;
       const uint64_t smem = (((uint64_t)rows * ng * 8 + ((uint64_t)rows * ng + n1pad * ng) * 2) + 15) & ~(uint64_t)15;
-      if (smem <= e->smem_optin && bound0 + per_step * (n1pad + rows) <= sa::kBias) return false;
+      if (smem <= e->smem_optin && bound0 + per_step * (n1pad + rows) <= sa::kBias &&
+          (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, (uint32_t)n1pad, rows)))
+        return false;
     }
     return true;
   };

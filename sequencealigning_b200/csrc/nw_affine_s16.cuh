@@ -15,10 +15,13 @@
 //     does two max operations and returns BOTH "a >= b" predicates, which are exactly the
 //     traceback tie bits.  Plain 32-bit IADD does two subtractions because no half can
 //     borrow (range proven below).
-//   * Scores are stored as V' = 2*V - match*(x+y) + BIAS.  Every comparison in the
-//     recurrence is between values of the same cell, so the per-cell offset cancels; the
-//     diagonal step then costs 0 for a match and 2*(match-mismatch) for a mismatch, which
-//     makes the substitution score one XOR + one VIMNMX.U16x2 (min(q^d, penalty)).
+//   * Scores are stored as V' = 2*V - 2*ext*(x+y) + bias.  Every comparison in the
+//     recurrence is between values of the same cell, so the per-cell offset cancels, and a gap
+//     EXTENSION becomes free: I'[x][y+1] = max(M' - open', I') with no add, likewise D'.  The
+//     diagonal step is + (2*match - 4*ext) for a match and 2*(match-mismatch) less for a
+//     mismatch: one XOR + one VIMNMX.U16x2 (min(q^d, penalty)) + one three-operand IADD3.
+//     A cell therefore costs 2 adds, 5 VIMNMX, 1 XOR and 8 predicated bit-sets = 16
+//     instructions per two cells; values stay within bias + (2*match-4*ext)*min(x,y).
 //   * The factor 2 leaves the low bit free: boundary-chain cells get +1 ("panic bonus"),
 //     the bonus can only break ties, and it survives to the end cell iff some co-optimal
 //     path starts with a gap -- the condition under which the reference panics
@@ -35,10 +38,12 @@
 
 namespace sa {
 
-constexpr uint32_t kBias = 0xFF00u;  // stored = V' + kBias; V' <= 1 always
-// Largest n1pad + n2 for which no 16-bit half can underflow: the most negative V' is a path
-// of gaps only, 2*(open+ext) + ext'*(n1+n2) with ext' = 2*ext - match, plus one mismatch,
-// one open and one extension of look-ahead.  The engine checks the bound with the scheme.
+constexpr uint32_t kBias = 0xFF00u;  // linear aligner (S' = 2S - match*(i+j) + kBias, S' <= kBias)
+// Sentinel guard, in doubled score units: twice the most negative true score of any state of
+// any cell (a path of gaps only, plus one mismatch, one open and one extension of look-ahead)
+// plus the anti-diagonal term.  While it stays below kBias no score comes near the reference's
+// -32768 sentinel (nw_affine:183-216), so the packed kernels may ignore the sentinel; pairs
+// beyond it go to the literal 32-bit kernel.  The linear aligner's 16-bit range is the same bound.
 __host__ __device__ inline uint32_t s16_min_value_bound(int match, int mismatch, int open, int ext,
                                                         uint32_t n1pad, uint32_t n2) {
   const int extp = match - 2 * ext;                  // > 0 magnitude per boundary step
@@ -47,6 +52,23 @@ __host__ __device__ inline uint32_t s16_min_value_bound(int match, int mismatch,
   // worst case: every step is the costliest of (ext', pen/2 per unit of x+y)
   const int per_step = extp > (pen + 1) / 2 ? extp : (pen + 1) / 2;
   return (uint32_t)(2 * (openp + extp) + per_step * (int)(n1pad + n2 + 2) + pen + openp + extp);
+}
+
+// Range of the affine transform: every state of every cell lies in
+//   [bias - (2*open' + ext'' + max(0, pen - cm)), bias + cm*min(x,y) + 1]
+// with open' = -2*open, ext'' = -2*ext, cm = 2*match - 4*ext, pen = 2*(match-mismatch): the
+// lower end because D'(x,y) >= D'(1,y) = H'(0,y) = bias - (open' + ext'') (extensions are free),
+// M' = H'diag + cm - {0,pen} and the look-ahead M' - open'; the upper end because a diagonal
+// step adds at most cm and gap steps add nothing (+1: panic bonus).
+__host__ __device__ inline uint32_t s16_affine_bias(int match, int mismatch, int open, int ext) {
+  const int cm = 2 * match - 4 * ext, pen = 2 * (match - mismatch);
+  return (uint32_t)(-4 * open - 2 * ext + (pen > cm ? pen - cm : 0) + 16);
+}
+__host__ __device__ inline bool s16_affine_in_range(int match, int mismatch, int open, int ext,
+                                                    uint32_t n1pad, uint32_t n2) {
+  const uint64_t cm = (uint64_t)(2 * match - 4 * ext);
+  const uint64_t nmin = n1pad < n2 ? n1pad : n2;
+  return s16_affine_bias(match, mismatch, open, ext) + cm * (nmin + 1) + 2 <= 0xFFFFull;
 }
 
 // Residue access for both input formats of sa_batch_t: packing 0 = one byte per residue, offsets
@@ -75,9 +97,11 @@ struct AffineS16Params {
   // scheme in transformed units (all positive magnitudes)
   uint32_t pen2;    // 2*(match-mismatch), packed in both halves
   uint32_t open2;   // -2*open, packed
-  uint32_t ext2;    // match - 2*ext, packed
-  uint32_t row0;    // kBias - 2*(-(open+ext)) + bonus, packed: H'[0][y] = row0 - y*ext2
-  uint32_t origin;  // kBias packed: H'[0][0]
+  uint32_t ext2;    // linear aligner only: what a set gap flag saves, 2*(ext-open), packed
+  uint32_t cm2;     // affine: diagonal constant 2*match - 4*ext, packed
+  uint32_t row0;    // affine: bias + 2*(open+ext) + bonus, packed = H'[0][y] = H'[x][0] for all x,y >= 1
+                    // linear: kBias + open', H'[0][y] = row0 - y*step2
+  uint32_t origin;  // bias packed: H'[0][0]
   uint32_t zero;    // always 0; opaque to ptxas so that `or` bit-sets stay LOP3 (alu pipe)
   uint32_t step2;   // linear aligner: boundary step magnitude match - 2*ext, packed
   uint32_t packing; // input format (see load_residue)
@@ -131,23 +155,21 @@ struct StripCells {
   static __device__ __forceinline__ void run(uint32_t (&Hrow)[K], uint32_t (&F)[K],
                                              const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
                                              uint32_t& E, uint32_t pen2, uint32_t open2,
-                                             uint32_t ext2, uint32_t& acc_a, uint32_t& acc_b,
+                                             uint32_t cm2, uint32_t& acc_a, uint32_t& acc_b,
                                              uint32_t (&Mv)[K], uint32_t (&Ev)[K]) {
     constexpr int c = C;
     const uint32_t hup = Hrow[c];
     const uint32_t m = __vminu2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
-    const uint32_t M = hdiag - m;                 // M'[x][y]; no borrow (range bound)
+    const uint32_t M = hdiag + cm2 - m;           // M'[x][y]: one IADD3; no half leaves [0, 65535]
     Mv[c] = M;  // kept only for the end-cell capture (a rarely taken branch after the row)
     Ev[c] = E;
     const uint32_t t = vmax_tie<(1u << (4 * c)), (ORMASK >> 0) & 1, (ORMASK >> 1) & 1>(E, M, acc_a, acc_b);     // I >= M
     const uint32_t H = vmax_tie<(2u << (4 * c)), (ORMASK >> 2) & 1, (ORMASK >> 3) & 1>(F[c], t, acc_a, acc_b);  // D >= max(I,M)
     const uint32_t Mo = M - open2;
-    const uint32_t En = vmax_tie<(4u << (4 * c)), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a, acc_b);     // open ties/wins: I[x][y+1]
-    const uint32_t Fn = vmax_tie<(8u << (4 * c)), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D[x+1][y]
-    E = En - ext2;
-    F[c] = Fn - ext2;
+    E = vmax_tie<(4u << (4 * c)), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a, acc_b);        // open ties/wins: I'[x][y+1]
+    F[c] = vmax_tie<(8u << (4 * c)), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D'[x+1][y]
     Hrow[c] = H;
-    StripCells<K, C + 1, ORMASK>::run(Hrow, F, q, d, hup, E, pen2, open2, ext2, acc_a, acc_b, Mv, Ev);
+    StripCells<K, C + 1, ORMASK>::run(Hrow, F, q, d, hup, E, pen2, open2, cm2, acc_a, acc_b, Mv, Ev);
   }
 };
 template <int K, uint32_t ORMASK>
@@ -351,7 +373,8 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (size_t)p.smem_bnd_rows * NG);  // [rows][NG]
   uint16_t* qp = dp + p.smem_d_halfs;                                              // [n1pad][NG]
 
-  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = p.ext2, zero = p.zero;
+  // ext2: the per-cell constant of the recurrence (affine: diagonal constant; linear: flag saving)
+  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = (ALGO == kLinear) ? p.ext2 : p.cm2, zero = p.zero;
 
   // ---- stage the residues; they are widened to (byte << 7) per 16-bit half when read, so the
   //      XOR of two different residues is >= 128 >= pen2 and the XOR of equal residues is 0 ----
@@ -370,8 +393,7 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
     if (ALGO == kLinear) {
       bnd[x * NG + grp] = make_uint2(p.row0 - (x + 1) * p.step2, open2 - ext2);
     } else {
-      const uint32_t h = p.row0 - (x + 1) * ext2;
-      bnd[x * NG + grp] = make_uint2(h, h - ext2);
+      bnd[x * NG + grp] = make_uint2(p.row0, p.row0);  // extensions are free in V'
     }
   }
   __syncwarp();
@@ -393,15 +415,15 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
         st.Hrow[c] = p.row0 - y * p.step2;  // S'[0][j], gap flag set (needleman_wunsch.rs:45-54)
         st.F[c] = open2 - ext2;             // -> the cell below pays an extension
       } else {
-        st.Hrow[c] = p.row0 - y * ext2;  // H'[0][y] = D'[0][y]  (nw_affine:194-198)
-        st.F[c] = st.Hrow[c] - ext2;     // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
+        st.Hrow[c] = p.row0;  // H'[0][y] = D'[0][y]  (nw_affine:194-198), constant in V'
+        st.F[c] = p.row0;     // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
       }
       st.q[c] = widen(qp[(y - 1) * NG + grp]);
     }
     if (ALGO == kLinear)
       st.hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * p.step2;  // S'[0][j0]; S[0][0] = 2*open
     else
-      st.hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * ext2;  // H'[0][y0]
+      st.hd_prev = (y0 == 0) ? p.origin : p.row0;  // H'[0][y0]
     st.out_h = 0;
     st.out_e = 0;
     st.capx_a = (s == sa_) ? n2a : 0u;

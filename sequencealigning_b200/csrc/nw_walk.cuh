@@ -67,6 +67,9 @@ struct WalkParams {
   // only pairs with more runs are walked a second time.
   uint32_t* __restrict__ tmp_runs;  // [segment pairs][kTmpRuns], indexed by (id - tmp_base)
   uint32_t tmp_base;
+  // decoding of the fill's end word: 2*score (+ taint bit) = H' - bias + diag2*(n1+n2)
+  // (affine: diag2 = 2*ext; linear: diag2 = match)
+  int32_t bias, diag2;
 };
 
 constexpr uint32_t kTmpRuns = 24;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   const uint32_t w = p.end[i];
   uint32_t st = (w >> 16) & 3u;
   if (MODE == 0) {
-    const int32_t t2 = (int32_t)(w & 0xffffu) - (int32_t)kBias + p.match * (int32_t)(n1 + n2);
+    const int32_t t2 = (int32_t)(w & 0xffffu) - p.bias + p.diag2 * (int32_t)(n1 + n2);
     const int32_t taint = t2 & 1;
     if (p.phase == 0) {
       p.score[id] = (t2 - taint) / 2;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
     if (n1 == 0 || n2 == 0) {  // border cells (:44-65); scores[0][0] gets both increments
       score = (n1 == 0 && n2 == 0) ? 2 * p.open : p.open + (int32_t)(n1 + n2) * p.ext;
     } else {
-      const int32_t t2 = (int32_t)(p.end[i_launch] & 0xffffu) - (int32_t)kBias + p.match * (int32_t)(n1 + n2);
+      const int32_t t2 = (int32_t)(p.end[i_launch] & 0xffffu) - p.bias + p.diag2 * (int32_t)(n1 + n2);
       score = t2 / 2;
     }
     p.score[id] = score;
