@@ -153,9 +153,15 @@ struct Geometry {
   uint32_t ng = 8, ppt = 16;
   uint32_t nstrips_pad = 0, n1pad = 0, tb_rows = 0;
   uint64_t tile_stride = 0;  // uint2 per tile
-  uint32_t d_halfs = 0, q_halfs = 0;
+  uint32_t d_halfs = 0;
   size_t smem_bytes = 0;
 };
+
+// dynamic shared memory of one fill warp: the boundary column (uint2 per row per pair-of-pairs)
+// and the db residue panel (u16 per row per pair-of-pairs)
+inline uint64_t fill_smem_bytes(uint64_t rows, uint64_t ng) {
+  return (rows * ng * (8 + 2) + 15) & ~(uint64_t)15;
+}
 
 Geometry make_geometry(int G, uint32_t n1max, uint32_t n2max) {
   Geometry g;
@@ -169,9 +175,7 @@ Geometry make_geometry(int G, uint32_t n1max, uint32_t n2max) {
   g.tb_rows = std::max(1u, n2max);
   g.tile_stride = (uint64_t)g.nstrips_pad * g.tb_rows * g.ng;
   g.d_halfs = g.tb_rows * g.ng;  // one u16 (two residues) per row per pair-of-pairs
-  g.q_halfs = g.n1pad * g.ng;
-  g.smem_bytes = (size_t)g.tb_rows * g.ng * 8 + (size_t)(g.d_halfs + g.q_halfs) * 2;
-  g.smem_bytes = (g.smem_bytes + 15) & ~(size_t)15;
+  g.smem_bytes = (size_t)fill_smem_bytes(g.tb_rows, g.ng);
   return g;
 }
 
@@ -415,14 +419,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const uint64_t max_sum = per_step ? (sa::kBias - std::min<uint32_t>(bound0, sa::kBias)) / per_step : 0;
   auto is_long = [&](uint32_t cols, uint32_t rows) -> bool {
     // fast path: with G = 32 (least shared memory, at most 255 columns of padding) the pair fits
-    if ((uint64_t)cols + rows + 256 <= max_sum && (uint64_t)rows * 10 + ((uint64_t)cols + 256) * 2 + 64 <= e->smem_optin &&
+    if ((uint64_t)cols + rows + 256 <= max_sum && fill_smem_bytes(rows, 1) <= e->smem_optin &&
         (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, cols + 256, rows)))
       return false;
     if (!cols || !rows) return false;
     for (uint32_t g = 1; g <= 32; g <<= 1) {
       const uint64_t n1pad = ((uint64_t)cols + kK * g - 1) / (kK * g) * (kK * g);
       const uint64_t ng = 32 / g;
-      const uint64_t smem = (((uint64_t)rows * ng * 8 + ((uint64_t)rows * ng + n1pad * ng) * 2) + 15) & ~(uint64_t)15;
+      const uint64_t smem = fill_smem_bytes(rows, ng);
       if (smem <= e->smem_optin && bound0 + per_step * (n1pad + rows) <= sa::kBias &&
           (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, (uint32_t)n1pad, rows)))
         return false;

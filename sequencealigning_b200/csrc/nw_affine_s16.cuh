@@ -244,9 +244,10 @@ struct LinearCells<K, K> {
                                              uint32_t, uint32_t, uint32_t, uint32_t&, uint32_t&) {}
 };
 
-// one residue byte per pair -> (byte << 7) in each 16-bit half
+// one residue byte per pair (pair A in byte 0, pair B in byte 1) -> (byte << 8) in each 16-bit
+// half: a single PRMT.  Different residues then XOR to >= 256 > penalty, equal ones to 0.
 __device__ __forceinline__ uint32_t widen(uint32_t v) {
-  return ((v & 0xffu) << 7) | ((v & 0xff00u) << 15);
+  return __byte_perm(v, 0u, 0x1404u);
 }
 
 // start state of the traceback at the end cell (nw_affine:251-280: pushed I, M, D; popped
@@ -371,18 +372,14 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   // panels hold one byte per pair per position: low byte pair A, high byte pair B
   uint2* bnd = reinterpret_cast<uint2*>(smem);                                     // [rows][NG]
   uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (size_t)p.smem_bnd_rows * NG);  // [rows][NG]
-  uint16_t* qp = dp + p.smem_d_halfs;                                              // [n1pad][NG]
 
   // ext2: the per-cell constant of the recurrence (affine: diagonal constant; linear: flag saving)
   const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = (ALGO == kLinear) ? p.ext2 : p.cm2, zero = p.zero;
 
-  // ---- stage the residues; they are widened to (byte << 7) per 16-bit half when read, so the
-  //      XOR of two different residues is >= 128 >= pen2 and the XOR of equal residues is 0 ----
-  for (uint32_t y = j; y < n1pad; y += G) {
-    const uint32_t a = (y < n1a) ? load_residue(p.residues, qoa + y, p.packing) : 0u;
-    const uint32_t b = (y < n1b) ? load_residue(p.residues, qob + y, p.packing) : 0u;
-    qp[y * NG + grp] = (uint16_t)(a | (b << 8));
-  }
+  // ---- stage the db residues (one per row, read by every strip); they are widened to
+  //      (byte << 8) per 16-bit half when read, so the XOR of two different residues is >= 256 >
+  //      pen2 and the XOR of equal residues is 0.  Query residues are read once per strip,
+  //      straight from global memory into registers: shared memory bounds the warps per SM ----
   for (uint32_t x = j; x < n2t; x += G) {
     const uint32_t a = (x < n2a) ? load_residue(p.residues, doa + x, p.packing) : 0u;
     const uint32_t b = (x < n2b) ? load_residue(p.residues, dob + x, p.packing) : 0u;
@@ -418,7 +415,9 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
         st.Hrow[c] = p.row0;  // H'[0][y] = D'[0][y]  (nw_affine:194-198), constant in V'
         st.F[c] = p.row0;     // D'[1][y] extends D[0][y]; M[0][y]+open is the sentinel
       }
-      st.q[c] = widen(qp[(y - 1) * NG + grp]);
+      const uint32_t qa = (y <= n1a) ? load_residue(p.residues, qoa + y - 1, p.packing) : 0u;
+      const uint32_t qb = (y <= n1b) ? load_residue(p.residues, qob + y - 1, p.packing) : 0u;
+      st.q[c] = widen(qa | (qb << 8));
     }
     if (ALGO == kLinear)
       st.hd_prev = (y0 == 0) ? p.origin : p.row0 - y0 * p.step2;  // S'[0][j0]; S[0][0] = 2*open
