@@ -416,7 +416,7 @@ def main():
             k_cups = pr["cells"] / (pr["ms"] * 1e-3)
             roof = {
                 "bound": "int-issue (integer max-plus DP: neither HBM nor tensor cores bind; DESIGN.md 4.1)",
-                "kernel": "nw_affine_fill_s16<8,G,0x00>",
+                "kernel": "nw_affine_fill_s16<K,G> (150 bp: K=19 columns per lane, G=8 lanes per pair-of-pairs, single pass)",
                 "achieved": k_cups * OPS_PER_CELL_ISSUED / 1e12, "peak": ipeak / 1e12, "unit": "T lane-instr/s",
                 "frac": k_cups * OPS_PER_CELL_ISSUED / ipeak,
                 "lane_instr_per_cell": OPS_PER_CELL_ISSUED,

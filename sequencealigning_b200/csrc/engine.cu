@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -100,7 +101,7 @@ struct sa_engine {
   sa_timing_t timing = {};
   int sm_count = 0;
   size_t smem_optin = 0;
-  int force_g = 0;
+  int force_g = 0, force_k = 0, minb = 0;
   uint32_t ormask = 0x00;
   size_t tb_budget = 0;
   size_t budget_cached = 0;
@@ -149,64 +150,83 @@ sa_status_t ensure(sa_engine* e, DevBuf& b, size_t bytes) {
 }
 
 struct Geometry {
-  int G = 4;
+  int K = 8;  // columns per lane per row (8, 16 or 19)
+  int G = 4;  // lanes per pair-of-pairs
+  bool single = false;  // K*G covers every column: one pass, no boundary column
+  uint32_t w = 1;       // traceback words (uint2) per strip row
   uint32_t ng = 8, ppt = 16;
   uint32_t nstrips_pad = 0, n1pad = 0, tb_rows = 0;
   uint64_t tile_stride = 0;  // uint2 per tile
-  uint32_t d_halfs = 0;
   size_t smem_bytes = 0;
 };
 
-// dynamic shared memory of one fill warp: the boundary column (uint2 per row per pair-of-pairs)
-// and the db residue panel (u16 per row per pair-of-pairs)
-inline uint64_t fill_smem_bytes(uint64_t rows, uint64_t ng) {
-  return (rows * ng * (8 + 2) + 15) & ~(uint64_t)15;
+// dynamic shared memory of one fill warp: the db residue panel (u16 per row per pair-of-pairs)
+// and, for multi-pass launches, the boundary column (uint2 per row per pair-of-pairs)
+inline uint64_t fill_smem_bytes(uint64_t rows, uint64_t ng, bool single = false) {
+  return (rows * ng * (single ? 2 : 10) + 15) & ~(uint64_t)15;
 }
 
-Geometry make_geometry(int G, uint32_t n1max, uint32_t n2max) {
+Geometry make_geometry(int K, int G, uint32_t n1max, uint32_t n2max) {
   Geometry g;
+  g.K = K;
   g.G = G;
+  g.w = (uint32_t)(K + 7) / 8;
   g.ng = 32 / G;
   g.ppt = 2 * g.ng;
-  const uint32_t nstrips = (n1max + kK - 1) / kK;
-  const uint32_t npass = (nstrips + G - 1) / G;
-  g.nstrips_pad = std::max(1u, npass * G);
-  g.n1pad = g.nstrips_pad * kK;
+  const uint32_t nstrips = (n1max + K - 1) / K;
+  const uint32_t npass = std::max(1u, (nstrips + G - 1) / G);
+  g.single = (K != 8) && npass == 1;  // the 8-column kernels keep the general multi-pass form
+  g.nstrips_pad = npass * G;
+  g.n1pad = g.nstrips_pad * K;
   g.tb_rows = std::max(1u, n2max);
-  g.tile_stride = (uint64_t)g.nstrips_pad * g.tb_rows * g.ng;
-  g.d_halfs = g.tb_rows * g.ng;  // one u16 (two residues) per row per pair-of-pairs
-  g.smem_bytes = (size_t)fill_smem_bytes(g.tb_rows, g.ng);
+  g.tile_stride = (uint64_t)g.nstrips_pad * g.tb_rows * g.ng * g.w;
+  g.smem_bytes = (size_t)fill_smem_bytes(g.tb_rows, g.ng, g.single);
   return g;
 }
 
-// Lanes per pair-of-pairs: least padded work (passes x rows incl. the G-1 ramp rows, per pair),
-// discounted when fewer than 12 warps fit one SM's shared memory (the fill is latency-bound
-// below that: ncu shows "wait" stalls dominating at 10 warps/SM).
-int choose_g(const sa_engine* e, uint32_t n1max, uint32_t n2max) {
-  if (e->force_g) return e->force_g;
-  int best = 0;
+// The (K, G) forms that are compiled.  K = 16 and 19 exist only as single-pass kernels.
+struct Form {
+  int K, G, regs;  // regs: registers per thread of the instantiation (cuobjdump -res-usage)
+};
+constexpr Form kForms[] = {{8, 1, 98},  {8, 2, 98},  {8, 4, 98},   {8, 8, 98},   {8, 16, 98},
+                           {8, 32, 98}, {16, 8, 116}, {16, 16, 116}, {19, 8, 142}, {19, 16, 142}};
+
+// Cost model for one shape class, in issue slots per pair:
+//   steps = passes x (rows + G - 1 ramp rows), 16 instructions per column + ~24 per row step,
+//   divided by the fraction of issue slots w resident warps keep busy (1 - 0.71^(w/4): fitted
+//   to ncu at 14 and 16 warps per SM; the fill is bound by the latency of its tie-bit predicates).
+Geometry choose_geometry(const sa_engine* e, uint32_t n1max, uint32_t n2max, bool linear) {
+  Geometry best;
+  best.G = 0;
   double best_cost = 1e300;
-  for (int G : {1, 2, 4, 8, 16, 32}) {
-    const Geometry g = make_geometry(G, n1max, n2max);
+  for (const Form& f : kForms) {
+    if (e->force_g && f.G != e->force_g) continue;
+    if (e->force_k && f.K != e->force_k) continue;
+    if (linear && f.K != 8) continue;
+    const Geometry g = make_geometry(f.K, f.G, n1max, n2max);
+    if (f.K != 8 && !g.single) continue;
     if (g.smem_bytes > e->smem_optin) continue;
-    const double warps = std::min(24.0, std::floor(227.0 * 1024 / (double)(g.smem_bytes + 1024)));
+    const double by_smem = std::floor(228.0 * 1024 / (double)(g.smem_bytes + 1024));
+    const double by_regs = std::floor(65536.0 / (32.0 * ((f.regs + 7) / 8 * 8)));
+    const double warps = std::min(32.0, std::min(by_smem, by_regs));
     if (warps < 1) continue;
-    const double npass = g.nstrips_pad / G;
-    double cost = npass * (n2max + G - 1) / (double)g.ppt;
-    const double occ = std::min(1.0, warps / 12.0);
-    cost /= (0.45 + 0.55 * occ);
+    const double npass = g.nstrips_pad / f.G;
+    const double steps = npass * (n2max + f.G - 1);
+    const double instr = 16.0 * f.K + (g.single ? 21.0 : 25.0);
+    const double busy = 1.0 - std::pow(0.71, warps / 4.0);
+    const double cost = steps * instr / (double)g.ppt / busy;
     if (cost < best_cost - 1e-12) {
       best_cost = cost;
-      best = G;
+      best = g;
     }
   }
   return best;
 }
 
-template <int G, uint32_t ORMASK, int ALGO = sa::kAffine>
+template <int K, int G, uint32_t ORMASK, int ALGO, bool SINGLE, int MINB = 1>
 sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
                           uint32_t n_tiles, cudaStream_t stream) {
-  auto kern = sa::nw_affine_fill_s16<kK, G, ORMASK, ALGO>;
+  auto kern = sa::nw_affine_fill_s16<K, G, ORMASK, ALGO, SINGLE, MINB>;
   size_t& configured = e->smem_configured[(const void*)kern];  // per engine = per device; only grows
   if (g.smem_bytes > configured) {
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -219,32 +239,40 @@ sa_status_t launch_fill_m(sa_engine* e, const sa::AffineS16Params& p, const Geom
   return SA_OK;
 }
 
+// 8-column multi-pass forms: every lane-group width, the linear aligner, the pipe-split knob
 template <int G>
-sa_status_t launch_fill(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
-                        uint32_t n_tiles, cudaStream_t stream, int algo) {
-  if (algo == SA_ALGO_NW_LINEAR) return launch_fill_m<G, 0x0F, sa::kLinear>(e, p, g, n_tiles, stream);
+sa_status_t launch_fill8(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
+                         uint32_t n_tiles, cudaStream_t stream, int algo) {
+  if (algo == SA_ALGO_NW_LINEAR) return launch_fill_m<8, G, 0x0F, sa::kLinear, false>(e, p, g, n_tiles, stream);
   switch (e->ormask) {
-    case 0x00: return launch_fill_m<G, 0x00>(e, p, g, n_tiles, stream);
-    case 0x03: return launch_fill_m<G, 0x03>(e, p, g, n_tiles, stream);
-    case 0x05: return launch_fill_m<G, 0x05>(e, p, g, n_tiles, stream);
-    case 0x0F: return launch_fill_m<G, 0x0F>(e, p, g, n_tiles, stream);
-    case 0x3F: return launch_fill_m<G, 0x3F>(e, p, g, n_tiles, stream);
-    case 0xFF: return launch_fill_m<G, 0xFF>(e, p, g, n_tiles, stream);
+    case 0x00: return launch_fill_m<8, G, 0x00, sa::kAffine, false>(e, p, g, n_tiles, stream);
+    case 0x0F: return launch_fill_m<8, G, 0x0F, sa::kAffine, false>(e, p, g, n_tiles, stream);
   }
   return fail(e, SA_E_ARG, "SA_ORMASK 0x%x has no instantiation", e->ormask);
 }
 
 sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geometry& g,
                           uint32_t n_tiles, cudaStream_t stream, int algo = SA_ALGO_NW_AFFINE) {
-  switch (g.G) {
-    case 1: return launch_fill<1>(e, p, g, n_tiles, stream, algo);
-    case 2: return launch_fill<2>(e, p, g, n_tiles, stream, algo);
-    case 4: return launch_fill<4>(e, p, g, n_tiles, stream, algo);
-    case 8: return launch_fill<8>(e, p, g, n_tiles, stream, algo);
-    case 16: return launch_fill<16>(e, p, g, n_tiles, stream, algo);
-    case 32: return launch_fill<32>(e, p, g, n_tiles, stream, algo);
+  if (g.K == 8) {
+    switch (g.G) {
+      case 1: return launch_fill8<1>(e, p, g, n_tiles, stream, algo);
+      case 2: return launch_fill8<2>(e, p, g, n_tiles, stream, algo);
+      case 4: return launch_fill8<4>(e, p, g, n_tiles, stream, algo);
+      case 8: return launch_fill8<8>(e, p, g, n_tiles, stream, algo);
+      case 16: return launch_fill8<16>(e, p, g, n_tiles, stream, algo);
+      case 32: return launch_fill8<32>(e, p, g, n_tiles, stream, algo);
+    }
+  } else if (g.single && algo == SA_ALGO_NW_AFFINE) {
+    // single-pass forms
+    if (g.K == 16 && g.G == 8) return launch_fill_m<16, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 16 && g.G == 16) return launch_fill_m<16, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && e->minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && e->minb == 18) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 18>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && e->minb == 20) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 20>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
   }
-  return fail(e, SA_E_ARG, "bad G %d", g.G);
+  return fail(e, SA_E_ARG, "no fill kernel for K %d G %d", g.K, g.G);
 }
 
 uint32_t pack2(uint32_t v) { return v | (v << 16); }
@@ -397,20 +425,21 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
 
   Coverage cov;
   // Scans the next segment on the host: extent, shape maxima, residue ranges, geometry.
-  auto fits_packed = [&](uint32_t cols, uint32_t rows, int G) {
-    const uint32_t n1pad = std::max(1u, ((cols + kK * G - 1) / (kK * G)) * (kK * G));
-    return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows) + 64 <= sa::kBias &&
-           (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, n1pad, rows));
+  auto fits_packed = [&](uint32_t n1pad, uint32_t rows) {
+    return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, std::max(1u, n1pad), rows) + 64 <= sa::kBias &&
+           (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, std::max(1u, n1pad), rows));
   };
-  // lane-group width for a class: choose_g among the widths whose padded shape stays in range
-  auto pick_g = [&](uint32_t cols, uint32_t rows) -> int {
-    const int G = choose_g(e, cols, rows);
-    if (G && fits_packed(cols, rows, G)) return G;
-    for (int g : {1, 2, 4, 8, 16, 32}) {
-      const Geometry gg = make_geometry(g, cols, rows);
-      if (gg.smem_bytes <= e->smem_optin && fits_packed(cols, rows, g)) return g;
+  // kernel form for a class: the cheapest (K, G) whose padded shape stays in range, else any
+  // 8-column form that does.  G == 0: none.
+  auto pick_geometry = [&](uint32_t cols, uint32_t rows) -> Geometry {
+    Geometry g = choose_geometry(e, cols, rows, linear);
+    if (g.G && fits_packed(g.n1pad, rows)) return g;
+    for (int G : {1, 2, 4, 8, 16, 32}) {
+      g = make_geometry(8, G, cols, rows);
+      if (g.smem_bytes <= e->smem_optin && fits_packed(g.n1pad, rows)) return g;
     }
-    return 0;
+    g.G = 0;
+    return g;
   };
   // cheap per-pair test: no lane-group width keeps the pair inside the packed range and inside
   // one SM's shared memory (same arithmetic as make_geometry / s16_min_value_bound, no structs)
@@ -452,9 +481,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     }
     if (n_long && linear)
       return fail(e, SA_E_UNSUPPORTED, "linear NW: a pair exceeds the 16-bit packed range (no long-pair kernel for this aligner yet)");
-    int G = pick_g(sg.n1max, sg.n2max);
-    if (!G) G = 1;  // only possible when the segment has no short pair at all
-    sg.g = make_geometry(G, sg.n1max, sg.n2max);
+    sg.g = pick_geometry(sg.n1max, sg.n2max);
+    if (!sg.g.G) sg.g = make_geometry(8, 1, sg.n1max, sg.n2max);  // only possible when the segment has no short pair at all
     const size_t tile_bytes = (size_t)sg.g.tile_stride * 8;
     const uint64_t tiles_fit = std::max<uint64_t>(1, budget_main / tile_bytes);
     if ((uint64_t)cn > tiles_fit * sg.g.ppt) {
@@ -529,13 +557,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         Segment::Sub sub;
         sub.off = off;
         sub.cnt = cnt;
-        int Gc = pick_g(cmax, rmax);
-        if (!Gc) {
+        sub.g = pick_geometry(cmax, rmax);
+        if (!sub.g.G) {
           if (cmax && rmax)
             return fail(e, SA_E_UNSUPPORTED, "pair shape %u x %u fits no packed-kernel configuration", cmax, rmax);
-          Gc = 1;  // a class of empty pairs: nothing to fill
+          sub.g = make_geometry(8, 1, cmax, rmax);  // a class of empty pairs: nothing to fill
         }
-        sub.g = make_geometry(Gc, cmax, rmax);
         sub.tb_off = sg.tb_total;
         sg.tb_total += (uint64_t)((cnt + sub.g.ppt - 1) / sub.g.ppt) * sub.g.tile_stride;
         sg.subs.push_back(sub);
@@ -625,10 +652,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     fp.tb_tile_stride = g.tile_stride;
     fp.tb_rows = g.tb_rows;
     fp.smem_bnd_rows = g.tb_rows;
-    fp.smem_d_halfs = g.d_halfs;
     wp.tb_tile_stride = g.tile_stride;
     wp.tb_rows = g.tb_rows;
     wp.ng = g.ng;
+    wp.k = (uint32_t)g.K;
+    wp.k_inv = (uint32_t)((0x100000000ull + (uint32_t)g.K - 1) / (uint32_t)g.K);
+    wp.w = g.w;
   };
   // Streams the CIGAR pool to the host as segments finish.  After segment i's write walks a
   // copy of the running total is queued (slot i&1); one segment later the host reads it (by then
@@ -1128,6 +1157,8 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
     CUDA_TRY(e, cudaEventCreate(ev));
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
+  if (const char* s = getenv("SA_FORCE_K")) e->force_k = atoi(s);
+  if (const char* s = getenv("SA_MINB")) e->minb = atoi(s);
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);

@@ -30,8 +30,12 @@
 //     each, in registers) and runs one row behind lane j-1; the strip's right-edge H and E
 //     go to lane j+1 by __shfl_up_sync and from the last lane of the group to shared memory
 //     for the next pass.  Sequence words are staged once per tile in shared memory.
-//   * Traceback bits (4 per cell) leave the SM as one coalesced 8-byte store per lane per
-//     row-strip: [strip][row][group] uint2 = {pair A's 8 cells, pair B's 8 cells}.
+//   * Traceback bits (4 per cell) leave the SM as coalesced 8-byte stores per lane per
+//     row-strip: [strip][row][group][W] uint2 = {pair A's 8 cells, pair B's 8 cells}.
+//   * K (columns per lane) and G are chosen per shape class.  When K*G covers the whole query
+//     (150 bp: K = 19, G = 8) the launch is SINGLE-pass: no boundary column, no shared memory
+//     beyond the db panel, and the per-row overhead (shuffles, loads, stores) is spread over
+//     19 columns instead of 8.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -93,7 +97,7 @@ struct AffineS16Params {
   uint64_t tb_tile_stride;       // uint2 per tile
   uint32_t tb_rows;              // row stride (launch-wide max n2)
   uint32_t* __restrict__ end;    // per launch index: H'(16) | start_state << 16 | valid << 31
-  uint32_t smem_bnd_rows, smem_d_halfs;  // per-warp layout: boundary rows, then db panel (u16), then query panel
+  uint32_t smem_bnd_rows;        // rows of the boundary column that precedes the db panel (multi-pass)
   // scheme in transformed units (all positive magnitudes)
   uint32_t pen2;    // 2*(match-mismatch), packed in both halves
   uint32_t open2;   // -2*open, packed
@@ -150,34 +154,50 @@ __device__ __forceinline__ uint32_t vmax_tie(uint32_t a, uint32_t b, uint32_t& a
 
 // ORMASK: bit (2*k + half) set -> the tie bit of comparison k (0 pI, 1 pD, 2 pE, 3 pF) for
 // that half is set with `or` (alu pipe), else with `add` (fma-heavy pipe).
-template <int K, int C, uint32_t ORMASK>
+// The traceback nibble of column c lives in word c/8 of the pair's accumulators.
+// CAP: also keep M' and the incoming I' of every column (only the rarely executed copy of the
+// row that holds a pair's end cell needs them).
+template <int K, int C, uint32_t ORMASK, bool CAP>
 struct StripCells {
+  static constexpr int W = (K + 7) / 8;
   static __device__ __forceinline__ void run(uint32_t (&Hrow)[K], uint32_t (&F)[K],
                                              const uint32_t (&q)[K], uint32_t d, uint32_t hdiag,
                                              uint32_t& E, uint32_t pen2, uint32_t open2,
-                                             uint32_t cm2, uint32_t& acc_a, uint32_t& acc_b,
-                                             uint32_t (&Mv)[K], uint32_t (&Ev)[K]) {
+                                             uint32_t cm2, uint32_t zero, uint32_t (&acc_a)[W], uint32_t (&acc_b)[W],
+                                             uint32_t (&Mv)[CAP ? K : 1], uint32_t (&Ev)[CAP ? K : 1]) {
     constexpr int c = C;
+    constexpr int w = c / 8;
+    constexpr uint32_t sh = 4 * (c % 8);
+    // A new accumulator word starts from the previous one (AND 0): one dependency chain for all
+    // tie-bit sets keeps ptxas from hoisting the VIMNMXs of later columns, whose predicates it
+    // would otherwise have to spill (there are only seven predicate registers).
+    if (c > 0 && c % 8 == 0) {
+      acc_a[w] = acc_a[w - 1] & zero;
+      acc_b[w] = acc_b[w - 1] & zero;
+    }
     const uint32_t hup = Hrow[c];
     const uint32_t m = __vminu2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
     const uint32_t M = hdiag + cm2 - m;           // M'[x][y]: one IADD3; no half leaves [0, 65535]
-    Mv[c] = M;  // kept only for the end-cell capture (a rarely taken branch after the row)
-    Ev[c] = E;
-    const uint32_t t = vmax_tie<(1u << (4 * c)), (ORMASK >> 0) & 1, (ORMASK >> 1) & 1>(E, M, acc_a, acc_b);     // I >= M
-    const uint32_t H = vmax_tie<(2u << (4 * c)), (ORMASK >> 2) & 1, (ORMASK >> 3) & 1>(F[c], t, acc_a, acc_b);  // D >= max(I,M)
+    if (CAP) {
+      Mv[CAP ? c : 0] = M;
+      Ev[CAP ? c : 0] = E;
+    }
+    const uint32_t t = vmax_tie<(1u << sh), (ORMASK >> 0) & 1, (ORMASK >> 1) & 1>(E, M, acc_a[w], acc_b[w]);     // I >= M
+    const uint32_t H = vmax_tie<(2u << sh), (ORMASK >> 2) & 1, (ORMASK >> 3) & 1>(F[c], t, acc_a[w], acc_b[w]);  // D >= max(I,M)
     const uint32_t Mo = M - open2;
-    E = vmax_tie<(4u << (4 * c)), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a, acc_b);        // open ties/wins: I'[x][y+1]
-    F[c] = vmax_tie<(8u << (4 * c)), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a, acc_b);  // open ties/wins: D'[x+1][y]
+    E = vmax_tie<(4u << sh), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a[w], acc_b[w]);        // open ties/wins: I'[x][y+1]
+    F[c] = vmax_tie<(8u << sh), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a[w], acc_b[w]);  // open ties/wins: D'[x+1][y]
     Hrow[c] = H;
-    StripCells<K, C + 1, ORMASK>::run(Hrow, F, q, d, hup, E, pen2, open2, cm2, acc_a, acc_b, Mv, Ev);
+    StripCells<K, C + 1, ORMASK, CAP>::run(Hrow, F, q, d, hup, E, pen2, open2, cm2, zero, acc_a, acc_b, Mv, Ev);
   }
 };
-template <int K, uint32_t ORMASK>
-struct StripCells<K, K, ORMASK> {
+template <int K, uint32_t ORMASK, bool CAP>
+struct StripCells<K, K, ORMASK, CAP> {
+  static constexpr int W = (K + 7) / 8;
   static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K],
                                              uint32_t, uint32_t, uint32_t&, uint32_t, uint32_t,
-                                             uint32_t, uint32_t&, uint32_t&, uint32_t (&)[K],
-                                             uint32_t (&)[K]) {}
+                                             uint32_t, uint32_t, uint32_t (&)[W], uint32_t (&)[W],
+                                             uint32_t (&)[CAP ? K : 1], uint32_t (&)[CAP ? K : 1]) {}
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,19 +285,22 @@ struct StripState {
   uint32_t out_h, out_e; // right boundary of the row just computed: H'[x][yK], E'[x][yK+1]
   uint32_t x;            // row this lane computes next (1-based)
   const uint16_t* dptr;  // shared: db residues of row x (both pairs)
-  uint2* bptr;           // shared: boundary column entry of row x
-  uint2* tptr;           // global: traceback word of (strip, row x)
+  uint2* bptr;           // shared: boundary column entry of row x (multi-pass launches only)
+  uint2* tptr;           // global: traceback words of (strip, row x)
   uint32_t capx_a, capx_b;  // row of pair A's / B's end cell if it lies in this strip, else 0
 };
 
 // One row of the lane's strip.  CHECKED = the lane may be outside [1, n2t] (ramp rows of a
-// pass, where the G lanes of a group are not all active yet / any more).
-template <int K, int G, uint32_t ORMASK, bool CHECKED, int ALGO>
+// pass, where the G lanes of a group are not all active yet / any more).  SINGLE = the launch
+// has one pass: the left edge of lane 0 is column 0 (a constant in V') and nothing is handed
+// to a next pass, so no boundary column exists at all.
+template <int K, int G, uint32_t ORMASK, bool CHECKED, int ALGO, bool SINGLE>
 __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Params& p, int j,
                                          uint32_t n2t, uint32_t pen2, uint32_t open2,
                                          uint32_t ext2, uint32_t zero, uint32_t la, uint32_t lb,
                                          uint32_t ca_, uint32_t cb_) {
   constexpr int NG = 32 / G;
+  constexpr int W = (K + 7) / 8;
   uint32_t rh = 0, re = 0;
   if (G > 1) {
     rh = __shfl_up_sync(0xffffffffu, st.out_h, 1);
@@ -285,59 +308,92 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
   }
   const bool active = !CHECKED || (st.x >= 1 && st.x <= n2t);
   if (active) {
-    if (j == 0) {  // left edge of the group: column 0 (pass 0, staged in the prologue) or the
-      const uint2 b = *st.bptr;  // previous pass's last strip
-      rh = b.x;
-      re = b.y;
+    if (j == 0) {  // left edge of the group
+      if (SINGLE) {
+        rh = re = p.row0;  // H'[x][0] = I'[x][0], and I'[x][1] extends it for free (:200-216)
+      } else {
+        const uint2 b = *st.bptr;  // column 0 (staged in the prologue) or the previous pass's last strip
+        rh = b.x;
+        re = b.y;
+      }
     }
     const uint32_t d = widen(*st.dptr);
-    uint32_t E = re, acc_a = zero, acc_b = zero;
-    uint32_t Mv[K], Ev[K];
-    if (ALGO == kLinear) {
+    uint32_t E = re;
+    uint32_t acc_a[W], acc_b[W];
+    acc_a[0] = acc_b[0] = zero;  // the other words are started inside StripCells
+    if constexpr (ALGO == kLinear) {
       // open2 = open' magnitude, ext2 = open' - ext' (what a set gap flag saves), per half
       uint32_t sl = rh;
       LinearCells<K, 0>::run(st.Hrow, st.F, st.q, d, st.hd_prev, sl, E, pen2, open2, ext2 & 0xffffu,
-                             ext2 & 0xffff0000u, acc_a, acc_b);
-#pragma unroll
-      for (int c = 0; c < K; ++c) Mv[c] = Ev[c] = 0;
-    } else {
-      StripCells<K, 0, ORMASK>::run(st.Hrow, st.F, st.q, d, st.hd_prev, E, pen2, open2, ext2, acc_a,
-                                    acc_b, Mv, Ev);
-    }
-    if (st.x == st.capx_a || st.x == st.capx_b) {  // rare: this row holds a pair's end cell
+                             ext2 & 0xffff0000u, acc_a[0], acc_b[0]);
+    } else if (st.x != st.capx_a && st.x != st.capx_b) {
+      uint32_t Mv[1], Ev[1];
+      StripCells<K, 0, ORMASK, false>::run(st.Hrow, st.F, st.q, d, st.hd_prev, E, pen2, open2, ext2,
+                                           zero, acc_a, acc_b, Mv, Ev);
+    } else {  // rare: this row holds a pair's end cell -- same cells, M' and I' kept
+      uint32_t Mv[K], Ev[K];
+      StripCells<K, 0, ORMASK, true>::run(st.Hrow, st.F, st.q, d, st.hd_prev, E, pen2, open2, ext2,
+                                          zero, acc_a, acc_b, Mv, Ev);
       if (st.x == st.capx_a) {
-        uint32_t H = 0, M = 0, Ei = 0;
+        uint32_t H = 0, M = 0, Ei = 0, dw = 0;
 #pragma unroll
         for (int c = 0; c < K; ++c)
-          if ((uint32_t)c == ca_) { H = st.Hrow[c] & 0xffffu; M = Mv[c] & 0xffffu; Ei = Ev[c] & 0xffffu; }
-        p.end[la] = end_word(H, M, Ei, (acc_a >> (4 * ca_ + 1)) & 1u);
+          if ((uint32_t)c == ca_) {
+            H = st.Hrow[c] & 0xffffu; M = Mv[c] & 0xffffu; Ei = Ev[c] & 0xffffu;
+            dw = (acc_a[c / 8] >> (4 * (c % 8) + 1)) & 1u;
+          }
+        p.end[la] = end_word(H, M, Ei, dw);
       }
       if (st.x == st.capx_b) {
-        uint32_t H = 0, M = 0, Ei = 0;
+        uint32_t H = 0, M = 0, Ei = 0, dw = 0;
 #pragma unroll
         for (int c = 0; c < K; ++c)
-          if ((uint32_t)c == cb_) { H = st.Hrow[c] >> 16; M = Mv[c] >> 16; Ei = Ev[c] >> 16; }
-        p.end[lb] = end_word(H, M, Ei, (acc_b >> (4 * cb_ + 1)) & 1u);
+          if ((uint32_t)c == cb_) {
+            H = st.Hrow[c] >> 16; M = Mv[c] >> 16; Ei = Ev[c] >> 16;
+            dw = (acc_b[c / 8] >> (4 * (c % 8) + 1)) & 1u;
+          }
+        p.end[lb] = end_word(H, M, Ei, dw);
+      }
+    }
+    if (ALGO == kLinear) if (st.x == st.capx_a || st.x == st.capx_b) {
+      // the linear aligner's end word is just S' (its walk needs no start state)
+      if (st.x == st.capx_a) {
+        uint32_t H = 0;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if ((uint32_t)c == ca_) H = st.Hrow[c] & 0xffffu;
+        p.end[la] = end_word(H, 0, 0, false);
+      }
+      if (st.x == st.capx_b) {
+        uint32_t H = 0;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if ((uint32_t)c == cb_) H = st.Hrow[c] >> 16;
+        p.end[lb] = end_word(H, 0, 0, false);
       }
     }
     st.hd_prev = rh;
     st.out_h = st.Hrow[K - 1];
     st.out_e = E;
-    if (j == G - 1) *st.bptr = make_uint2(st.out_h, st.out_e);
-    *st.tptr = make_uint2(acc_a, acc_b);
+    if (!SINGLE && j == G - 1) *st.bptr = make_uint2(st.out_h, st.out_e);
+#pragma unroll
+    for (int w = 0; w < W; ++w) st.tptr[w] = make_uint2(acc_a[w], acc_b[w]);
   }
   // the cursor advances whether or not the row was in range, so that x == t - j always
   st.x += 1;
   st.dptr += NG;
-  st.bptr += NG;
-  st.tptr += NG;
+  if (!SINGLE) st.bptr += NG;
+  st.tptr += NG * W;
 }
 
-template <int K, int G, uint32_t ORMASK, int ALGO = kAffine>
-__global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p) {
-  static_assert(K == 8, "traceback word layout assumes 8 cells x 4 bits");
+// Traceback layout: [tile][strip][row][group][W] uint2 = {pair A's word w, pair B's word w};
+// word w of a strip holds the nibbles of its columns 8w .. 8w+7.
+template <int K, int G, uint32_t ORMASK, int ALGO = kAffine, bool SINGLE = false, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB) nw_affine_fill_s16(const AffineS16Params p) {
   constexpr int NG = 32 / G;       // pair-of-pairs per warp tile
   constexpr int PPT = 2 * NG;      // pairs per tile
+  constexpr int W = (K + 7) / 8;   // traceback words per pair per strip row
+  static_assert(ALGO == kAffine || (K == 8 && !SINGLE), "the linear aligner uses the 8-column multi-pass form");
   extern __shared__ uint32_t smem[];
   const int lane = threadIdx.x;
   const int grp = lane / G, j = lane % G;
@@ -366,12 +422,12 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
   }
   if (n1t == 0 || n2t == 0) return;
   const uint32_t nstrips = (n1t + K - 1) / K;
-  const uint32_t npass = (nstrips + G - 1) / G;
-  const uint32_t n1pad = npass * G * K;
+  const uint32_t npass = SINGLE ? 1u : (nstrips + G - 1) / G;
 
-  // panels hold one byte per pair per position: low byte pair A, high byte pair B
-  uint2* bnd = reinterpret_cast<uint2*>(smem);                                     // [rows][NG]
-  uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (size_t)p.smem_bnd_rows * NG);  // [rows][NG]
+  // shared memory: [boundary column, multi-pass only: uint2 [rows][NG]] [db panel: u16 [rows][NG]]
+  // the panel holds one byte per pair per row: low byte pair A, high byte pair B
+  uint2* bnd = reinterpret_cast<uint2*>(smem);
+  uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (SINGLE ? 0 : (size_t)p.smem_bnd_rows * NG));
 
   // ext2: the per-cell constant of the recurrence (affine: diagonal constant; linear: flag saving)
   const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = (ALGO == kLinear) ? p.ext2 : p.cm2, zero = p.zero;
@@ -384,13 +440,15 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
     const uint32_t a = (x < n2a) ? load_residue(p.residues, doa + x, p.packing) : 0u;
     const uint32_t b = (x < n2b) ? load_residue(p.residues, dob + x, p.packing) : 0u;
     dp[x * NG + grp] = (uint16_t)(a | (b << 8));
-    // column 0 as the "previous pass" of pass 0.  Affine: H'[x][0] = I'[x][0] (:200-216), and
-    // I'[x][1] extends it (M[x][0] + open is the sentinel).  Linear: S'[i][0] with its gap flag
-    // set (needleman_wunsch.rs:55-64), i.e. the cell to its right pays an extension.
-    if (ALGO == kLinear) {
-      bnd[x * NG + grp] = make_uint2(p.row0 - (x + 1) * p.step2, open2 - ext2);
-    } else {
-      bnd[x * NG + grp] = make_uint2(p.row0, p.row0);  // extensions are free in V'
+    if (!SINGLE) {
+      // column 0 as the "previous pass" of pass 0.  Affine: H'[x][0] = I'[x][0] (:200-216), and
+      // I'[x][1] extends it (M[x][0] + open is the sentinel).  Linear: S'[i][0] with its gap flag
+      // set (needleman_wunsch.rs:55-64), i.e. the cell to its right pays an extension.
+      if (ALGO == kLinear) {
+        bnd[x * NG + grp] = make_uint2(p.row0 - (x + 1) * p.step2, open2 - ext2);
+      } else {
+        bnd[x * NG + grp] = make_uint2(p.row0, p.row0);  // extensions are free in V'
+      }
     }
   }
   __syncwarp();
@@ -431,19 +489,19 @@ __global__ void __launch_bounds__(32) nw_affine_fill_s16(const AffineS16Params p
     st.x = 1u - (uint32_t)j;
     st.dptr = dp + grp - (ptrdiff_t)j * NG;
     st.bptr = bnd + grp - (ptrdiff_t)j * NG;
-    st.tptr = tb_tile + ((uint64_t)s * p.tb_rows) * NG + grp - (ptrdiff_t)j * NG;
+    st.tptr = tb_tile + (((uint64_t)s * p.tb_rows) * NG + grp - (ptrdiff_t)j * NG) * W;
 
     uint32_t t = 1;
     // ramp-up: lanes j >= t are not active yet
     for (; t < (uint32_t)G && t <= n2t + G - 1; ++t)
-      row_step<K, G, ORMASK, true, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
+      row_step<K, G, ORMASK, true, ALGO, SINGLE>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     // steady state: every lane is inside [1, n2t]
 #pragma unroll 2
     for (; t <= n2t; ++t)
-      row_step<K, G, ORMASK, false, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
+      row_step<K, G, ORMASK, false, ALGO, SINGLE>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     // ramp-down
     for (; t <= n2t + G - 1; ++t)
-      row_step<K, G, ORMASK, true, ALGO>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
+      row_step<K, G, ORMASK, true, ALGO, SINGLE>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     __syncwarp();
   }
 }

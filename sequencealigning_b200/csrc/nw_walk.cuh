@@ -49,6 +49,7 @@ struct WalkParams {
   uint64_t tb_tile_stride;
   uint32_t tb_rows;
   uint32_t ng;           // pair-of-pairs per tile (32 / G)
+  uint32_t k, k_inv, w;  // columns per strip, ceil(2^32 / k), traceback words per strip row
   const uint32_t* __restrict__ end;  // per launch index
   int32_t match, open, ext;
   // outputs, indexed by pair id
@@ -76,9 +77,10 @@ constexpr uint32_t kTmpRuns = 24;
 
 __device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile_base, uint32_t grp,
                                               uint32_t half, uint32_t x, uint32_t y) {
-  const uint32_t s = (y - 1) >> 3, c = (y - 1) & 7;
-  const uint2 w = __ldg(&p.tb[tile_base + ((uint64_t)s * p.tb_rows + (x - 1)) * p.ng + grp]);
-  return ((half ? w.y : w.x) >> (4 * c)) & 15u;
+  // strip and column-in-strip of column y-1; the reciprocal is exact for every y < 2^32 / k
+  const uint32_t s = __umulhi(y - 1, p.k_inv), c = (y - 1) - s * p.k;
+  const uint2 w = __ldg(&p.tb[tile_base + (((uint64_t)s * p.tb_rows + (x - 1)) * p.ng + grp) * p.w + (c >> 3)]);
+  return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
 }
 
 // MODE 0: classify + count runs (writes score/status/cigar_len, queues tainted pairs)
