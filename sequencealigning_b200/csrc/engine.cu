@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstddef>
@@ -91,6 +92,9 @@ struct sa_engine {
     DevBuf g_ids, g_meta, g_tb, g_rows, g_info, g_runs;  // long pairs (nw_general.cuh)
     cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
                                     // the next fill overlaps the tail of the previous one
+    cudaStream_t fill_stream = nullptr;  // LOW priority: only the fill kernels.  The walks, scans and
+                                         // copies of other segments then get SMs as fill CTAs retire,
+                                         // instead of queueing behind a whole fill
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
   } slot[2];
   // scratch (grow-only)
@@ -331,6 +335,7 @@ struct Segment {
   uint64_t long_tb_total = 0, long_runs_total = 0;
   uint32_t long_n1max = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
+  uint64_t cells = 0;  // sum of n1*n2 over the segment
   Geometry g;
 };
 
@@ -446,10 +451,15 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const uint32_t bound0 = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, 0, 0) + 64;
   const uint32_t per_step = sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, 1, 0) + 64 - bound0;
   const uint64_t max_sum = per_step ? (sa::kBias - std::min<uint32_t>(bound0, sa::kBias)) / per_step : 0;
+  // fast path in three compares: with G = 32 (least shared memory, at most 255 columns of
+  // padding) the pair is inside the sentinel guard, the affine range and one SM's shared memory
+  const uint64_t cm_aff = (uint64_t)(2 * sc.match - 4 * sc.gap_ext);
+  const uint64_t bias_aff = sa::s16_affine_bias(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
+  const uint64_t nmin_fast = linear ? ~0ull : (cm_aff && bias_aff + 2 + cm_aff <= 0xFFFFull ? (0xFFFFull - bias_aff - 2) / cm_aff - 1 : 0);
+  const uint64_t rows_fast = e->smem_optin >= 16 ? (e->smem_optin - 15) / 10 : 0;  // fill_smem_bytes(rows, 1) fits
   auto is_long = [&](uint32_t cols, uint32_t rows) -> bool {
-    // fast path: with G = 32 (least shared memory, at most 255 columns of padding) the pair fits
-    if ((uint64_t)cols + rows + 256 <= max_sum && fill_smem_bytes(rows, 1) <= e->smem_optin &&
-        (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, cols + 256, rows)))
+    if ((uint64_t)cols + rows + 256 <= max_sum && rows <= rows_fast &&
+        std::min<uint64_t>((uint64_t)cols + 256, rows) <= nmin_fast)
       return false;
     if (!cols || !rows) return false;
     for (uint32_t g = 1; g <= 32; g <<= 1) {
@@ -466,29 +476,73 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     sg = Segment{};
     sg.base = base;
     uint32_t cn = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(seg_target, 1u << 24), n - base);
-    // streaming from the host: ramp the segment size up so the first copy-in is short
-    if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
-    // shape maxima over the pairs the packed kernel can take; the others are "long"
-    uint32_t n_long = 0;
-    for (uint32_t i = 0; i < cn; ++i) {
-      const uint32_t a = h_cols[base + i], b = h_rows[base + i];
-      if (is_long(a, b)) {
-        ++n_long;
-        continue;
-      }
-      sg.n1max = std::max(sg.n1max, a);
-      sg.n2max = std::max(sg.n2max, b);
+    if (in && !e->seg_pairs_forced) {
+      // Streaming from the host: segment sizes ramp up so the first copy-in is short, and the
+      // batch ends with a ~128 K and a ~64 K segment so that little work (stage B of the last two
+      // segments, their copy-out) is left when the last fill ends.
+      const uint64_t rem = n - base, last = 65536, second_last = 131072;
+      if (rem <= last + last / 2)
+        cn = (uint32_t)rem;
+      else if (rem <= last + second_last + last / 2)
+        cn = (uint32_t)(rem - last);
+      else
+        cn = (uint32_t)std::min<uint64_t>(cn, rem - last - second_last);
     }
+    if (seg_target < seg_max) seg_target = std::min<uint64_t>(seg_max, seg_target * 2);
+    // ONE pass over the segment's pairs (this scan is host time the GPU may be waiting on):
+    // shape maxima over the pairs the packed kernel can take (the others are "long"), real
+    // cells, and -- when streaming from the host -- the residue ranges to upload
+    uint32_t n_long = 0;
+    uint64_t real = 0;
+    auto scan = [&](uint32_t count) {
+      n_long = 0;
+      real = 0;
+      sg.n1max = sg.n2max = 0;
+      uint32_t n1m = 0, n2m = 0;
+      uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0, cells = 0;
+      const bool ranges = in != nullptr;
+      for (uint32_t i = 0; i < count; ++i) {
+        const uint64_t p = base + i;
+        const uint32_t ql = h_q_len[p], dl = h_d_len[p];
+        const uint64_t c = (uint64_t)ql * dl;
+        cells += c;
+        if (ranges) {
+          const uint64_t qo = in->q_off[p], dO = in->d_off[p];
+          if (ql) {
+            qlo = std::min(qlo, qo);
+            qhi = std::max(qhi, qo + ql);
+          }
+          if (dl) {
+            dlo = std::min(dlo, dO);
+            dhi = std::max(dhi, dO + dl);
+          }
+        }
+        const uint32_t a = linear ? dl : ql, b = linear ? ql : dl;
+        if (is_long(a, b)) {
+          ++n_long;
+          continue;
+        }
+        real += c;
+        n1m = std::max(n1m, a);
+        n2m = std::max(n2m, b);
+      }
+      sg.n1max = n1m;
+      sg.n2max = n2m;
+      sg.qlo = qlo; sg.qhi = qhi; sg.dlo = dlo; sg.dhi = dhi;
+      sg.cells = cells;
+    };
+    scan(cn);
     if (n_long && linear)
       return fail(e, SA_E_UNSUPPORTED, "linear NW: a pair exceeds the 16-bit packed range (no long-pair kernel for this aligner yet)");
     sg.g = pick_geometry(sg.n1max, sg.n2max);
     if (!sg.g.G) sg.g = make_geometry(8, 1, sg.n1max, sg.n2max);  // only possible when the segment has no short pair at all
     const size_t tile_bytes = (size_t)sg.g.tile_stride * 8;
     const uint64_t tiles_fit = std::max<uint64_t>(1, budget_main / tile_bytes);
-    if ((uint64_t)cn > tiles_fit * sg.g.ppt) {
+    if ((uint64_t)cn > tiles_fit * sg.g.ppt) {  // the traceback scratch cannot hold the segment: shorten it
       cn = (uint32_t)(tiles_fit * sg.g.ppt);
-      n_long = 0;
-      for (uint32_t i = 0; i < cn; ++i) n_long += is_long(h_cols[base + i], h_rows[base + i]);
+      const Geometry keep = sg.g;
+      scan(cn);
+      sg.g = keep;
     }
     sg.n = cn;
     if (n_long) {
@@ -522,18 +576,22 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       // Ragged segment: the 16-64 pairs of a warp tile all run to the tile's largest shape, so
       // bucket pairs by (rows, columns) when the padded work of the given order exceeds the real
       // work by more than ~15 % (uniform read sets skip this; the sort is host time).
-      uint64_t real = 0, padded = 0;
+      // Cheap bound first: if even padding every pair to the segment's largest shape stays within
+      // 15 % of the real cells, the per-tile padding does too and the tile scan is skipped.
       const uint32_t ppt = sg.g.ppt;
-      for (uint32_t t0 = 0; t0 < ns; t0 += ppt) {
-        uint32_t a = 0, b = 0;
-        const uint32_t t1 = std::min(ns, t0 + ppt);
-        for (uint32_t i = t0; i < t1; ++i) {
-          const uint32_t id = id_at(i);
-          a = std::max(a, h_cols[id]);
-          b = std::max(b, h_rows[id]);
-          real += (uint64_t)h_cols[id] * h_rows[id];
+      uint64_t padded = (uint64_t)sg.n1max * sg.n2max * ns;
+      if (e->sort_mode == 0 && padded > real + real / 7 && ns > ppt) {
+        padded = 0;
+        for (uint32_t t0 = 0; t0 < ns; t0 += ppt) {
+          uint32_t a = 0, b = 0;
+          const uint32_t t1 = std::min(ns, t0 + ppt);
+          for (uint32_t i = t0; i < t1; ++i) {
+            const uint32_t id = id_at(i);
+            a = std::max(a, h_cols[id]);
+            b = std::max(b, h_rows[id]);
+          }
+          padded += (uint64_t)a * b * (t1 - t0);
         }
-        padded += (uint64_t)a * b * (t1 - t0);
       }
       if (e->sort_mode == 1 || (e->sort_mode == 0 && padded > real + real / 7 && ns > ppt)) {
         // stable counting sort by columns, then by rows (LSD): O(n + longest sequence)
@@ -595,19 +653,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         if (rr != SA_OK) return rr;
       }
     }
+    e->timing.cells += sg.cells;
     if (in) {
-      for (uint32_t i = 0; i < cn; ++i) {
-        const uint64_t p = base + i;
-        if (h_q_len[p]) {
-          sg.qlo = std::min(sg.qlo, in->q_off[p]);
-          sg.qhi = std::max(sg.qhi, in->q_off[p] + h_q_len[p]);
-        }
-        if (h_d_len[p]) {
-          sg.dlo = std::min(sg.dlo, in->d_off[p]);
-          sg.dhi = std::max(sg.dhi, in->d_off[p] + h_d_len[p]);
-        }
-        e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
-      }
       const uint64_t limit = in->packing ? in->residues_len * 4 : in->residues_len;
       if (sg.qhi > limit || sg.dhi > limit)
         return fail(e, SA_E_ARG, "a pair in [%llu, %llu) reaches past residues_len",
@@ -701,6 +748,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     }
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
+    CUDA_TRY(e, cudaStreamWaitEvent(sl.fill_stream, sl.ev_f0, 0));
     for (const Segment::Sub& sub : sg.subs) {
       set_geometry(sub.g);
       fp.pair_ids = d_order ? d_order + sub.off : nullptr;
@@ -709,9 +757,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       fp.tb = (uint2*)sl.tb.p + sub.tb_off;
       fp.end = (uint32_t*)sl.end.p + sub.off;
       fp.row0 = pack2(row0_clean + (linear ? 0u : 1u));  // affine: panic bonus on
-      if ((r = launch_fill_g(e, fp, sub.g, (sub.cnt + sub.g.ppt - 1) / sub.g.ppt, sx, s2.algo)) != SA_OK) return r;
+      if ((r = launch_fill_g(e, fp, sub.g, (sub.cnt + sub.g.ppt - 1) / sub.g.ppt, sl.fill_stream, s2.algo)) != SA_OK) return r;
     }
-    CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sx));
+    CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sl.fill_stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_f1, 0));
     for (const Segment::Sub& sub : sg.subs) {
       set_geometry(sub.g);
       wp.pair_ids = d_order ? d_order + sub.off : nullptr;
@@ -790,6 +839,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
     sa_status_t r;
     CUDA_TRY(e, cudaEventSynchronize(sl.ev_count));
+    if (getenv("SA_TRACE")) fprintf(stderr, "[sa trace]   count of segment at %llu arrived\n", (unsigned long long)sg.base);
     CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sl.ev_count, 0));
     const uint32_t n_re = e->h_count[4 + k];
     e->timing.pairs_rerun += n_re;
@@ -924,26 +974,53 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
 
   // Software pipeline over segments: A(0); then for each i: A(i+1) is queued BEFORE the host
   // waits for segment i's refill count, so the GPU never idles across the host round trip.
-  Segment seg[2];
+  // SA_TRACE=1: host-side timeline of the pipeline on stderr (developer aid)
+  static const bool trace = getenv("SA_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what, uint64_t a) {
+    if (trace)
+      fprintf(stderr, "[sa trace] %8.1f us  %s %llu\n",
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(), what,
+              (unsigned long long)a);
+  };
+  // The host scan (and copy-in) of segment i+2 is done before the host blocks on segment i's
+  // count, so stage A of i+2 can be queued the moment stage B of i is.
+  Segment seg[3];
+  bool have[3] = {false, false, false};
   if ((st = prepare(0, seg[0])) != SA_OK) return st;
+  have[0] = true;
+  mark("prepared", seg[0].n);
   if ((st = upload(seg[0])) != SA_OK) return st;
   if ((st = stage_a(seg[0], 0)) != SA_OK) return st;
-  for (int k = 0;; k ^= 1) {
-    const uint64_t next_base = seg[k].base + seg[k].n;
-    const bool have_next = next_base < n;
-    if (have_next) {
-      if ((st = prepare(next_base, seg[k ^ 1])) != SA_OK) return st;
-      if ((st = upload(seg[k ^ 1])) != SA_OK) return st;
-      if ((st = stage_a(seg[k ^ 1], k ^ 1)) != SA_OK) return st;
+  mark("queued A", seg[0].n);
+  auto prepare_ahead = [&](int cur, int nxt) -> sa_status_t {  // segment after seg[cur] into seg[nxt]
+    have[nxt] = false;
+    const uint64_t nb = seg[cur].base + seg[cur].n;
+    if (nb >= n) return SA_OK;
+    sa_status_t r = prepare(nb, seg[nxt]);
+    if (r != SA_OK) return r;
+    have[nxt] = true;
+    mark("prepared", seg[nxt].n);
+    return upload(seg[nxt]);
+  };
+  if ((st = prepare_ahead(0, 1)) != SA_OK) return st;
+  for (int i = 0;; ++i) {
+    const int cur = i % 3, nxt = (i + 1) % 3, nn = (i + 2) % 3;
+    if (have[nxt]) {
+      if ((st = stage_a(seg[nxt], (i + 1) & 1)) != SA_OK) return st;
+      mark("queued A", seg[nxt].n);
+      if ((st = prepare_ahead(nxt, nn)) != SA_OK) return st;
     }
-    if ((st = stage_b(seg[k], k)) != SA_OK) return st;
-    if (!have_next) break;
+    if ((st = stage_b(seg[cur], i & 1)) != SA_OK) return st;
+    mark("queued B", seg[cur].n);
+    if (!have[nxt]) break;
   }
   CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->stream));
   if (out || want_cigar) {
     // total CIGAR words (also the overflow check)
     CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 2, db.carry, 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    mark("main stream drained", 0);
     memcpy(used_out, e->h_count + 2, 8);
     if (out && want_cigar) {
       CUDA_TRY(e, send_pool_upto((seg_index - 1) & 1));  // the last segment's words
@@ -1145,10 +1222,15 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
                 prop.major, prop.minor);
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
-  CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_TRY(e, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_TRY(e, cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_greatest));
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
   CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-  for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->slot[k].stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(e, cudaStreamCreateWithPriority(&e->slot[k].stream, cudaStreamNonBlocking, prio_greatest));
+    CUDA_TRY(e, cudaStreamCreateWithPriority(&e->slot[k].fill_stream, cudaStreamNonBlocking, prio_least));
+  }
   for (cudaEvent_t* ev : {&e->ev_in, &e->ev_done, &e->ev_carry[0], &e->ev_carry[1], &e->slot[0].ev_count, &e->slot[1].ev_count,
                           &e->slot[0].ev_bdone, &e->slot[1].ev_bdone})
     CUDA_TRY(e, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -1187,8 +1269,10 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
       if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     cudaStreamDestroy(e->stream);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
       if (e->slot[k].stream) cudaStreamDestroy(e->slot[k].stream);
+      if (e->slot[k].fill_stream) cudaStreamDestroy(e->slot[k].fill_stream);
+    }
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
   }

@@ -1,0 +1,15 @@
+import os, sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np
+from sequencealigning_b200 import Engine, synth
+from sequencealigning_b200.engine import PinnedResult, pin_batch
+batch = synth.random_pairs(1000000, 150, 0.05, True, seed=0x5A02)
+packed = pin_batch(batch.packed())
+with Engine(0) as eng:
+    pres = PinnedResult(batch.n_pairs, 40_000_000)
+    for _ in range(3):
+        eng.align(packed, out=pres)
+    os.environ["SA_TRACE"] = "1"
+    t0 = time.perf_counter()
+    eng.align(packed, out=pres)
+    print("total ms", (time.perf_counter() - t0) * 1e3, file=sys.stderr)
