@@ -31,7 +31,7 @@
 //     go to lane j+1 by __shfl_up_sync and from the last lane of the group to shared memory
 //     for the next pass.  Sequence words are staged once per tile in shared memory.
 //   * Traceback bits (4 per cell) leave the SM as coalesced 8-byte stores per lane per
-//     row-strip: [strip][row][group][W] uint2 = {pair A's 8 cells, pair B's 8 cells}.
+//     row-strip: [strip][row][W][group] uint2 = {pair A's 8 cells, pair B's 8 cells}.
 //   * K (columns per lane) and G are chosen per shape class.  When K*G covers the whole query
 //     (150 bp: K = 19, G = 8) the launch is SINGLE-pass: no boundary column, no shared memory
 //     beyond the db panel, and the per-row overhead (shuffles, loads, stores) is spread over
@@ -377,7 +377,7 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
     st.out_e = E;
     if (!SINGLE && j == G - 1) *st.bptr = make_uint2(st.out_h, st.out_e);
 #pragma unroll
-    for (int w = 0; w < W; ++w) st.tptr[w] = make_uint2(acc_a[w], acc_b[w]);
+    for (int w = 0; w < W; ++w) st.tptr[w * NG] = make_uint2(acc_a[w], acc_b[w]);
   }
   // the cursor advances whether or not the row was in range, so that x == t - j always
   st.x += 1;
@@ -386,8 +386,10 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
   st.tptr += NG * W;
 }
 
-// Traceback layout: [tile][strip][row][group][W] uint2 = {pair A's word w, pair B's word w};
-// word w of a strip holds the nibbles of its columns 8w .. 8w+7.
+// Traceback layout: [tile][strip][row][W][group] uint2 = {pair A's word w, pair B's word w};
+// word w of a strip holds the nibbles of its columns 8w .. 8w+7.  The groups of a warp that
+// share a strip (same lane index j) write one contiguous run of NG * 8 bytes per word: whole
+// 32-byte sectors for NG >= 4.
 template <int K, int G, uint32_t ORMASK, int ALGO = kAffine, bool SINGLE = false, int MINB = 1>
 __global__ void __launch_bounds__(32, MINB) nw_affine_fill_s16(const AffineS16Params p) {
   constexpr int NG = 32 / G;       // pair-of-pairs per warp tile
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(32, MINB) nw_affine_fill_s16(const AffineS16Pa
     st.x = 1u - (uint32_t)j;
     st.dptr = dp + grp - (ptrdiff_t)j * NG;
     st.bptr = bnd + grp - (ptrdiff_t)j * NG;
-    st.tptr = tb_tile + (((uint64_t)s * p.tb_rows) * NG + grp - (ptrdiff_t)j * NG) * W;
+    st.tptr = tb_tile + ((uint64_t)s * p.tb_rows - (ptrdiff_t)j) * (NG * W) + grp;
 
     uint32_t t = 1;
     // ramp-up: lanes j >= t are not active yet

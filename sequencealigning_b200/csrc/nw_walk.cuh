@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile
                                               uint32_t half, uint32_t x, uint32_t y) {
   // strip and column-in-strip of column y-1; the reciprocal is exact for every y < 2^32 / k
   const uint32_t s = __umulhi(y - 1, p.k_inv), c = (y - 1) - s * p.k;
-  const uint2 w = __ldg(&p.tb[tile_base + (((uint64_t)s * p.tb_rows + (x - 1)) * p.ng + grp) * p.w + (c >> 3)]);
+  const uint2 w = __ldg(&p.tb[tile_base + (((uint64_t)s * p.tb_rows + (x - 1)) * p.w + (c >> 3)) * p.ng + grp]);
   return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
 }
 
