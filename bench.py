@@ -427,10 +427,10 @@ def main():
                 # u16x2 recurrence does that work in 8 issued instructions, so this ratio can pass 1
                 "s32_equivalent": {"ops_per_cell": OPS_PER_CELL_S32_EQUIV, "achieved": k_cups * OPS_PER_CELL_S32_EQUIV / 1e12,
                                    "frac": k_cups * OPS_PER_CELL_S32_EQUIV / ipeak},
-                "traffic": (11743 + 324) * pr["pairs"] if args.length == 150 else None,
+                "traffic": (14133 + 325) * pr["pairs"] if args.length == 150 else None,
                 "traffic_detail": {"unit": "DRAM bytes per fill launch",
                                    "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
-                                   "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 12067 B per 150 bp pair)"},
+                                   "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14458 B per 150 bp pair: 96-bit rows of 19 four-bit cells, rows padded to the tile)"},
                 "per_gpu": True,
                 "fill_ms_per_step_summed": fill_ms_step,
                 "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
