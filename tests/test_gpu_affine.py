@@ -318,3 +318,42 @@ def test_argument_errors_are_per_call_codes(engine):
     with Engine(0) as e2:
         r1, r2 = engine.align(b), e2.align(b)
         assert np.array_equal(r1.score, r2.score) and np.array_equal(r1.cigar, r2.cigar)
+
+
+@pytest.mark.parametrize("k,g", [(8, 4), (16, 8), (16, 16), (19, 8), (19, 16)])
+def test_every_kernel_form_at_its_column_boundaries(oracle, k, g, monkeypatch):
+    """Each compiled (K columns per lane, G lanes) form of the fill kernel, forced, on query
+    lengths around its strip and pass boundaries (single-pass forms fall back to the 8-column
+    kernel when K*G does not cover the query: that hand-over is part of what is tested)."""
+    from sequencealigning_b200 import Engine
+    import random
+    from tests.util import mutate, random_seq
+    monkeypatch.setenv("SA_FORCE_K", str(k))
+    monkeypatch.setenv("SA_FORCE_G", str(g))
+    rng = random.Random(1000 * k + g)
+    lens = sorted({1, 2, k - 1, k, k + 1, 8 * 3 + 1, k * g - k, k * g - 1, k * g, min(k * g + 1, 330), 150, 151})
+    with Engine(0) as eng:
+        for n1 in lens:
+            pairs = []
+            for _ in range(48):
+                q = random_seq(rng, n1, b"ACGTN")
+                d = mutate(rng, q, rng.choice((0.03, 0.1, 0.3)), True, b"ACGTN") if rng.random() < 0.8 else random_seq(rng, rng.randint(1, 200), b"ACGTN")
+                pairs.append((q, d))
+            b = _batch(pairs)
+            r = eng.align(b)
+            check_against_oracle(oracle, b, r, what=f"K={k} G={g} n1={n1}")
+
+
+@pytest.mark.parametrize("scheme", [(1, -1, -1, -1), (2, -3, -5, -2), (5, -4, 0, -6), (1, -30, -2, -1), (10, 0, -20, 0)])
+def test_other_scoring_schemes(engine, oracle, scheme):
+    """The transform constants (diagonal constant, bias, penalty) are functions of the scheme:
+    mismatch costlier than two extensions, zero open, zero extension."""
+    b = _batch(random_pair_list(sum(scheme) & 0xFF, 1500, 1, 180))
+    r = engine.align(b, scheme=scheme)
+    stride = int((b.q_len.astype(np.int64) + b.d_len.astype(np.int64)).max()) + 1
+    ref = oracle.affine_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=stride, n_threads=8, scheme=scheme)
+    assert np.array_equal(ref.score, r.score)
+    assert np.array_equal(ref.status, r.status)
+    assert np.array_equal(ref.cigar_len, r.cigar_len)
+    mask = np.arange(stride)[None, :] < ref.cigar_len[:, None]
+    assert np.array_equal(ref.cigar_pool[mask], r.cigar)
