@@ -154,7 +154,7 @@ sa_status_t ensure(sa_engine* e, DevBuf& b, size_t bytes) {
 }
 
 struct Geometry {
-  int K = 8;  // columns per lane per row (8, 16 or 19)
+  int K = 8;  // columns per lane per row (8, 13, 16 or 19)
   int G = 4;  // lanes per pair-of-pairs
   bool single = false;  // K*G covers every column: one pass, no boundary column
   uint32_t w = 1;       // traceback words (uint2) per strip row
@@ -188,12 +188,13 @@ Geometry make_geometry(int K, int G, uint32_t n1max, uint32_t n2max) {
   return g;
 }
 
-// The (K, G) forms that are compiled.  K = 16 and 19 exist only as single-pass kernels.
+// The (K, G) forms that are compiled.  K = 13, 16 and 19 exist only as single-pass kernels
+// (100/200 bp, 125/250 bp and 150/300 bp reads).
 struct Form {
   int K, G, regs;  // regs: registers per thread of the instantiation (cuobjdump -res-usage)
 };
 constexpr Form kForms[] = {{8, 1, 98},  {8, 2, 98},  {8, 4, 98},   {8, 8, 98},   {8, 16, 98},
-                           {8, 32, 98}, {16, 8, 116}, {16, 16, 116}, {19, 8, 142}, {19, 16, 142}};
+                           {8, 32, 98}, {13, 8, 104}, {13, 16, 104}, {16, 8, 116}, {16, 16, 116}, {19, 8, 142}, {19, 16, 142}};
 
 // Cost model for one shape class, in issue slots per pair:
 //   steps = passes x (rows + G - 1 ramp rows), 16 instructions per column + ~24 per row step,
@@ -268,6 +269,8 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     }
   } else if (g.single && algo == SA_ALGO_NW_AFFINE) {
     // single-pass forms
+    if (g.K == 13 && g.G == 8) return launch_fill_m<13, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 13 && g.G == 16) return launch_fill_m<13, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 8) return launch_fill_m<16, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 16) return launch_fill_m<16, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 8 && e->minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);

@@ -320,7 +320,7 @@ def test_argument_errors_are_per_call_codes(engine):
         assert np.array_equal(r1.score, r2.score) and np.array_equal(r1.cigar, r2.cigar)
 
 
-@pytest.mark.parametrize("k,g", [(8, 4), (16, 8), (16, 16), (19, 8), (19, 16)])
+@pytest.mark.parametrize("k,g", [(8, 4), (13, 8), (13, 16), (16, 8), (16, 16), (19, 8), (19, 16)])
 def test_every_kernel_form_at_its_column_boundaries(oracle, k, g, monkeypatch):
     """Each compiled (K columns per lane, G lanes) form of the fill kernel, forced, on query
     lengths around its strip and pass boundaries (single-pass forms fall back to the 8-column
