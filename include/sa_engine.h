@@ -180,6 +180,15 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
                                  uint32_t n2, const sa_scheme_t* scheme, uint64_t max_alignments,
                                  char* buf, size_t cap, uint64_t* n_printed, int32_t* panicked);
 
+/* Number of co-optimal alignments per pair = how many alignments the reference's traceback
+ * (needleman_wunsch_affine.rs:246-329) prints for the pair when nothing panics: the number of
+ * parent-list paths (:96-153) from the best end states (:247-280) to the origin.  Paths into the
+ * boundary chains (where the reference panics, :299/:303) are not counted; saturates at
+ * INT64_MAX / 4.  counts: host array of n_pairs.  Exact 32-bit recurrences, one thread per pair:
+ * a side API (about 20x the cost of sa_align_batch), not the hot path. */
+sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme, const sa_batch_t* batch,
+                                      int64_t* counts);
+
 /* Packer for packing = 1: appends n residues (A/C/G/T) to dst starting at residue index dst_pos.
  * SA_E_ARG at the first other byte.  Pure host code. */
 sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_pos);

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "sa_batch_upload", "sa_batch_free", "sa_align_resident", "sa_resident_download",
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
+    "sa_affine_count_cooptimal",
 ]
 
 
@@ -106,5 +107,7 @@ def lib() -> C.CDLL:
     l.sa_affine_all_alignments.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(Scheme), C.c_uint64,
                                            C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     l.sa_affine_all_alignments.restype = C.c_int64
+    l.sa_affine_count_cooptimal.argtypes = [vp, C.POINTER(Scheme), C.POINTER(Batch), vp]
+    l.sa_affine_count_cooptimal.restype = C.c_int
     _lib = l
     return l

@@ -33,6 +33,7 @@
 #include "wfa.cuh"
 #include "nw_parents.cuh"
 #include "nw_general.cuh"
+#include "nw_count.cuh"
 
 namespace {
 
@@ -1593,6 +1594,71 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   cudaGetLastError();
   e->timing.total_ms = e->timing.fill_ms;
   return rc;
+}
+
+// Co-optimal alignment counts for a whole batch (nw_count.cuh), in chunks that bound the scratch.
+sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme, const sa_batch_t* b,
+                                      int64_t* counts) {
+  if (!e || !b) return SA_E_ARG;
+  if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
+  const uint64_t n = b->n_pairs;
+  if (n == 0) return SA_OK;
+  if (!counts || !b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len))
+    return fail(e, SA_E_ARG, "null array");
+  if (n >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)n);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  sa_scheme_t sc = sa_scheme_t{5, -4, -8, -6};  // nw_affine.rs:15-20
+  if (scheme) sc = *scheme;
+  const uint64_t limit = b->packing ? b->residues_len * 4 : b->residues_len;
+  uint32_t n1max = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if ((b->q_len[i] && b->q_off[i] + b->q_len[i] > limit) || (b->d_len[i] && b->d_off[i] + b->d_len[i] > limit))
+      return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
+    n1max = std::max(n1max, b->q_len[i]);
+  }
+  sa_status_t st;
+  if ((st = ensure(e, e->b_res, b->residues_len)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_qoff, n * 8)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_doff, n * 8)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_qlen, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_dlen, n * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->b_coff, n * 8)) != SA_OK) return st;  // the counts
+  cudaStream_t s = e->stream;
+  CUDA_TRY(e, cudaMemcpyAsync(e->b_res.p, b->residues, b->residues_len, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(e, cudaMemcpyAsync(e->b_qoff.p, b->q_off, n * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(e, cudaMemcpyAsync(e->b_doff.p, b->d_off, n * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(e, cudaMemcpyAsync(e->b_qlen.p, b->q_len, n * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(e, cudaMemcpyAsync(e->b_dlen.p, b->d_len, n * 4, cudaMemcpyHostToDevice, s));
+  // rolling rows: 36 bytes per column per pair in flight; at most ~1 GB of scratch
+  const uint64_t cols = (uint64_t)n1max + 1;
+  uint64_t chunk = std::max<uint64_t>(128, std::min<uint64_t>(n, ((uint64_t)1 << 30) / (36 * cols)));
+  chunk = std::min<uint64_t>(chunk, (uint64_t)1 << 20);
+  if ((st = ensure(e, e->par_rows, chunk * cols * 12)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_bytes, chunk * cols * 24)) != SA_OK) return st;
+  sa::CountParams cp{};
+  cp.residues = (const uint8_t*)e->b_res.p;
+  cp.q_off = (const uint64_t*)e->b_qoff.p;
+  cp.q_len = (const uint32_t*)e->b_qlen.p;
+  cp.d_off = (const uint64_t*)e->b_doff.p;
+  cp.d_len = (const uint32_t*)e->b_dlen.p;
+  cp.packing = b->packing;
+  cp.match = sc.match;
+  cp.mismatch = sc.mismatch;
+  cp.open = sc.gap_open;
+  cp.ext = sc.gap_ext;
+  cp.rows = (int32_t*)e->par_rows.p;
+  cp.cnts = (int64_t*)e->par_bytes.p;
+  cp.cols = (uint32_t)cols;
+  cp.out = (int64_t*)e->b_coff.p;
+  for (uint64_t base = 0; base < n; base += chunk) {
+    cp.pair_base = (uint32_t)base;
+    cp.n_pairs = (uint32_t)std::min<uint64_t>(chunk, n - base);
+    sa::nw_affine_count_kernel<<<(cp.n_pairs + 127) / 128, 128, 0, s>>>(cp);
+    CUDA_TRY(e, cudaGetLastError());
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(counts, e->b_coff.p, n * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  return SA_OK;
 }
 
 // Every co-optimal alignment of one pair, in the order and text of the reference's traceback

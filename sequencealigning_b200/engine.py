@@ -294,6 +294,15 @@ class Engine:
         return buf.value.decode("latin1"), n.value, bool(pan.value)
 
     # ---- device-resident path (benchmarks: inputs already in HBM) -------------------------
+    def count_cooptimal(self, batch: PairBatch, scheme=None) -> np.ndarray:
+        """Per pair, how many alignments the reference's traceback prints when nothing panics
+        (sa_affine_count_cooptimal; saturates at INT64_MAX // 4)."""
+        counts = np.zeros(batch.n_pairs, np.int64)
+        cb = self._c_batch(batch)
+        sc = _scheme(scheme)
+        self._check(self._lib.sa_affine_count_cooptimal(self._h, C.byref(sc) if sc else None, C.byref(cb), counts.ctypes.data))
+        return counts
+
     def upload(self, batch: PairBatch) -> "ResidentBatch":
         h = C.c_void_p()
         cb = self._c_batch(batch)

@@ -357,3 +357,34 @@ def test_other_scoring_schemes(engine, oracle, scheme):
     assert np.array_equal(ref.cigar_len, r.cigar_len)
     mask = np.arange(stride)[None, :] < ref.cigar_len[:, None]
     assert np.array_equal(ref.cigar_pool[mask], r.cigar)
+
+
+def test_cooptimal_counts_match_the_oracle(engine, oracle):
+    """sa_affine_count_cooptimal: per pair, the number of alignments the reference prints when
+    nothing panics (oracle: n_cooptimal, the same parent-list path count), incl. empty sides,
+    repeats (many co-optimal paths), saturation, the 2-bit input format and another scheme."""
+    pairs = random_pair_list(77, 600, 0, 90)
+    pairs += [(b"", b""), (b"ACGT", b""), (b"", b"ACGT"), (b"A" * 60, b"A" * 40), (b"AC" * 40, b"CA" * 38),
+              (b"ACGT" * 30, b"ACGT" * 30), (b"A" * 200, b"A" * 120)]
+    b = _batch(pairs)
+    got = engine.count_cooptimal(b)
+    exp = np.array([oracle.affine_align(q, d).n_cooptimal for q, d in pairs], np.int64)
+    assert np.array_equal(got, exp), np.nonzero(got != exp)[0][:8]
+    assert (exp > 1).any() and (exp == 0).any()
+    # consistent with the enumeration (sa_affine_all_alignments) on pairs the reference completes
+    for i in [k for k in range(len(pairs)) if 0 < exp[k] <= 50][:10]:
+        _, n_printed, panicked = engine.all_alignments(*pairs[i])
+        if not panicked:
+            assert n_printed == exp[i], (i, n_printed, exp[i])
+    sch = (2, -3, -5, -2)
+    got2 = engine.count_cooptimal(b, scheme=sch)
+    exp2 = np.array([oracle.affine_align(q, d, sch).n_cooptimal for q, d in pairs], np.int64)
+    assert np.array_equal(got2, exp2)
+    # free gap opening: splitting a gap costs nothing, the count explodes and saturates
+    sch0 = (5, -4, 0, -6)
+    got3 = engine.count_cooptimal(b, scheme=sch0)
+    exp3 = np.array([oracle.affine_align(q, d, sch0).n_cooptimal for q, d in pairs], np.int64)
+    assert np.array_equal(got3, exp3)
+    assert exp3.max() == (2**63 - 1) // 4
+    acgt = _batch(random_pair_list(78, 300, 1, 120, alphabet=b"ACGT"))
+    assert np.array_equal(engine.count_cooptimal(acgt), engine.count_cooptimal(acgt.packed()))
