@@ -6,8 +6,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <memory>
+#include <new>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/sa_engine.h"
 
@@ -40,63 +49,187 @@ int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t*
   if (!path) return SA_E_ARG;
   // parse.rs:55-60: anything but .fa/.fasta/.fna is FastaError(InvalidInput)
   if (!(has_ext(path, "fa") || has_ext(path, "fasta") || has_ext(path, "fna"))) return SA_E_ARG;
-  FILE* f = fopen(path, "rb");
-  if (!f) return SA_E_ARG;  // parse.rs:62 `read(path)?`
-  std::vector<uint8_t> buf;
-  uint8_t tmp[1 << 16];
-  size_t got;
-  while ((got = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
-  fclose(f);
-
-  // The state machine of parse.rs:66-89.  A record's name is complete before its first
-  // residue arrives, so records are appended to `out` as name bytes then sequence bytes.
-  size_t cur = 0, nerr = 0;
-  int64_t nrec = -1;  // -1 while inside the default record that parse.rs:91 removes
-  RecordSpan r{0, 0, 0, 0};
-  bool in_name = false;
-  auto flush = [&]() {
-    if (nrec >= 0 && (size_t)nrec < index_cap && index) {
-      index[4 * nrec + 0] = r.name_off;
-      index[4 * nrec + 1] = r.name_len;
-      index[4 * nrec + 2] = r.seq_off;
-      index[4 * nrec + 3] = r.seq_len;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return SA_E_ARG;  // parse.rs:62 `read(path)?`
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(nt, 16u));
+  // The whole file in one (uninitialised) buffer.  A regular file is read by all threads at once
+  // (pread of disjoint ranges); anything else (pipe, /dev/stdin) by a plain read loop.
+  std::unique_ptr<uint8_t[]> storage;
+  size_t size = 0;
+  {
+    struct stat sb;
+    const bool regular = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0;
+    size_t cap = regular ? (size_t)sb.st_size : ((size_t)1 << 20);
+    storage.reset(new (std::nothrow) uint8_t[cap + 1]);
+    if (!storage) {
+      close(fd);
+      return SA_E_NOMEM;
     }
-  };
-  auto put = [&](uint8_t c) {
-    if (cur < out_cap && out) out[cur] = c;
-    ++cur;
-  };
-  for (uint8_t c : buf) {
-    if (c == '>') {
-      flush();
-      ++nrec;
-      if (nrec == 0) cur = 0;
-      r = RecordSpan{cur, 1, cur + 1, 0};
-      put(c);
-      in_name = true;
-      continue;
-    }
-    if (in_name) {
-      if (c == '\n') {
-        in_name = false;
-        continue;
+    if (regular) {
+      const unsigned rt = cap >= ((size_t)8 << 20) ? nt : 1;
+      std::vector<size_t> got(rt, 0);
+      auto rd = [&](unsigned k) {
+        size_t lo = cap / rt * k, hi = (k + 1 == rt) ? cap : cap / rt * (k + 1);
+        while (lo < hi) {
+          const ssize_t n = pread(fd, storage.get() + lo, hi - lo, (off_t)lo);
+          if (n <= 0) break;
+          lo += (size_t)n;
+          got[k] += (size_t)n;
+        }
+      };
+      if (rt == 1) {
+        rd(0);
+      } else {
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < rt; ++k) th.emplace_back(rd, k);
+        for (auto& t : th) t.join();
       }
-      put(c);
-      ++r.name_len;
-      r.seq_off = cur;
-    } else if (c == '\n') {
-      continue;
-    } else if (!allowed(c)) {
-      if (err_chars && nerr < err_cap) err_chars[nerr] = c;
-      ++nerr;
-    } else if (nrec >= 0) {
-      put(c);
-      ++r.seq_len;
+      // (a file truncated while being read ends at the first short range)
+      for (unsigned k = 0; k < rt; ++k) {
+        const size_t want = ((k + 1 == rt) ? cap : cap / rt * (k + 1)) - cap / rt * k;
+        size += got[k];
+        if (got[k] < want) break;
+      }
+    } else {
+      for (;;) {
+        if (size == cap) {
+          std::unique_ptr<uint8_t[]> bigger(new (std::nothrow) uint8_t[cap * 2 + 1]);
+          if (!bigger) {
+            close(fd);
+            return SA_E_NOMEM;
+          }
+          memcpy(bigger.get(), storage.get(), size);
+          storage.swap(bigger);
+          cap *= 2;
+        }
+        const ssize_t n = read(fd, storage.get() + size, cap - size);
+        if (n <= 0) break;
+        size += (size_t)n;
+      }
     }
   }
-  flush();
+  close(fd);
+  uint8_t* const data = storage.get();
+  const bool trace = getenv("SA_TRACE") != nullptr;
+  const auto t_read = std::chrono::steady_clock::now();
+
+  // The state machine of parse.rs:66-89, restated over byte classes: '>' ANYWHERE starts a
+  // record (also inside a header line); a header runs to the next '\n'; elsewhere '\n' is
+  // skipped, a byte outside ACGTN is reported, an allowed byte is appended -- to the default
+  // record before the first '>', which parse.rs:91 then removes.
+  //
+  // Parallel form: the file is cut at '>' bytes into one chunk per thread; a chunk is parsed IN
+  // PLACE (the output of a chunk is never longer than its input), then the compacted chunks are
+  // copied to `out` at their prefix offsets.  Chunk 0 starts at byte 0 (in the default record).
+  if (size < ((size_t)1 << 20)) nt = 1;
+  std::vector<size_t> start(nt + 1, size);
+  start[0] = 0;
+  for (unsigned k = 1; k < nt; ++k) {
+    const size_t from = std::max(start[k - 1], size / nt * k);
+    const void* gt = from < size ? memchr(data + from, '>', size - from) : nullptr;
+    start[k] = gt ? (size_t)((const uint8_t*)gt - data) : size;
+  }
+  struct Chunk {
+    size_t bytes = 0;                 // compacted output bytes, at data[start .. start + bytes)
+    std::vector<RecordSpan> recs;     // offsets relative to the chunk's start
+    std::vector<uint8_t> errs;        // first err_cap offending bytes, in order
+    size_t nerr = 0;
+  };
+  std::vector<Chunk> chunks(nt);
+  auto work = [&](unsigned k) {
+    Chunk& ch = chunks[k];
+    uint8_t* const base = data + start[k];
+    const uint8_t* p = base;
+    const uint8_t* const end = data + start[k + 1];
+    uint8_t* w = base;
+    bool have_rec = false;  // chunk 0 begins inside the default record
+    RecordSpan r{0, 0, 0, 0};
+    while (p < end) {
+      if (*p == '>') {
+        if (have_rec) ch.recs.push_back(r);
+        have_rec = true;
+        // header: '>' and everything up to the next '\n' or '>' (a '>' starts the next record)
+        const uint8_t* q = p + 1;
+        while (q < end && *q != '\n' && *q != '>') ++q;
+        r.name_off = (uint64_t)(w - base);
+        r.name_len = (uint64_t)(q - p);
+        memmove(w, p, (size_t)(q - p));
+        w += q - p;
+        r.seq_off = (uint64_t)(w - base);
+        r.seq_len = 0;
+        p = (q < end && *q == '\n') ? q + 1 : q;
+        continue;
+      }
+      // sequence bytes up to the next '>' : runs of allowed bytes are copied in one piece
+      const uint8_t* q = p;
+      while (q < end && allowed(*q)) ++q;
+      if (q > p) {
+        if (have_rec) {
+          memmove(w, p, (size_t)(q - p));
+          w += q - p;
+          r.seq_len += (uint64_t)(q - p);
+        }
+        p = q;
+        continue;
+      }
+      if (*p != '\n') {
+        if (ch.errs.size() < err_cap) ch.errs.push_back(*p);
+        ++ch.nerr;
+      }
+      ++p;
+    }
+    if (have_rec) ch.recs.push_back(r);
+    ch.bytes = (size_t)(w - base);
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; ++k) th.emplace_back(work, k);
+    for (auto& t : th) t.join();
+  }
+  const auto t_parse = std::chrono::steady_clock::now();
+  size_t cur = 0, nerr = 0;
+  int64_t nrec = 0;
+  struct Copy {
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t n;
+  };
+  std::vector<Copy> copies;
+  for (unsigned k = 0; k < nt; ++k) {
+    const Chunk& ch = chunks[k];
+    if (out && cur < out_cap) copies.push_back({out + cur, data + start[k], std::min(ch.bytes, out_cap - cur)});
+    for (const RecordSpan& r : ch.recs) {
+      if (index && (size_t)nrec < index_cap) {
+        index[4 * nrec + 0] = r.name_off + cur;
+        index[4 * nrec + 1] = r.name_len;
+        index[4 * nrec + 2] = r.seq_off + cur;
+        index[4 * nrec + 3] = r.seq_len;
+      }
+      ++nrec;
+    }
+    for (uint8_t c : ch.errs) {
+      if (err_chars && nerr < err_cap) err_chars[nerr] = c;
+      ++nerr;
+    }
+    nerr += ch.nerr - ch.errs.size();
+    cur += ch.bytes;
+  }
+  if (copies.size() <= 1) {
+    for (const Copy& c : copies) memcpy(c.dst, c.src, c.n);
+  } else {
+    std::vector<std::thread> th;
+    for (const Copy& c : copies) th.emplace_back([c] { memcpy(c.dst, c.src, c.n); });
+    for (auto& t : th) t.join();
+  }
   if (n_err) *n_err = nerr;
-  return nrec + 1;
+  if (trace)
+    fprintf(stderr, "[sa trace] parse_fasta %zu bytes, %u threads: parse %.1f ms, gather %.1f ms\n", size, nt,
+            std::chrono::duration<double, std::milli>(t_parse - t_read).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parse).count());
+  return nrec;
 }
 
 // 2-bit packer for sa_batch_t.packing = 1: appends n residues (A, C, G, T only) to `dst`

@@ -73,3 +73,36 @@ def test_quirks(tmp_path, oracle, ext):
     empty = _write(tmp_path, f"f.{ext}", b"")
     for parse in _parsers(oracle):
         assert parse(empty) == ([], [], b"")
+
+
+def test_large_file_takes_the_parallel_path_and_agrees_with_the_oracle(tmp_path, oracle):
+    """Files above 1 MB are cut at '>' bytes and parsed by several threads; the quirks must
+    survive the cuts: '>' inside header lines and inside sequence lines, bytes outside ACGTN
+    (reported in order), CRLF, blank lines, residues before the first header, no final newline."""
+    import random
+    rng = random.Random(5)
+    parts = [b"ACGTNN\nGG\n"]  # default record: dropped (parse.rs:91)
+    for i in range(30000):
+        name = b">r%d" % i
+        k = rng.random()
+        if k < 0.02:
+            name += b" with > inside"        # starts another record (a header of its own)
+        elif k < 0.04:
+            name += b"\r"
+        parts.append(name + b"\n")
+        for _ in range(rng.randint(0, 3)):
+            line = bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(0, 70)))
+            if rng.random() < 0.03:
+                pos = rng.randint(0, len(line))
+                line = line[:pos] + rng.choice([b"x", b"K", b"\r", b" ", b">mid"]) + line[pos:]
+            parts.append(line + (b"\n" if rng.random() < 0.98 else b"\n\n"))
+    parts.append(b">last\nACGT")
+    data = b"".join(parts)
+    assert len(data) > (1 << 20)
+    path = _write(tmp_path, "big.fasta", data)
+    product, orc = _parsers(oracle)
+    a, b = product(path), orc(path)
+    assert a[0] == b[0]
+    assert a[1] == b[1]
+    assert a[2] == b[2] and len(a[2]) > 100
+    assert len(a[0]) > 30000
