@@ -83,6 +83,23 @@ __device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile
   return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
 }
 
+// Next-state tables of the walk, 2 bits per nibble value (0 = M, 1 = I, 2 = D):
+//   from M: D if bit1, else I if bit0, else M      (:120-153 push M,I,D)
+//   from I: M if bit2 (opening ties/wins) else I   (:108-119)
+//   from D: M if bit3 else D                       (:96-107)
+__host__ __device__ constexpr uint32_t walk_lut(int st) {
+  uint32_t v = 0;
+  for (uint32_t nb = 0; nb < 16; ++nb) {
+    uint32_t nx = 0;
+    if (st == 0) nx = (nb & 2u) ? 2u : ((nb & 1u) ? 1u : 0u);
+    if (st == 1) nx = (nb & 4u) ? 0u : 1u;
+    if (st == 2) nx = (nb & 8u) ? 0u : 2u;
+    v |= nx << (2 * nb);
+  }
+  return v;
+}
+constexpr uint32_t kLutM = walk_lut(0), kLutI = walk_lut(1), kLutD = walk_lut(2);
+
 // MODE 0: classify + count runs (writes score/status/cigar_len, queues tainted pairs)
 // MODE 1: write runs into the pool (needs cigar_off)
 template <int MODE>
@@ -150,25 +167,16 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
       ++nruns;
     }
     ++run_len;
-    if (st == 0) {  // InM: emit a diagonal column, the next state is the best state of (x-1,y-1)
-      --x;
-      --y;
-      if (x > 0 && y > 0) {
-        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
-        st = (nb & 2u) ? 2u : ((nb & 1u) ? 1u : 0u);
-      }
-    } else if (st == 1) {  // InI: seq1[y-1] against '-'
-      --y;
-      if (y > 0) {
-        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
-        st = (nb & 4u) ? 0u : 1u;
-      }
-    } else {  // InD: '-' against seq2[x-1]
-      --x;
-      if (x > 0) {
-        const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
-        st = (nb & 8u) ? 0u : 2u;
-      }
+    // One step, the same instructions for every state (lanes of a warp are in different states):
+    //   M: emit a diagonal column, go to (x-1,y-1), next state = its best state, priority D > I > M
+    //   I: seq1[y-1] against '-', go to (x,y-1), next state M if opening ties/wins else I
+    //   D: '-' against seq2[x-1], go to (x-1,y), next state M if opening ties/wins else D
+    x -= (st != 1u);
+    y -= (st != 2u);
+    if (x > 0 && y > 0) {
+      const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
+      const uint32_t lut = st == 0 ? kLutM : (st == 1 ? kLutI : kLutD);
+      st = (lut >> (2 * nb)) & 3u;
     }
   }
   const bool complete = (x == 0 && y == 0);
