@@ -201,29 +201,34 @@ constexpr Form kForms[] = {{8, 1, 98},  {8, 2, 98},  {8, 4, 98},   {8, 8, 98},  
 //   steps = passes x (rows + G - 1 ramp rows), 16 instructions per column + ~24 per row step,
 //   divided by the fraction of issue slots w resident warps keep busy (1 - 0.71^(w/4): fitted
 //   to ncu at 14 and 16 warps per SM; the fill is bound by the latency of its tie-bit predicates).
-Geometry choose_geometry(const sa_engine* e, uint32_t n1max, uint32_t n2max, bool linear) {
+template <class Fits>
+Geometry choose_geometry(const sa_engine* e, uint32_t n1max, uint32_t n2max, bool linear, Fits&& fits) {
   Geometry best;
   best.G = 0;
-  double best_cost = 1e300;
-  for (const Form& f : kForms) {
-    if (e->force_g && f.G != e->force_g) continue;
-    if (e->force_k && f.K != e->force_k) continue;
-    if (linear && f.K != 8) continue;
-    const Geometry g = make_geometry(f.K, f.G, n1max, n2max);
-    if (f.K != 8 && !g.single) continue;
-    if (g.smem_bytes > e->smem_optin) continue;
-    const double by_smem = std::floor(228.0 * 1024 / (double)(g.smem_bytes + 1024));
-    const double by_regs = std::floor(65536.0 / (32.0 * ((f.regs + 7) / 8 * 8)));
-    const double warps = std::min(32.0, std::min(by_smem, by_regs));
-    if (warps < 1) continue;
-    const double npass = g.nstrips_pad / f.G;
-    const double steps = npass * (n2max + f.G - 1);
-    const double instr = 16.0 * f.K + (g.single ? 21.0 : 25.0);
-    const double busy = 1.0 - std::pow(0.71, warps / 4.0);
-    const double cost = steps * instr / (double)g.ppt / busy;
-    if (cost < best_cost - 1e-12) {
-      best_cost = cost;
-      best = g;
+  // a forced form (SA_FORCE_K / SA_FORCE_G) that cannot take the shape is ignored
+  for (int forced = (e->force_g || e->force_k) ? 1 : 0; forced >= 0 && !best.G; --forced) {
+    double best_cost = 1e300;
+    for (const Form& f : kForms) {
+      if (forced && e->force_g && f.G != e->force_g) continue;
+      if (forced && e->force_k && f.K != e->force_k) continue;
+      if (linear && f.K != 8) continue;
+      const Geometry g = make_geometry(f.K, f.G, n1max, n2max);
+      if (f.K != 8 && !g.single) continue;
+      if (g.smem_bytes > e->smem_optin || !fits(g.n1pad, n2max)) continue;
+      const double by_smem = std::floor(228.0 * 1024 / (double)(g.smem_bytes + 1024));
+      const double by_regs = std::floor(65536.0 / (32.0 * ((f.regs + 7) / 8 * 8)));
+      const double warps = std::min(32.0, std::min(by_smem, by_regs));
+      if (warps < 1) continue;
+      const double npass = g.nstrips_pad / f.G;
+      const double steps = npass * (n2max + f.G - 1);
+      const double instr = 16.0 * f.K + (g.single ? 21.0 : 25.0);
+      const double busy = 1.0 - std::pow(0.71, warps / 4.0);
+      // (multi-pass forms measure ~6 % slower than this count says: boundary-column traffic)
+      const double cost = steps * instr / (double)g.ppt / busy * (g.single ? 1.0 : 1.06);
+      if (cost < best_cost - 1e-12) {
+        best_cost = cost;
+        best = g;
+      }
     }
   }
   return best;
@@ -438,17 +443,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     return sa::s16_min_value_bound(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, std::max(1u, n1pad), rows) + 64 <= sa::kBias &&
            (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, std::max(1u, n1pad), rows));
   };
-  // kernel form for a class: the cheapest (K, G) whose padded shape stays in range, else any
-  // 8-column form that does.  G == 0: none.
+  // kernel form for a class: the cheapest compiled (K, G) whose padded shape stays in range and
+  // in shared memory.  G == 0: none.
   auto pick_geometry = [&](uint32_t cols, uint32_t rows) -> Geometry {
-    Geometry g = choose_geometry(e, cols, rows, linear);
-    if (g.G && fits_packed(g.n1pad, rows)) return g;
-    for (int G : {1, 2, 4, 8, 16, 32}) {
-      g = make_geometry(8, G, cols, rows);
-      if (g.smem_bytes <= e->smem_optin && fits_packed(g.n1pad, rows)) return g;
-    }
-    g.G = 0;
-    return g;
+    return choose_geometry(e, cols, rows, linear, fits_packed);
   };
   // cheap per-pair test: no lane-group width keeps the pair inside the packed range and inside
   // one SM's shared memory (same arithmetic as make_geometry / s16_min_value_bound, no structs)
