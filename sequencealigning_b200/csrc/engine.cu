@@ -341,6 +341,7 @@ struct Segment {
   // pairs outside the packed 16-bit range go to the general 32-bit kernel (nw_general.cuh)
   std::vector<uint32_t> long_ids;
   std::vector<uint64_t> long_meta;  // per long pair: tb offset (uint16 units, ~0 = none), runs end
+  std::vector<uint32_t> long_waves; // indices into long_ids where a new wave (reusing the tb words) starts
   uint64_t long_tb_total = 0, long_runs_total = 0;
   uint32_t long_n1max = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
@@ -550,16 +551,26 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if (n_long) {
       // explicit order without the long pairs; the long ones get their own launch
       sg.order.reserve(cn - n_long);
-      uint64_t tb_room = budget_re;  // bytes of 16-bit traceback words the general kernel may use
+      // 16-bit traceback words of the general kernel: the pairs are launched in WAVES that each
+      // fit the scratch (a wave's kernel also walks, so the next wave can reuse the words); only
+      // a pair that would take more than 1/8 of the scratch goes without (SA_ALIGNMENT_OMITTED:
+      // score and status are still exact)
+      uint64_t wave_used = 0;
+      // a segment of long pairs only does not need the packed kernel's scratch: use its share
+      const uint64_t room = (n_long == cn) ? (uint64_t)budget_main + budget_re : (uint64_t)budget_re;
       for (uint32_t i = 0; i < cn; ++i) {
         const uint32_t a = h_cols[base + i], b = h_rows[base + i];
         if (is_long(a, b)) {
           const uint64_t words = (uint64_t)a * b;
           uint64_t off = ~0ull;
-          if (words * 2 <= tb_room) {
-            off = sg.long_tb_total;
-            sg.long_tb_total += words;
-            tb_room -= words * 2;
+          if (words * 2 <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
+            if ((wave_used + words) * 2 > room) {
+              sg.long_waves.push_back((uint32_t)sg.long_ids.size());
+              wave_used = 0;
+            }
+            off = wave_used;
+            wave_used += words;
+            sg.long_tb_total = std::max(sg.long_tb_total, wave_used);
           }
           sg.long_runs_total += (uint64_t)a + b + 1;
           sg.long_ids.push_back((uint32_t)(base + i));
@@ -784,9 +795,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       e->timing.kernel_launches++;
     }
     if (!sg.long_ids.empty()) {
-      // pairs outside the packed range: literal 32-bit kernel, one thread per pair
+      // pairs outside the packed range: literal 32-bit kernel, one thread block per pair
       const uint32_t nl = (uint32_t)sg.long_ids.size();
-      const uint32_t stride = sg.long_n1max + 1;
+      const bool wide = sg.long_n1max >= 8192;  // more lanes per pair when the pairs are few and long
+      const uint32_t stride = sg.long_n1max + 1 + sa::kGeneralThreadsWide;  // ceil(n1 / threads) * threads entries
       if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_meta, (size_t)nl * 16)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total * 2 + 256)) != SA_OK) return r;
@@ -824,9 +836,25 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       gp.score = db.score;
       gp.status = db.status;
       gp.cigar_len = db.cigar_len;
-      sa::nw_affine_general_kernel<<<(nl + 31) / 32, 32, 0, sx>>>(gp);
-      CUDA_TRY(e, cudaGetLastError());
-      e->timing.kernel_launches++;
+      // one block per pair, one launch per wave (waves share the traceback words: stream order)
+      for (size_t wv = 0; wv <= sg.long_waves.size(); ++wv) {
+        const uint32_t lo = wv ? sg.long_waves[wv - 1] : 0u;
+        const uint32_t hi = wv < sg.long_waves.size() ? sg.long_waves[wv] : nl;
+        if (lo >= hi) continue;
+        sa::GeneralParams gw = gp;
+        gw.ids = gp.ids + lo;
+        gw.n_ids = hi - lo;
+        gw.tb_off = gp.tb_off + lo;
+        gw.runs_end = gp.runs_end + lo;
+        gw.rows = gp.rows + (uint64_t)lo * 6 * stride;
+        gw.info = gp.info + (uint64_t)lo * 4 * stride;
+        if (wide)
+          sa::nw_affine_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+        else
+          sa::nw_affine_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+        CUDA_TRY(e, cudaGetLastError());
+        e->timing.kernel_launches++;
+      }
     }
     CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));

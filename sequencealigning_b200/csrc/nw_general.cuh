@@ -1,7 +1,7 @@
 // nw_general.cuh -- affine NW for pairs OUTSIDE the packed 16-bit kernel's range (long pairs,
 // n1 + n2 above ~3.6 k): the literal recurrences in 32-bit integers with the finite -32768
-// sentinel, one thread per pair.  Slow by design (it is the completeness path, the batched hot
-// path is nw_affine_s16.cuh) but exact in every regime the reference has, including the one
+// sentinel, one thread block per pair.  It is the completeness path (the batched hot path is
+// nw_affine_s16.cuh): exact in every regime the reference has, including the one
 // where the sentinel leaks (n1 + n2 > ~5.4 k) and the traceback meets dead ends:
 //
 //   per cell and state the kernel keeps what the reference's LIFO DFS
@@ -50,90 +50,163 @@ constexpr uint8_t kAlignmentOmitted = 0x80;  // ORed into status: the CIGAR was 
 // fe/taint byte of a cell: bits 0-1 fe(M), 2-3 fe(D), 4-5 fe(I), 6 unused; taint kept separately
 __device__ __forceinline__ uint32_t fe_of(uint32_t info, int st) { return (info >> (2 * st)) & 3u; }
 
-__global__ void __launch_bounds__(32) nw_affine_general_kernel(const GeneralParams p) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+// One BLOCK of kGeneralThreads per pair.  Thread g owns the columns [g*C + 1, (g+1)*C]
+// (C = ceil(n1 / threads)) and runs one row behind thread g-1: at step t it computes row
+// x = t - g of its columns, left to right, over a rolling row kept in place in global scratch
+// (layout [column-in-thread][thread]: the threads of a warp touch one line per access, and a
+// pair's whole row stays in L1/L2).  What a thread needs from its left neighbour -- the cell
+// (x, y_lo - 1), and one step later the same record as the diagonal cell of row x + 1 -- goes
+// through a double-buffered shared-memory slot, one __syncthreads per step.  Thread 0's left
+// neighbour is column 0 (:200-216).
+constexpr int kGeneralThreads = 256;       // pairs up to ~8 k columns
+constexpr int kGeneralThreadsWide = 1024;  // longer pairs: four times the lanes per pair
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const GeneralParams p) {
+  constexpr uint32_t T = THREADS;
+  const uint32_t k = blockIdx.x;
   if (k >= p.n_ids) return;
+  const uint32_t g = threadIdx.x;
   enum { ST_M = 0, ST_D = 1, ST_I = 2 };
   constexpr int32_t kNegInf = -32768;
   const uint32_t id = p.ids[k];
   const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
   const uint64_t qo = p.q_off[id], dof = p.d_off[id];
-  const uint32_t w = p.row_stride;
+  const uint32_t w = p.row_stride;  // >= n1 + T: room for C * T entries
   int32_t* base = p.rows + (uint64_t)k * 6 * w;
-  int32_t *pm = base, *pi = base + w, *pd = base + 2 * w, *cm = base + 3 * w, *ci = base + 4 * w, *cd = base + 5 * w;
-  // info rows: low 6 bits fe (M, D, I), bits 6.. taint is kept in a second array
-  uint8_t* pinfo = p.info + (uint64_t)k * 4 * w;
-  uint8_t* cinfo = pinfo + w;
-  uint8_t* ptaint = pinfo + 2 * w;
-  uint8_t* ctaint = pinfo + 3 * w;
+  int32_t *rm = base + g, *ri = base + w + g, *rd = base + 2 * w + g;  // entry c of this thread at [c * T]
+  uint8_t* rinfo = p.info + (uint64_t)k * 4 * w + g;                   // fe bits: M (0-1), D (2-3), I (4-5)
+  uint8_t* rtaint = rinfo + w;                                         // taint bits by state
   const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
   uint16_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
 
-  // row 0 (:172-199).  M[0][0]: popped at (0,0) -> PRINT.  D[0][0], I[0][0]: sentinels without
-  // parents; if ever popped at (0,0) they print too (:283).  D[0][y>=1] is the boundary chain:
-  // it has a parent and x == 0 -> expanding it panics (:299).  M[0][y], I[0][y]: dead ends.
-  pm[0] = 0; pi[0] = kNegInf; pd[0] = kNegInf;
-  pinfo[0] = (uint8_t)(kFePrint | (kFePrint << 2) | (kFePrint << 4));
-  ptaint[0] = 0;
-  for (uint32_t y = 1; y <= n1; ++y) {
-    pm[y] = kNegInf;
-    pi[y] = kNegInf;
-    pd[y] = ((int32_t)y + 1) * p.ext + p.open;
-    pinfo[y] = (uint8_t)(kFePanic << 2);
-    ptaint[y] = (uint8_t)(1u << ST_D);
-  }
-  for (uint32_t x = 1; x <= n2; ++x) {
-    const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
-    cm[0] = kNegInf;  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
-    cd[0] = kNegInf;
-    ci[0] = p.open + ((int32_t)x + 1) * p.ext;
-    cinfo[0] = (uint8_t)(kFePanic << 4);
-    ctaint[0] = (uint8_t)(1u << ST_I);
-    for (uint32_t y = 1; y <= n1; ++y) {
-      const int32_t sub = load_residue(p.residues, qo + y - 1, p.packing) == b2 ? p.match : p.mismatch;
-      const int32_t dm = pm[y - 1], di = pi[y - 1], dd = pd[y - 1];
-      const int32_t mm = max(max(dm, di), dd) + sub;
-      const int32_t ii = max(cm[y - 1] + p.open, ci[y - 1]) + p.ext;
-      const int32_t dv = max(pm[y] + p.open, pd[y]) + p.ext;
-      uint32_t bits = 0;
-      if (mm == dm + sub) bits |= 1u;
-      if (mm == di + sub) bits |= 2u;
-      if (mm == dd + sub) bits |= 4u;
-      if (ii == ci[y - 1] + p.ext) bits |= 8u;
-      if (ii == cm[y - 1] + p.open + p.ext) bits |= 16u;
-      if (dv == pd[y] + p.ext) bits |= 32u;
-      if (dv == pm[y] + p.open + p.ext) bits |= 64u;
-      // DFS bookkeeping, parents in reverse push order
-      const uint32_t idg = pinfo[y - 1], tdg = ptaint[y - 1];  // (x-1, y-1)
-      const uint32_t ilf = cinfo[y - 1], tlf = ctaint[y - 1];  // (x, y-1)
-      const uint32_t iup = pinfo[y], tup = ptaint[y];          // (x-1, y)
-      uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
-      if (bits & 4u) { if (!feM) feM = fe_of(idg, ST_D); tM |= (tdg >> ST_D) & 1u; }
-      if (bits & 2u) { if (!feM) feM = fe_of(idg, ST_I); tM |= (tdg >> ST_I) & 1u; }
-      if (bits & 1u) { if (!feM) feM = fe_of(idg, ST_M); tM |= (tdg >> ST_M) & 1u; }
-      if (bits & 16u) { if (!feI) feI = fe_of(ilf, ST_M); tI |= (tlf >> ST_M) & 1u; }
-      if (bits & 8u) { if (!feI) feI = fe_of(ilf, ST_I); tI |= (tlf >> ST_I) & 1u; }
-      if (bits & 64u) { if (!feD) feD = fe_of(iup, ST_M); tD |= (tup >> ST_M) & 1u; }
-      if (bits & 32u) { if (!feD) feD = fe_of(iup, ST_D); tD |= (tup >> ST_D) & 1u; }
-      cm[y] = mm;
-      ci[y] = ii;
-      cd[y] = dv;
-      cinfo[y] = (uint8_t)(feM | (feD << 2) | (feI << 4));
-      ctaint[y] = (uint8_t)((tM << ST_M) | (tD << ST_D) | (tI << ST_I));
-      if (tb) tb[(uint64_t)(x - 1) * n1 + (y - 1)] = (uint16_t)(bits | (feM << 7) | (feD << 9) | (feI << 11));
+  const uint32_t C = (n1 + T - 1) / T;
+  const uint32_t y_lo = g * C + 1, y_hi = min(n1, (g + 1) * C);
+  const bool owns = C > 0 && y_lo <= n1;
+  const uint32_t owner = C ? (n1 - 1) / C : 0;  // thread that holds column n1
+
+  __shared__ int32_t xM[2][T], xI[2][T], xD[2][T];
+  __shared__ uint32_t xP[2][T];
+
+  // row 0 (:172-199) of this thread's columns: D[0][y>=1] is the boundary chain (has a parent and
+  // x == 0: expanding it panics, :299); M[0][y], I[0][y] are sentinels without parents.
+  if (owns)
+    for (uint32_t y = y_lo, c = 0; y <= y_hi; ++y, ++c) {
+      rm[c * T] = kNegInf;
+      ri[c * T] = kNegInf;
+      rd[c * T] = ((int32_t)y + 1) * p.ext + p.open;
+      rinfo[c * T] = (uint8_t)(kFePanic << 2);
+      rtaint[c * T] = (uint8_t)(1u << ST_D);
     }
-    int32_t* t;
-    t = pm; pm = cm; cm = t;
-    t = pi; pi = ci; ci = t;
-    t = pd; pd = cd; cd = t;
-    uint8_t* u;
-    u = pinfo; pinfo = cinfo; cinfo = u;
-    u = ptaint; ptaint = ctaint; ctaint = u;
+  // the cell (0, y_lo - 1): diagonal input of row 1
+  int32_t gM, gI, gD;
+  uint32_t gInfo, gTaint;
+  if (g == 0) {  // origin: M[0][0] = 0 is popped at (0,0) -> PRINT; D/I[0][0] print too if popped (:283)
+    gM = 0; gI = kNegInf; gD = kNegInf;
+    gInfo = kFePrint | (kFePrint << 2) | (kFePrint << 4);
+    gTaint = 0;
+  } else {
+    gM = kNegInf; gI = kNegInf; gD = ((int32_t)(y_lo - 1) + 1) * p.ext + p.open;
+    gInfo = kFePanic << 2;
+    gTaint = 1u << ST_D;
+  }
+  int32_t em = 0, ei = 0, ed = 0;  // end cell (owner thread)
+  uint32_t einfo = 0, etaint = 0;
+
+  const uint32_t steps = (n1 && n2) ? n2 + T - 1 : 0;
+  for (uint32_t t = 1; t <= steps; ++t) {
+    const uint32_t buf = t & 1u;
+    const uint32_t x = t - g;  // (wraps for t < g: then x > n2)
+    if (owns && x >= 1 && x <= n2) {
+      // the cell to the left of this thread's first column, row x (written by thread g-1 at step t-1)
+      int32_t lM, lI, lD;
+      uint32_t lInfo, lTaint;
+      if (g == 0) {  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
+        lM = kNegInf; lD = kNegInf; lI = p.open + ((int32_t)x + 1) * p.ext;
+        lInfo = kFePanic << 4;
+        lTaint = 1u << ST_I;
+      } else {
+        lM = xM[buf ^ 1u][g - 1]; lI = xI[buf ^ 1u][g - 1]; lD = xD[buf ^ 1u][g - 1];
+        const uint32_t inP = xP[buf ^ 1u][g - 1];
+        lInfo = inP & 0xffu;
+        lTaint = inP >> 8;
+      }
+      const int32_t nextM = lM, nextI = lI, nextD = lD;  // becomes the diagonal input of row x + 1
+      const uint32_t nextInfo = lInfo, nextTaint = lTaint;
+      const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
+      int32_t dm = gM, di = gI, dd = gD;  // (x-1, y-1)
+      uint32_t idg = gInfo, tdg = gTaint;
+      for (uint32_t y = y_lo, c = 0; y <= y_hi; ++y, ++c) {
+        const int32_t um = rm[c * T], ui = ri[c * T], ud = rd[c * T];  // (x-1, y)
+        const uint32_t iup = rinfo[c * T], tup = rtaint[c * T];
+        const int32_t sub = load_residue(p.residues, qo + y - 1, p.packing) == b2 ? p.match : p.mismatch;
+        const int32_t mm = max(max(dm, di), dd) + sub;
+        const int32_t ii = max(lM + p.open, lI) + p.ext;
+        const int32_t dv = max(um + p.open, ud) + p.ext;
+        uint32_t bits = 0;
+        if (mm == dm + sub) bits |= 1u;
+        if (mm == di + sub) bits |= 2u;
+        if (mm == dd + sub) bits |= 4u;
+        if (ii == lI + p.ext) bits |= 8u;
+        if (ii == lM + p.open + p.ext) bits |= 16u;
+        if (dv == ud + p.ext) bits |= 32u;
+        if (dv == um + p.open + p.ext) bits |= 64u;
+        // DFS bookkeeping, parents in reverse push order
+        uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
+        if (bits & 4u) { if (!feM) feM = fe_of(idg, ST_D); tM |= (tdg >> ST_D) & 1u; }
+        if (bits & 2u) { if (!feM) feM = fe_of(idg, ST_I); tM |= (tdg >> ST_I) & 1u; }
+        if (bits & 1u) { if (!feM) feM = fe_of(idg, ST_M); tM |= (tdg >> ST_M) & 1u; }
+        if (bits & 16u) { if (!feI) feI = fe_of(lInfo, ST_M); tI |= (lTaint >> ST_M) & 1u; }
+        if (bits & 8u) { if (!feI) feI = fe_of(lInfo, ST_I); tI |= (lTaint >> ST_I) & 1u; }
+        if (bits & 64u) { if (!feD) feD = fe_of(iup, ST_M); tD |= (tup >> ST_M) & 1u; }
+        if (bits & 32u) { if (!feD) feD = fe_of(iup, ST_D); tD |= (tup >> ST_D) & 1u; }
+        const uint32_t ninfo = feM | (feD << 2) | (feI << 4);
+        const uint32_t ntaint = (tM << ST_M) | (tD << ST_D) | (tI << ST_I);
+        rm[c * T] = mm;
+        ri[c * T] = ii;
+        rd[c * T] = dv;
+        rinfo[c * T] = (uint8_t)ninfo;
+        rtaint[c * T] = (uint8_t)ntaint;
+        if (tb) tb[(uint64_t)(x - 1) * n1 + (y - 1)] = (uint16_t)(bits | (feM << 7) | (feD << 9) | (feI << 11));
+        dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
+        idg = iup; tdg = tup;
+        lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
+        lInfo = ninfo; lTaint = ntaint;
+      }
+      xM[buf][g] = lM; xI[buf][g] = lI; xD[buf][g] = lD;
+      xP[buf][g] = lInfo | (lTaint << 8);
+      gM = nextM; gI = nextI; gD = nextD;
+      gInfo = nextInfo; gTaint = nextTaint;
+      if (g == owner && x == n2) {
+        em = lM; ei = lI; ed = lD;
+        einfo = lInfo; etaint = lTaint;
+      }
+    }
+    __syncthreads();
+  }
+  __threadfence_block();  // the owner's walk reads traceback words written by the other threads
+  __syncthreads();
+  if (steps == 0) {
+    // an empty side: the end cell is a border cell of row 0 / column 0
+    if (g != 0) return;
+    if (n1 == 0 && n2 == 0) {
+      em = 0; ei = kNegInf; ed = kNegInf;
+      einfo = kFePrint | (kFePrint << 2) | (kFePrint << 4);
+      etaint = 0;
+    } else if (n2 == 0) {  // (0, n1): the D chain of row 0
+      em = kNegInf; ei = kNegInf; ed = ((int32_t)n1 + 1) * p.ext + p.open;
+      einfo = kFePanic << 2;
+      etaint = 1u << ST_D;
+    } else {  // (n2, 0): the I chain of column 0
+      em = kNegInf; ed = kNegInf; ei = p.open + ((int32_t)n2 + 1) * p.ext;
+      einfo = kFePanic << 4;
+      etaint = 1u << ST_I;
+    }
+  } else if (g != owner) {
+    return;
   }
   // end cell (:246-280): start states pushed I, M, D, popped D, M, I
-  const int32_t em = pm[n1], ei = pi[n1], ed = pd[n1];
   const int32_t mx = max(max(ei, ed), em);
-  const uint32_t einfo = pinfo[n1], etaint = ptaint[n1];
   int first = -1;
   uint32_t fe = kFeNone, any_panic = 0;
   const int order[3] = {ST_D, ST_M, ST_I};

@@ -266,7 +266,9 @@ class Engine:
             return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)])
         cap = 0
         if cigar:
-            cap = cigar_capacity if cigar_capacity is not None else max(64, 32 * n)
+            # 32 runs per pair covers read pairs; long pairs get a share of their length
+            cap = cigar_capacity if cigar_capacity is not None else max(
+                64, 32 * n, int(np.minimum(batch.q_len, batch.d_len).sum(dtype=np.int64)) // 8)
         sc = _scheme(scheme)
         cb = self._c_batch(batch)
         while True:
