@@ -535,8 +535,6 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       sg.cells = cells;
     };
     scan(cn);
-    if (n_long && linear)
-      return fail(e, SA_E_UNSUPPORTED, "linear NW: a pair exceeds the 16-bit packed range (no long-pair kernel for this aligner yet)");
     sg.g = pick_geometry(sg.n1max, sg.n2max);
     if (!sg.g.G) sg.g = make_geometry(8, 1, sg.n1max, sg.n2max);  // only possible when the segment has no short pair at all
     const size_t tile_bytes = (size_t)sg.g.tile_stride * 8;
@@ -848,7 +846,11 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         gw.runs_end = gp.runs_end + lo;
         gw.rows = gp.rows + (uint64_t)lo * 6 * stride;
         gw.info = gp.info + (uint64_t)lo * 4 * stride;
-        if (wide)
+        if (linear && wide)
+          sa::nw_linear_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+        else if (linear)
+          sa::nw_linear_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+        else if (wide)
           sa::nw_affine_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
         else
           sa::nw_affine_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);

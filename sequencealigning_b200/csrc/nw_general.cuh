@@ -271,6 +271,117 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
   p.cigar_len[id] = nruns;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Linear ("pseudo-affine") NW for pairs outside the packed range: the literal recurrences of
+// /root/reference/src/needleman_wunsch.rs:36-117 in 32-bit integers, same block-per-pair layout
+// as above.  Rows i walk seq1 (query), columns j walk seq2 (db) (:38); thread g owns the columns
+// [g*C + 1, (g+1)*C], C = ceil(n2 / threads).  Per column of the rolling row: (S << 1) | gap flag.
+//   diag  = S[i-1][j-1] + (eq ? match : mismatch)
+//   down  = S[i-1][j]   + (gap[i-1][j] ? ext : open)      Down  = seq1[i-1] over '-'  -> SA_OP_I
+//   right = S[i][j-1]   + (gap[i][j-1] ? ext : open)      Right = '-' over seq2[j-1]  -> SA_OP_D
+//   S = max3; gap = (S == down || S == right); moves pushed Down, Right, Diag (:92-100)
+// Borders (:44-65): S[0][j] = open + j*ext, S[i][0] = open + i*ext, S[0][0] = 2*open, gap set.
+// The first hit of get_next (:205-254) follows the first stored move; the traceback word keeps
+// that move (1 Down, 2 Right, 0 Diag).  Nothing panics; status is always OK.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nw_linear_general_kernel(const GeneralParams p) {
+  constexpr uint32_t T = THREADS;
+  const uint32_t k = blockIdx.x;
+  if (k >= p.n_ids) return;
+  const uint32_t g = threadIdx.x;
+  const uint32_t id = p.ids[k];
+  const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
+  const uint64_t qo = p.q_off[id], dof = p.d_off[id];
+  const uint32_t w = p.row_stride;  // >= n2 + T
+  int32_t* row = p.rows + (uint64_t)k * 6 * w + g;  // entry c of this thread at [c * T]: (S << 1) | gap
+  const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
+  uint16_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
+
+  const uint32_t C = (n2 + T - 1) / T;
+  const uint32_t j_lo = g * C + 1, j_hi = min(n2, (g + 1) * C);
+  const bool owns = C > 0 && j_lo <= n2;
+  const uint32_t owner = C ? (n2 - 1) / C : 0;
+  __shared__ int32_t xS[2][T];
+
+  if (owns)
+    for (uint32_t j = j_lo, c = 0; j <= j_hi; ++j, ++c) row[c * T] = ((p.open + (int32_t)j * p.ext) << 1) | 1;
+  // S[0][j_lo - 1], gap set: the diagonal input of row 1
+  int32_t dg = g == 0 ? ((2 * p.open) << 1) | 1 : ((p.open + (int32_t)(j_lo - 1) * p.ext) << 1) | 1;
+  int32_t end_s = 0;
+
+  const uint32_t steps = (n1 && n2) ? n1 + T - 1 : 0;
+  for (uint32_t t = 1; t <= steps; ++t) {
+    const uint32_t buf = t & 1u;
+    const uint32_t i = t - g;
+    if (owns && i >= 1 && i <= n1) {
+      int32_t lf = g == 0 ? ((p.open + (int32_t)i * p.ext) << 1) | 1 : xS[buf ^ 1u][g - 1];  // (i, j_lo - 1)
+      const int32_t next_dg = lf;
+      const uint32_t b1 = load_residue(p.residues, qo + i - 1, p.packing);
+      int32_t d = dg;
+      for (uint32_t j = j_lo, c = 0; j <= j_hi; ++j, ++c) {
+        const int32_t up = row[c * T];
+        const int32_t diag = (d >> 1) + (load_residue(p.residues, dof + j - 1, p.packing) == b1 ? p.match : p.mismatch);
+        const int32_t down = (up >> 1) + ((up & 1) ? p.ext : p.open);
+        const int32_t right = (lf >> 1) + ((lf & 1) ? p.ext : p.open);
+        const int32_t mx = max(max(down, right), diag);
+        const int32_t gap = (mx == down || mx == right) ? 1 : 0;  // :85-87, even when diag ties
+        const uint32_t mv = mx == down ? 1u : (mx == right ? 2u : 0u);
+        const int32_t v = (mx << 1) | gap;
+        row[c * T] = v;
+        if (tb) tb[(uint64_t)(i - 1) * n2 + (j - 1)] = (uint16_t)mv;
+        d = up;
+        lf = v;
+      }
+      xS[buf][g] = lf;
+      dg = next_dg;
+      if (g == owner && i == n1) end_s = lf >> 1;
+    }
+    __syncthreads();
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (steps == 0) {
+    if (g != 0) return;
+    end_s = (n1 == 0 && n2 == 0) ? 2 * p.open : p.open + (int32_t)(n1 + n2) * p.ext;  // border cell
+  } else if (g != owner) {
+    return;
+  }
+  uint32_t nruns = 0;
+  if (n1 | n2) {
+    if (!tb && n1 && n2) {
+      p.score[id] = end_s;
+      p.status[id] = (uint8_t)(kOk | kAlignmentOmitted);
+      p.cigar_len[id] = 0;
+      return;
+    }
+    uint32_t i = n1, j = n2, run_op = 3, run_len = 0;
+    uint32_t* out = p.runs + p.runs_end[k];
+    while (i > 0 || j > 0) {
+      uint32_t op;
+      if (i == 0) { op = 2; --j; }        // row 0 holds [Right]
+      else if (j == 0) { op = 1; --i; }   // column 0 holds [Down]
+      else {
+        const uint32_t mv = tb[(uint64_t)(i - 1) * n2 + (j - 1)];
+        if (mv == 1u) { op = 1; --i; }
+        else if (mv == 2u) { op = 2; --j; }
+        else { op = 0; --i; --j; }
+      }
+      if (op != run_op) {
+        if (run_len) *--out = (run_len << 2) | run_op;
+        run_op = op;
+        run_len = 0;
+        ++nruns;
+      }
+      ++run_len;
+    }
+    if (run_len) *--out = (run_len << 2) | run_op;
+  }
+  p.score[id] = end_s;
+  p.status[id] = kOk;
+  p.cigar_len[id] = nruns;
+}
+
 // moves the runs of the general kernel's pairs from their staging area into the pool
 __global__ void __launch_bounds__(128) general_runs_to_pool(const uint32_t* __restrict__ ids, uint32_t n_ids,
                                                             const uint32_t* __restrict__ runs,

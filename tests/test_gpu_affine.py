@@ -138,7 +138,7 @@ def test_maximum_packed_size_and_range_extremes(engine, oracle):
     """Pairs at the edge of the 16-bit packed range (n1pad + n2 ~ 3.6 k), including the most
     negative scores the range bound has to cover (nothing matches) and the most positive."""
     import random
-    from sequencealigning_b200 import ALGO_NW_LINEAR, EngineError
+    from sequencealigning_b200 import ALGO_NW_LINEAR
     rng = random.Random(9)
     q = bytes(rng.choice(b"ACGT") for _ in range(1740))
     d = bytearray(q)
@@ -156,10 +156,11 @@ def test_maximum_packed_size_and_range_extremes(engine, oracle):
     # beyond the packed range the affine path switches to the general 32-bit kernel ...
     big = _batch([(b"A" * 2000, b"C" * 2000)])
     check_against_oracle(oracle, big, engine.align(big), what="beyond packed range")
-    # ... the linear aligner has no long-pair kernel yet: a clean per-call error, not a wrong answer
-    with pytest.raises(EngineError) as ei:
-        engine.align(big, algo=ALGO_NW_LINEAR)
-    assert ei.value.code == -5
+    # ... and so does the linear aligner (literal 32-bit kernel, nw_general.cuh)
+    rb = engine.align(big, algo=ALGO_NW_LINEAR)
+    refb = oracle.linear_batch(big.residues, big.q_off, big.q_len, big.d_off, big.d_len, cigar_stride=4001, n_threads=1)
+    assert np.array_equal(refb.score, rb.score) and np.array_equal(refb.cigar_len, rb.cigar_len)
+    assert list(refb.cigar_pool[0, :refb.cigar_len[0]]) == rb.cigar_of(0)
 
 
 def test_score_only_and_capacity(engine, oracle):

@@ -56,3 +56,22 @@ def test_lane_group_widths(oracle, g, monkeypatch):
     with Engine(0) as eng:
         b = PairBatch.from_pairs(random_pair_list(300 + g, 500, 1, 150))
         _check(oracle, b, eng.align(b, algo=ALGO_NW_LINEAR), f"G={g}")
+
+
+def test_long_pairs_take_the_literal_kernel(engine, oracle):
+    """Pairs beyond the packed 16-bit range, mixed with short ones in one call: the long ones run
+    through the block-per-pair 32-bit kernel (256 and 1024 threads), results in pair order."""
+    import random
+    from sequencealigning_b200 import ALGO_NW_LINEAR, PairBatch
+    from tests.util import mutate, random_seq
+    rng = random.Random(77)
+    pairs = random_pair_list(400, 200, 1, 150)
+    for n in (2100, 2600, 3000):
+        q = random_seq(rng, n, b"ACGT")
+        pairs.insert(rng.randrange(len(pairs)), (q, mutate(rng, q, 0.08, True, b"ACGT")))
+    pairs.append((random_seq(rng, 2500, b"ACGT"), random_seq(rng, 1900, b"ACGT")))
+    pairs.append((b"A" * 4000, b"C" * 2))
+    b = PairBatch.from_pairs(pairs)
+    _check(oracle, b, engine.align(b, algo=ALGO_NW_LINEAR), "long linear")
+    wide = PairBatch.from_pairs([(random_seq(rng, 300, b"ACGT"), random_seq(rng, 9000, b"ACGT")), (b"ACGT", b"AGT")])
+    _check(oracle, wide, engine.align(wide, algo=ALGO_NW_LINEAR), "wide linear")
