@@ -278,6 +278,43 @@ def test_long_pairs_take_the_general_kernel(engine, oracle):
     assert r.cigar_len[7] > 0 and r.cigar_len[150] > 0
 
 
+def test_long_pairs_in_waves_and_omitted_alignments(oracle, monkeypatch):
+    """A small scratch budget: long pairs are launched in several waves that reuse the traceback
+    words; a pair that does not fit its share keeps exact score and status, flagged
+    SA_ALIGNMENT_OMITTED, with an empty CIGAR."""
+    import random
+    from sequencealigning_b200 import Engine
+    from tests.util import mutate, random_seq
+    monkeypatch.setenv("SA_TB_BUDGET_MB", "400")   # refill/long share 80 MB: ~9 pairs of 2.1 kbp per wave
+    rng = random.Random(41)
+    longs = []
+    for _ in range(22):
+        q = random_seq(rng, rng.randint(2000, 2150), b"ACGT")
+        longs.append((q, mutate(rng, q, 0.06, True, b"ACGT")))
+    big = random_seq(rng, 4200, b"ACGT")
+    longs.append((big, mutate(rng, big, 0.03, True, b"ACGT")))   # 35 MB of words: more than 1/8 of the share
+    with Engine(0) as eng:
+        mixed = random_pair_list(55, 150, 1, 160) + longs
+        rng.shuffle(mixed)
+        for pairs in (mixed, longs):   # mixed with short pairs / a segment of long pairs only
+            b = _batch(pairs)
+            r = eng.align(b)
+            stride = int((b.q_len.astype(np.int64) + b.d_len.astype(np.int64)).max()) + 1
+            ref = oracle.affine_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=stride, n_threads=8)
+            omitted = (r.status & 0x80) != 0
+            assert np.array_equal(ref.score, r.score)
+            assert np.array_equal(ref.status, r.status & 0x7F)
+            assert (r.cigar_len[omitted] == 0).all()
+            keep = ~omitted
+            assert np.array_equal(ref.cigar_len[keep], r.cigar_len[keep])
+            for i in np.nonzero(keep)[0]:
+                assert list(ref.cigar_pool[i, :ref.cigar_len[i]]) == r.cigar_of(int(i)), i
+            n_long = sum(1 for q, d in pairs if len(q) >= 2000)
+            assert omitted.sum() <= 1 and keep.sum() >= len(pairs) - 1
+            if pairs is mixed:
+                assert omitted.sum() == 1   # the 4.2 kbp pair (its words exceed 1/8 of the 80 MB share)
+
+
 def test_sentinel_regime_long_pairs(engine, oracle):
     """n1 + n2 > ~5.4 k: the reference's finite -32768 'minus infinity' leaks into the matrix
     (SURVEY 7); the general kernel reproduces score, status and first alignment there too."""
