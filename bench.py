@@ -334,14 +334,12 @@ def main():
     e1 = torch.cuda.Event(enable_timing=True)
     launches = 0
     reruns = 0
-    fill_ms = 0.0
     e0.record(stream)
     for _ in range(args.steps):
         rb.align(algo=algo)
         t = eng.timing()
         launches += t["kernel_launches"]
         reruns = t["pairs_rerun"]
-        fill_ms += t["walk_ms"]      # sum of the fill kernel's launch durations (CUDA events on its streams)
     e1.record(stream)
     e1.synchronize()
     barrier()
@@ -411,7 +409,6 @@ def main():
     if rank == 0:
         peak = int_peak()
         step_issued = gcups * 1e9 * OPS_PER_CELL_ISSUED / world
-        fill_ms_step = fill_ms / max(args.steps, 1)
         tb_bytes = cells / 2.0
         hbm_bytes = tb_bytes + batch.residues.size + batch.n_pairs * (24 + 17) + res_dev.cigar.size * 4
         peaks = {}
@@ -443,7 +440,6 @@ def main():
                                    "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
                                    "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14458 B per 150 bp pair: 96-bit rows of 19 four-bit cells, rows padded to the tile)"},
                 "per_gpu": True,
-                "fill_ms_per_step_summed": fill_ms_step,
                 "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
                         "/ fill-kernel time, i.e. the share of all issue slots doing recurrence work; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
