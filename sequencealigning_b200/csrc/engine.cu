@@ -343,7 +343,7 @@ struct Segment {
   std::vector<uint64_t> long_meta;  // per long pair: tb offset (uint16 units, ~0 = none), runs end
   std::vector<uint32_t> long_waves; // indices into long_ids where a new wave (reusing the tb words) starts
   uint64_t long_tb_total = 0, long_runs_total = 0;
-  uint32_t long_n1max = 0;
+  uint32_t long_n1max = 0, long_n2max = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
   uint64_t cells = 0;  // sum of n1*n2 over the segment
   Geometry g;
@@ -575,6 +575,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           sg.long_meta.push_back(off);
           sg.long_meta.push_back(sg.long_runs_total);
           sg.long_n1max = std::max(sg.long_n1max, a);
+          sg.long_n2max = std::max(sg.long_n2max, b);
         } else {
           sg.order.push_back((uint32_t)(base + i));
         }
@@ -796,7 +797,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       // pairs outside the packed range: literal 32-bit kernel, one thread block per pair
       const uint32_t nl = (uint32_t)sg.long_ids.size();
       const bool wide = sg.long_n1max >= 8192;  // more lanes per pair when the pairs are few and long
-      const uint32_t stride = sg.long_n1max + 1 + sa::kGeneralThreadsWide;  // ceil(n1 / threads) * threads entries
+      // per pair 6 * stride ints: the affine kernel's edge column (4 ints per row), the linear
+      // kernel's rolling row (ceil(columns / threads) * threads entries); even, for 16-byte alignment
+      const uint32_t stride = (std::max(sg.long_n1max, sg.long_n2max) + 2 + sa::kGeneralThreadsWide + 1) & ~1u;
       if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_meta, (size_t)nl * 16)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total * 2 + 256)) != SA_OK) return r;

@@ -34,7 +34,7 @@ struct GeneralParams {
   int32_t match, mismatch, open, ext;
   uint16_t* __restrict__ tb;               // per launch index: [n2][n1] words at tb_off[k]; may be nullptr
   const uint64_t* __restrict__ tb_off;     // (uint16 units); UINT64_MAX = no room: score/status only
-  int32_t* __restrict__ rows;              // per launch index: 6 * row_stride ints
+  int32_t* __restrict__ rows;              // per launch index: 6 * row_stride ints (affine: the edge column, 4 per row)
   uint8_t* __restrict__ info;              // per launch index: 2 * row_stride bytes (fe/taint of two rows)
   uint32_t row_stride;                     // max n1 + 1
   uint32_t* __restrict__ runs;             // per launch index: runs written back to front, ending at runs_end[k]
@@ -50,20 +50,24 @@ constexpr uint8_t kAlignmentOmitted = 0x80;  // ORed into status: the CIGAR was 
 // fe/taint byte of a cell: bits 0-1 fe(M), 2-3 fe(D), 4-5 fe(I), 6 unused; taint kept separately
 __device__ __forceinline__ uint32_t fe_of(uint32_t info, int st) { return (info >> (2 * st)) & 3u; }
 
-// One BLOCK of kGeneralThreads per pair.  Thread g owns the columns [g*C + 1, (g+1)*C]
-// (C = ceil(n1 / threads)) and runs one row behind thread g-1: at step t it computes row
-// x = t - g of its columns, left to right, over a rolling row kept in place in global scratch
-// (layout [column-in-thread][thread]: the threads of a warp touch one line per access, and a
-// pair's whole row stays in L1/L2).  What a thread needs from its left neighbour -- the cell
-// (x, y_lo - 1), and one step later the same record as the diagonal cell of row x + 1 -- goes
-// through a double-buffered shared-memory slot, one __syncthreads per step.  Thread 0's left
-// neighbour is column 0 (:200-216).
-constexpr int kGeneralThreads = 256;       // pairs up to ~8 k columns
-constexpr int kGeneralThreadsWide = 1024;  // longer pairs: four times the lanes per pair
+// One BLOCK per pair, columns in PASSES of THREADS * kGeneralCols.  In a pass thread g owns
+// kGeneralCols consecutive columns, whose rolling row (three scores and the packed fe/taint bits
+// per column) it keeps in REGISTERS, and runs one row behind thread g-1: at step t it computes
+// row x = t - g, left to right.  What a thread needs from its left neighbour -- the cell
+// (x, y0), and one step later the same record as the diagonal cell of row x + 1 -- goes through a
+// double-buffered shared-memory slot, one __syncthreads per step.  The last thread of a pass
+// leaves its right edge, one record per row, in global scratch (16 bytes per row); thread 0 of
+// the next pass reads it back one row ahead of use.  Thread 0 of pass 0 has column 0 to its left
+// (:200-216).  Memory traffic is the edge column and (if kept) the traceback words -- not the
+// rolling row, which is what made a row longer than L2's share slow.
+constexpr int kGeneralThreads = 256;       // pairs of a few thousand residues
+constexpr int kGeneralThreadsWide = 512;   // longer pairs: twice the lanes per pair
+constexpr int kGeneralCols = 8;
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const GeneralParams p) {
   constexpr uint32_t T = THREADS;
+  constexpr int C = kGeneralCols;
   const uint32_t k = blockIdx.x;
   if (k >= p.n_ids) return;
   const uint32_t g = threadIdx.x;
@@ -72,120 +76,133 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
   const uint32_t id = p.ids[k];
   const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
   const uint64_t qo = p.q_off[id], dof = p.d_off[id];
-  const uint32_t w = p.row_stride;  // >= n1 + T: room for C * T entries
-  int32_t* base = p.rows + (uint64_t)k * 6 * w;
-  int32_t *rm = base + g, *ri = base + w + g, *rd = base + 2 * w + g;  // entry c of this thread at [c * T]
-  uint8_t* rinfo = p.info + (uint64_t)k * 4 * w + g;                   // fe bits: M (0-1), D (2-3), I (4-5)
-  uint8_t* rtaint = rinfo + w;                                         // taint bits by state
+  int4* edge = reinterpret_cast<int4*>(p.rows + (uint64_t)k * 6 * p.row_stride);  // [row]: M, I, D, info | taint << 8
   const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
   uint16_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
 
-  const uint32_t C = (n1 + T - 1) / T;
-  const uint32_t y_lo = g * C + 1, y_hi = min(n1, (g + 1) * C);
-  const bool owns = C > 0 && y_lo <= n1;
-  const uint32_t owner = C ? (n1 - 1) / C : 0;  // thread that holds column n1
-
+  const uint32_t P = T * C;
+  const uint32_t npass = (n1 + P - 1) / P;
   __shared__ int32_t xM[2][T], xI[2][T], xD[2][T];
   __shared__ uint32_t xP[2][T];
 
-  // row 0 (:172-199) of this thread's columns: D[0][y>=1] is the boundary chain (has a parent and
-  // x == 0: expanding it panics, :299); M[0][y], I[0][y] are sentinels without parents.
-  if (owns)
-    for (uint32_t y = y_lo, c = 0; y <= y_hi; ++y, ++c) {
-      rm[c * T] = kNegInf;
-      ri[c * T] = kNegInf;
-      rd[c * T] = ((int32_t)y + 1) * p.ext + p.open;
-      rinfo[c * T] = (uint8_t)(kFePanic << 2);
-      rtaint[c * T] = (uint8_t)(1u << ST_D);
-    }
-  // the cell (0, y_lo - 1): diagonal input of row 1
-  int32_t gM, gI, gD;
-  uint32_t gInfo, gTaint;
-  if (g == 0) {  // origin: M[0][0] = 0 is popped at (0,0) -> PRINT; D/I[0][0] print too if popped (:283)
-    gM = 0; gI = kNegInf; gD = kNegInf;
-    gInfo = kFePrint | (kFePrint << 2) | (kFePrint << 4);
-    gTaint = 0;
-  } else {
-    gM = kNegInf; gI = kNegInf; gD = ((int32_t)(y_lo - 1) + 1) * p.ext + p.open;
-    gInfo = kFePanic << 2;
-    gTaint = 1u << ST_D;
-  }
-  int32_t em = 0, ei = 0, ed = 0;  // end cell (owner thread)
+  int32_t em = 0, ei = 0, ed = 0;  // end cell
   uint32_t einfo = 0, etaint = 0;
-
   const uint32_t steps = (n1 && n2) ? n2 + T - 1 : 0;
-  for (uint32_t t = 1; t <= steps; ++t) {
-    const uint32_t buf = t & 1u;
-    const uint32_t x = t - g;  // (wraps for t < g: then x > n2)
-    if (owns && x >= 1 && x <= n2) {
-      // the cell to the left of this thread's first column, row x (written by thread g-1 at step t-1)
-      int32_t lM, lI, lD;
-      uint32_t lInfo, lTaint;
-      if (g == 0) {  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
-        lM = kNegInf; lD = kNegInf; lI = p.open + ((int32_t)x + 1) * p.ext;
-        lInfo = kFePanic << 4;
-        lTaint = 1u << ST_I;
-      } else {
-        lM = xM[buf ^ 1u][g - 1]; lI = xI[buf ^ 1u][g - 1]; lD = xD[buf ^ 1u][g - 1];
-        const uint32_t inP = xP[buf ^ 1u][g - 1];
-        lInfo = inP & 0xffu;
-        lTaint = inP >> 8;
-      }
-      const int32_t nextM = lM, nextI = lI, nextD = lD;  // becomes the diagonal input of row x + 1
-      const uint32_t nextInfo = lInfo, nextTaint = lTaint;
-      const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
-      int32_t dm = gM, di = gI, dd = gD;  // (x-1, y-1)
-      uint32_t idg = gInfo, tdg = gTaint;
-      for (uint32_t y = y_lo, c = 0; y <= y_hi; ++y, ++c) {
-        const int32_t um = rm[c * T], ui = ri[c * T], ud = rd[c * T];  // (x-1, y)
-        const uint32_t iup = rinfo[c * T], tup = rtaint[c * T];
-        const int32_t sub = load_residue(p.residues, qo + y - 1, p.packing) == b2 ? p.match : p.mismatch;
-        const int32_t mm = max(max(dm, di), dd) + sub;
-        const int32_t ii = max(lM + p.open, lI) + p.ext;
-        const int32_t dv = max(um + p.open, ud) + p.ext;
-        uint32_t bits = 0;
-        if (mm == dm + sub) bits |= 1u;
-        if (mm == di + sub) bits |= 2u;
-        if (mm == dd + sub) bits |= 4u;
-        if (ii == lI + p.ext) bits |= 8u;
-        if (ii == lM + p.open + p.ext) bits |= 16u;
-        if (dv == ud + p.ext) bits |= 32u;
-        if (dv == um + p.open + p.ext) bits |= 64u;
-        // DFS bookkeeping, parents in reverse push order
-        uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
-        if (bits & 4u) { if (!feM) feM = fe_of(idg, ST_D); tM |= (tdg >> ST_D) & 1u; }
-        if (bits & 2u) { if (!feM) feM = fe_of(idg, ST_I); tM |= (tdg >> ST_I) & 1u; }
-        if (bits & 1u) { if (!feM) feM = fe_of(idg, ST_M); tM |= (tdg >> ST_M) & 1u; }
-        if (bits & 16u) { if (!feI) feI = fe_of(lInfo, ST_M); tI |= (lTaint >> ST_M) & 1u; }
-        if (bits & 8u) { if (!feI) feI = fe_of(lInfo, ST_I); tI |= (lTaint >> ST_I) & 1u; }
-        if (bits & 64u) { if (!feD) feD = fe_of(iup, ST_M); tD |= (tup >> ST_M) & 1u; }
-        if (bits & 32u) { if (!feD) feD = fe_of(iup, ST_D); tD |= (tup >> ST_D) & 1u; }
-        const uint32_t ninfo = feM | (feD << 2) | (feI << 4);
-        const uint32_t ntaint = (tM << ST_M) | (tD << ST_D) | (tI << ST_I);
-        rm[c * T] = mm;
-        ri[c * T] = ii;
-        rd[c * T] = dv;
-        rinfo[c * T] = (uint8_t)ninfo;
-        rtaint[c * T] = (uint8_t)ntaint;
-        if (tb) tb[(uint64_t)(x - 1) * n1 + (y - 1)] = (uint16_t)(bits | (feM << 7) | (feD << 9) | (feI << 11));
-        dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
-        idg = iup; tdg = tup;
-        lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
-        lInfo = ninfo; lTaint = ntaint;
-      }
-      xM[buf][g] = lM; xI[buf][g] = lI; xD[buf][g] = lD;
-      xP[buf][g] = lInfo | (lTaint << 8);
-      gM = nextM; gI = nextI; gD = nextD;
-      gInfo = nextInfo; gTaint = nextTaint;
-      if (g == owner && x == n2) {
-        em = lM; ei = lI; ed = lD;
-        einfo = lInfo; etaint = lTaint;
-      }
+  const uint32_t owner = n1 ? ((n1 - 1) % P) / C : 0, owner_c = n1 ? (n1 - 1) % C : 0;
+
+  for (uint32_t pass = 0; pass < npass && steps; ++pass) {
+    const uint32_t y0 = pass * P + g * C;  // this thread's columns are y0+1 .. y0+C
+    const bool owns = y0 < n1;
+    // row 0 (:172-199): D[0][y>=1] is the boundary chain (has a parent and x == 0: expanding it
+    // panics, :299); M[0][y], I[0][y] are sentinels without parents.
+    int32_t rM[C], rI[C], rD[C];
+    uint32_t rP[C], q[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t y = y0 + c + 1;
+      rM[c] = kNegInf;
+      rI[c] = kNegInf;
+      rD[c] = ((int32_t)y + 1) * p.ext + p.open;
+      rP[c] = (kFePanic << 2) | ((1u << ST_D) << 8);
+      q[c] = y <= n1 ? load_residue(p.residues, qo + y - 1, p.packing) : 0xffffffffu;
     }
+    // the cell (0, y0): diagonal input of row 1
+    int32_t gM, gI, gD;
+    uint32_t gP;
+    if (y0 == 0) {  // origin: M[0][0] = 0 is popped at (0,0) -> PRINT; D/I[0][0] print too if popped (:283)
+      gM = 0; gI = kNegInf; gD = kNegInf;
+      gP = kFePrint | (kFePrint << 2) | (kFePrint << 4);
+    } else {
+      gM = kNegInf; gI = kNegInf; gD = ((int32_t)y0 + 1) * p.ext + p.open;
+      gP = (kFePanic << 2) | ((1u << ST_D) << 8);
+    }
+    // thread 0 of a later pass: the previous pass's right edge, fetched one row ahead
+    int4 ahead = make_int4(0, 0, 0, 0);
+    if (g == 0 && pass > 0) ahead = __ldcg(&edge[1]);
+
+    for (uint32_t t = 1; t <= steps; ++t) {
+      const uint32_t buf = t & 1u;
+      const uint32_t x = t - g;  // (wraps for t < g: then x > n2)
+      if (owns && x >= 1 && x <= n2) {
+        // the cell to the left of this thread's first column, row x
+        int32_t lM, lI, lD;
+        uint32_t lP;
+        if (g == 0) {
+          if (pass == 0) {  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
+            lM = kNegInf; lD = kNegInf; lI = p.open + ((int32_t)x + 1) * p.ext;
+            lP = (kFePanic << 4) | ((1u << ST_I) << 8);
+          } else {
+            lM = ahead.x; lI = ahead.y; lD = ahead.z; lP = (uint32_t)ahead.w;
+            if (x < n2) ahead = __ldcg(&edge[x + 1]);
+          }
+        } else {
+          lM = xM[buf ^ 1u][g - 1]; lI = xI[buf ^ 1u][g - 1]; lD = xD[buf ^ 1u][g - 1];
+          lP = xP[buf ^ 1u][g - 1];
+        }
+        const int32_t nextM = lM, nextI = lI, nextD = lD;  // becomes the diagonal input of row x + 1
+        const uint32_t nextP = lP;
+        const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
+        int32_t dm = gM, di = gI, dd = gD;  // (x-1, y-1)
+        uint32_t pdg = gP;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int32_t um = rM[c], ui = rI[c], ud = rD[c];  // (x-1, y)
+          const uint32_t pup = rP[c];
+          const int32_t sub = q[c] == b2 ? p.match : p.mismatch;
+          const int32_t mm = max(max(dm, di), dd) + sub;
+          const int32_t ii = max(lM + p.open, lI) + p.ext;
+          const int32_t dv = max(um + p.open, ud) + p.ext;
+          uint32_t bits = 0;
+          if (mm == dm + sub) bits |= 1u;
+          if (mm == di + sub) bits |= 2u;
+          if (mm == dd + sub) bits |= 4u;
+          if (ii == lI + p.ext) bits |= 8u;
+          if (ii == lM + p.open + p.ext) bits |= 16u;
+          if (dv == ud + p.ext) bits |= 32u;
+          if (dv == um + p.open + p.ext) bits |= 64u;
+          // DFS bookkeeping, parents in reverse push order (info in bits 0-5, taint in bits 8-10)
+          const uint32_t idg = pdg & 0xffu, tdg = pdg >> 8;
+          const uint32_t ilf = lP & 0xffu, tlf = lP >> 8;
+          const uint32_t iup = pup & 0xffu, tup = pup >> 8;
+          uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
+          if (bits & 4u) { if (!feM) feM = fe_of(idg, ST_D); tM |= (tdg >> ST_D) & 1u; }
+          if (bits & 2u) { if (!feM) feM = fe_of(idg, ST_I); tM |= (tdg >> ST_I) & 1u; }
+          if (bits & 1u) { if (!feM) feM = fe_of(idg, ST_M); tM |= (tdg >> ST_M) & 1u; }
+          if (bits & 16u) { if (!feI) feI = fe_of(ilf, ST_M); tI |= (tlf >> ST_M) & 1u; }
+          if (bits & 8u) { if (!feI) feI = fe_of(ilf, ST_I); tI |= (tlf >> ST_I) & 1u; }
+          if (bits & 64u) { if (!feD) feD = fe_of(iup, ST_M); tD |= (tup >> ST_M) & 1u; }
+          if (bits & 32u) { if (!feD) feD = fe_of(iup, ST_D); tD |= (tup >> ST_D) & 1u; }
+          const uint32_t np = feM | (feD << 2) | (feI << 4) | (((tM << ST_M) | (tD << ST_D) | (tI << ST_I)) << 8);
+          rM[c] = mm;
+          rI[c] = ii;
+          rD[c] = dv;
+          rP[c] = np;
+          if (tb && y0 + c < n1)
+            tb[(uint64_t)(x - 1) * n1 + (y0 + c)] = (uint16_t)(bits | (feM << 7) | (feD << 9) | (feI << 11));
+          dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
+          pdg = pup;
+          lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
+          lP = np;
+        }
+        xM[buf][g] = lM; xI[buf][g] = lI; xD[buf][g] = lD;
+        xP[buf][g] = lP;
+        if (g == T - 1 && pass + 1 < npass) edge[x] = make_int4(lM, lI, lD, (int)lP);
+        gM = nextM; gI = nextI; gD = nextD;
+        gP = nextP;
+        if (pass + 1 == npass && g == owner && x == n2) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if ((uint32_t)c == owner_c) {
+              em = rM[c]; ei = rI[c]; ed = rD[c];
+              einfo = rP[c] & 0xffu; etaint = rP[c] >> 8;
+            }
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence_block();  // the pass's edge column (and traceback words) before the next readers
     __syncthreads();
   }
-  __threadfence_block();  // the owner's walk reads traceback words written by the other threads
-  __syncthreads();
   if (steps == 0) {
     // an empty side: the end cell is a border cell of row 0 / column 0
     if (g != 0) return;
