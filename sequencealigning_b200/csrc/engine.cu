@@ -549,7 +549,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if (n_long) {
       // explicit order without the long pairs; the long ones get their own launch
       sg.order.reserve(cn - n_long);
-      // 16-bit traceback words of the general kernel: the pairs are launched in WAVES that each
+      // traceback bytes (one per cell) of the general kernel: the pairs are launched in WAVES that each
       // fit the scratch (a wave's kernel also walks, so the next wave can reuse the words); only
       // a pair that would take more than 1/8 of the scratch goes without (SA_ALIGNMENT_OMITTED:
       // score and status are still exact)
@@ -561,8 +561,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         if (is_long(a, b)) {
           const uint64_t words = (uint64_t)a * b;
           uint64_t off = ~0ull;
-          if (words * 2 <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
-            if ((wave_used + words) * 2 > room) {
+          if (words <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
+            if (wave_used + words > room) {
               sg.long_waves.push_back((uint32_t)sg.long_ids.size());
               wave_used = 0;
             }
@@ -802,7 +802,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       const uint32_t stride = (std::max(sg.long_n1max, sg.long_n2max) + 2 + sa::kGeneralThreadsWide + 1) & ~1u;
       if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_meta, (size_t)nl * 16)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total * 2 + 256)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total + 256)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_rows, (size_t)nl * 6 * stride * 4)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_info, (size_t)nl * 4 * stride)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_runs, (size_t)sg.long_runs_total * 4 + 256)) != SA_OK) return r;
@@ -827,7 +827,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       gp.mismatch = sc.mismatch;
       gp.open = sc.gap_open;
       gp.ext = sc.gap_ext;
-      gp.tb = want_cigar ? (uint16_t*)sl.g_tb.p : nullptr;
+      gp.tb = want_cigar ? (uint8_t*)sl.g_tb.p : nullptr;
       gp.tb_off = (const uint64_t*)sl.g_meta.p;
       gp.rows = (int32_t*)sl.g_rows.p;
       gp.info = (uint8_t*)sl.g_info.p;

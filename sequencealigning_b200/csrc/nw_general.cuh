@@ -12,9 +12,10 @@
 //   parent list (:96-153) in REVERSE push order because the stack is LIFO.  The first printed
 //   alignment follows, at every cell, the first parent in that order whose fe is not NONE.
 //
-// Traceback storage: one 16-bit word per interior cell =
-//   bits 0-6  parent set (bit0 M<-M, 1 M<-I, 2 M<-D, 3 I<-I, 4 I<-M, 5 D<-D, 6 D<-M)
-//   bits 7-8  fe of the M state, 9-10 fe of D, 11-12 fe of I
+// Traceback storage: one BYTE per interior cell: for each state of the cell (M bits 0-1, D bits
+// 2-3, I bits 4-5) the parent the first printed alignment continues with -- the first parent in
+// reverse push order whose fe is not NONE -- as 0 = none (dead end), 1 = M, 2 = D, 3 = I.  The
+// parents precede the cell in fill order, so the choice is known when the cell is computed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,8 +33,8 @@ struct GeneralParams {
   const uint32_t* __restrict__ ids;   // pairs handled by this launch
   uint32_t n_ids, packing;
   int32_t match, mismatch, open, ext;
-  uint16_t* __restrict__ tb;               // per launch index: [n2][n1] words at tb_off[k]; may be nullptr
-  const uint64_t* __restrict__ tb_off;     // (uint16 units); UINT64_MAX = no room: score/status only
+  uint8_t* __restrict__ tb;                // per launch index: [n2][n1] bytes at tb_off[k]; may be nullptr
+  const uint64_t* __restrict__ tb_off;     // (bytes); UINT64_MAX = no room: score/status only
   int32_t* __restrict__ rows;              // per launch index: 6 * row_stride ints (affine: the edge column, 4 per row)
   uint8_t* __restrict__ info;              // per launch index: 2 * row_stride bytes (fe/taint of two rows)
   uint32_t row_stride;                     // max n1 + 1
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
   const uint64_t qo = p.q_off[id], dof = p.d_off[id];
   int4* edge = reinterpret_cast<int4*>(p.rows + (uint64_t)k * 6 * p.row_stride);  // [row]: M, I, D, info | taint << 8
   const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
-  uint16_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
+  uint8_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
 
   const uint32_t P = T * C;
   const uint32_t npass = (n1 + P - 1) / P;
@@ -165,20 +166,21 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
           const uint32_t ilf = lP & 0xffu, tlf = lP >> 8;
           const uint32_t iup = pup & 0xffu, tup = pup >> 8;
           uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
-          if (bits & 4u) { if (!feM) feM = fe_of(idg, ST_D); tM |= (tdg >> ST_D) & 1u; }
-          if (bits & 2u) { if (!feM) feM = fe_of(idg, ST_I); tM |= (tdg >> ST_I) & 1u; }
-          if (bits & 1u) { if (!feM) feM = fe_of(idg, ST_M); tM |= (tdg >> ST_M) & 1u; }
-          if (bits & 16u) { if (!feI) feI = fe_of(ilf, ST_M); tI |= (tlf >> ST_M) & 1u; }
-          if (bits & 8u) { if (!feI) feI = fe_of(ilf, ST_I); tI |= (tlf >> ST_I) & 1u; }
-          if (bits & 64u) { if (!feD) feD = fe_of(iup, ST_M); tD |= (tup >> ST_M) & 1u; }
-          if (bits & 32u) { if (!feD) feD = fe_of(iup, ST_D); tD |= (tup >> ST_D) & 1u; }
+          uint32_t chM = 0, chI = 0, chD = 0;  // parent the first alignment continues with (state + 1)
+          if (bits & 4u) { if (!feM) { feM = fe_of(idg, ST_D); if (feM) chM = ST_D + 1; } tM |= (tdg >> ST_D) & 1u; }
+          if (bits & 2u) { if (!feM) { feM = fe_of(idg, ST_I); if (feM) chM = ST_I + 1; } tM |= (tdg >> ST_I) & 1u; }
+          if (bits & 1u) { if (!feM) { feM = fe_of(idg, ST_M); if (feM) chM = ST_M + 1; } tM |= (tdg >> ST_M) & 1u; }
+          if (bits & 16u) { if (!feI) { feI = fe_of(ilf, ST_M); if (feI) chI = ST_M + 1; } tI |= (tlf >> ST_M) & 1u; }
+          if (bits & 8u) { if (!feI) { feI = fe_of(ilf, ST_I); if (feI) chI = ST_I + 1; } tI |= (tlf >> ST_I) & 1u; }
+          if (bits & 64u) { if (!feD) { feD = fe_of(iup, ST_M); if (feD) chD = ST_M + 1; } tD |= (tup >> ST_M) & 1u; }
+          if (bits & 32u) { if (!feD) { feD = fe_of(iup, ST_D); if (feD) chD = ST_D + 1; } tD |= (tup >> ST_D) & 1u; }
           const uint32_t np = feM | (feD << 2) | (feI << 4) | (((tM << ST_M) | (tD << ST_D) | (tI << ST_I)) << 8);
           rM[c] = mm;
           rI[c] = ii;
           rD[c] = dv;
           rP[c] = np;
           if (tb && y0 + c < n1)
-            tb[(uint64_t)(x - 1) * n1 + (y0 + c)] = (uint16_t)(bits | (feM << 7) | (feD << 9) | (feI << 11));
+            tb[(uint64_t)(x - 1) * n1 + (y0 + c)] = (uint8_t)((chM << (2 * ST_M)) | (chD << (2 * ST_D)) | (chI << (2 * ST_I)));
           dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
           pdg = pup;
           lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
@@ -252,32 +254,12 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
           ++nruns;
         }
         ++run_len;
+        // border cells have no continuing parent: the walk ends there (a dead end or, for (0,0), the print)
         const uint32_t wd = (x >= 1 && y >= 1) ? tb[(uint64_t)(x - 1) * n1 + (y - 1)] : 0u;
-        // fe of a neighbour's state: interior cells from their word, border cells by rule
-        auto nfe = [&](uint32_t nx, uint32_t ny, int nst) -> uint32_t {
-          if (nx >= 1 && ny >= 1) {
-            const uint32_t nw = tb[(uint64_t)(nx - 1) * n1 + (ny - 1)];
-            return (nw >> (nst == ST_M ? 7 : (nst == ST_D ? 9 : 11))) & 3u;
-          }
-          if (nx == 0 && ny == 0) return kFePrint;
-          if (nx == 0) return nst == ST_D ? kFePanic : kFeNone;
-          return nst == ST_I ? kFePanic : kFeNone;
-        };
-        int nst = -1;
-        if (st == ST_M) {
-          if ((wd & 4u) && nfe(x - 1, y - 1, ST_D)) nst = ST_D;
-          else if ((wd & 2u) && nfe(x - 1, y - 1, ST_I)) nst = ST_I;
-          else if ((wd & 1u) && nfe(x - 1, y - 1, ST_M)) nst = ST_M;
-          --x; --y;
-        } else if (st == ST_I) {
-          if ((wd & 16u) && nfe(x, y - 1, ST_M)) nst = ST_M;
-          else if ((wd & 8u) && nfe(x, y - 1, ST_I)) nst = ST_I;
-          --y;
-        } else {
-          if ((wd & 64u) && nfe(x - 1, y, ST_M)) nst = ST_M;
-          else if ((wd & 32u) && nfe(x - 1, y, ST_D)) nst = ST_D;
-          --x;
-        }
+        const int nst = (int)((wd >> (2 * st)) & 3u) - 1;
+        if (st == ST_M) { --x; --y; }
+        else if (st == ST_I) --y;
+        else --x;
         st = nst;
       }
       if (run_len) *--out = (run_len << 2) | run_op;
@@ -313,7 +295,7 @@ __global__ void __launch_bounds__(THREADS) nw_linear_general_kernel(const Genera
   const uint32_t w = p.row_stride;  // >= n2 + T
   int32_t* row = p.rows + (uint64_t)k * 6 * w + g;  // entry c of this thread at [c * T]: (S << 1) | gap
   const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
-  uint16_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
+  uint8_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
 
   const uint32_t C = (n2 + T - 1) / T;
   const uint32_t j_lo = g * C + 1, j_hi = min(n2, (g + 1) * C);
@@ -346,7 +328,7 @@ __global__ void __launch_bounds__(THREADS) nw_linear_general_kernel(const Genera
         const uint32_t mv = mx == down ? 1u : (mx == right ? 2u : 0u);
         const int32_t v = (mx << 1) | gap;
         row[c * T] = v;
-        if (tb) tb[(uint64_t)(i - 1) * n2 + (j - 1)] = (uint16_t)mv;
+        if (tb) tb[(uint64_t)(i - 1) * n2 + (j - 1)] = (uint8_t)mv;
         d = up;
         lf = v;
       }
