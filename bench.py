@@ -38,10 +38,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "config5nw"],
                     help="config2 (default, the headline): 150 bp affine NW; config3: 250 bp affine NW; "
                          "config4: WFA (standard mode) on 1-10 kbp pairs at 1-15 %% error; "
-                         "config5: WFA (standard mode) on 1 k pairs of 100 kbp at 5 %%")
+                         "config5: WFA (standard mode) on 1 k pairs of 100 kbp at 5 %%; "
+                         "config5nw: affine NW on 148 pairs of 100 kbp (score + status; the literal long-pair kernel)")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (0 = the workload's default)")
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--divergence", type=float, default=0.05)
@@ -106,6 +107,7 @@ WORKLOADS = {  # name -> (default pairs per GPU, length, BASELINE.json index)
     "config3": (1_000_000, 250, 2),
     "config4": (20_000, 0, 3),
     "config5": (1_000, 100_000, 4),
+    "config5nw": (148, 100_000, 4),
 }
 WFA_WORKLOADS = ("config4", "config5")
 
@@ -120,13 +122,19 @@ def make_batch(args, rank: int):
     from sequencealigning_b200 import synth
     if args.workload == "config4":
         return synth.config4(args.pairs, seed=synth.SEEDS["config4"] + 7919 * rank)
-    if args.workload == "config5":
+    if args.workload in ("config5", "config5nw"):
         return synth.random_pairs(args.pairs, args.length, 0.05, True, seed=synth.SEEDS["config5"] + 7919 * rank)
     return synth.random_pairs(args.pairs, args.length, args.divergence, not args.no_indels,
                               seed=synth.SEEDS[args.workload] + 7919 * rank)
 
 
 def workload_config(args, n_gpus: int) -> dict:
+    if args.workload == "config5nw":
+        return {"workload": f"affine NW, {args.pairs} synthetic pairs per GPU of {args.length} bp at 5 % divergence (sub:ins:del 2:1:1) "
+                            f"(BASELINE.json configs[4], NW half): exact score and status through the literal 32-bit long-pair kernel "
+                            f"(the reference's -32768 sentinel is live at this length); no CIGAR (SA_ALIGNMENT_OMITTED)",
+                "pairs_per_gpu": args.pairs, "length": args.length, "n_gpus": n_gpus,
+                "scheme": "match 5 / mismatch -4 / open -8 / ext -6 (nw_affine.rs:15-20)"}
     if args.workload == "config5":
         return {"workload": f"gap-affine WFA (standard mode, x=4 o=2 e=6), {args.pairs} synthetic pairs per GPU of {args.length} bp "
                             f"at 5 % divergence (sub:ins:del 2:1:1) (BASELINE.json configs[4], WFA half); GCUPS is EQUIVALENT cells n1*n2/s",
@@ -163,6 +171,19 @@ def cpu_baseline_wfa(batch, n_sample: int) -> dict:
     return {"value": cells / dt / 1e9, "unit": "GCUPS (equivalent cells)", "cores": 1, "kind": "port",
             "alignments_per_s": n_sample / dt, "seconds": dt,
             "sample": f"first {n_sample} pairs, oracle/wfa.c sao_wfa_standard (the reference's own wfa.rs produces no result on these inputs)"}
+
+
+def cpu_baseline_long(batch, prefix: int = 20000) -> dict:
+    """config5nw: the oracle's score-only affine DP (same recurrences and sentinel, O(n1) memory) on a
+    prefix of the first pair, 1 core."""
+    from oracle import binding as ob
+    ob.build()
+    q, d = batch.query(0)[:prefix], batch.db(0)[:prefix]
+    t0 = time.perf_counter()
+    ob.affine_score(q, d)
+    dt = time.perf_counter() - t0
+    return {"value": len(q) * len(d) / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": dt,
+            "sample": f"first {len(q)} x {len(d)} residues of pair 0, oracle/nw_affine.c sao_affine_score"}
 
 
 def cpu_baseline(batch, n_sample: int, n_threads: int, min_seconds: float = 0.0) -> dict:
@@ -419,7 +440,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         ipeak = peak["issue_lane_ops_per_s"]
         roof = None
-        if args.workload not in WFA_WORKLOADS:
+        if args.workload not in WFA_WORKLOADS and args.workload != "config5nw":
             pr = fill_kernel_probe(batch, local)
             k_cups = pr["cells"] / (pr["ms"] * 1e-3)
             roof = {
@@ -455,7 +476,13 @@ def main():
             "clocks": clocks, "e2e": e2e,
             "roofline": roof,
         }
-        if args.workload in WFA_WORKLOADS:
+        if args.workload == "config5nw":
+            out["roofline"] = {"bound": "int-issue", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                               "note": "literal 32-bit recurrences + DFS first-event bookkeeping, ~140 lane-instructions per cell "
+                                       "(nw_general.cuh); not the packed hot kernel, no roofline claimed"}
+            if not args.skip_cpu:
+                out["cpu_baseline"] = cpu_baseline_long(batch)
+        elif args.workload in WFA_WORKLOADS:
             out["roofline"] = {"bound": "latency (wavefront dependency chain)", "achieved": None, "peak": None, "unit": None,
                                "frac": None, "traffic": None,
                                "note": "WFA does O(s^2) work, not n1*n2: GCUPS here is equivalent cells; no roofline is claimed this round"}

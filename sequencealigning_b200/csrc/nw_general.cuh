@@ -165,15 +165,26 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
           const uint32_t idg = pdg & 0xffu, tdg = pdg >> 8;
           const uint32_t ilf = lP & 0xffu, tlf = lP >> 8;
           const uint32_t iup = pup & 0xffu, tup = pup >> 8;
-          uint32_t feM = kFeNone, feI = kFeNone, feD = kFeNone, tM = 0, tI = 0, tD = 0;
-          uint32_t chM = 0, chI = 0, chD = 0;  // parent the first alignment continues with (state + 1)
-          if (bits & 4u) { if (!feM) { feM = fe_of(idg, ST_D); if (feM) chM = ST_D + 1; } tM |= (tdg >> ST_D) & 1u; }
-          if (bits & 2u) { if (!feM) { feM = fe_of(idg, ST_I); if (feM) chM = ST_I + 1; } tM |= (tdg >> ST_I) & 1u; }
-          if (bits & 1u) { if (!feM) { feM = fe_of(idg, ST_M); if (feM) chM = ST_M + 1; } tM |= (tdg >> ST_M) & 1u; }
-          if (bits & 16u) { if (!feI) { feI = fe_of(ilf, ST_M); if (feI) chI = ST_M + 1; } tI |= (tlf >> ST_M) & 1u; }
-          if (bits & 8u) { if (!feI) { feI = fe_of(ilf, ST_I); if (feI) chI = ST_I + 1; } tI |= (tlf >> ST_I) & 1u; }
-          if (bits & 64u) { if (!feD) { feD = fe_of(iup, ST_M); if (feD) chD = ST_M + 1; } tD |= (tup >> ST_M) & 1u; }
-          if (bits & 32u) { if (!feD) { feD = fe_of(iup, ST_D); if (feD) chD = ST_D + 1; } tD |= (tup >> ST_D) & 1u; }
+          // Per state: first event = that of the first parent, in reverse push order, whose own
+          // first event is not NONE; that parent is where the first alignment continues (ch =
+          // state + 1, 0 = dead end); taint = OR over all parents.  Selects only, no branches:
+          // the lanes of a warp sit on unrelated cells.
+          const uint32_t mD = (bits & 4u) ? fe_of(idg, ST_D) : 0u;   // M <- D, I, M (:120-153, popped in reverse)
+          const uint32_t mI = (bits & 2u) ? fe_of(idg, ST_I) : 0u;
+          const uint32_t mM = (bits & 1u) ? fe_of(idg, ST_M) : 0u;
+          const uint32_t feM = mD ? mD : (mI ? mI : mM);
+          const uint32_t chM = mD ? ST_D + 1u : (mI ? ST_I + 1u : (mM ? ST_M + 1u : 0u));
+          const uint32_t tM = (((bits >> 2) & (tdg >> ST_D)) | ((bits >> 1) & (tdg >> ST_I)) | (bits & (tdg >> ST_M))) & 1u;
+          const uint32_t iM = (bits & 16u) ? fe_of(ilf, ST_M) : 0u;  // I <- M, I (:108-119)
+          const uint32_t iI = (bits & 8u) ? fe_of(ilf, ST_I) : 0u;
+          const uint32_t feI = iM ? iM : iI;
+          const uint32_t chI = iM ? ST_M + 1u : (iI ? ST_I + 1u : 0u);
+          const uint32_t tI = (((bits >> 4) & (tlf >> ST_M)) | ((bits >> 3) & (tlf >> ST_I))) & 1u;
+          const uint32_t dM = (bits & 64u) ? fe_of(iup, ST_M) : 0u;  // D <- M, D (:96-107)
+          const uint32_t dD = (bits & 32u) ? fe_of(iup, ST_D) : 0u;
+          const uint32_t feD = dM ? dM : dD;
+          const uint32_t chD = dM ? ST_M + 1u : (dD ? ST_D + 1u : 0u);
+          const uint32_t tD = (((bits >> 6) & (tup >> ST_M)) | ((bits >> 5) & (tup >> ST_D))) & 1u;
           const uint32_t np = feM | (feD << 2) | (feI << 4) | (((tM << ST_M) | (tD << ST_D) | (tI << ST_I)) << 8);
           rM[c] = mm;
           rI[c] = ii;
