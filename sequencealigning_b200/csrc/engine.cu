@@ -106,7 +106,7 @@ struct sa_engine {
   sa_timing_t timing = {};
   int sm_count = 0;
   size_t smem_optin = 0;
-  int force_g = 0, force_k = 0, minb = 0;
+  int force_g = 0, force_k = 0;
   uint32_t ormask = 0x00;
   size_t tb_budget = 0;
   size_t budget_cached = 0;
@@ -279,9 +279,6 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     if (g.K == 13 && g.G == 16) return launch_fill_m<13, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 8) return launch_fill_m<16, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 16) return launch_fill_m<16, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 8 && e->minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 8 && e->minb == 18) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 18>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 8 && e->minb == 20) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 20>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
   }
@@ -1275,7 +1272,6 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
   if (const char* s = getenv("SA_FORCE_K")) e->force_k = atoi(s);
-  if (const char* s = getenv("SA_MINB")) e->minb = atoi(s);
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);

@@ -1,5 +1,5 @@
-"""Kernel-form sweep (developer tool): times the device-resident affine path for each K:G[:MINB]
-form (SA_FORCE_K / SA_FORCE_G / SA_MINB) on one workload; checks results against the first."""
+"""Kernel-form sweep (developer tool): times the device-resident affine path for each K:G form
+(SA_FORCE_K / SA_FORCE_G) on one workload; checks results against the first."""
 import json
 import os
 import sys
@@ -20,12 +20,10 @@ def main():
     ref = None
     for f in forms:
         parts = f.split(":")
-        for k in ("SA_FORCE_K", "SA_FORCE_G", "SA_MINB"):
+        for k in ("SA_FORCE_K", "SA_FORCE_G"):
             os.environ.pop(k, None)
         if parts[0] != "auto":
             os.environ["SA_FORCE_K"], os.environ["SA_FORCE_G"] = parts[0], parts[1]
-            if len(parts) > 2:
-                os.environ["SA_MINB"] = parts[2]
         os.environ["SA_SEG_PAIRS"] = str(pairs)  # one segment: the fill launch is timed alone
         with Engine(0) as eng:
             rb = eng.upload(batch)
