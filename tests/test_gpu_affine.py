@@ -315,6 +315,24 @@ def test_long_pairs_in_waves_and_omitted_alignments(oracle, monkeypatch):
                 assert omitted.sum() == 1   # the 4.2 kbp pair (its words exceed 1/8 of the 80 MB share)
 
 
+def test_wide_long_pair_kernel_and_pass_boundaries(engine, oracle):
+    """Queries of 8192+ columns take the 512-thread form of the long-pair kernel; query lengths
+    around the pass width (threads x 8 columns) and the thread width exercise the edge column and
+    the end-cell owner; short db sides keep the oracle cheap."""
+    import random
+    from tests.util import mutate, random_seq
+    rng = random.Random(91)
+    pairs = []
+    for n1, n2 in [(8192, 37), (8193, 120), (12289, 64), (4096, 300), (4097, 300), (2049, 900), (2048, 2000), (6150, 5),
+                   (40, 8200), (300, 9000)]:
+        q = random_seq(rng, n1, b"ACGT")
+        d = mutate(rng, q[: max(n2, 1) * 2], 0.1, True, b"ACGT")[:n2] if rng.random() < 0.7 else random_seq(rng, n2, b"ACGT")
+        pairs.append((q, d))
+    b = _batch(pairs)
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, n_threads=8, what="wide long pairs")
+
+
 def test_sentinel_regime_long_pairs(engine, oracle):
     """n1 + n2 > ~5.4 k: the reference's finite -32768 'minus infinity' leaks into the matrix
     (SURVEY 7); the general kernel reproduces score, status and first alignment there too."""
