@@ -107,6 +107,7 @@ struct sa_engine {
   int sm_count = 0;
   size_t smem_optin = 0;
   int force_g = 0, force_k = 0;
+  bool long_ckpt_always = false;  // SA_LONG_CKPT: checkpointed traceback for every long pair (tests)
   uint32_t ormask = 0x00;
   size_t tb_budget = 0;
   size_t budget_cached = 0;
@@ -337,7 +338,8 @@ struct Segment {
   uint32_t n_short = 0;         // pairs handled by the packed kernel (= order.size() if explicit)
   // pairs outside the packed 16-bit range go to the general 32-bit kernel (nw_general.cuh)
   std::vector<uint32_t> long_ids;
-  std::vector<uint64_t> long_meta;  // per long pair: tb offset (uint16 units, ~0 = none), runs end
+  std::vector<uint64_t> long_meta;  // per long pair: tb offset (bytes, ~0 = none), runs end, checkpoint offset
+                                    // (records, ~0 = none), block offset (bytes)
   std::vector<uint32_t> long_waves; // indices into long_ids where a new wave (reusing the tb words) starts
   uint64_t long_tb_total = 0, long_runs_total = 0;
   uint32_t long_n1max = 0, long_n2max = 0;
@@ -553,25 +555,46 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       uint64_t wave_used = 0;
       // a segment of long pairs only does not need the packed kernel's scratch: use its share
       const uint64_t room = (n_long == cn) ? (uint64_t)budget_main + budget_re : (uint64_t)budget_re;
+      // Pairs too large for that get a CHECKPOINTED traceback instead (nw_general.cuh): the right
+      // edge of every column pass (16 bytes per row per pass) plus one pass-wide block of bytes.
+      for (uint32_t i = 0; i < cn; ++i)
+        if (is_long(h_cols[base + i], h_rows[base + i])) sg.long_n1max = std::max(sg.long_n1max, h_cols[base + i]);
+      const uint64_t pass_cols = (uint64_t)(sg.long_n1max >= 8192 ? sa::kGeneralThreadsWide : sa::kGeneralThreads) * sa::kGeneralCols;
       for (uint32_t i = 0; i < cn; ++i) {
         const uint32_t a = h_cols[base + i], b = h_rows[base + i];
         if (is_long(a, b)) {
           const uint64_t words = (uint64_t)a * b;
-          uint64_t off = ~0ull;
-          if (words <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
-            if (wave_used + words > room) {
+          uint64_t off = ~0ull, ck_off = ~0ull, blk_off = ~0ull;
+          auto take = [&](uint64_t bytes) -> uint64_t {  // 16-byte aligned room in the current wave
+            bytes = (bytes + 15) & ~(uint64_t)15;
+            if (wave_used + bytes > room) {
               sg.long_waves.push_back((uint32_t)sg.long_ids.size());
               wave_used = 0;
             }
-            off = wave_used;
-            wave_used += words;
+            const uint64_t at = wave_used;
+            wave_used += bytes;
             sg.long_tb_total = std::max(sg.long_tb_total, wave_used);
+            return at;
+          };
+          const uint64_t npass = (a + pass_cols - 1) / pass_cols;
+          const uint64_t ck_bytes = npass * ((uint64_t)b + 2) * 16, blk_bytes = (uint64_t)b * pass_cols;
+          // full traceback bytes up to 128 MB per pair (~11 kbp x 11 kbp: one kernel, no recomputation);
+          // beyond that the checkpointed form: a quarter or less of the memory, so many more pairs
+          // per wave, at the price of computing the visited part of every pass twice
+          const bool can_ckpt = !linear && ck_bytes + blk_bytes <= room / 2;
+          if (can_ckpt && (e->long_ckpt_always || words > ((uint64_t)128 << 20))) {
+            const uint64_t at = take(ck_bytes + blk_bytes);
+            ck_off = at / 16;
+            blk_off = at + ck_bytes;
+          } else if (words <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
+            off = take(words);
           }
           sg.long_runs_total += (uint64_t)a + b + 1;
           sg.long_ids.push_back((uint32_t)(base + i));
           sg.long_meta.push_back(off);
           sg.long_meta.push_back(sg.long_runs_total);
-          sg.long_n1max = std::max(sg.long_n1max, a);
+          sg.long_meta.push_back(ck_off);
+          sg.long_meta.push_back(blk_off);
           sg.long_n2max = std::max(sg.long_n2max, b);
         } else {
           sg.order.push_back((uint32_t)(base + i));
@@ -798,19 +821,19 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       // kernel's rolling row (ceil(columns / threads) * threads entries); even, for 16-byte alignment
       const uint32_t stride = (std::max(sg.long_n1max, sg.long_n2max) + 2 + sa::kGeneralThreadsWide + 1) & ~1u;
       if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_meta, (size_t)nl * 16)) != SA_OK) return r;
+      if ((r = ensure(e, sl.g_meta, (size_t)nl * (32 + sizeof(sa::LongWalkState)))) != SA_OK) return r;
       if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total + 256)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_rows, (size_t)nl * 6 * stride * 4)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_info, (size_t)nl * 4 * stride)) != SA_OK) return r;
       if ((r = ensure(e, sl.g_runs, (size_t)sg.long_runs_total * 4 + 256)) != SA_OK) return r;
-      std::vector<uint64_t> tb_off(nl), runs_end(nl);
+      std::vector<uint64_t> meta((size_t)4 * nl);  // [tb_off | runs_end | ck_off | blk_off]
+      bool any_ckpt = false;
       for (uint32_t t = 0; t < nl; ++t) {
-        tb_off[t] = sg.long_meta[2 * t];
-        runs_end[t] = sg.long_meta[2 * t + 1];
+        for (int f = 0; f < 4; ++f) meta[(size_t)f * nl + t] = sg.long_meta[4 * t + f];
+        any_ckpt |= sg.long_meta[4 * t + 2] != ~0ull;
       }
       CUDA_TRY(e, cudaMemcpyAsync(sl.g_ids.p, sg.long_ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, sx));
-      CUDA_TRY(e, cudaMemcpyAsync(sl.g_meta.p, tb_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
-      CUDA_TRY(e, cudaMemcpyAsync((uint64_t*)sl.g_meta.p + nl, runs_end.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+      CUDA_TRY(e, cudaMemcpyAsync(sl.g_meta.p, meta.data(), (size_t)nl * 32, cudaMemcpyHostToDevice, sx));
       sa::GeneralParams gp{};
       gp.residues = db.residues;
       gp.q_off = db.q_off;
@@ -825,12 +848,17 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       gp.open = sc.gap_open;
       gp.ext = sc.gap_ext;
       gp.tb = want_cigar ? (uint8_t*)sl.g_tb.p : nullptr;
+      gp.ck = want_cigar ? (int4*)sl.g_tb.p : nullptr;  // checkpoints and blocks share the wave's scratch
+      gp.ck_off = (const uint64_t*)sl.g_meta.p + 2 * (size_t)nl;
+      gp.blk = (uint8_t*)sl.g_tb.p;
+      gp.blk_off = (const uint64_t*)sl.g_meta.p + 3 * (size_t)nl;
+      gp.ws = (sa::LongWalkState*)((uint64_t*)sl.g_meta.p + 4 * (size_t)nl);
       gp.tb_off = (const uint64_t*)sl.g_meta.p;
       gp.rows = (int32_t*)sl.g_rows.p;
       gp.info = (uint8_t*)sl.g_info.p;
       gp.row_stride = stride;
       gp.runs = (uint32_t*)sl.g_runs.p;
-      gp.runs_end = (const uint64_t*)sl.g_meta.p + nl;
+      gp.runs_end = (const uint64_t*)sl.g_meta.p + (size_t)nl;
       gp.score = db.score;
       gp.status = db.status;
       gp.cigar_len = db.cigar_len;
@@ -846,6 +874,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         gw.runs_end = gp.runs_end + lo;
         gw.rows = gp.rows + (uint64_t)lo * 6 * stride;
         gw.info = gp.info + (uint64_t)lo * 4 * stride;
+        gw.ck_off = gp.ck_off + lo;
+        gw.blk_off = gp.blk_off + lo;
+        gw.ws = gp.ws + lo;
         if (linear && wide)
           sa::nw_linear_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
         else if (linear)
@@ -854,6 +885,13 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           sa::nw_affine_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
         else
           sa::nw_affine_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+        if (!linear && any_ckpt && want_cigar) {  // second kernel of a checkpointed traceback (idle blocks leave at once)
+          if (wide)
+            sa::nw_affine_general_back<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+          else
+            sa::nw_affine_general_back<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+          e->timing.kernel_launches++;
+        }
         CUDA_TRY(e, cudaGetLastError());
         e->timing.kernel_launches++;
       }
@@ -1272,6 +1310,7 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
   if (const char* s = getenv("SA_FORCE_K")) e->force_k = atoi(s);
+  if (const char* s = getenv("SA_LONG_CKPT")) e->long_ckpt_always = atoi(s) != 0;
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);

@@ -43,6 +43,22 @@ struct GeneralParams {
   int32_t* __restrict__ score;
   uint8_t* __restrict__ status;
   uint32_t* __restrict__ cigar_len;
+  // Checkpointed traceback (pairs whose [n2][n1] traceback bytes do not fit): the forward kernel
+  // keeps the right edge of EVERY column pass (ck: per pair passes x (n2 + 2) records), and the
+  // backward kernel recomputes one pass at a time, last to first, into a block of traceback bytes
+  // (blk: per pair n2 x pass-width) and walks the alignment through it.
+  int4* __restrict__ ck;
+  const uint64_t* __restrict__ ck_off;   // (records); UINT64_MAX = not checkpointed
+  uint8_t* __restrict__ blk;
+  const uint64_t* __restrict__ blk_off;  // (bytes)
+  struct LongWalkState* __restrict__ ws;  // per launch index
+};
+
+// where the walk of a checkpointed pair stands between the two kernels
+struct LongWalkState {
+  uint32_t x, y;
+  int32_t st;
+  uint32_t pending;  // 1: the backward kernel has to produce the alignment
 };
 
 enum { kFeNone = 0, kFePrint = 1, kFePanic = 2 };
@@ -66,6 +82,188 @@ constexpr int kGeneralThreadsWide = 512;   // longer pairs: twice the lanes per 
 constexpr int kGeneralCols = 8;
 
 template <int THREADS>
+struct GeneralShared {
+  int32_t xM[2][THREADS], xI[2][THREADS], xD[2][THREADS];
+  uint32_t xP[2][THREADS];
+};
+
+struct GeneralEnd {
+  int32_t em = 0, ei = 0, ed = 0;
+  uint32_t einfo = 0, etaint = 0;
+};
+
+// One column pass over rows 1..nrows.  edge_r: the previous pass's right edge (pass > 0);
+// edge_w: where this pass leaves its own (or nullptr); tb: traceback bytes of this call's cells,
+// row stride tb_stride, column (y - 1 - tb_col0); end: the end cell's record if it lies in this
+// pass and row nrows == n2.
+template <int THREADS>
+__device__ __forceinline__ void general_pass(const GeneralParams& p, GeneralShared<THREADS>& sh, uint32_t n1,
+                                             uint32_t n2, uint64_t qo, uint64_t dof, uint32_t pass,
+                                             uint32_t nrows, const int4* edge_r, int4* edge_w, uint8_t* tb,
+                                             uint32_t tb_stride, uint32_t tb_col0, bool want_end,
+                                             GeneralEnd& end) {
+  constexpr uint32_t T = THREADS;
+  constexpr int C = kGeneralCols;
+  enum { ST_M = 0, ST_D = 1, ST_I = 2 };
+  constexpr int32_t kNegInf = -32768;
+  const uint32_t g = threadIdx.x;
+  const uint32_t P = T * C;
+  const uint32_t owner = n1 ? ((n1 - 1) % P) / C : 0, owner_c = n1 ? (n1 - 1) % C : 0;
+  const uint32_t y0 = pass * P + g * C;  // this thread's columns are y0+1 .. y0+C
+  const bool owns = y0 < n1;
+  // row 0 (:172-199): D[0][y>=1] is the boundary chain (has a parent and x == 0: expanding it
+  // panics, :299); M[0][y], I[0][y] are sentinels without parents.
+  int32_t rM[C], rI[C], rD[C];
+  uint32_t rP[C], q[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const uint32_t y = y0 + c + 1;
+    rM[c] = kNegInf;
+    rI[c] = kNegInf;
+    rD[c] = ((int32_t)y + 1) * p.ext + p.open;
+    rP[c] = (kFePanic << 2) | ((1u << ST_D) << 8);
+    q[c] = y <= n1 ? load_residue(p.residues, qo + y - 1, p.packing) : 0xffffffffu;
+  }
+  // the cell (0, y0): diagonal input of row 1
+  int32_t gM, gI, gD;
+  uint32_t gP;
+  if (y0 == 0) {  // origin: M[0][0] = 0 is popped at (0,0) -> PRINT; D/I[0][0] print too if popped (:283)
+    gM = 0; gI = kNegInf; gD = kNegInf;
+    gP = kFePrint | (kFePrint << 2) | (kFePrint << 4);
+  } else {
+    gM = kNegInf; gI = kNegInf; gD = ((int32_t)y0 + 1) * p.ext + p.open;
+    gP = (kFePanic << 2) | ((1u << ST_D) << 8);
+  }
+  // thread 0 of a later pass: the previous pass's right edge, fetched one row ahead
+  int4 ahead = make_int4(0, 0, 0, 0);
+  if (g == 0 && pass > 0) ahead = __ldcg(&edge_r[1]);
+
+  const uint32_t steps = nrows + T - 1;
+  for (uint32_t t = 1; t <= steps; ++t) {
+    const uint32_t buf = t & 1u;
+    const uint32_t x = t - g;  // (wraps for t < g: then x > nrows)
+    if (owns && x >= 1 && x <= nrows) {
+      // the cell to the left of this thread's first column, row x
+      int32_t lM, lI, lD;
+      uint32_t lP;
+      if (g == 0) {
+        if (pass == 0) {  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
+          lM = kNegInf; lD = kNegInf; lI = p.open + ((int32_t)x + 1) * p.ext;
+          lP = (kFePanic << 4) | ((1u << ST_I) << 8);
+        } else {
+          lM = ahead.x; lI = ahead.y; lD = ahead.z; lP = (uint32_t)ahead.w;
+          if (x < nrows) ahead = __ldcg(&edge_r[x + 1]);
+        }
+      } else {
+        lM = sh.xM[buf ^ 1u][g - 1]; lI = sh.xI[buf ^ 1u][g - 1]; lD = sh.xD[buf ^ 1u][g - 1];
+        lP = sh.xP[buf ^ 1u][g - 1];
+      }
+      const int32_t nextM = lM, nextI = lI, nextD = lD;  // becomes the diagonal input of row x + 1
+      const uint32_t nextP = lP;
+      const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
+      int32_t dm = gM, di = gI, dd = gD;  // (x-1, y-1)
+      uint32_t pdg = gP;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int32_t um = rM[c], ui = rI[c], ud = rD[c];  // (x-1, y)
+        const uint32_t pup = rP[c];
+        const int32_t sub = q[c] == b2 ? p.match : p.mismatch;
+        const int32_t mm = max(max(dm, di), dd) + sub;
+        const int32_t ii = max(lM + p.open, lI) + p.ext;
+        const int32_t dv = max(um + p.open, ud) + p.ext;
+        uint32_t bits = 0;
+        if (mm == dm + sub) bits |= 1u;
+        if (mm == di + sub) bits |= 2u;
+        if (mm == dd + sub) bits |= 4u;
+        if (ii == lI + p.ext) bits |= 8u;
+        if (ii == lM + p.open + p.ext) bits |= 16u;
+        if (dv == ud + p.ext) bits |= 32u;
+        if (dv == um + p.open + p.ext) bits |= 64u;
+        // DFS bookkeeping (info in bits 0-5, taint in bits 8-10 of the packed records)
+        const uint32_t idg = pdg & 0xffu, tdg = pdg >> 8;
+        const uint32_t ilf = lP & 0xffu, tlf = lP >> 8;
+        const uint32_t iup = pup & 0xffu, tup = pup >> 8;
+        // Per state: first event = that of the first parent, in reverse push order, whose own
+        // first event is not NONE; that parent is where the first alignment continues (ch =
+        // state + 1, 0 = dead end); taint = OR over all parents.  Selects only, no branches:
+        // the lanes of a warp sit on unrelated cells.
+        const uint32_t mD = (bits & 4u) ? fe_of(idg, ST_D) : 0u;   // M <- D, I, M (:120-153, popped in reverse)
+        const uint32_t mI = (bits & 2u) ? fe_of(idg, ST_I) : 0u;
+        const uint32_t mM = (bits & 1u) ? fe_of(idg, ST_M) : 0u;
+        const uint32_t feM = mD ? mD : (mI ? mI : mM);
+        const uint32_t chM = mD ? ST_D + 1u : (mI ? ST_I + 1u : (mM ? ST_M + 1u : 0u));
+        const uint32_t tM = (((bits >> 2) & (tdg >> ST_D)) | ((bits >> 1) & (tdg >> ST_I)) | (bits & (tdg >> ST_M))) & 1u;
+        const uint32_t iM = (bits & 16u) ? fe_of(ilf, ST_M) : 0u;  // I <- M, I (:108-119)
+        const uint32_t iI = (bits & 8u) ? fe_of(ilf, ST_I) : 0u;
+        const uint32_t feI = iM ? iM : iI;
+        const uint32_t chI = iM ? ST_M + 1u : (iI ? ST_I + 1u : 0u);
+        const uint32_t tI = (((bits >> 4) & (tlf >> ST_M)) | ((bits >> 3) & (tlf >> ST_I))) & 1u;
+        const uint32_t dM = (bits & 64u) ? fe_of(iup, ST_M) : 0u;  // D <- M, D (:96-107)
+        const uint32_t dD = (bits & 32u) ? fe_of(iup, ST_D) : 0u;
+        const uint32_t feD = dM ? dM : dD;
+        const uint32_t chD = dM ? ST_M + 1u : (dD ? ST_D + 1u : 0u);
+        const uint32_t tD = (((bits >> 6) & (tup >> ST_M)) | ((bits >> 5) & (tup >> ST_D))) & 1u;
+        const uint32_t np = feM | (feD << 2) | (feI << 4) | (((tM << ST_M) | (tD << ST_D) | (tI << ST_I)) << 8);
+        rM[c] = mm;
+        rI[c] = ii;
+        rD[c] = dv;
+        rP[c] = np;
+        if (tb && y0 + c < n1)
+          tb[(uint64_t)(x - 1) * tb_stride + (y0 + c - tb_col0)] =
+              (uint8_t)((chM << (2 * ST_M)) | (chD << (2 * ST_D)) | (chI << (2 * ST_I)));
+        dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
+        pdg = pup;
+        lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
+        lP = np;
+      }
+      sh.xM[buf][g] = lM; sh.xI[buf][g] = lI; sh.xD[buf][g] = lD;
+      sh.xP[buf][g] = lP;
+      if (g == T - 1 && edge_w) edge_w[x] = make_int4(lM, lI, lD, (int)lP);
+      gM = nextM; gI = nextI; gD = nextD;
+      gP = nextP;
+      if (want_end && g == owner && x == n2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if ((uint32_t)c == owner_c) {
+            end.em = rM[c]; end.ei = rI[c]; end.ed = rD[c];
+            end.einfo = rP[c] & 0xffu; end.etaint = rP[c] >> 8;
+          }
+      }
+    }
+    __syncthreads();
+  }
+  __threadfence_block();  // the pass's edge column and traceback bytes before the next readers
+  __syncthreads();
+}
+
+// One step of the walk of the first printed alignment through a block of traceback bytes; the
+// runs are produced last to first.
+struct LongWalk {
+  uint32_t x, y;
+  int st;
+  uint32_t nruns, run_op, run_len;
+  uint32_t* out;
+  __device__ __forceinline__ void emit() {
+    const uint32_t op = st == 0 ? 0u : (st == 2 ? 1u : 2u);  // M -> SA_OP_M, I -> SA_OP_I, D -> SA_OP_D
+    if (op != run_op) {
+      if (run_len) *--out = (run_len << 2) | run_op;
+      run_op = op;
+      run_len = 0;
+      ++nruns;
+    }
+    ++run_len;
+  }
+  __device__ __forceinline__ void step(uint32_t wd) {  // wd: the byte of cell (x, y), 0 on the border
+    const int nst = (int)((wd >> (2 * st)) & 3u) - 1;
+    if (st == 0) { --x; --y; }
+    else if (st == 2) --y;
+    else --x;
+    st = nst;
+  }
+  __device__ __forceinline__ bool alive() const { return !(x == 0 && y == 0) && st >= 0; }
+};
+
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const GeneralParams p) {
   constexpr uint32_t T = THREADS;
   constexpr int C = kGeneralCols;
@@ -80,143 +278,26 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
   int4* edge = reinterpret_cast<int4*>(p.rows + (uint64_t)k * 6 * p.row_stride);  // [row]: M, I, D, info | taint << 8
   const bool keep_tb = p.tb != nullptr && p.tb_off[k] != ~0ull;
   uint8_t* tb = keep_tb ? p.tb + p.tb_off[k] : nullptr;
+  const bool ckpt = !keep_tb && p.ck != nullptr && p.ck_off[k] != ~0ull;
+  int4* ck = ckpt ? p.ck + p.ck_off[k] : nullptr;
+  const uint64_t S = (uint64_t)n2 + 2;  // records per checkpointed edge
 
   const uint32_t P = T * C;
   const uint32_t npass = (n1 + P - 1) / P;
-  __shared__ int32_t xM[2][T], xI[2][T], xD[2][T];
-  __shared__ uint32_t xP[2][T];
+  __shared__ GeneralShared<THREADS> sh;
+  GeneralEnd end;
+  const bool interior = n1 && n2;
+  const uint32_t owner = n1 ? ((n1 - 1) % P) / C : 0;
+  if (p.ws && g == 0) p.ws[k].pending = 0;
 
-  int32_t em = 0, ei = 0, ed = 0;  // end cell
-  uint32_t einfo = 0, etaint = 0;
-  const uint32_t steps = (n1 && n2) ? n2 + T - 1 : 0;
-  const uint32_t owner = n1 ? ((n1 - 1) % P) / C : 0, owner_c = n1 ? (n1 - 1) % C : 0;
-
-  for (uint32_t pass = 0; pass < npass && steps; ++pass) {
-    const uint32_t y0 = pass * P + g * C;  // this thread's columns are y0+1 .. y0+C
-    const bool owns = y0 < n1;
-    // row 0 (:172-199): D[0][y>=1] is the boundary chain (has a parent and x == 0: expanding it
-    // panics, :299); M[0][y], I[0][y] are sentinels without parents.
-    int32_t rM[C], rI[C], rD[C];
-    uint32_t rP[C], q[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const uint32_t y = y0 + c + 1;
-      rM[c] = kNegInf;
-      rI[c] = kNegInf;
-      rD[c] = ((int32_t)y + 1) * p.ext + p.open;
-      rP[c] = (kFePanic << 2) | ((1u << ST_D) << 8);
-      q[c] = y <= n1 ? load_residue(p.residues, qo + y - 1, p.packing) : 0xffffffffu;
-    }
-    // the cell (0, y0): diagonal input of row 1
-    int32_t gM, gI, gD;
-    uint32_t gP;
-    if (y0 == 0) {  // origin: M[0][0] = 0 is popped at (0,0) -> PRINT; D/I[0][0] print too if popped (:283)
-      gM = 0; gI = kNegInf; gD = kNegInf;
-      gP = kFePrint | (kFePrint << 2) | (kFePrint << 4);
-    } else {
-      gM = kNegInf; gI = kNegInf; gD = ((int32_t)y0 + 1) * p.ext + p.open;
-      gP = (kFePanic << 2) | ((1u << ST_D) << 8);
-    }
-    // thread 0 of a later pass: the previous pass's right edge, fetched one row ahead
-    int4 ahead = make_int4(0, 0, 0, 0);
-    if (g == 0 && pass > 0) ahead = __ldcg(&edge[1]);
-
-    for (uint32_t t = 1; t <= steps; ++t) {
-      const uint32_t buf = t & 1u;
-      const uint32_t x = t - g;  // (wraps for t < g: then x > n2)
-      if (owns && x >= 1 && x <= n2) {
-        // the cell to the left of this thread's first column, row x
-        int32_t lM, lI, lD;
-        uint32_t lP;
-        if (g == 0) {
-          if (pass == 0) {  // column 0 (:200-216): I[x][0] is the boundary chain (:303)
-            lM = kNegInf; lD = kNegInf; lI = p.open + ((int32_t)x + 1) * p.ext;
-            lP = (kFePanic << 4) | ((1u << ST_I) << 8);
-          } else {
-            lM = ahead.x; lI = ahead.y; lD = ahead.z; lP = (uint32_t)ahead.w;
-            if (x < n2) ahead = __ldcg(&edge[x + 1]);
-          }
-        } else {
-          lM = xM[buf ^ 1u][g - 1]; lI = xI[buf ^ 1u][g - 1]; lD = xD[buf ^ 1u][g - 1];
-          lP = xP[buf ^ 1u][g - 1];
-        }
-        const int32_t nextM = lM, nextI = lI, nextD = lD;  // becomes the diagonal input of row x + 1
-        const uint32_t nextP = lP;
-        const uint32_t b2 = load_residue(p.residues, dof + x - 1, p.packing);
-        int32_t dm = gM, di = gI, dd = gD;  // (x-1, y-1)
-        uint32_t pdg = gP;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int32_t um = rM[c], ui = rI[c], ud = rD[c];  // (x-1, y)
-          const uint32_t pup = rP[c];
-          const int32_t sub = q[c] == b2 ? p.match : p.mismatch;
-          const int32_t mm = max(max(dm, di), dd) + sub;
-          const int32_t ii = max(lM + p.open, lI) + p.ext;
-          const int32_t dv = max(um + p.open, ud) + p.ext;
-          uint32_t bits = 0;
-          if (mm == dm + sub) bits |= 1u;
-          if (mm == di + sub) bits |= 2u;
-          if (mm == dd + sub) bits |= 4u;
-          if (ii == lI + p.ext) bits |= 8u;
-          if (ii == lM + p.open + p.ext) bits |= 16u;
-          if (dv == ud + p.ext) bits |= 32u;
-          if (dv == um + p.open + p.ext) bits |= 64u;
-          // DFS bookkeeping, parents in reverse push order (info in bits 0-5, taint in bits 8-10)
-          const uint32_t idg = pdg & 0xffu, tdg = pdg >> 8;
-          const uint32_t ilf = lP & 0xffu, tlf = lP >> 8;
-          const uint32_t iup = pup & 0xffu, tup = pup >> 8;
-          // Per state: first event = that of the first parent, in reverse push order, whose own
-          // first event is not NONE; that parent is where the first alignment continues (ch =
-          // state + 1, 0 = dead end); taint = OR over all parents.  Selects only, no branches:
-          // the lanes of a warp sit on unrelated cells.
-          const uint32_t mD = (bits & 4u) ? fe_of(idg, ST_D) : 0u;   // M <- D, I, M (:120-153, popped in reverse)
-          const uint32_t mI = (bits & 2u) ? fe_of(idg, ST_I) : 0u;
-          const uint32_t mM = (bits & 1u) ? fe_of(idg, ST_M) : 0u;
-          const uint32_t feM = mD ? mD : (mI ? mI : mM);
-          const uint32_t chM = mD ? ST_D + 1u : (mI ? ST_I + 1u : (mM ? ST_M + 1u : 0u));
-          const uint32_t tM = (((bits >> 2) & (tdg >> ST_D)) | ((bits >> 1) & (tdg >> ST_I)) | (bits & (tdg >> ST_M))) & 1u;
-          const uint32_t iM = (bits & 16u) ? fe_of(ilf, ST_M) : 0u;  // I <- M, I (:108-119)
-          const uint32_t iI = (bits & 8u) ? fe_of(ilf, ST_I) : 0u;
-          const uint32_t feI = iM ? iM : iI;
-          const uint32_t chI = iM ? ST_M + 1u : (iI ? ST_I + 1u : 0u);
-          const uint32_t tI = (((bits >> 4) & (tlf >> ST_M)) | ((bits >> 3) & (tlf >> ST_I))) & 1u;
-          const uint32_t dM = (bits & 64u) ? fe_of(iup, ST_M) : 0u;  // D <- M, D (:96-107)
-          const uint32_t dD = (bits & 32u) ? fe_of(iup, ST_D) : 0u;
-          const uint32_t feD = dM ? dM : dD;
-          const uint32_t chD = dM ? ST_M + 1u : (dD ? ST_D + 1u : 0u);
-          const uint32_t tD = (((bits >> 6) & (tup >> ST_M)) | ((bits >> 5) & (tup >> ST_D))) & 1u;
-          const uint32_t np = feM | (feD << 2) | (feI << 4) | (((tM << ST_M) | (tD << ST_D) | (tI << ST_I)) << 8);
-          rM[c] = mm;
-          rI[c] = ii;
-          rD[c] = dv;
-          rP[c] = np;
-          if (tb && y0 + c < n1)
-            tb[(uint64_t)(x - 1) * n1 + (y0 + c)] = (uint8_t)((chM << (2 * ST_M)) | (chD << (2 * ST_D)) | (chI << (2 * ST_I)));
-          dm = um; di = ui; dd = ud;  // the cell above becomes the diagonal of the next column
-          pdg = pup;
-          lM = mm; lI = ii; lD = dv;  // and this cell its left neighbour
-          lP = np;
-        }
-        xM[buf][g] = lM; xI[buf][g] = lI; xD[buf][g] = lD;
-        xP[buf][g] = lP;
-        if (g == T - 1 && pass + 1 < npass) edge[x] = make_int4(lM, lI, lD, (int)lP);
-        gM = nextM; gI = nextI; gD = nextD;
-        gP = nextP;
-        if (pass + 1 == npass && g == owner && x == n2) {
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-            if ((uint32_t)c == owner_c) {
-              em = rM[c]; ei = rI[c]; ed = rD[c];
-              einfo = rP[c] & 0xffu; etaint = rP[c] >> 8;
-            }
-        }
-      }
-      __syncthreads();
-    }
-    __threadfence_block();  // the pass's edge column (and traceback words) before the next readers
-    __syncthreads();
+  for (uint32_t pass = 0; pass < npass && interior; ++pass) {
+    const int4* er = pass ? (ckpt ? ck + (uint64_t)(pass - 1) * S : edge) : nullptr;
+    int4* ew = pass + 1 < npass ? (ckpt ? ck + (uint64_t)pass * S : edge) : nullptr;
+    general_pass<THREADS>(p, sh, n1, n2, qo, dof, pass, n2, er, ew, tb, n1, 0, pass + 1 == npass, end);
   }
-  if (steps == 0) {
+  int32_t em = end.em, ei = end.ei, ed = end.ed;
+  uint32_t einfo = end.einfo, etaint = end.etaint;
+  if (!interior) {
     // an empty side: the end cell is a border cell of row 0 / column 0
     if (g != 0) return;
     if (n1 == 0 && n2 == 0) {
@@ -249,36 +330,82 @@ __global__ void __launch_bounds__(THREADS) nw_affine_general_kernel(const Genera
   uint8_t status = fe == kFePrint ? (any_panic ? kRefPanic : kOk) : (fe == kFePanic ? kRefPanicEarly : kRefNoOutput);
   uint32_t nruns = 0;
   if (fe == kFePrint && (n1 | n2)) {
-    if (!tb) {
-      status |= kAlignmentOmitted;
-    } else {
-      // first printed alignment: at every cell the first parent (reverse push order) with an event
-      uint32_t x = n2, y = n1, run_op = 3, run_len = 0;
-      int st = first;
-      uint32_t* out = p.runs + p.runs_end[k];
-      while (!(x == 0 && y == 0) && st >= 0) {
-        const uint32_t op = st == ST_M ? 0u : (st == ST_I ? 1u : 2u);
-        if (op != run_op) {
-          if (run_len) *--out = (run_len << 2) | run_op;
-          run_op = op;
-          run_len = 0;
-          ++nruns;
-        }
-        ++run_len;
-        // border cells have no continuing parent: the walk ends there (a dead end or, for (0,0), the print)
-        const uint32_t wd = (x >= 1 && y >= 1) ? tb[(uint64_t)(x - 1) * n1 + (y - 1)] : 0u;
-        const int nst = (int)((wd >> (2 * st)) & 3u) - 1;
-        if (st == ST_M) { --x; --y; }
-        else if (st == ST_I) --y;
-        else --x;
-        st = nst;
+    if (tb) {
+      // first printed alignment: at every cell the parent chosen at fill time
+      LongWalk wk{n2, n1, first, 0, 3, 0, p.runs + p.runs_end[k]};
+      while (wk.alive()) {
+        wk.emit();
+        // border cells have no continuing parent: the walk ends there (a dead end or, at (0,0), the print)
+        wk.step((wk.x >= 1 && wk.y >= 1) ? tb[(uint64_t)(wk.x - 1) * n1 + (wk.y - 1)] : 0u);
       }
-      if (run_len) *--out = (run_len << 2) | run_op;
+      if (wk.run_len) *--wk.out = (wk.run_len << 2) | wk.run_op;
+      nruns = wk.nruns;
+    } else if (ckpt && p.ws) {
+      p.ws[k].x = n2;
+      p.ws[k].y = n1;
+      p.ws[k].st = first;
+      p.ws[k].pending = 1;  // nw_affine_general_back produces the alignment and cigar_len
+    } else {
+      status |= kAlignmentOmitted;
     }
   }
   p.score[id] = mx;
   p.status[id] = status;
   p.cigar_len[id] = nruns;
+}
+
+// Checkpointed traceback, second kernel: passes last to first.  A pass is recomputed from the
+// edge its left neighbour left behind, only down to the row the walk stands on, with its
+// traceback bytes going to the pair's block; thread 0 then walks until the path leaves the
+// pass on the left (or ends).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nw_affine_general_back(const GeneralParams p) {
+  constexpr uint32_t T = THREADS;
+  constexpr int C = kGeneralCols;
+  const uint32_t k = blockIdx.x;
+  if (k >= p.n_ids || !p.ws || !p.ws[k].pending) return;  // (uniform per block)
+  const uint32_t g = threadIdx.x;
+  const uint32_t id = p.ids[k];
+  const uint32_t n1 = p.q_len[id], n2 = p.d_len[id];
+  const uint64_t qo = p.q_off[id], dof = p.d_off[id];
+  const int4* ck = p.ck + p.ck_off[k];
+  uint8_t* blk = p.blk + p.blk_off[k];
+  const uint64_t S = (uint64_t)n2 + 2;
+  const uint32_t P = T * C;
+  const uint32_t npass = (n1 + P - 1) / P;
+  __shared__ GeneralShared<THREADS> sh;
+  __shared__ LongWalk wk;
+  if (g == 0) wk = LongWalk{p.ws[k].x, p.ws[k].y, p.ws[k].st, 0, 3, 0, p.runs + p.runs_end[k]};
+  __syncthreads();
+  GeneralEnd unused;
+  for (int pass = (int)npass - 1; pass >= 0; --pass) {
+    const uint32_t y_base = (uint32_t)pass * P;
+    const bool here = wk.alive() && wk.y > y_base && wk.x >= 1;  // (shared: uniform)
+    if (!here) {
+      if (!wk.alive() || wk.x == 0) break;
+      continue;
+    }
+    const uint32_t nrows = wk.x;
+    __syncthreads();
+    general_pass<THREADS>(p, sh, n1, n2, qo, dof, (uint32_t)pass, nrows, pass ? ck + (uint64_t)(pass - 1) * S : nullptr,
+                          nullptr, blk, P, y_base, false, unused);
+    if (g == 0) {
+      while (wk.alive() && wk.y > y_base) {
+        wk.emit();
+        wk.step(wk.x >= 1 ? blk[(uint64_t)(wk.x - 1) * P + (wk.y - 1 - y_base)] : 0u);
+      }
+    }
+    __syncthreads();
+  }
+  if (g == 0) {
+    // what is left runs along the border: column 0 / row 0 cells have no continuing parent
+    while (wk.alive()) {
+      wk.emit();
+      wk.step(0u);
+    }
+    if (wk.run_len) *--wk.out = (wk.run_len << 2) | wk.run_op;
+    p.cigar_len[id] = wk.nruns;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

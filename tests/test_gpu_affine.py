@@ -333,6 +333,35 @@ def test_wide_long_pair_kernel_and_pass_boundaries(engine, oracle):
     check_against_oracle(oracle, b, r, n_threads=8, what="wide long pairs")
 
 
+def test_checkpointed_traceback_of_long_pairs(oracle, monkeypatch):
+    """SA_LONG_CKPT=1 sends every long pair through the checkpointed traceback (forward kernel keeps
+    the right edge of every column pass; the backward kernel recomputes pass by pass into a block
+    and walks through it) -- the path that 100 kbp pairs take.  Same bits as the oracle: one,
+    two and several passes, the 512-thread form, the sentinel regime, panics and dead ends."""
+    import random
+    from sequencealigning_b200 import Engine
+    from tests.util import mutate, random_seq
+    monkeypatch.setenv("SA_LONG_CKPT", "1")
+    rng = random.Random(97)
+    pairs = random_pair_list(56, 60, 1, 150)
+    for n1, n2, err in [(2100, 2050, 0.05), (2500, 2600, 0.02), (4100, 700, 0.1), (6200, 300, 0.08), (8200, 120, 0.1),
+                        (12300, 60, 0.2), (1900, 1950, 0.3), (300, 4000, 0.1)]:
+        q = random_seq(rng, n1, b"ACGT")
+        d = mutate(rng, (q * 2)[: n2 * 2], err, True, b"ACGT")[:n2]
+        pairs.insert(rng.randrange(len(pairs)), (q, d))
+    pairs.append((b"A" * 2000, b"C" * 2200))               # deeply negative scores
+    pairs.append((b"A" * 5600, b"C" * 3))                   # sentinel regime
+    pairs.append((b"ACGT" * 700, b"TTGCA" * 600))
+    pairs.append((b"G" + random_seq(rng, 2300, b"ACGT"), random_seq(rng, 2300, b"ACGT")))
+    b = _batch(pairs)
+    with Engine(0) as eng:
+        r = eng.align(b)
+        assert not (r.status & 0x80).any()
+        check_against_oracle(oracle, b, r, n_threads=8, what="checkpointed traceback")
+        only_long = _batch([pq for pq in pairs if len(pq[0]) + len(pq[1]) > 3700])
+        check_against_oracle(oracle, only_long, eng.align(only_long), n_threads=8, what="checkpointed, long pairs only")
+
+
 def test_sentinel_regime_long_pairs(engine, oracle):
     """n1 + n2 > ~5.4 k: the reference's finite -32768 'minus infinity' leaks into the matrix
     (SURVEY 7); the general kernel reproduces score, status and first alignment there too."""
