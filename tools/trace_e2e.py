@@ -1,5 +1,6 @@
+"""Developer tool: SA_TRACE timeline of one streamed sa_align_batch call (1 M x 150 bp, 2-bit input)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from sequencealigning_b200 import Engine, synth
 from sequencealigning_b200.engine import PinnedResult, pin_batch
