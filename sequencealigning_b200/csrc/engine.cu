@@ -372,7 +372,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if (!e->budget_cached || held > e->budget_cached) {
       size_t free_b = 0, total_b = 0;
       CUDA_TRY(e, cudaMemGetInfo(&free_b, &total_b));
-      e->budget_cached = std::min<size_t>((size_t)((double)(free_b + held) * 0.6), (size_t)32 << 30);
+      e->budget_cached = std::min<size_t>((size_t)((double)(free_b + held) * 0.6), (size_t)96 << 30);
     }
     budget = e->budget_cached;
   }
