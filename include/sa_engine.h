@@ -32,9 +32,9 @@
 extern "C" {
 #endif
 
-#define SA_ABI_VERSION 1
+#define SA_ABI_VERSION 2
 
-typedef struct sa_engine sa_engine_t; /* opaque; one per (process, device) */
+typedef struct sa_engine sa_engine_t; /* opaque; one per process and device SET (sa_engine_create_multi) */
 
 /* parse.rs:36-42 `enum Algo` (A* is out of scope for the GPU path) */
 typedef enum {
@@ -129,14 +129,25 @@ typedef struct {
 
 /* -- lifecycle ------------------------------------------------------------------------ */
 sa_status_t sa_engine_create(int device_id, sa_engine_t** out);
+/* One engine over several GPUs of the box.  sa_align_batch then shards ONE pair
+ * list -- what the loop of src/main.rs:61-62 iterates -- over the devices, balanced on n1*n2,
+ * with one worker thread, one set of streams and one scratch budget per device, and puts every
+ * result back in input order; there is no collective: pairs are independent.  The same device id
+ * may be listed more than once (several pipelines on one GPU).  The device-resident entry
+ * points (sa_batch_upload ..) stay single-device and return SA_E_UNSUPPORTED here. */
+sa_status_t sa_engine_create_multi(const int* device_ids, int n_devices, sa_engine_t** out);
+int sa_engine_device_count(const sa_engine_t* e); /* 1 for sa_engine_create */
 sa_status_t sa_engine_destroy(sa_engine_t* e);
 const char* sa_last_error(const sa_engine_t* e); /* never NULL; "" when none */
 int sa_abi_version(void);
 
 /* -- the hot path --------------------------------------------------------------------- */
-/* Align every pair of `batch` (host buffers in, host buffers out).  Blocking.  Shards
- * nothing: one engine drives one GPU; multi-GPU callers create one engine per device (one
- * process or thread each) and split the pair list (see sa_partition_lpt). */
+/* Align every pair of `batch` (host buffers in, host buffers out).  Blocking.
+ * On a multi-device engine the pair list is sharded over the devices inside this call
+ * (sa_plan_shards says how) and the results come back in input order: per-pair arrays exactly as
+ * from one device; the CIGAR pool holds one region per device, so cigar_off stays monotone in p
+ * but may skip words between regions, and cigar_used is the end of the last region.  When a
+ * region overflows the call returns SA_E_CIGAR_CAPACITY with cigar_used = a capacity that fits. */
 sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
                            const sa_scheme_t* scheme, const sa_batch_t* batch,
                            sa_result_t* result);
@@ -159,6 +170,27 @@ sa_status_t sa_last_timing(const sa_engine_t* e, sa_timing_t* out);
 /* -- host helpers --------------------------------------------------------------------- */
 void* sa_alloc_pinned(size_t bytes);
 void sa_free_pinned(void* p);
+
+/* How a multi-device call was sharded (one entry per device of the engine, in creation order). */
+typedef struct {
+  int32_t device;      /* CUDA device id                                                      */
+  uint32_t contiguous; /* 1: the shard is the pair range [first_pair, first_pair + pairs)     */
+  uint64_t first_pair, pairs, cells;
+  uint64_t h2d_bytes, d2h_bytes, kernel_launches;
+  double device_ms;    /* first to last kernel of the shard (CUDA events)                     */
+  double host_ms;      /* wall clock of the shard's worker, submit to results on the host     */
+} sa_shard_info_t;
+sa_status_t sa_last_shards(const sa_engine_t* e, sa_shard_info_t* out, int cap, int* n_out);
+
+/* The shard plan of a multi-device call, pure host code.  Pairs are weighted by n1*n2 + 1.
+ * begin[0..n_parts] : the cell-balanced CONTIGUOUS split (part k = pairs [begin[k], begin[k+1])),
+ *                     used when no part exceeds the mean weight by more than 2 % -- always the
+ *                     case for many small pairs; it needs no gather and keeps pair order.
+ * part[0..n_pairs)  : otherwise (few, uneven pairs) the greedy LPT assignment of
+ *                     sa_partition_lpt; *contiguous says which of the two a call would use.
+ * part may be NULL (then only begin and *contiguous are produced). */
+sa_status_t sa_plan_shards(const uint32_t* q_len, const uint32_t* d_len, uint64_t n_pairs, int n_parts,
+                           uint64_t* begin, int32_t* part, int* contiguous);
 
 /* Greedy longest-processing-time partition of pairs over n_parts GPUs by n1*n2 cells
  * (SURVEY 8e).  part[p] in [0, n_parts).  Deterministic.  Pure host code. */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG, "_lib", "libsa_engine.so")
 
 # sa_status_t
 OK, REF_PANIC, REF_NO_CONVERGENCE, NOT_IMPLEMENTED, REF_PANIC_EARLY, REF_NO_OUTPUT = range(6)
+ALIGNMENT_OMITTED = 0x80  # flag ORed into a per-pair status (score and status exact, no CIGAR)
 E_CUDA, E_ARG, E_NOMEM, E_CIGAR_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4, -5
 ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD = 0, 1, 2, 3
 MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL = 0, 1, 2
@@ -24,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "sa_batch_upload", "sa_batch_free", "sa_align_resident", "sa_resident_download",
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
-    "sa_affine_count_cooptimal",
+    "sa_affine_count_cooptimal", "sa_engine_create_multi", "sa_engine_device_count", "sa_last_shards", "sa_plan_shards",
 ]
 
 
@@ -55,6 +56,14 @@ class Timing(C.Structure):
     ]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("contiguous", C.c_uint32), ("first_pair", C.c_uint64), ("pairs", C.c_uint64),
+        ("cells", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("device_ms", C.c_double), ("host_ms", C.c_double),
+    ]
+
+
 _lib = None
 
 
@@ -72,6 +81,14 @@ def lib() -> C.CDLL:
     l.sa_abi_version.restype = C.c_int
     l.sa_engine_create.argtypes = [C.c_int, C.POINTER(vp)]
     l.sa_engine_create.restype = C.c_int
+    l.sa_engine_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    l.sa_engine_create_multi.restype = C.c_int
+    l.sa_engine_device_count.argtypes = [vp]
+    l.sa_engine_device_count.restype = C.c_int
+    l.sa_last_shards.argtypes = [vp, C.POINTER(ShardInfo), C.c_int, C.POINTER(C.c_int)]
+    l.sa_last_shards.restype = C.c_int
+    l.sa_plan_shards.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    l.sa_plan_shards.restype = C.c_int
     l.sa_engine_destroy.argtypes = [vp]
     l.sa_engine_destroy.restype = C.c_int
     l.sa_last_error.argtypes = [vp]

@@ -56,9 +56,23 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
     deps = _sources(CSRC, os.path.join(_ROOT, "include"))
     extra = ["-Xptxas", "-v"] if verbose else []
     if force or _newer(LIB_PATH, deps):
+        # one object per translation unit, compiled concurrently, then one link
         srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-shared", "-o", LIB_PATH, *srcs, "-I", os.path.join(_ROOT, "include")]
-        subprocess.run(cmd, check=True)
+        obj_dir = os.path.join(LIB_DIR, "obj")
+        os.makedirs(obj_dir, exist_ok=True)
+        headers = [d for d in deps if not d.endswith(".cu")]
+        jobs = []
+        objs = []
+        for src in srcs:
+            obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            if force or _newer(obj, [src] + headers):
+                cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", obj, src, "-I", os.path.join(_ROOT, "include")]
+                jobs.append((src, subprocess.Popen(cmd)))
+        for src, proc in jobs:
+            if proc.wait() != 0:
+                raise RuntimeError(f"nvcc failed on {src}")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs], check=True)
     mb = os.path.join(CSRC, "microbench", "int_peak.cu")
     if force or _newer(INT_PEAK_PATH, [mb]):
         subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", INT_PEAK_PATH, mb], check=True)

@@ -75,6 +75,7 @@ static void usage() {
           "      --strict                   exit 101 where the reference would panic\n"
           "      --all                      needleman-wunsch: print EVERY co-optimal alignment, like the reference\n"
           "      --device <N>               CUDA device [default: 0]\n"
+          "      --devices <LIST>           several CUDA devices, e.g. 0,1,2,3: the pair list is sharded over them\n"
           "  -h, --help                     Print help\n  -V, --version                  Print version\n");
 }
 
@@ -90,8 +91,8 @@ static std::string duration_debug(double seconds) {
 
 int main(int argc, char** argv) {
   std::string qpath, dpath, mode = "global", algo = "needleman-wunsch";
-  bool verbose = false, strict = false, all = false;
-  int device = 0;
+  bool verbose = false, strict = false, all = false, algo_given = false;
+  std::vector<int> devices;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto val = [&](const char* s, const char* l) -> const char* {
@@ -107,8 +108,17 @@ int main(int argc, char** argv) {
     else if (const char* v = val("-d", "--db-file")) dpath = v;
     else if (const char* v = val("-o", "--out-path")) (void)v;  // parsed and unused, as in the reference
     else if (const char* v = val("-m", "--mode")) mode = v;
-    else if (const char* v = val("-a", "--algo")) algo = v;
-    else if (const char* v = val("--device", "--device")) device = atoi(v);
+    else if (const char* v = val("-a", "--algo")) { algo = v; algo_given = true; }
+    else if (const char* v = val("--device", "--device")) devices.assign(1, atoi(v));
+    else if (const char* v = val("--devices", "--devices")) {  // 0,1,2,3: one engine over several GPUs
+      devices.clear();
+      for (const char* c = v; *c;) {
+        char* end = nullptr;
+        devices.push_back((int)strtol(c, &end, 10));
+        if (end == c) { fprintf(stderr, "error: invalid value '%s' for '--devices <LIST>'\n", v); return 2; }
+        c = *end == ',' ? end + 1 : end;
+      }
+    }
     else if (a == "-v" || a == "--verbose") verbose = true;
     else if (a == "--strict") strict = true;
     else if (a == "--all") all = true;
@@ -117,6 +127,9 @@ int main(int argc, char** argv) {
     else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
   }
   if (qpath.empty() || dpath.empty()) { usage(); return 2; }
+  if (devices.empty()) devices.push_back(0);
+  if (!algo_given)  // parse.rs:36-42: the reference's default is a-star, which is not part of the GPU path
+    fprintf(stderr, "note: no -a given; the reference defaults to a-star, this tool to needleman-wunsch\n");
   sa_mode_t m;
   if (mode == "global") m = SA_MODE_GLOBAL;
   else if (mode == "local") m = SA_MODE_LOCAL;
@@ -148,7 +161,9 @@ int main(int argc, char** argv) {
       d_off[p] = off[nq + d]; d_len[p] = (uint32_t)db[d].seq.size();
     }
   sa_engine_t* eng = nullptr;
-  if (sa_engine_create(device, &eng) != SA_OK) {
+  const sa_status_t created = devices.size() == 1 ? sa_engine_create(devices[0], &eng)
+                                                   : sa_engine_create_multi(devices.data(), (int)devices.size(), &eng);
+  if (created != SA_OK) {
     fprintf(stderr, "sa_engine_create: %s\n", sa_last_error(eng));
     sa_engine_destroy(eng);
     return 1;
@@ -174,9 +189,18 @@ int main(int argc, char** argv) {
     return 1;
   }
   int exit_code = 0;
+  // SA_ALIGNMENT_OMITTED is a flag on top of the status: report it, then treat the status as usual
+  std::vector<uint8_t> omitted(n, 0);
+  for (size_t p = 0; p < n; ++p) {
+    omitted[p] = (status[p] & SA_ALIGNMENT_OMITTED) ? 1 : 0;
+    status[p] &= 0x7f;
+  }
   for (size_t d = 0, p = 0; d < nd && !exit_code; ++d)
     for (size_t q = 0; q < nq; ++q, ++p) {
       const Rec &Q = query[q], &D = db[d];
+      if (omitted[p])
+        fprintf(stderr, "%s vs %s: the alignment was not materialised (traceback exceeds the scratch budget); score %d and status are exact\n",
+                Q.name.c_str(), D.name.c_str(), score[p]);
       if (status[p] == SA_NOT_IMPLEMENTED) {  // main.rs:68-74 + errors.rs:11-12
         fprintf(stderr, "An error occured during alignment of %s and %s\nError in alignment: not implemented\n",
                 Q.name.c_str(), D.name.c_str());
@@ -193,7 +217,7 @@ int main(int argc, char** argv) {
       }
       if (al == SA_ALGO_NW_LINEAR)  // needleman_wunsch.rs:196-200
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
-      const bool has_alignment = clen[p] > 0 || (Q.seq.empty() && D.seq.empty());
+      const bool has_alignment = !omitted[p] && (clen[p] > 0 || (Q.seq.empty() && D.seq.empty()));
       if (all && al == SA_ALGO_NW_AFFINE) {
         // the reference's full output for the pair: every co-optimal alignment in DFS order,
         // up to the point where it would panic

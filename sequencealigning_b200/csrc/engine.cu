@@ -27,7 +27,7 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/sa_engine.h"
+#include "engine_internal.h"
 #include "nw_affine_s16.cuh"
 #include "nw_walk.cuh"
 #include "wfa.cuh"
@@ -35,89 +35,7 @@
 #include "nw_general.cuh"
 #include "nw_count.cuh"
 
-namespace {
-
-constexpr int kK = 8;  // columns per strip (8 cells x 4 bits = one 32-bit traceback word)
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-};
-
-// device views the kernels work on (either engine-owned staging or a resident batch)
-struct DeviceBatch {
-  uint8_t* residues = nullptr;
-  uint64_t *q_off = nullptr, *d_off = nullptr;
-  uint32_t *q_len = nullptr, *d_len = nullptr;
-  int32_t* score = nullptr;
-  uint8_t* status = nullptr;
-  uint32_t* cigar_len = nullptr;
-  uint64_t* cigar_off = nullptr;
-  uint32_t* pool = nullptr;
-  uint64_t pool_cap = 0;
-  uint64_t* carry = nullptr;
-  uint32_t packing = 0;
-};
-
-}  // namespace
-
-struct sa_resident {
-  uint64_t n_pairs = 0;
-  uint64_t residues_len = 0;
-  DeviceBatch d;
-  std::vector<uint32_t> h_q_len, h_d_len;
-  uint64_t cells = 0;
-  uint64_t used = 0;  // CIGAR words of the last alignment
-  bool aligned = false;
-  bool want_cigar = false;
-  // segment plan of the last alignment (shapes do not change while the batch is resident):
-  // opaque here, owned through the deleter
-  void* plan = nullptr;
-  void (*plan_free)(void*) = nullptr;
-  uint64_t plan_key = 0;
-  size_t plan_budget = 0;
-  ~sa_resident() {
-    if (plan && plan_free) plan_free(plan);
-  }
-};
-
-struct sa_engine {
-  int device = 0;
-  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_carry[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
-  std::string err;
-  // Two segments are in flight on the compute stream (the fill of segment i+1 is queued before
-  // the host reads segment i's refill count), so per-segment scratch is double-buffered.
-  struct Slot {
-    DevBuf tb, end, rerun_ids, tmp_runs, order;
-    DevBuf g_ids, g_meta, g_tb, g_rows, g_info, g_runs;  // long pairs (nw_general.cuh)
-    cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
-                                    // the next fill overlaps the tail of the previous one
-    cudaStream_t fill_stream = nullptr;  // LOW priority: only the fill kernels.  The walks, scans and
-                                         // copies of other segments then get SMs as fill CTAs retire,
-                                         // instead of queueing behind a whole fill
-    cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
-  } slot[2];
-  // scratch (grow-only)
-  DevBuf tb2, end2, misc, block_sums, wfa_scratch, par_bytes, par_rows, par_in;
-  // staging for sa_align_batch (grow-only)
-  DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry;
-  uint32_t* h_count = nullptr;  // pinned
-  sa_timing_t timing = {};
-  int sm_count = 0;
-  size_t smem_optin = 0;
-  int force_g = 0, force_k = 0;
-  bool long_ckpt_always = false;  // SA_LONG_CKPT: checkpointed traceback for every long pair (tests)
-  uint32_t ormask = 0x00;
-  size_t tb_budget = 0;
-  size_t budget_cached = 0;
-  uint32_t seg_pairs = 524288;
-  std::map<const void*, size_t> smem_configured;  // kernel -> opted-in dynamic smem ON THIS DEVICE
-  int sort_mode = 0;  // 0 auto, 1 always, 2 never (SA_SORT)
-  bool seg_pairs_forced = false;
-};
-
-namespace {
+namespace sa_host {
 
 sa_status_t fail(sa_engine* e, sa_status_t st, const char* fmt, ...) {
   char buf[512];
@@ -128,6 +46,12 @@ sa_status_t fail(sa_engine* e, sa_status_t st, const char* fmt, ...) {
   if (e) e->err = buf;
   return st;
 }
+
+}  // namespace sa_host
+
+namespace {
+
+using sa_host::fail;
 
 #define CUDA_TRY(e, call)                                                                   \
   do {                                                                                      \
@@ -288,6 +212,10 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
 
 uint32_t pack2(uint32_t v) { return v | (v << 16); }
 
+// end of a residue view, saturating: a garbage 64-bit offset must not wrap past the bounds check
+inline uint64_t view_end(uint64_t off, uint32_t len) { return off + len < off ? ~0ull : off + len; }
+inline bool view_in_bounds(uint64_t off, uint32_t len, uint64_t limit) { return off <= limit && len <= limit - off; }
+
 // Byte ranges of the residue buffer already resident on the device (sorted, disjoint).
 struct Coverage {
   std::vector<std::pair<uint64_t, uint64_t>> iv;
@@ -361,7 +289,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const sa_scheme_t& sc = s2.sc;
   sa_status_t st;
   *used_out = 0;
-  *pool_sent_out = 0;
+  *pool_sent_out = db.pool_base;
 
   // ---- scratch budget ---------------------------------------------------------------------
   size_t budget = e->tb_budget;
@@ -459,20 +387,15 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   const uint64_t bias_aff = sa::s16_affine_bias(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
   const uint64_t nmin_fast = linear ? ~0ull : (cm_aff && bias_aff + 2 + cm_aff <= 0xFFFFull ? (0xFFFFull - bias_aff - 2) / cm_aff - 1 : 0);
   const uint64_t rows_fast = e->smem_optin >= 16 ? (e->smem_optin - 15) / 10 : 0;  // fill_smem_bytes(rows, 1) fits
+  // The test is SEPARABLE (one limit per dimension), so that a shape class, whose column and row
+  // maxima come from different pairs, fits a compiled form whenever each of its pairs does:
+  // cols_lim + 256 + rows_lim <= max_sum, rows_lim <= rows_fast, rows_lim <= nmin_fast.  Skewed
+  // pairs beyond a limit (3000 x 150, say) take the long-pair path.
+  const uint64_t rows_lim = std::min<uint64_t>(std::min<uint64_t>(rows_fast, nmin_fast), max_sum > 256 ? (max_sum - 256) / 2 : 0);
+  const uint64_t cols_lim = max_sum > 256 + rows_lim ? max_sum - 256 - rows_lim : 0;
   auto is_long = [&](uint32_t cols, uint32_t rows) -> bool {
-    if ((uint64_t)cols + rows + 256 <= max_sum && rows <= rows_fast &&
-        std::min<uint64_t>((uint64_t)cols + 256, rows) <= nmin_fast)
-      return false;
     if (!cols || !rows) return false;
-    for (uint32_t g = 1; g <= 32; g <<= 1) {
-      const uint64_t n1pad = ((uint64_t)cols + kK * g - 1) / (kK * g) * (kK * g);
-      const uint64_t ng = 32 / g;
-      const uint64_t smem = fill_smem_bytes(rows, ng);
-      if (smem <= e->smem_optin && bound0 + per_step * (n1pad + rows) <= sa::kBias &&
-          (linear || sa::s16_affine_in_range(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext, (uint32_t)n1pad, rows)))
-        return false;
-    }
-    return true;
+    return cols > cols_lim || rows > rows_lim;
   };
   auto prepare_fresh = [&](uint64_t base, Segment& sg) -> sa_status_t {
     sg = Segment{};
@@ -512,11 +435,11 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           const uint64_t qo = in->q_off[p], dO = in->d_off[p];
           if (ql) {
             qlo = std::min(qlo, qo);
-            qhi = std::max(qhi, qo + ql);
+            qhi = std::max(qhi, view_end(qo, ql));
           }
           if (dl) {
             dlo = std::min(dlo, dO);
-            dhi = std::max(dhi, dO + dl);
+            dhi = std::max(dhi, view_end(dO, dl));
           }
         }
         const uint32_t a = linear ? dl : ql, b = linear ? ql : dl;
@@ -685,7 +608,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         if (rr != SA_OK) return rr;
       }
     }
-    e->timing.cells += sg.cells;
+    if (in) e->timing.cells += sg.cells;  // (a resident batch knows its cells from the upload)
     if (in) {
       const uint64_t limit = in->packing ? in->residues_len * 4 : in->residues_len;
       if (sg.qhi > limit || sg.dhi > limit)
@@ -741,7 +664,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   // Streams the CIGAR pool to the host as segments finish.  After segment i's write walks a
   // copy of the running total is queued (slot i&1); one segment later the host reads it (by then
   // the walks are complete) and queues pool[pool_sent, total) on the copy-out stream.
-  uint64_t pool_sent = 0;
+  uint64_t pool_sent = db.pool_base;
   int seg_index = 0;
   auto send_pool_upto = [&](int slot) -> cudaError_t {
     cudaError_t er = cudaEventSynchronize(e->ev_carry[slot]);
@@ -1037,6 +960,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   };
 
   CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, e->stream));
+  if (db.pool_base) {  // offsets continue from the slice's start
+    memcpy(e->h_count + 12, &db.pool_base, 8);
+    CUDA_TRY(e, cudaMemcpyAsync(db.carry, e->h_count + 12, 8, cudaMemcpyHostToDevice, e->stream));
+  }
   CUDA_TRY(e, cudaEventRecord(e->ev_t0, e->stream));
   for (int k = 0; k < 2; ++k) {  // order the slot streams after everything queued so far
     CUDA_TRY(e, cudaEventRecord(e->slot[k].ev_bdone, e->stream));
@@ -1120,7 +1047,7 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
   if (in) {
     uint64_t max_end = 0;
     for (uint64_t p = 0; p < n; ++p) {
-      max_end = std::max(max_end, std::max(in->q_off[p] + h_q_len[p], in->d_off[p] + h_d_len[p]));
+      max_end = std::max(max_end, std::max(view_end(in->q_off[p], h_q_len[p]), view_end(in->d_off[p], h_d_len[p])));
       e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
     }
     if (max_end > (in->packing ? in->residues_len * 4 : in->residues_len))
@@ -1265,13 +1192,9 @@ sa_status_t check_algo(sa_engine* e, sa_algo_t algo, sa_mode_t mode, bool* not_i
 
 }  // namespace
 
-extern "C" {
+namespace sa_host {
 
-int sa_abi_version(void) { return SA_ABI_VERSION; }
-
-const char* sa_last_error(const sa_engine_t* e) { return e ? e->err.c_str() : "null engine"; }
-
-sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
+sa_status_t sd_create(int device_id, sa_engine** out) {
   if (!out) return SA_E_ARG;
   *out = nullptr;
   sa_engine* e = new (std::nothrow) sa_engine();
@@ -1321,7 +1244,7 @@ sa_status_t sa_engine_create(int device_id, sa_engine_t** out) {
   return SA_OK;
 }
 
-sa_status_t sa_engine_destroy(sa_engine_t* e) {
+sa_status_t sd_destroy(sa_engine* e) {
   if (!e) return SA_OK;
   if (e->stream) {
     cudaSetDevice(e->device);
@@ -1350,9 +1273,7 @@ sa_status_t sa_engine_destroy(sa_engine_t* e) {
   return SA_OK;
 }
 
-void* sa_engine_stream(sa_engine_t* e) { return e ? (void*)e->stream : nullptr; }
-
-sa_status_t sa_engine_synchronize(sa_engine_t* e) {
+sa_status_t sd_synchronize(sa_engine* e) {
   if (!e) return SA_E_ARG;
   for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaStreamSynchronize(e->slot[k].stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1361,26 +1282,7 @@ sa_status_t sa_engine_synchronize(sa_engine_t* e) {
   return SA_OK;
 }
 
-sa_status_t sa_last_timing(const sa_engine_t* e, sa_timing_t* out) {
-  if (!e || !out) return SA_E_ARG;
-  *out = e->timing;
-  return SA_OK;
-}
-
-void* sa_alloc_pinned(size_t bytes) {
-  void* p = nullptr;
-  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  return p;
-}
-
-void sa_free_pinned(void* p) {
-  if (p) cudaFreeHost(p);
-}
-
-sa_status_t sa_batch_free(sa_engine_t* e, sa_resident_t* r) {
+sa_status_t sd_batch_free(sa_engine* e, sa_resident_t* r) {
   if (!r) return SA_OK;
   if (e) {
     cudaSetDevice(e->device);
@@ -1394,13 +1296,13 @@ sa_status_t sa_batch_free(sa_engine_t* e, sa_resident_t* r) {
   return SA_OK;
 }
 
-sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t** out) {
+sa_status_t sd_batch_upload(sa_engine* e, const sa_batch_t* b, sa_resident_t** out) {
   if (!e || !b || !out) return SA_E_ARG;
   *out = nullptr;
   if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
   if (b->n_pairs >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)b->n_pairs);
-  if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len))
-    return fail(e, SA_E_ARG, "null offset/length array");
+  if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len)))
+    return fail(e, SA_E_ARG, "null input array");
   CUDA_TRY(e, cudaSetDevice(e->device));
   sa_resident* r = new (std::nothrow) sa_resident();
   if (!r) return SA_E_NOMEM;
@@ -1412,7 +1314,7 @@ sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t**
   r->h_d_len.assign(b->d_len, b->d_len + n);
   for (uint64_t i = 0; i < n; ++i) {
     const uint64_t limit = b->packing ? b->residues_len * 4 : b->residues_len;
-    if (b->q_off[i] + b->q_len[i] > limit || b->d_off[i] + b->d_len[i] > limit) {
+    if (!view_in_bounds(b->q_off[i], b->q_len[i], limit) || !view_in_bounds(b->d_off[i], b->d_len[i], limit)) {
       delete r;
       return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
     }
@@ -1433,7 +1335,7 @@ sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t**
   if (err == cudaSuccess) err = alloc((void**)&r->d.carry, 16);
   if (err != cudaSuccess) {
     cudaGetLastError();
-    sa_batch_free(e, r);
+    sd_batch_free(e, r);
     return fail(e, SA_E_NOMEM, "device allocation for the batch failed: %s", cudaGetErrorString(err));
   }
   if (b->residues_len)
@@ -1446,14 +1348,14 @@ sa_status_t sa_batch_upload(sa_engine_t* e, const sa_batch_t* b, sa_resident_t**
   }
   cudaError_t last = cudaStreamSynchronize(e->stream);
   if (last != cudaSuccess) {
-    sa_batch_free(e, r);
+    sd_batch_free(e, r);
     return fail(e, SA_E_CUDA, "upload failed: %s", cudaGetErrorString(last));
   }
   *out = r;
   return SA_OK;
 }
 
-sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
+sa_status_t sd_align_resident(sa_engine* e, sa_algo_t algo, sa_mode_t mode,
                               const sa_scheme_t* scheme, sa_resident_t* r, int want_cigar) {
   if (!e || !r) return SA_E_ARG;
   CUDA_TRY(e, cudaSetDevice(e->device));
@@ -1525,7 +1427,7 @@ sa_status_t sa_align_resident(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
   return SA_OK;
 }
 
-sa_status_t sa_resident_download(sa_engine_t* e, sa_resident_t* r, sa_result_t* res) {
+sa_status_t sd_resident_download(sa_engine* e, sa_resident_t* r, sa_result_t* res) {
   if (!e || !r || !res) return SA_E_ARG;
   if (!r->aligned) return fail(e, SA_E_ARG, "sa_align_resident has not run on this batch");
   CUDA_TRY(e, cudaSetDevice(e->device));
@@ -1550,8 +1452,8 @@ sa_status_t sa_resident_download(sa_engine_t* e, sa_resident_t* r, sa_result_t* 
   return rc;
 }
 
-sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
-                           const sa_scheme_t* scheme, const sa_batch_t* b, sa_result_t* res) {
+sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const sa_scheme_t* scheme,
+                           const sa_batch_t* b, sa_result_t* res, uint64_t pool_base) {
   if (!e || !b || !res) return SA_E_ARG;
   if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
   if (b->n_pairs >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)b->n_pairs);
@@ -1608,8 +1510,10 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     cudaGetLastError();
     return st;
   }
-  uint64_t want_pool = want_cigar ? std::max<uint64_t>(res->cigar_capacity, 1024) : 0;
-  uint64_t used = 0, sent = 0;
+  if (want_cigar && res->cigar_capacity < pool_base) return fail(e, SA_E_ARG, "pool slice ends before it starts");
+  uint64_t want_pool = want_cigar ? std::max<uint64_t>(res->cigar_capacity - pool_base, 1024) : 0;
+  uint64_t used = 0, sent = pool_base;  // absolute word positions in the caller's pool
+  uint32_t* dev_pool = nullptr;          // device buffer shifted down by pool_base
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (want_cigar && (st = ensure(e, e->b_pool, want_pool * 4)) != SA_OK) return st;
     DeviceBatch db;
@@ -1622,13 +1526,16 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     db.status = (uint8_t*)e->b_status.p;
     db.cigar_len = (uint32_t*)e->b_clen.p;
     db.cigar_off = (uint64_t*)e->b_coff.p;
-    db.pool = want_cigar ? (uint32_t*)e->b_pool.p : nullptr;
-    db.pool_cap = want_cigar ? e->b_pool.cap / 4 : 0;
+    dev_pool = want_cigar ? (uint32_t*)e->b_pool.p - pool_base : nullptr;
+    db.pool = dev_pool;
+    db.pool_cap = want_cigar ? pool_base + e->b_pool.cap / 4 : 0;
+    db.pool_base = want_cigar ? pool_base : 0;
     db.carry = (uint64_t*)e->b_carry.p;
     db.packing = b->packing;
     e->timing.h2d_bytes = 0;
     e->timing.d2h_bytes = 0;
     e->timing.cells = 0;
+    sent = pool_base;
     st = run_affine(e, db, n, b->q_len, b->d_len, s2, want_cigar, b, res, &used, &sent);
     if (st != SA_OK) {
       cudaStreamSynchronize(e->s_in);
@@ -1639,17 +1546,17 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
     if (!want_cigar || used <= db.pool_cap) break;
     // The caller cannot take it either if it exceeds cigar_capacity; otherwise redo with room.
     if (used > res->cigar_capacity) break;
-    want_pool = used + 1024;
+    want_pool = used - pool_base + 1024;
   }
-  res->cigar_used = used;
+  if (want_cigar && used < pool_base) used = pool_base;
+  res->cigar_used = want_cigar ? used : 0;
   sa_status_t rc = SA_OK;
-  if (want_cigar && used) {
+  if (want_cigar && used > pool_base) {
     if (used > res->cigar_capacity) {
       rc = fail(e, SA_E_CIGAR_CAPACITY, "cigar pool needs %llu words, capacity is %llu",
-                (unsigned long long)used, (unsigned long long)res->cigar_capacity);
+                (unsigned long long)(used - pool_base), (unsigned long long)(res->cigar_capacity - pool_base));
     } else if (sent < used) {  // (normally everything was streamed out already)
-      CUDA_TRY(e, cudaMemcpyAsync(res->cigar + sent, (uint32_t*)e->b_pool.p + sent, (used - sent) * 4,
-                                  cudaMemcpyDeviceToHost, e->s_out));
+      CUDA_TRY(e, cudaMemcpyAsync(res->cigar + sent, dev_pool + sent, (used - sent) * 4, cudaMemcpyDeviceToHost, e->s_out));
       e->timing.d2h_bytes += (used - sent) * 4;
     }
   }
@@ -1663,8 +1570,7 @@ sa_status_t sa_align_batch(sa_engine_t* e, sa_algo_t algo, sa_mode_t mode,
 }
 
 // Co-optimal alignment counts for a whole batch (nw_count.cuh), in chunks that bound the scratch.
-sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme, const sa_batch_t* b,
-                                      int64_t* counts) {
+sa_status_t sd_count_cooptimal(sa_engine* e, const sa_scheme_t* scheme, const sa_batch_t* b, int64_t* counts) {
   if (!e || !b) return SA_E_ARG;
   if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
   const uint64_t n = b->n_pairs;
@@ -1678,7 +1584,7 @@ sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme,
   const uint64_t limit = b->packing ? b->residues_len * 4 : b->residues_len;
   uint32_t n1max = 0;
   for (uint64_t i = 0; i < n; ++i) {
-    if ((b->q_len[i] && b->q_off[i] + b->q_len[i] > limit) || (b->d_len[i] && b->d_off[i] + b->d_len[i] > limit))
+    if ((b->q_len[i] && !view_in_bounds(b->q_off[i], b->q_len[i], limit)) || (b->d_len[i] && !view_in_bounds(b->d_off[i], b->d_len[i], limit)))
       return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
     n1max = std::max(n1max, b->q_len[i]);
   }
@@ -1730,9 +1636,9 @@ sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme,
 // Every co-optimal alignment of one pair, in the order and text of the reference's traceback
 // (needleman_wunsch_affine.rs:246-329, Display :390-411): the device computes the parent sets,
 // the host walks them with the reference's LIFO stack.  snprintf-style return (bytes needed).
-int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2,
-                                 uint32_t n2, const sa_scheme_t* scheme, uint64_t max_alignments,
-                                 char* buf, size_t cap, uint64_t* n_printed, int32_t* panicked) {
+int64_t sd_all_alignments(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                          const sa_scheme_t* scheme, uint64_t max_alignments, char* buf, size_t cap,
+                          uint64_t* n_printed, int32_t* panicked) {
   if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
   if (n_printed) *n_printed = 0;
   if (panicked) *panicked = 0;
@@ -1803,9 +1709,13 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
   if (mx == ed) stack.push_back({ST_D, n2, n1, -1});
   uint64_t printed = 0;
   bool pan = false;
+  uint64_t needed = 0;  // bytes of the whole text; only the first cap - 1 are kept
+  const size_t keep = (buf && cap) ? cap - 1 : 0;
   while (!stack.empty() && !pan) {
     const Frame f = stack.back();
     stack.pop_back();
+    // columns made after this frame was pushed belong to subtrees that are finished: drop them
+    cols.resize((size_t)(f.cols + 1));
     if (f.x == 0 && f.y == 0) {  // :283-286
       if (printed >= max_alignments) break;
       std::string r1, r2;
@@ -1816,7 +1726,9 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
       std::string bars(r1.size(), ' ');
       for (size_t k = 0; k < r1.size(); ++k)
         if (r1[k] == r2[k]) bars[k] = '|';
-      text += "alignment found\n\nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\n";
+      const std::string piece = "alignment found\n\nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\n";
+      needed += piece.size();
+      if (text.size() < keep) text.append(piece, 0, keep - text.size());
       ++printed;
     }
     // the popped cell's parent list, in push order
@@ -1863,29 +1775,7 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
     memcpy(buf, text.data(), n);
     buf[n] = 0;
   }
-  return (int64_t)text.size();
+  return (int64_t)needed;
 }
 
-sa_status_t sa_partition_lpt(const uint32_t* q_len, const uint32_t* d_len, uint64_t n_pairs,
-                             int n_parts, int32_t* part) {
-  if (n_parts < 1 || (n_pairs && (!q_len || !d_len || !part))) return SA_E_ARG;
-  // Greedy LPT on n1*n2.  Equal-cost pairs are dealt in index order, so the result is
-  // deterministic and, for uniform batches, cyclic.
-  std::vector<uint64_t> order(n_pairs);
-  for (uint64_t i = 0; i < n_pairs; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
-    return (uint64_t)q_len[a] * d_len[a] > (uint64_t)q_len[b] * d_len[b];
-  });
-  std::vector<uint64_t> load(n_parts, 0);
-  for (uint64_t k = 0; k < n_pairs; ++k) {
-    const uint64_t i = order[k];
-    int best = 0;
-    for (int p = 1; p < n_parts; ++p)
-      if (load[p] < load[best]) best = p;
-    part[i] = best;
-    load[best] += (uint64_t)q_len[i] * d_len[i] + 1;
-  }
-  return SA_OK;
-}
-
-}  // extern "C"
+}  // namespace sa_host

@@ -16,7 +16,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
-from ._capi import (ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
+from ._capi import (ALIGNMENT_OMITTED, ALGO_NW_AFFINE, ALGO_NW_LINEAR, ALGO_WFA, ALGO_WFA_STANDARD, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL,
                     NOT_IMPLEMENTED, OK, REF_NO_CONVERGENCE, REF_NO_OUTPUT, REF_PANIC, REF_PANIC_EARLY)
 
 STATUS_NAMES = {
@@ -192,6 +192,12 @@ def pin_batch(batch: "PairBatch"):
     return out
 
 
+def status_name(status: int) -> str:
+    """Name of a per-pair status byte; the ALIGNMENT_OMITTED flag (0x80) is shown as a suffix."""
+    base = STATUS_NAMES.get(int(status) & 0x7F, f"status {int(status) & 0x7F}")
+    return base + ("|ALIGNMENT_OMITTED" if int(status) & ALIGNMENT_OMITTED else "")
+
+
 def _scheme(s) -> Optional[_capi.Scheme]:
     if s is None:
         return None
@@ -201,12 +207,19 @@ def _scheme(s) -> Optional[_capi.Scheme]:
 
 
 class Engine:
-    """One engine per (process, GPU).  Multi-GPU: one process per GPU, see shard.py."""
+    """One engine per process.  `device` = one GPU; `devices=[..]` = ONE engine over several GPUs
+    (sa_engine_create_multi): align() then shards the pair list over them inside the call and
+    returns everything in input order (see shards())."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None):
         self._lib = _capi.lib()
         self._h = C.c_void_p()
-        rc = self._lib.sa_engine_create(device, C.byref(self._h))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.sa_engine_create_multi(ids, len(devices), C.byref(self._h))
+            device = int(devices[0]) if len(devices) else 0
+        else:
+            rc = self._lib.sa_engine_create(device, C.byref(self._h))
         if rc != 0:
             msg = self._lib.sa_last_error(self._h).decode() if self._h else "allocation failed"
             if self._h:
@@ -214,6 +227,18 @@ class Engine:
                 self._h = C.c_void_p()
             raise EngineError(rc, msg)
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
+
+    @property
+    def device_count(self) -> int:
+        return int(self._lib.sa_engine_device_count(self._h))
+
+    def shards(self) -> List[dict]:
+        """How the last align() was split over the devices (sa_last_shards)."""
+        n = C.c_int()
+        arr = (_capi.ShardInfo * 64)()
+        self._check(self._lib.sa_last_shards(self._h, arr, 64, C.byref(n)))
+        return [{k: getattr(arr[i], k) for k, _ in _capi.ShardInfo._fields_} for i in range(n.value)]
 
     def close(self):
         if getattr(self, "_h", None):

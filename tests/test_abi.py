@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_capi.EXPORTED_SYMBOLS)
     for name in sorted(declared):
         assert hasattr(lib, name), f"libsa_engine.so does not export {name}"
-    assert lib.sa_abi_version() == 1
+    assert lib.sa_abi_version() == 2
 
 
 def test_no_oracle_in_the_product():
@@ -64,6 +64,47 @@ def test_partition_lpt(lib):
     # uniform batches are dealt round-robin
     u = np.full(64, 150, np.uint32)
     assert np.array_equal(partition_lpt(u, u, 4), np.arange(64) % 4)
+
+
+def test_plan_shards_contiguous_for_many_reads(lib):
+    """sa_plan_shards: what a multi-device sa_align_batch does with a pair list.  Many reads ->
+    contiguous, cell-balanced ranges of the caller's arrays (no gather, input order kept)."""
+    from sequencealigning_b200.shard import plan_shards
+    rng = np.random.default_rng(1)
+    q = rng.integers(100, 300, 200_000).astype(np.uint32)
+    d = (q.astype(np.int64) + rng.integers(-8, 9, q.size)).astype(np.uint32)
+    w = q.astype(np.float64) * d + 1
+    for parts in (1, 2, 3, 4, 8):
+        begin, part, contiguous = plan_shards(q, d, parts)
+        assert contiguous
+        assert begin[0] == 0 and begin[-1] == q.size and (np.diff(begin.astype(np.int64)) > 0).all()
+        assert np.array_equal(part, np.repeat(np.arange(parts), np.diff(begin.astype(np.int64))))
+        load = np.array([w[int(begin[k]):int(begin[k + 1])].sum() for k in range(parts)])
+        assert load.max() / load.mean() < 1.002
+    # sorted by length (length-bucketed batches): the ranges differ in pair count, not in cells
+    order = np.argsort(q.astype(np.int64) * d, kind="stable")
+    begin, _, contiguous = plan_shards(q[order], d[order], 8)
+    assert contiguous
+    load = np.array([w[order][int(begin[k]):int(begin[k + 1])].sum() for k in range(8)])
+    assert load.max() / load.mean() < 1.002 and np.diff(begin.astype(np.int64)).max() > 1.5 * np.diff(begin.astype(np.int64)).min()
+
+
+def test_plan_shards_lpt_for_few_uneven_pairs(lib):
+    from sequencealigning_b200.shard import partition_lpt, plan_shards
+    q = np.array([100_000, 10, 100_000, 20, 50_000, 30, 50_000, 40, 7, 9], np.uint32)
+    d = q.copy()
+    begin, part, contiguous = plan_shards(q, d, 2)
+    assert not contiguous                      # no contiguous cut balances these
+    assert np.array_equal(part, partition_lpt(q, d, 2))
+    load = np.bincount(part, weights=q.astype(np.float64) * d, minlength=2)
+    assert load.max() / load.mean() < 1.0001   # LPT finds {100k, 50k, ..} twice: 1.25e10 cells each
+    # degenerate inputs
+    begin, part, contiguous = plan_shards(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 4)
+    assert contiguous and list(begin) == [0, 0, 0, 0, 0]
+    begin, part, contiguous = plan_shards(np.array([5], np.uint32), np.array([5], np.uint32), 4)
+    assert sorted(part.tolist()) == [part[0]] and 0 <= part[0] < 4
+    import ctypes as C
+    assert lib.sa_plan_shards(None, None, 3, 2, None, None, C.byref(C.c_int())) == -2
 
 
 def test_render_affine_text(lib):
