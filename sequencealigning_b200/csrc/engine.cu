@@ -33,6 +33,7 @@
 #include "wfa.cuh"
 #include "nw_parents.cuh"
 #include "nw_general.cuh"
+#include "nw_long.cuh"
 #include "nw_count.cuh"
 
 namespace sa_host {
@@ -249,6 +250,31 @@ struct Scheme2 {
   int algo = SA_ALGO_NW_AFFINE;
 };
 
+// Launch plan of the literal long-pair kernels (nw_general.cuh) for a list of pairs.
+struct LitPlan {
+  std::vector<uint32_t> ids;
+  std::vector<uint64_t> meta;   // per pair: tb offset (bytes, ~0 = none), runs end, checkpoint offset
+                                // (records, ~0 = none), block offset (bytes)
+  std::vector<uint32_t> waves;  // indices into ids where a new wave (reusing the tb words) starts
+  uint64_t tb_total = 0, runs_total = 0;
+  uint32_t n1max = 0, n2max = 0;
+};
+
+// Launch plan of the tiled long-pair path (nw_long.cuh).
+struct FastPlan {
+  std::vector<uint32_t> ids;
+  std::vector<uint64_t> row_off, col_off, ck_off, runs_end;  // per pair (int2 units / words)
+  struct Wave {
+    uint32_t lo = 0, hi = 0;          // range of ids
+    uint32_t tr_max = 0, tc_max = 0;  // tiles per dimension of the wave's largest pair
+  };
+  std::vector<Wave> waves;
+  uint64_t edges_total = 0;  // int2 units (the largest wave)
+  uint64_t runs_total = 0;   // words
+  uint32_t R = 1024, S = 4;
+  uint32_t back_warps = 0;
+};
+
 struct Segment {
   uint64_t base = 0;
   uint32_t n = 0;
@@ -264,13 +290,12 @@ struct Segment {
   std::vector<Sub> subs;
   uint64_t tb_total = 0;        // uint2 for the whole segment
   uint32_t n_short = 0;         // pairs handled by the packed kernel (= order.size() if explicit)
-  // pairs outside the packed 16-bit range go to the general 32-bit kernel (nw_general.cuh)
-  std::vector<uint32_t> long_ids;
-  std::vector<uint64_t> long_meta;  // per long pair: tb offset (bytes, ~0 = none), runs end, checkpoint offset
-                                    // (records, ~0 = none), block offset (bytes)
-  std::vector<uint32_t> long_waves; // indices into long_ids where a new wave (reusing the tb words) starts
-  uint64_t long_tb_total = 0, long_runs_total = 0;
-  uint32_t long_n1max = 0, long_n2max = 0;
+  // Pairs outside the packed 16-bit range.  Affine: the tiled 32-bit path (nw_long.cuh), with the
+  // literal kernel (nw_general.cuh) as the fallback for pairs whose traceback can meet a dead end.
+  // Linear: the literal kernel.
+  LitPlan lit;
+  FastPlan fast;
+  uint32_t n_long = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
   uint64_t cells = 0;  // sum of n1*n2 over the segment
   Geometry g;
@@ -397,6 +422,108 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     if (!cols || !rows) return false;
     return cols > cols_lim || rows > rows_lim;
   };
+  // Literal long-pair kernels (nw_general.cuh): traceback bytes (one per cell), the pairs launched in
+  // WAVES that each fit `room` (a wave's kernel also walks, so the next wave can reuse the bytes);
+  // beyond 128 MB per pair the CHECKPOINTED form (right edge of every column pass + one pass-wide
+  // block); only a pair that fits neither goes without (SA_ALIGNMENT_OMITTED: score and status exact).
+  auto plan_literal = [&](const std::vector<uint32_t>& ids, uint64_t room) -> LitPlan {
+    LitPlan lp;
+    uint64_t wave_used = 0;
+    for (uint32_t id : ids) lp.n1max = std::max(lp.n1max, h_cols[id]);
+    const uint64_t pass_cols = (uint64_t)(lp.n1max >= 8192 ? sa::kGeneralThreadsWide : sa::kGeneralThreads) * sa::kGeneralCols;
+    for (uint32_t id : ids) {
+      const uint32_t a = h_cols[id], b = h_rows[id];
+      const uint64_t words = (uint64_t)a * b;
+      uint64_t off = ~0ull, ck_off = ~0ull, blk_off = ~0ull;
+      auto take = [&](uint64_t bytes) -> uint64_t {  // 16-byte aligned room in the current wave
+        bytes = (bytes + 15) & ~(uint64_t)15;
+        if (wave_used + bytes > room) {
+          lp.waves.push_back((uint32_t)lp.ids.size());
+          wave_used = 0;
+        }
+        const uint64_t at = wave_used;
+        wave_used += bytes;
+        lp.tb_total = std::max(lp.tb_total, wave_used);
+        return at;
+      };
+      const uint64_t npass = (a + pass_cols - 1) / pass_cols;
+      const uint64_t ck_bytes = npass * ((uint64_t)b + 2) * 16, blk_bytes = (uint64_t)b * pass_cols;
+      const bool can_ckpt = !linear && ck_bytes + blk_bytes <= room / 2;
+      if (can_ckpt && (e->long_ckpt_always || words > ((uint64_t)128 << 20))) {
+        const uint64_t at = take(ck_bytes + blk_bytes);
+        ck_off = at / 16;
+        blk_off = at + ck_bytes;
+      } else if (words <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
+        off = take(words);
+      }
+      lp.runs_total += (uint64_t)a + b + 1;
+      lp.ids.push_back(id);
+      lp.meta.push_back(off);
+      lp.meta.push_back(lp.runs_total);
+      lp.meta.push_back(ck_off);
+      lp.meta.push_back(blk_off);
+      lp.n2max = std::max(lp.n2max, b);
+    }
+    return lp;
+  };
+  // Tiled long-pair path (nw_long.cuh): tile shape by the number of pairs (few pairs -> small tiles,
+  // more of them in flight), edge storage per pair, waves that each fit `room`.
+  auto plan_fast = [&](const std::vector<uint32_t>& ids, uint64_t room) -> FastPlan {
+    FastPlan fp_;
+    const size_t nl = ids.size();
+    fp_.S = e->long_s ? e->long_s : (nl >= 64 ? 4u : (nl >= 16 ? 2u : 1u));
+    fp_.R = e->long_r ? e->long_r : (nl >= 64 ? 1024u : (nl >= 16 ? 512u : 256u));
+    // backward warps: two CTAs of four per SM (shared memory bound), no more than pairs
+    fp_.back_warps = (uint32_t)std::min<uint64_t>(((uint64_t)nl + 3) / 4 * 4, (uint64_t)e->sm_count * 8);
+    auto edges_of = [&](uint32_t a, uint32_t b, uint32_t S, uint64_t* row, uint64_t* col, uint64_t* ck) {
+      const uint64_t n1pad = ((uint64_t)a + sa::kLongStrip - 1) / sa::kLongStrip * sa::kLongStrip;
+      const uint64_t tc = ((uint64_t)a + (uint64_t)S * sa::kLongStrip - 1) / ((uint64_t)S * sa::kLongStrip);
+      *row = n1pad;
+      *col = (tc - 1) * ((uint64_t)b + 1);
+      *ck = (((uint64_t)b - 1) / sa::kLongMr) * n1pad;
+    };
+    // wider tiles (fewer kept column edges) when even one pair would not fit otherwise
+    for (;;) {
+      uint64_t worst = 0;
+      for (uint32_t id : ids) {
+        uint64_t r, c, k;
+        edges_of(h_cols[id], h_rows[id], fp_.S, &r, &c, &k);
+        worst = std::max(worst, (r + c + k) * 8);
+      }
+      const uint64_t back = (uint64_t)fp_.back_warps * fp_.S * 32 * sa::kLongMr * 8;
+      if (worst + back <= room || fp_.S >= 16 || e->long_s) break;
+      fp_.S *= 2;
+    }
+    const uint64_t back = (uint64_t)fp_.back_warps * fp_.S * 32 * sa::kLongMr * 8;
+    const uint64_t room_edges = room > back + (1u << 20) ? (room - back) / 8 : (1u << 17);  // int2 units
+    FastPlan::Wave w;
+    uint64_t used = 0;
+    for (uint32_t id : ids) {
+      const uint32_t a = h_cols[id], b = h_rows[id];
+      uint64_t r, c, k;
+      edges_of(a, b, fp_.S, &r, &c, &k);
+      if (used && used + r + c + k > room_edges) {
+        w.hi = (uint32_t)fp_.ids.size();
+        fp_.waves.push_back(w);
+        w = FastPlan::Wave{};
+        w.lo = (uint32_t)fp_.ids.size();
+        used = 0;
+      }
+      fp_.row_off.push_back(used);
+      fp_.col_off.push_back(used + r);
+      fp_.ck_off.push_back(used + r + c);
+      used += r + c + k;
+      fp_.edges_total = std::max(fp_.edges_total, used);
+      fp_.runs_total += (uint64_t)a + b + 1;
+      fp_.runs_end.push_back(fp_.runs_total);
+      fp_.ids.push_back(id);
+      w.tr_max = std::max<uint32_t>(w.tr_max, (b + fp_.R - 1) / fp_.R);
+      w.tc_max = std::max<uint32_t>(w.tc_max, (uint32_t)(((uint64_t)a + (uint64_t)fp_.S * sa::kLongStrip - 1) / ((uint64_t)fp_.S * sa::kLongStrip)));
+    }
+    w.hi = (uint32_t)fp_.ids.size();
+    if (w.hi > w.lo) fp_.waves.push_back(w);
+    return fp_;
+  };
   auto prepare_fresh = [&](uint64_t base, Segment& sg) -> sa_status_t {
     sg = Segment{};
     sg.base = base;
@@ -468,61 +595,20 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       sg.g = keep;
     }
     sg.n = cn;
+    sg.n_long = n_long;
     if (n_long) {
-      // explicit order without the long pairs; the long ones get their own launch
+      // explicit order without the long pairs; the long ones get their own launches
       sg.order.reserve(cn - n_long);
-      // traceback bytes (one per cell) of the general kernel: the pairs are launched in WAVES that each
-      // fit the scratch (a wave's kernel also walks, so the next wave can reuse the words); only
-      // a pair that would take more than 1/8 of the scratch goes without (SA_ALIGNMENT_OMITTED:
-      // score and status are still exact)
-      uint64_t wave_used = 0;
+      std::vector<uint32_t> long_ids;
+      long_ids.reserve(n_long);
+      for (uint32_t i = 0; i < cn; ++i) {
+        if (is_long(h_cols[base + i], h_rows[base + i])) long_ids.push_back((uint32_t)(base + i));
+        else sg.order.push_back((uint32_t)(base + i));
+      }
       // a segment of long pairs only does not need the packed kernel's scratch: use its share
       const uint64_t room = (n_long == cn) ? (uint64_t)budget_main + budget_re : (uint64_t)budget_re;
-      // Pairs too large for that get a CHECKPOINTED traceback instead (nw_general.cuh): the right
-      // edge of every column pass (16 bytes per row per pass) plus one pass-wide block of bytes.
-      for (uint32_t i = 0; i < cn; ++i)
-        if (is_long(h_cols[base + i], h_rows[base + i])) sg.long_n1max = std::max(sg.long_n1max, h_cols[base + i]);
-      const uint64_t pass_cols = (uint64_t)(sg.long_n1max >= 8192 ? sa::kGeneralThreadsWide : sa::kGeneralThreads) * sa::kGeneralCols;
-      for (uint32_t i = 0; i < cn; ++i) {
-        const uint32_t a = h_cols[base + i], b = h_rows[base + i];
-        if (is_long(a, b)) {
-          const uint64_t words = (uint64_t)a * b;
-          uint64_t off = ~0ull, ck_off = ~0ull, blk_off = ~0ull;
-          auto take = [&](uint64_t bytes) -> uint64_t {  // 16-byte aligned room in the current wave
-            bytes = (bytes + 15) & ~(uint64_t)15;
-            if (wave_used + bytes > room) {
-              sg.long_waves.push_back((uint32_t)sg.long_ids.size());
-              wave_used = 0;
-            }
-            const uint64_t at = wave_used;
-            wave_used += bytes;
-            sg.long_tb_total = std::max(sg.long_tb_total, wave_used);
-            return at;
-          };
-          const uint64_t npass = (a + pass_cols - 1) / pass_cols;
-          const uint64_t ck_bytes = npass * ((uint64_t)b + 2) * 16, blk_bytes = (uint64_t)b * pass_cols;
-          // full traceback bytes up to 128 MB per pair (~11 kbp x 11 kbp: one kernel, no recomputation);
-          // beyond that the checkpointed form: a quarter or less of the memory, so many more pairs
-          // per wave, at the price of computing the visited part of every pass twice
-          const bool can_ckpt = !linear && ck_bytes + blk_bytes <= room / 2;
-          if (can_ckpt && (e->long_ckpt_always || words > ((uint64_t)128 << 20))) {
-            const uint64_t at = take(ck_bytes + blk_bytes);
-            ck_off = at / 16;
-            blk_off = at + ck_bytes;
-          } else if (words <= room / 8) {  // (at least 8 pairs per wave: one block per pair)
-            off = take(words);
-          }
-          sg.long_runs_total += (uint64_t)a + b + 1;
-          sg.long_ids.push_back((uint32_t)(base + i));
-          sg.long_meta.push_back(off);
-          sg.long_meta.push_back(sg.long_runs_total);
-          sg.long_meta.push_back(ck_off);
-          sg.long_meta.push_back(blk_off);
-          sg.long_n2max = std::max(sg.long_n2max, b);
-        } else {
-          sg.order.push_back((uint32_t)(base + i));
-        }
-      }
+      if (linear || e->long_literal) sg.lit = plan_literal(long_ids, room);
+      else sg.fast = plan_fast(long_ids, room);
     }
     const uint32_t ns = n_long ? (uint32_t)sg.order.size() : cn;
     sg.n_short = ns;
@@ -680,6 +766,206 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     }
     return er;
   };
+  // Launches the literal long-pair kernels for a plan: one thread block per pair, one launch per wave.
+  auto launch_literal = [&](const LitPlan& lp, sa_engine::LitBufs& gb, cudaStream_t sx) -> sa_status_t {
+    sa_status_t r;
+    const uint32_t nl = (uint32_t)lp.ids.size();
+    const bool wide = lp.n1max >= 8192;  // more lanes per pair when the pairs are few and long
+    // per pair 6 * stride ints: the affine kernel's edge column (4 ints per row), the linear
+    // kernel's rolling row (ceil(columns / threads) * threads entries); even, for 16-byte alignment
+    const uint32_t stride = (std::max(lp.n1max, lp.n2max) + 2 + sa::kGeneralThreadsWide + 1) & ~1u;
+    if ((r = ensure(e, gb.ids, (size_t)nl * 4)) != SA_OK) return r;
+    if ((r = ensure(e, gb.meta, (size_t)nl * (32 + sizeof(sa::LongWalkState)))) != SA_OK) return r;
+    if ((r = ensure(e, gb.tb, (size_t)lp.tb_total + 256)) != SA_OK) return r;
+    if ((r = ensure(e, gb.rows, (size_t)nl * 6 * stride * 4)) != SA_OK) return r;
+    if ((r = ensure(e, gb.info, (size_t)nl * 4 * stride)) != SA_OK) return r;
+    if ((r = ensure(e, gb.runs, (size_t)lp.runs_total * 4 + 256)) != SA_OK) return r;
+    std::vector<uint64_t> meta((size_t)4 * nl);  // [tb_off | runs_end | ck_off | blk_off]
+    bool any_ckpt = false;
+    for (uint32_t t = 0; t < nl; ++t) {
+      for (int f = 0; f < 4; ++f) meta[(size_t)f * nl + t] = lp.meta[4 * t + f];
+      any_ckpt |= lp.meta[4 * t + 2] != ~0ull;
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(gb.ids.p, lp.ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemcpyAsync(gb.meta.p, meta.data(), (size_t)nl * 32, cudaMemcpyHostToDevice, sx));
+    sa::GeneralParams gp{};
+    gp.residues = db.residues;
+    gp.q_off = db.q_off;
+    gp.q_len = db.q_len;
+    gp.d_off = db.d_off;
+    gp.d_len = db.d_len;
+    gp.ids = (const uint32_t*)gb.ids.p;
+    gp.n_ids = nl;
+    gp.packing = db.packing;
+    gp.match = sc.match;
+    gp.mismatch = sc.mismatch;
+    gp.open = sc.gap_open;
+    gp.ext = sc.gap_ext;
+    gp.tb = want_cigar ? (uint8_t*)gb.tb.p : nullptr;
+    gp.ck = want_cigar ? (int4*)gb.tb.p : nullptr;  // checkpoints and blocks share the wave's scratch
+    gp.ck_off = (const uint64_t*)gb.meta.p + 2 * (size_t)nl;
+    gp.blk = (uint8_t*)gb.tb.p;
+    gp.blk_off = (const uint64_t*)gb.meta.p + 3 * (size_t)nl;
+    gp.ws = (sa::LongWalkState*)((uint64_t*)gb.meta.p + 4 * (size_t)nl);
+    gp.tb_off = (const uint64_t*)gb.meta.p;
+    gp.rows = (int32_t*)gb.rows.p;
+    gp.info = (uint8_t*)gb.info.p;
+    gp.row_stride = stride;
+    gp.runs = (uint32_t*)gb.runs.p;
+    gp.runs_end = (const uint64_t*)gb.meta.p + (size_t)nl;
+    gp.score = db.score;
+    gp.status = db.status;
+    gp.cigar_len = db.cigar_len;
+    // one block per pair, one launch per wave (waves share the traceback words: stream order)
+    for (size_t wv = 0; wv <= lp.waves.size(); ++wv) {
+      const uint32_t lo = wv ? lp.waves[wv - 1] : 0u;
+      const uint32_t hi = wv < lp.waves.size() ? lp.waves[wv] : nl;
+      if (lo >= hi) continue;
+      sa::GeneralParams gw = gp;
+      gw.ids = gp.ids + lo;
+      gw.n_ids = hi - lo;
+      gw.tb_off = gp.tb_off + lo;
+      gw.runs_end = gp.runs_end + lo;
+      gw.rows = gp.rows + (uint64_t)lo * 6 * stride;
+      gw.info = gp.info + (uint64_t)lo * 4 * stride;
+      gw.ck_off = gp.ck_off + lo;
+      gw.blk_off = gp.blk_off + lo;
+      gw.ws = gp.ws + lo;
+      if (linear && wide)
+        sa::nw_linear_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+      else if (linear)
+        sa::nw_linear_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+      else if (wide)
+        sa::nw_affine_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+      else
+        sa::nw_affine_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+      if (!linear && any_ckpt && want_cigar) {  // second kernel of a checkpointed traceback (idle blocks leave at once)
+        if (wide)
+          sa::nw_affine_general_back<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
+        else
+          sa::nw_affine_general_back<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
+        e->timing.kernel_launches++;
+      }
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches++;
+    }
+    return SA_OK;
+  };
+  // runs of the literal kernels' pairs -> pool (after the scan)
+  auto literal_runs_to_pool = [&](const LitPlan& lp, sa_engine::LitBufs& gb, cudaStream_t sx) -> sa_status_t {
+    const uint32_t nl = (uint32_t)lp.ids.size();
+    if (!nl) return SA_OK;
+    sa::general_runs_to_pool<<<nl, 128, 0, sx>>>((const uint32_t*)gb.ids.p, nl, (const uint32_t*)gb.runs.p,
+                                                  (const uint64_t*)gb.meta.p + nl, db.cigar_len, db.cigar_off, db.pool, db.pool_cap);
+    CUDA_TRY(e, cudaGetLastError());
+    e->timing.kernel_launches++;
+    return SA_OK;
+  };
+  // Tiled long-pair path (nw_long.cuh): per wave one forward launch per tile anti-diagonal, the
+  // classification, the backward (traceback) kernel.  fb_count: the slot's fallback counter.
+  auto launch_fast = [&](const FastPlan& fq, sa_engine::Slot& sl, uint32_t* fb_count, cudaStream_t sx) -> sa_status_t {
+    sa_status_t r;
+    const uint32_t nl = (uint32_t)fq.ids.size();
+    // meta: [ids u32 | fb_ids u32 | end_h i32 | flag u8 (padded to 4)] [row_off | col_off | ck_off | runs_end] u64, [next_back u32 x waves]
+    const size_t m32 = (size_t)nl * 4;
+    const size_t meta_bytes = 4 * m32 + 4 * (size_t)nl * 8 + (fq.waves.size() + 1) * 4 + 64;
+    if ((r = ensure(e, sl.f_meta, meta_bytes)) != SA_OK) return r;
+    if ((r = ensure(e, sl.f_edges, (size_t)fq.edges_total * 8 + 256)) != SA_OK) return r;
+    if ((r = ensure(e, sl.f_tb, (size_t)fq.back_warps * fq.S * 32 * sa::kLongMr * 8)) != SA_OK) return r;
+    if ((r = ensure(e, sl.f_runs, (size_t)fq.runs_total * 4 + 256)) != SA_OK) return r;
+    uint8_t* mb = (uint8_t*)sl.f_meta.p;
+    uint32_t* d_ids = (uint32_t*)mb;
+    uint32_t* d_fb = (uint32_t*)(mb + m32);
+    int32_t* d_endh = (int32_t*)(mb + 2 * m32);
+    uint8_t* d_flag = mb + 3 * m32;
+    uint64_t* d_off = (uint64_t*)(mb + 4 * m32);
+    uint32_t* d_next = (uint32_t*)(mb + 4 * m32 + 4 * (size_t)nl * 8);
+    CUDA_TRY(e, cudaMemcpyAsync(d_ids, fq.ids.data(), m32, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemcpyAsync(d_off, fq.row_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemcpyAsync(d_off + nl, fq.col_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemcpyAsync(d_off + 2 * (size_t)nl, fq.ck_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemcpyAsync(d_off + 3 * (size_t)nl, fq.runs_end.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, sx));
+    CUDA_TRY(e, cudaMemsetAsync(d_next, 0, (fq.waves.size() + 1) * 4, sx));
+    const size_t smem_f = (size_t)sa::kLongWarps * sa::long_smem_per_warp(fq.R, fq.S > 1);
+    const size_t smem_b = (size_t)sa::kLongWarps * sa::long_smem_per_warp(sa::kLongMr, true);
+    for (auto kv : {std::make_pair((const void*)sa::nw_long_fwd, smem_f), std::make_pair((const void*)sa::nw_long_back, smem_b)}) {
+      size_t& configured = e->smem_configured[kv.first];
+      if (kv.second > configured) {
+        CUDA_TRY(e, cudaFuncSetAttribute(kv.first, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)std::min(e->smem_optin, std::max<size_t>(kv.second, 48 * 1024))));
+        configured = std::max<size_t>(kv.second, 48 * 1024);
+      }
+    }
+    sa::LongParams lp{};
+    lp.residues = db.residues;
+    lp.q_off = db.q_off;
+    lp.q_len = db.q_len;
+    lp.d_off = db.d_off;
+    lp.d_len = db.d_len;
+    lp.packing = db.packing;
+    lp.sc = sa::make_long_scheme(sc.match, sc.mismatch, sc.gap_open, sc.gap_ext);
+    lp.ext = sc.gap_ext;
+    lp.R = fq.R;
+    lp.S = fq.S;
+    lp.edges = (int2*)sl.f_edges.p;
+    lp.fb_count = fb_count;
+    lp.fb_ids = d_fb;
+    lp.tb = (uint2*)sl.f_tb.p;
+    lp.runs = want_cigar ? (uint32_t*)sl.f_runs.p : nullptr;
+    lp.want_runs = want_cigar ? 1 : 0;
+    lp.score = db.score;
+    lp.status = db.status;
+    lp.cigar_len = db.cigar_len;
+    for (size_t wv = 0; wv < fq.waves.size(); ++wv) {
+      const FastPlan::Wave& w = fq.waves[wv];
+      const uint32_t cnt = w.hi - w.lo;
+      if (!cnt) continue;
+      sa::LongParams lw = lp;
+      lw.ids = d_ids + w.lo;
+      lw.n_ids = cnt;
+      lw.row_off = d_off + w.lo;
+      lw.col_off = d_off + nl + w.lo;
+      lw.ck_off = d_off + 2 * (size_t)nl + w.lo;
+      lw.runs_end = d_off + 3 * (size_t)nl + w.lo;
+      lw.end_h = d_endh + w.lo;
+      lw.flag = d_flag + w.lo;
+      lw.next_back = d_next + wv;
+      const uint32_t ndiag = w.tr_max + w.tc_max - 1;
+      for (uint32_t d = 0; d < ndiag; ++d) {
+        const uint32_t i_lo = d >= w.tc_max ? d - (w.tc_max - 1) : 0u, i_hi = std::min(d, w.tr_max - 1);
+        const uint32_t tiles = i_hi - i_lo + 1;
+        lw.diag = d;
+        // pairs in grid.y (at most 65535 per launch)
+        for (uint32_t y0 = 0; y0 < cnt; y0 += 65535) {
+          sa::LongParams ly = lw;
+          const uint32_t ny = std::min<uint32_t>(65535, cnt - y0);
+          ly.ids = lw.ids + y0;
+          ly.row_off = lw.row_off + y0;
+          ly.col_off = lw.col_off + y0;
+          ly.ck_off = lw.ck_off + y0;
+          ly.end_h = lw.end_h + y0;
+          sa::nw_long_fwd<<<dim3((tiles + sa::kLongWarps - 1) / sa::kLongWarps, ny), 32 * sa::kLongWarps, smem_f, sx>>>(ly);
+          e->timing.kernel_launches++;
+        }
+      }
+      CUDA_TRY(e, cudaGetLastError());
+      sa::nw_long_classify<<<(cnt + 127) / 128, 128, 0, sx>>>(lw);
+      sa::nw_long_back<<<(std::min(fq.back_warps, (cnt + 3) / 4 * 4) + sa::kLongWarps - 1) / sa::kLongWarps, 32 * sa::kLongWarps, smem_b, sx>>>(lw);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches += 2;
+    }
+    return SA_OK;
+  };
+  auto fast_runs_to_pool = [&](const FastPlan& fq, sa_engine::Slot& sl, cudaStream_t sx) -> sa_status_t {
+    const uint32_t nl = (uint32_t)fq.ids.size();
+    if (!nl) return SA_OK;
+    const uint64_t* d_off = (const uint64_t*)((uint8_t*)sl.f_meta.p + 4 * (size_t)nl * 4);
+    sa::general_runs_to_pool<<<nl, 128, 0, sx>>>((const uint32_t*)sl.f_meta.p, nl, (const uint32_t*)sl.f_runs.p, d_off + 3 * (size_t)nl,
+                                                  db.cigar_len, db.cigar_off, db.pool, db.pool_cap);
+    CUDA_TRY(e, cudaGetLastError());
+    e->timing.kernel_launches++;
+    return SA_OK;
+  };
   // Stage A of a segment: fill with the panic bonus on, classify + count walk, queue length.
   auto stage_a = [&](const Segment& sg, int k) -> sa_status_t {
     sa_engine::Slot& sl = e->slot[k];
@@ -698,10 +984,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       // pageable source: the copy is staged by the runtime before the call returns
       CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), sg.order.size() * 4, cudaMemcpyHostToDevice, sx));
       d_order = (const uint32_t*)sl.order.p;
-    } else if (!sg.long_ids.empty()) {
-      d_order = (const uint32_t*)sl.order.p;  // every pair of the segment is long: nothing to launch
     }
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
+    CUDA_TRY(e, cudaMemsetAsync(d_counts + 2 + k, 0, 4, sx));  // fallback queue of the tiled long-pair path
     CUDA_TRY(e, cudaEventRecord(sl.ev_f0, sx));
     CUDA_TRY(e, cudaStreamWaitEvent(sl.fill_stream, sl.ev_f0, 0));
     for (const Segment::Sub& sub : sg.subs) {
@@ -736,89 +1021,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
     }
-    if (!sg.long_ids.empty()) {
-      // pairs outside the packed range: literal 32-bit kernel, one thread block per pair
-      const uint32_t nl = (uint32_t)sg.long_ids.size();
-      const bool wide = sg.long_n1max >= 8192;  // more lanes per pair when the pairs are few and long
-      // per pair 6 * stride ints: the affine kernel's edge column (4 ints per row), the linear
-      // kernel's rolling row (ceil(columns / threads) * threads entries); even, for 16-byte alignment
-      const uint32_t stride = (std::max(sg.long_n1max, sg.long_n2max) + 2 + sa::kGeneralThreadsWide + 1) & ~1u;
-      if ((r = ensure(e, sl.g_ids, (size_t)nl * 4)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_meta, (size_t)nl * (32 + sizeof(sa::LongWalkState)))) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_tb, (size_t)sg.long_tb_total + 256)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_rows, (size_t)nl * 6 * stride * 4)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_info, (size_t)nl * 4 * stride)) != SA_OK) return r;
-      if ((r = ensure(e, sl.g_runs, (size_t)sg.long_runs_total * 4 + 256)) != SA_OK) return r;
-      std::vector<uint64_t> meta((size_t)4 * nl);  // [tb_off | runs_end | ck_off | blk_off]
-      bool any_ckpt = false;
-      for (uint32_t t = 0; t < nl; ++t) {
-        for (int f = 0; f < 4; ++f) meta[(size_t)f * nl + t] = sg.long_meta[4 * t + f];
-        any_ckpt |= sg.long_meta[4 * t + 2] != ~0ull;
-      }
-      CUDA_TRY(e, cudaMemcpyAsync(sl.g_ids.p, sg.long_ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, sx));
-      CUDA_TRY(e, cudaMemcpyAsync(sl.g_meta.p, meta.data(), (size_t)nl * 32, cudaMemcpyHostToDevice, sx));
-      sa::GeneralParams gp{};
-      gp.residues = db.residues;
-      gp.q_off = db.q_off;
-      gp.q_len = db.q_len;
-      gp.d_off = db.d_off;
-      gp.d_len = db.d_len;
-      gp.ids = (const uint32_t*)sl.g_ids.p;
-      gp.n_ids = nl;
-      gp.packing = db.packing;
-      gp.match = sc.match;
-      gp.mismatch = sc.mismatch;
-      gp.open = sc.gap_open;
-      gp.ext = sc.gap_ext;
-      gp.tb = want_cigar ? (uint8_t*)sl.g_tb.p : nullptr;
-      gp.ck = want_cigar ? (int4*)sl.g_tb.p : nullptr;  // checkpoints and blocks share the wave's scratch
-      gp.ck_off = (const uint64_t*)sl.g_meta.p + 2 * (size_t)nl;
-      gp.blk = (uint8_t*)sl.g_tb.p;
-      gp.blk_off = (const uint64_t*)sl.g_meta.p + 3 * (size_t)nl;
-      gp.ws = (sa::LongWalkState*)((uint64_t*)sl.g_meta.p + 4 * (size_t)nl);
-      gp.tb_off = (const uint64_t*)sl.g_meta.p;
-      gp.rows = (int32_t*)sl.g_rows.p;
-      gp.info = (uint8_t*)sl.g_info.p;
-      gp.row_stride = stride;
-      gp.runs = (uint32_t*)sl.g_runs.p;
-      gp.runs_end = (const uint64_t*)sl.g_meta.p + (size_t)nl;
-      gp.score = db.score;
-      gp.status = db.status;
-      gp.cigar_len = db.cigar_len;
-      // one block per pair, one launch per wave (waves share the traceback words: stream order)
-      for (size_t wv = 0; wv <= sg.long_waves.size(); ++wv) {
-        const uint32_t lo = wv ? sg.long_waves[wv - 1] : 0u;
-        const uint32_t hi = wv < sg.long_waves.size() ? sg.long_waves[wv] : nl;
-        if (lo >= hi) continue;
-        sa::GeneralParams gw = gp;
-        gw.ids = gp.ids + lo;
-        gw.n_ids = hi - lo;
-        gw.tb_off = gp.tb_off + lo;
-        gw.runs_end = gp.runs_end + lo;
-        gw.rows = gp.rows + (uint64_t)lo * 6 * stride;
-        gw.info = gp.info + (uint64_t)lo * 4 * stride;
-        gw.ck_off = gp.ck_off + lo;
-        gw.blk_off = gp.blk_off + lo;
-        gw.ws = gp.ws + lo;
-        if (linear && wide)
-          sa::nw_linear_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
-        else if (linear)
-          sa::nw_linear_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
-        else if (wide)
-          sa::nw_affine_general_kernel<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
-        else
-          sa::nw_affine_general_kernel<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
-        if (!linear && any_ckpt && want_cigar) {  // second kernel of a checkpointed traceback (idle blocks leave at once)
-          if (wide)
-            sa::nw_affine_general_back<sa::kGeneralThreadsWide><<<gw.n_ids, sa::kGeneralThreadsWide, 0, sx>>>(gw);
-          else
-            sa::nw_affine_general_back<sa::kGeneralThreads><<<gw.n_ids, sa::kGeneralThreads, 0, sx>>>(gw);
-          e->timing.kernel_launches++;
-        }
-        CUDA_TRY(e, cudaGetLastError());
-        e->timing.kernel_launches++;
-      }
-    }
+    if (!sg.lit.ids.empty() && (r = launch_literal(sg.lit, sl.lit, sx)) != SA_OK) return r;
+    if (!sg.fast.ids.empty() && (r = launch_fast(sg.fast, sl, d_counts + 2 + k, sx)) != SA_OK) return r;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 6 + k, d_counts + 2 + k, 4, cudaMemcpyDeviceToHost, sx));
     CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
     CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));
     return SA_OK;
@@ -836,6 +1041,19 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sl.ev_count, 0));
     const uint32_t n_re = e->h_count[4 + k];
     e->timing.pairs_rerun += n_re;
+    // tiled long pairs whose traceback can meet a dead end (provenance class 2): literal kernel, now
+    const uint32_t n_fb = sg.fast.ids.empty() ? 0u : e->h_count[6 + k];
+    LitPlan fbp;
+    if (n_fb) {
+      std::vector<uint32_t> ids(n_fb);
+      CUDA_TRY(e, cudaMemcpyAsync(ids.data(), (const uint8_t*)sl.f_meta.p + sg.fast.ids.size() * 4, (size_t)n_fb * 4,
+                                  cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      std::sort(ids.begin(), ids.end());
+      if (getenv("SA_TRACE")) fprintf(stderr, "[sa trace]   %u long pair(s) handed to the literal kernel\n", n_fb);
+      fbp = plan_literal(ids, budget_re);
+      if ((r = launch_literal(fbp, e->fb_lit, e->stream)) != SA_OK) return r;
+    }
     float fms = 0;
     if (cudaEventElapsedTime(&fms, sl.ev_f0, sl.ev_f1) == cudaSuccess) e->timing.walk_ms += fms;
     const uint64_t tiles_re = std::max<uint64_t>(1, std::min<uint64_t>(ctiles, std::max<uint64_t>(1, budget_re / tile_bytes)));
@@ -900,14 +1118,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           (const uint32_t*)sl.tmp_runs.p, db.cigar_len, db.cigar_off, db.pool, db.pool_cap, (uint32_t)sg.base, cn);
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
-      if (!sg.long_ids.empty()) {
-        const uint32_t nl = (uint32_t)sg.long_ids.size();
-        sa::general_runs_to_pool<<<nl, 128, 0, e->stream>>>((const uint32_t*)sl.g_ids.p, nl, (const uint32_t*)sl.g_runs.p,
-                                                            (const uint64_t*)sl.g_meta.p + nl, db.cigar_len, db.cigar_off,
-                                                            db.pool, db.pool_cap);
-        CUDA_TRY(e, cudaGetLastError());
-        e->timing.kernel_launches++;
-      }
+      if ((r = literal_runs_to_pool(sg.lit, sl.lit, e->stream)) != SA_OK) return r;
+      if ((r = fast_runs_to_pool(sg.fast, sl, e->stream)) != SA_OK) return r;
+      if (n_fb && (r = literal_runs_to_pool(fbp, e->fb_lit, e->stream)) != SA_OK) return r;
       wp.tmp_runs = nullptr;
       for (const Segment::Sub& sub : sg.subs) {
         set_geometry(sub.g);
@@ -1234,6 +1447,9 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
   if (const char* s = getenv("SA_FORCE_K")) e->force_k = atoi(s);
   if (const char* s = getenv("SA_LONG_CKPT")) e->long_ckpt_always = atoi(s) != 0;
+  if (const char* s = getenv("SA_LONG_LITERAL")) e->long_literal = atoi(s) != 0;
+  if (const char* s = getenv("SA_LONG_S")) e->long_s = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_LONG_R")) e->long_r = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);
@@ -1249,12 +1465,20 @@ sa_status_t sd_destroy(sa_engine* e) {
   if (e->stream) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->slot[0].g_ids, &e->slot[0].g_meta, &e->slot[0].g_tb, &e->slot[0].g_rows, &e->slot[0].g_info,
-                      &e->slot[0].g_runs, &e->slot[1].g_ids, &e->slot[1].g_meta, &e->slot[1].g_tb, &e->slot[1].g_rows,
-                      &e->slot[1].g_info, &e->slot[1].g_runs, &e->slot[0].order, &e->slot[1].order, &e->slot[0].tmp_runs, &e->slot[1].tmp_runs, &e->slot[0].tb, &e->slot[0].end, &e->slot[0].rerun_ids, &e->slot[1].tb,
-                      &e->slot[1].end, &e->slot[1].rerun_ids, &e->tb2, &e->end2, &e->misc, &e->wfa_scratch, &e->par_bytes, &e->par_rows, &e->par_in,
-                      &e->block_sums, &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score,
-                      &e->b_status, &e->b_clen, &e->b_coff, &e->b_pool, &e->b_carry})
+    std::vector<DevBuf*> bufs = {&e->tb2, &e->end2, &e->misc, &e->wfa_scratch, &e->par_bytes, &e->par_rows, &e->par_in, &e->block_sums,
+                                 &e->b_res, &e->b_qoff, &e->b_doff, &e->b_qlen, &e->b_dlen, &e->b_score, &e->b_status, &e->b_clen,
+                                 &e->b_coff, &e->b_pool, &e->b_carry};
+    auto add_lit = [&](sa_engine::LitBufs& g) {
+      for (DevBuf* b : {&g.ids, &g.meta, &g.tb, &g.rows, &g.info, &g.runs}) bufs.push_back(b);
+    };
+    add_lit(e->fb_lit);
+    for (int k = 0; k < 2; ++k) {
+      sa_engine::Slot& sl = e->slot[k];
+      add_lit(sl.lit);
+      for (DevBuf* b : {&sl.tb, &sl.end, &sl.rerun_ids, &sl.tmp_runs, &sl.order, &sl.f_meta, &sl.f_edges, &sl.f_tb, &sl.f_runs})
+        bufs.push_back(b);
+    }
+    for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : {e->ev_in, e->ev_done, e->ev_carry[0], e->ev_carry[1], e->ev_t0, e->ev_t1, e->slot[0].ev_count,
                            e->slot[0].ev_f0, e->slot[0].ev_f1, e->slot[1].ev_count, e->slot[1].ev_f0,

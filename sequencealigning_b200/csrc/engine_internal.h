@@ -69,9 +69,13 @@ struct sa_engine {
   std::string err;
   // Two segments are in flight on the compute stream (the fill of segment i+1 is queued before
   // the host reads segment i's refill count), so per-segment scratch is double-buffered.
+  struct LitBufs {  // scratch of the literal long-pair kernels (nw_general.cuh)
+    DevBuf ids, meta, tb, rows, info, runs;
+  };
   struct Slot {
     DevBuf tb, end, rerun_ids, tmp_runs, order;
-    DevBuf g_ids, g_meta, g_tb, g_rows, g_info, g_runs;  // long pairs (nw_general.cuh)
+    LitBufs lit;
+    DevBuf f_meta, f_edges, f_tb, f_runs;  // tiled long pairs (nw_long.cuh)
     cudaStream_t stream = nullptr;  // stage A of alternating segments runs on its own stream, so
                                     // the next fill overlaps the tail of the previous one
     cudaStream_t fill_stream = nullptr;  // LOW priority: only the fill kernels.  The walks, scans and
@@ -89,6 +93,9 @@ struct sa_engine {
   size_t smem_optin = 0;
   int force_g = 0, force_k = 0;
   bool long_ckpt_always = false;  // SA_LONG_CKPT: checkpointed traceback for every long pair (tests)
+  bool long_literal = false;      // SA_LONG_LITERAL: affine long pairs through the literal kernel only (tests)
+  uint32_t long_s = 0, long_r = 0;  // SA_LONG_S / SA_LONG_R: tile shape of the tiled long-pair path (0 = auto)
+  LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;
   size_t tb_budget = 0;
   size_t budget_cached = 0;

@@ -285,6 +285,7 @@ def test_long_pairs_in_waves_and_omitted_alignments(oracle, monkeypatch):
     import random
     from sequencealigning_b200 import Engine
     from tests.util import mutate, random_seq
+    monkeypatch.setenv("SA_LONG_LITERAL", "1")     # the literal kernels (the tiled path's fallback)
     monkeypatch.setenv("SA_TB_BUDGET_MB", "400")   # refill/long share 80 MB: ~9 pairs of 2.1 kbp per wave
     rng = random.Random(41)
     longs = []
@@ -342,6 +343,7 @@ def test_checkpointed_traceback_of_long_pairs(oracle, monkeypatch):
     from sequencealigning_b200 import Engine
     from tests.util import mutate, random_seq
     monkeypatch.setenv("SA_LONG_CKPT", "1")
+    monkeypatch.setenv("SA_LONG_LITERAL", "1")
     rng = random.Random(97)
     pairs = random_pair_list(56, 60, 1, 150)
     for n1, n2, err in [(2100, 2050, 0.05), (2500, 2600, 0.02), (4100, 700, 0.1), (6200, 300, 0.08), (8200, 120, 0.1),
@@ -473,3 +475,98 @@ def test_cooptimal_counts_match_the_oracle(engine, oracle):
     assert exp3.max() == (2**63 - 1) // 4
     acgt = _batch(random_pair_list(78, 300, 1, 120, alphabet=b"ACGT"))
     assert np.array_equal(engine.count_cooptimal(acgt), engine.count_cooptimal(acgt.packed()))
+
+
+# ---- the tiled long-pair path (nw_long.cuh) -----------------------------------------------------
+
+def _cigar_score(q: bytes, d: bytes, words, match=5, mismatch=-4, gap_open=-8, gap_ext=-6):
+    """Score of an alignment given as (len << 2 | op) runs; checks that it consumes both sequences."""
+    qa, da = np.frombuffer(q, np.uint8), np.frombuffer(d, np.uint8)
+    y = x = score = 0
+    for w in words:
+        op, ln = int(w) & 3, int(w) >> 2
+        if op == 0:
+            eq = int((qa[y:y + ln] == da[x:x + ln]).sum())
+            score += eq * match + (ln - eq) * mismatch
+            y += ln; x += ln
+        elif op == 1:
+            score += gap_open + ln * gap_ext
+            y += ln
+        else:
+            score += gap_open + ln * gap_ext
+            x += ln
+    assert y == len(q) and x == len(d), (y, len(q), x, len(d))
+    return score
+
+
+@pytest.mark.parametrize("s_r", [(0, 0), (1, 256), (2, 512), (4, 1024), (1, 1024)])
+def test_tiled_long_pairs_every_tile_shape(oracle, s_r, monkeypatch):
+    """Pairs outside the packed range through the tiled 32-bit path, for every tile shape: query and
+    db lengths around the strip width (512), the tile heights and the checkpoint spacing (2048)."""
+    import random
+    from sequencealigning_b200 import Engine
+    from tests.util import mutate, random_seq
+    if s_r[0]:
+        monkeypatch.setenv("SA_LONG_S", str(s_r[0]))
+        monkeypatch.setenv("SA_LONG_R", str(s_r[1]))
+    rng = random.Random(101 + s_r[0] + s_r[1])
+    pairs = random_pair_list(61, 40, 1, 150)
+    shapes = [(2049, 2047), (2048, 2048), (4097, 300), (300, 4097), (513, 3600), (3600, 255), (1025, 2900), (4100, 2100),
+              (2047, 2049), (1800, 2050), (5000, 600), (2560, 2561)]
+    for n1, n2 in shapes:
+        q = random_seq(rng, n1, b"ACGT")
+        err = rng.choice([0.02, 0.08, 0.25])
+        d = mutate(rng, (q * 3)[: n2 * 2], err, True, b"ACGT")[:n2] if rng.random() < 0.8 else random_seq(rng, n2, b"ACGT")
+        pairs.insert(rng.randrange(len(pairs)), (q, d))
+    pairs.append((b"G" + random_seq(rng, 2300, b"ACGT"), random_seq(rng, 2300, b"ACGT")))
+    pairs.append((b"ACGT" * 600, b"ACGT" * 600))            # one run of 2400 M; a leading-gap alternative does not tie
+    pairs.append((b"T" + b"ACGT" * 600, b"ACGT" * 600))     # the best alignment starts with a gap: the reference panics
+    b = _batch(pairs)
+    with Engine(0) as eng:
+        r = eng.align(b)
+        assert not (r.status & 0x80).any()
+        check_against_oracle(oracle, b, r, n_threads=8, what=f"tiled long pairs S,R={s_r}")
+        only_long = _batch([pq for pq in pairs if len(pq[0]) + len(pq[1]) > 3700])
+        check_against_oracle(oracle, only_long, eng.align(only_long), n_threads=8, what="tiled, long pairs only")
+        ro = eng.align(b, cigar=False)
+        assert np.array_equal(ro.score, r.score) and np.array_equal(ro.status, r.status)
+
+
+def test_tiled_long_pairs_hand_dead_ends_to_the_literal_kernel(engine, oracle):
+    """A gap of more than ~5.4 k residues costs less through the reference's finite -32768 sentinel
+    than through the gap recurrences: the optimal path then STARTS at a parentless sentinel cell,
+    the reference prints nothing (or not the greedy path).  The tiled path detects this from the
+    provenance bonus of the end cell and hands the pair to the literal kernel."""
+    import random
+    from sequencealigning_b200 import REF_NO_OUTPUT
+    from tests.util import mutate, random_seq
+    rng = random.Random(7)
+    x = random_seq(rng, 600, b"ACGT")
+    pairs = [
+        (random_seq(rng, 7000, b"ACGT") + x, mutate(rng, x, 0.03, True, b"ACGT")),   # 7 k leading query residues
+        (mutate(rng, x, 0.03, True, b"ACGT"), random_seq(rng, 6500, b"ACGT") + x),   # 6.5 k leading db residues
+        (b"A" * 5600, b"C" * 3),
+        (random_seq(rng, 3000, b"ACGT"), random_seq(rng, 3100, b"ACGT")),             # unrelated: ordinary long pair
+    ]
+    q = random_seq(rng, 2600, b"ACGT")
+    pairs.append((q, mutate(rng, q, 0.05, True, b"ACGT")))
+    b = _batch(pairs)
+    r = engine.align(b)
+    ref = check_against_oracle(oracle, b, r, n_threads=5, what="dead ends")
+    assert (ref.status[:2] == REF_NO_OUTPUT).all()
+
+
+def test_long_pairs_score_pinned_at_30_and_100_kbp(engine, oracle):
+    """BASELINE.json configs[4] sizes, beyond what the full oracle can hold: the score is pinned by
+    the oracle's score-only DP (same recurrences and sentinel, O(n1) memory), the alignment by
+    re-scoring its CIGAR (it must consume both sequences and add up to the reported score)."""
+    from sequencealigning_b200 import synth
+    for length, n in ((30_000, 3), (100_000, 2)):
+        b = synth.random_pairs(n, length, 0.05, True, seed=0x5A05 + length)
+        r = engine.align(b)
+        assert not (r.status & 0x80).any()
+        for p in range(n):
+            if p == 0:   # one oracle pass per size (9e8 / 1e10 cells on one host core)
+                assert int(r.score[p]) == oracle.affine_score(b.query(p), b.db(p)), (length, p)
+            assert r.status[p] in (0, 1) and r.cigar_len[p] > 0
+            assert _cigar_score(b.query(p), b.db(p), r.cigar_of(p)) == int(r.score[p]), (length, p)
