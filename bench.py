@@ -42,7 +42,7 @@ def parse_args():
                     help="config2 (default, the headline): 150 bp affine NW; config3: 250 bp affine NW; "
                          "config4: WFA (standard mode) on 1-10 kbp pairs at 1-15 %% error; "
                          "config5: WFA (standard mode) on 1 k pairs of 100 kbp at 5 %%; "
-                         "config5nw: affine NW on 42 pairs of 100 kbp (score, status and CIGAR; the literal long-pair kernels)")
+                         "config5nw: affine NW on 1 k pairs of 100 kbp (score, status and CIGAR; the tiled long-pair path)")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (0 = the workload's default)")
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--divergence", type=float, default=0.05)
@@ -107,7 +107,7 @@ WORKLOADS = {  # name -> (default pairs per GPU, length, BASELINE.json index)
     "config3": (1_000_000, 250, 2),
     "config4": (20_000, 0, 3),
     "config5": (1_000, 100_000, 4),
-    "config5nw": (42, 100_000, 4),
+    "config5nw": (1_000, 100_000, 4),
 }
 WFA_WORKLOADS = ("config4", "config5")
 
@@ -131,8 +131,9 @@ def make_batch(args, rank: int):
 def workload_config(args, n_gpus: int) -> dict:
     if args.workload == "config5nw":
         return {"workload": f"affine NW, {args.pairs} synthetic pairs per GPU of {args.length} bp at 5 % divergence (sub:ins:del 2:1:1) "
-                            f"(BASELINE.json configs[4], NW half): exact score, status and first alignment through the literal 32-bit "
-                            f"long-pair kernels with checkpointed traceback (the reference's -32768 sentinel is live at this length)",
+                            f"(BASELINE.json configs[4], NW half): exact score, status and first alignment through the tiled 32-bit "
+                            f"long-pair path (nw_long.cuh: one warp per tile, tile anti-diagonals over all SMs, checkpointed edges, "
+                            f"region-wise traceback; the reference's -32768 sentinel is live at this length)",
                 "pairs_per_gpu": args.pairs, "length": args.length, "n_gpus": n_gpus,
                 "scheme": "match 5 / mismatch -4 / open -8 / ext -6 (nw_affine.rs:15-20)"}
     if args.workload == "config5":
