@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--configs", default="all", choices=["all", "sharded", "none"],
+                    help="with the default workload: also measure the other BASELINE.json configs at their stated sizes "
+                         "(`configs` block, N = 1 only) and config 3 (10 M x 250 bp) from ONE host list through ONE "
+                         "multi-device call (`sharded` block, every N)")
+    ap.add_argument("--sharded-pairs", type=int, default=10_000_000)
     return ap.parse_args()
 
 
@@ -105,11 +110,13 @@ class ClockSampler:
 WORKLOADS = {  # name -> (default pairs per GPU, length, BASELINE.json index)
     "config2": (1_000_000, 150, 1),
     "config3": (1_000_000, 250, 2),
-    "config4": (20_000, 0, 3),
+    "config4": (100_000, 0, 3),
     "config5": (1_000, 100_000, 4),
     "config5nw": (1_000, 100_000, 4),
 }
 WFA_WORKLOADS = ("config4", "config5")
+DTYPES = {"config2": "u16x2 (two pairs per 32-bit register; exact integer)", "config3": "u16x2 (two pairs per 32-bit register; exact integer)",
+          "config4": "s32 (wavefront offsets)", "config5": "s32 (wavefront offsets)", "config5nw": "s32 (4*V - 4*ext*(x+y) + provenance bits)"}
 
 
 def resolve_workload(args):
@@ -140,8 +147,7 @@ def workload_config(args, n_gpus: int) -> dict:
         return {"workload": f"gap-affine WFA (standard mode, x=4 o=2 e=6), {args.pairs} synthetic pairs per GPU of {args.length} bp "
                             f"at 5 % divergence (sub:ins:del 2:1:1) (BASELINE.json configs[4], WFA half); GCUPS is EQUIVALENT cells n1*n2/s",
                 "pairs_per_gpu": args.pairs, "length": args.length, "n_gpus": n_gpus,
-                "note": "score only; the reference's own WFA produces no result on inputs of this size; the affine-NW half of configs[4] "
-                        "runs through the exact but untiled long-pair kernel and is not a bench line"}
+                "note": "score only (an extension: the reference's own WFA produces no result on inputs of this size)"}
     if args.workload == "config4":
         return {"workload": f"gap-affine WFA (standard mode, x=4 o=2 e=6), {args.pairs} synthetic pairs per GPU of 1-10 kbp "
                             f"(log-uniform) at 1-15 % error (BASELINE.json configs[3]); GCUPS is EQUIVALENT cells n1*n2/s",
@@ -284,7 +290,7 @@ def int_peak() -> dict:
 def fill_kernel_probe(batch, device: int, reps: int = 7) -> dict:
     """The fill kernel timed alone: a second engine whose segment size is forced to the probe size,
     so the sub-batch is ONE fill launch; duration = CUDA events around that launch on its stream
-    (sa_last_timing.walk_ms), median of `reps` after 3 warm-ups."""
+    (sa_last_timing.fill_ms), median of `reps` after 3 warm-ups."""
     from sequencealigning_b200 import Engine
     n = min(batch.n_pairs, PROBE_PAIRS)
     sub = batch.select(np.arange(n, dtype=np.int64))
@@ -297,7 +303,7 @@ def fill_kernel_probe(batch, device: int, reps: int = 7) -> dict:
             for k in range(3 + reps):
                 rb.align()
                 if k >= 3:
-                    ms.append(eng.timing()["walk_ms"])
+                    ms.append(eng.timing()["fill_ms"])
             rb.free()
     finally:
         if old is None:
@@ -305,6 +311,327 @@ def fill_kernel_probe(batch, device: int, reps: int = 7) -> dict:
         else:
             os.environ["SA_SEG_PAIRS"] = old
     return {"pairs": int(n), "cells": int(sub.cells), "residue_bytes": int(sub.q_len.sum()) + int(sub.d_len.sum()), "ms": float(np.median(ms))}
+
+
+def _max_over_ranks(x: float, world: int, dist, torch) -> float:
+    if world <= 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x: float, world: int, dist, torch) -> float:
+    if world <= 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def measure(eng, batch, algo, steps: int, warmup: int, ctx, e2e: bool = True, packed: bool = True) -> dict:
+    """One workload on one engine: `value` leg (inputs resident in HBM, CUDA events on the engine's
+    stream around `steps` passes) and the e2e leg through sa_align_batch with pinned HOST buffers
+    (host wall clock, copies inside).  ctx = (torch, dist, world, local)."""
+    torch, dist, world, local = ctx
+    from sequencealigning_b200.engine import PinnedResult, pin_batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    cells_all = _sum_over_ranks(float(batch.cells), world, dist, torch)
+    pairs_all = _sum_over_ranks(float(batch.n_pairs), world, dist, torch)
+    rb = eng.upload(batch)
+    for _ in range(warmup):
+        rb.align(algo=algo)
+    eng.synchronize()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    launches = 0
+    tim = {}
+    e0.record(stream)
+    for _ in range(steps):
+        rb.align(algo=algo)
+        tim = eng.timing()
+        launches += tim["kernel_launches"]
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_step = _max_over_ranks(e0.elapsed_time(e1), world, dist, torch) / steps
+    res_dev = rb.download()
+    rb.free()
+    out = {"value": cells_all / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step, "alignments_per_s": pairs_all / (ms_step * 1e-3),
+           "gpu_launches": int(launches // max(steps, 1)), "timing": tim, "result": res_dev, "cells_all": cells_all}
+    if not e2e:
+        return out
+    pres = PinnedResult(batch.n_pairs, int(res_dev.cigar.size) + 1024)
+
+    def timed(host_batch, prepare=None):
+        for _ in range(2):
+            eng.align(prepare(host_batch) if prepare else host_batch, algo=algo, out=pres)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = eng.align(prepare(host_batch) if prepare else host_batch, algo=algo, out=pres)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks((time.perf_counter() - t0) / steps, world, dist, torch)
+        t = eng.timing()
+        assert np.array_equal(r.score, res_dev.score)
+        return {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(t["h2d_bytes"]),
+                "d2h_bytes_per_step": int(t["d2h_bytes"]), "alignments_per_s": pairs_all / dt}
+
+    pinned_bytes = pin_batch(batch)
+    by_bytes = timed(pinned_bytes)
+    by_bytes["input_format"] = "byte per residue (sa_batch_t.packing = 0), pinned"
+    if not packed:
+        e = by_bytes
+    else:
+        # The product's input format is what its packer writes (north star: "a packer that writes 2-bit DNA
+        # into pinned batches"), sa_batch_t.packing = 1.  Three figures: packed input prepared outside the
+        # timed region (like FASTA parsing), the packer INSIDE the timed region (bytes -> sa_pack_2bit_mt ->
+        # align, every step), and the byte format.
+        from sequencealigning_b200 import PairBatch, _capi
+        t0 = time.perf_counter()
+        pk = batch.packed()
+        pack_s = time.perf_counter() - t0
+        pinned_packed = pin_batch(pk)
+        e = timed(pinned_packed)
+        e["input_format"] = "2-bit packed residues (sa_batch_t.packing = 1), pinned"
+        e["packer_host_seconds_untimed"] = pack_s
+        lib = _capi.lib()
+        src = pinned_bytes.residues
+
+        def pack_then(b):   # the packer inside the timed region: pinned bytes -> pinned 2-bit image, all host threads
+            rc = lib.sa_pack_2bit_mt(src.ctypes.data, src.size, b.residues.ctypes.data, 0)
+            assert rc == 0
+            return b
+
+        e["packer_included"] = timed(pinned_packed, pack_then)
+        e["packer_included"]["input_format"] = "bytes in pinned memory -> sa_pack_2bit_mt (all host threads) -> 2-bit, every step, inside the timed region"
+        e["packer_included"]["packer_gb_per_s"] = src.size / max(pack_s, 1e-9) / 1e9
+        e["byte_per_residue"] = by_bytes
+    e["api"] = "sa_align_batch (C ABI) with pinned host buffers; host wall clock, max over ranks"
+    out["e2e"] = e
+    pres.free()
+    return out
+
+
+def parity_affine(batch, res, n_sample: int = 2000) -> dict:
+    """Spot check inside the run: the first pairs of the workload against the CPU oracle, bit for bit."""
+    from oracle import binding as ob
+    ob.build()
+    n = min(n_sample, batch.n_pairs)
+    sub = batch.select(np.arange(n))
+    stride = int((sub.q_len.astype(np.int64) + sub.d_len).max()) + 1
+    ref = ob.affine_batch(sub.residues, sub.q_off, sub.q_len, sub.d_off, sub.d_len, cigar_stride=stride, n_threads=os.cpu_count() or 1)
+    ok = bool(np.array_equal(ref.score, res.score[:n]) and np.array_equal(ref.status, res.status[:n])
+              and np.array_equal(ref.cigar_len, res.cigar_len[:n])
+              and all(list(ref.cigar_pool[p, :ref.cigar_len[p]]) == res.cigar_of(p) for p in range(0, n, max(1, n // 200))))
+    return {"ok": ok, "sample": f"first {n} pairs vs oracle/nw_affine.c: score, status, CIGAR length (all), CIGAR words (every {max(1, n // 200)}th)"}
+
+
+def roofline_fill(batch, ms_step, gcups, world, local, res_dev, args, peak, hbm_peak) -> dict:
+    ipeak = peak["issue_lane_ops_per_s"]
+    pr = fill_kernel_probe(batch, local)
+    k_cups = pr["cells"] / (pr["ms"] * 1e-3)
+    cells = batch.cells
+    hbm_bytes = cells / 2.0 + batch.residues.size + batch.n_pairs * (24 + 17) + res_dev.cigar.size * 4
+    return {
+        "bound": "int-issue (integer max-plus DP: neither HBM nor tensor cores bind; DESIGN.md 4.1)",
+        "kernel": "nw_affine_fill_s16<K,G> (150 bp: K=19 columns per lane, G=8 lanes per pair-of-pairs; 250 bp: K=16, G=16; single pass)",
+        "achieved": k_cups * OPS_PER_CELL_ISSUED / 1e12, "peak": ipeak / 1e12, "unit": "T lane-instr/s",
+        "frac": k_cups * OPS_PER_CELL_ISSUED / ipeak,
+        "frac_is": "issue-slot share: issued recurrence instructions (8 per cell) / measured issue rate",
+        "lane_instr_per_cell": OPS_PER_CELL_ISSUED,
+        "launch": {"pairs": pr["pairs"], "cells": pr["cells"], "ms": pr["ms"], "gcups": k_cups / 1e9,
+                   "timed": "one fill launch alone, CUDA events on its stream, median of 7 after 3 warm-ups"},
+        "whole_step_frac": gcups * 1e9 * OPS_PER_CELL_ISSUED / world / ipeak,
+        # SURVEY.md 8d's algorithmic count (16 s32 ops per cell for score + 4-bit traceback); the packed u16x2
+        # recurrence does that work in 8 issued instructions, so this ratio can pass 1
+        "s32_equivalent": {"ops_per_cell": OPS_PER_CELL_S32_EQUIV, "achieved": k_cups * OPS_PER_CELL_S32_EQUIV / 1e12,
+                           "frac": k_cups * OPS_PER_CELL_S32_EQUIV / ipeak,
+                           "note": "SURVEY 8d formula (16 s32-equivalent ops per cell / measured issue rate); above 1 because u16x2 does two cells "
+                                   "per lane-op and the VIMNMX predicate outputs replace the compare/select ops, not because work is skipped"},
+        "traffic": (14133 + 325) * pr["pairs"] if args.length == 150 else None,
+        "traffic_detail": {"unit": "DRAM bytes per fill launch", "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
+                           "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14458 B per 150 bp pair)"},
+        "per_gpu": True,
+        "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
+                "/ fill-kernel time; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",
+        "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, "bytes": "sequences + 0.5 B/cell traceback written + results, whole step"},
+    }
+
+
+def roofline_long(cells: float, tim: dict, peak: dict) -> dict:
+    """Tiled long-pair path: the forward launches (nw_long_fwd) timed by CUDA events on their stream
+    inside the step (sa_last_timing.long_fwd_ms), 6 issued lane-instructions per cell."""
+    ipeak = peak["issue_lane_ops_per_s"]
+    fwd_ms = tim.get("long_fwd_ms", 0.0) or float("nan")
+    cups = cells / (fwd_ms * 1e-3)
+    return {"bound": "int-issue", "kernel": "nw_long_fwd (32-bit, one warp per tile, 16 columns per lane; one launch per tile anti-diagonal)",
+            "achieved": cups * 6 / 1e12, "peak": ipeak / 1e12, "unit": "T lane-instr/s", "frac": cups * 6 / ipeak,
+            "frac_is": "issue-slot share: 6 issued recurrence instructions per cell (LOP3, VIMNMX, IADD3, VIMNMX3, 2 VIADDMNMX) / measured issue rate",
+            "lane_instr_per_cell": 6, "forward_ms": fwd_ms, "traceback_ms": tim.get("long_back_ms"), "forward_gcups": cups / 1e9,
+            "s32_equivalent": {"ops_per_cell": 8, "frac": cups * 8 / ipeak, "note": "SURVEY 8d: 8 s32-equivalent ops per cell, score only"},
+            "traffic": None, "timed": "all forward launches of the step, CUDA events on their stream (sa_last_timing.long_fwd_ms)"}
+
+
+def roofline_wfa(peak: dict, wf: dict, ms_step: float) -> dict:
+    """WFA: SURVEY 8d's unit is 8 ops per wavefront cell + 4 per 32 extended bases; the kernel counts both."""
+    ipeak = peak["issue_lane_ops_per_s"]
+    ops = 8.0 * wf["wavefront_cells"] + 4.0 * wf["extended_bases"] / 32.0
+    return {"bound": "latency (per-pair score loop) / int-issue", "kernel": "wfa_standard_kernel (one warp per pair)",
+            "achieved": ops / (ms_step * 1e-3) / 1e12, "peak": ipeak / 1e12, "unit": "T lane-ops/s", "frac": ops / (ms_step * 1e-3) / ipeak,
+            "wavefront_cells_per_s": wf["wavefront_cells"] / (ms_step * 1e-3), "extended_bases_per_s": wf["extended_bases"] / (ms_step * 1e-3),
+            "ops": "8 per wavefront cell + 4 per 32 extended bases (SURVEY.md 8d), counted by the kernel", "traffic": None}
+
+
+def make_sharded_batch(n_pairs: int, length: int, threads: int = 8):
+    """config 3 at its stated size: generated in 500 k-pair chunks on a thread pool (numpy releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from sequencealigning_b200 import PairBatch, synth
+    chunk = 500_000
+    counts = [min(chunk, n_pairs - i) for i in range(0, n_pairs, chunk)]
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda kv: synth.random_pairs(kv[1], length, 0.05, True, seed=synth.SEEDS["config3"] + 104729 * kv[0]), enumerate(counts)))
+    base = 0
+    res, qo, ql, do, dl = [], [], [], [], []
+    for p in parts:
+        res.append(p.residues)
+        qo.append(p.q_off + np.uint64(base)); do.append(p.d_off + np.uint64(base))
+        ql.append(p.q_len); dl.append(p.d_len)
+        base += int(p.residues.size)
+    return PairBatch(np.concatenate(res), np.concatenate(qo), np.concatenate(ql), np.concatenate(do), np.concatenate(dl))
+
+
+def sharded_block(args, world: int, steps: int = 3) -> dict:
+    """BASELINE.json configs[2]: 10 M x 250 bp pairs from ONE host list through ONE sa_align_batch call on a
+    multi-device engine (sa_engine_create_multi) over all `world` GPUs: sharding, H2D, kernels, D2H and the
+    gather into input order inside the timed region.  Runs in rank 0's process; the other ranks have closed
+    their engines and wait on a CPU (gloo) barrier."""
+    from sequencealigning_b200 import Engine, _capi
+    from sequencealigning_b200.engine import PinnedResult, pin_batch
+    n = args.sharded_pairs
+    t0 = time.perf_counter()
+    batch = make_sharded_batch(n, 250)
+    gen_s = time.perf_counter() - t0
+    packed = pin_batch(batch.packed())
+    pinned_bytes = pin_batch(batch)
+    pres = PinnedResult(n, 40 * n)
+    out = {"workload": f"affine NW score+traceback, {n} synthetic 250 bp pairs at 5 % (sub:ins:del 2:1:1), ONE host pair list, "
+                       f"ONE sa_align_batch call sharding it over {world} GPU(s) (BASELINE.json configs[2])",
+           "n_gpus": world, "pairs": n, "cells": int(batch.cells), "generation_seconds_untimed": gen_s,
+           "api": "sa_engine_create_multi + sa_align_batch, pinned host buffers; host wall clock around the call"}
+    with Engine(devices=list(range(world))) as eng:
+        def timed(hb, prepare=None):
+            for _ in range(2):
+                eng.align(prepare(hb) if prepare else hb, out=pres)
+            ts = []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                r = eng.align(prepare(hb) if prepare else hb, out=pres)
+                ts.append(time.perf_counter() - t0)
+            dt = float(np.median(ts))
+            tim, shards = eng.timing(), eng.shards()
+            cells = np.array([s["cells"] for s in shards], np.float64)
+            return r, {"value": batch.cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "alignments_per_s": n / dt,
+                       "h2d_bytes_per_step": int(tim["h2d_bytes"]), "d2h_bytes_per_step": int(tim["d2h_bytes"]),
+                       "gpu_launches": int(tim["kernel_launches"]), "slowest_device_kernels_ms": tim["kernels_ms"],
+                       "cell_imbalance_max_over_mean": float(cells.max() / cells.mean()),
+                       "shards": [{"device": s["device"], "pairs": s["pairs"], "cells": s["cells"], "contiguous": s["contiguous"],
+                                   "device_ms": round(s["device_ms"], 3), "host_ms": round(s["host_ms"], 3)} for s in shards]}
+        r, e = timed(packed)
+        out.update(e)
+        out["input_format"] = "2-bit packed residues (sa_batch_t.packing = 1), pinned"
+        lib = _capi.lib()
+        src = pinned_bytes.residues
+
+        def pack_then(b):
+            assert lib.sa_pack_2bit_mt(src.ctypes.data, src.size, b.residues.ctypes.data, 0) == 0
+            return b
+
+        out["packer_included"] = timed(packed, pack_then)[1]
+        out["packer_included"].pop("shards", None)
+        out["byte_per_residue"] = timed(pinned_bytes)[1]
+        out["byte_per_residue"].pop("shards", None)
+        if not args.skip_cpu:
+            out["parity"] = parity_affine(batch, r, 3000)
+            out["cpu_baseline"] = cpu_baseline(batch, 5000, 1)
+    pres.free()
+    return out
+
+
+def extra_configs(args, eng, ctx, peak) -> dict:
+    """The other BASELINE.json configs at their stated sizes (N = 1): value, e2e, cpu_baseline, parity flag."""
+    from oracle import binding as ob
+    from sequencealigning_b200 import ALGO_NW_AFFINE, ALGO_WFA_STANDARD, PairBatch, synth
+    out = {}
+    # ---- config4: WFA, 100 k pairs of 1-10 kbp --------------------------------------------------------
+    t0 = time.perf_counter()
+    b4 = synth.config4(100_000)
+    m = measure(eng, b4, ALGO_WFA_STANDARD, steps=3, warmup=1, ctx=ctx, packed=False)
+    r4 = m.pop("result"); m.pop("timing"); m.pop("cells_all")
+    # the work counters come back with the host-buffer call (sa_last_timing.wfa_cells / wfa_extended)
+    eng.align(b4, algo=ALGO_WFA_STANDARD, cigar=False)
+    wt = eng.timing()
+    m["roofline"] = roofline_wfa(peak, {"wavefront_cells": wt["wfa_cells"], "extended_bases": wt["wfa_extended"]}, m["ms_per_step"])
+    m.update({"unit": "GCUPS (equivalent cells n1*n2)", "dtype": DTYPES["config4"],
+              "workload": "gap-affine WFA (standard mode, x=4 o=2 e=6), 100000 synthetic pairs of 1-10 kbp (log-uniform) at 1-15 % error "
+                          "(BASELINE.json configs[3]); the reference's own wfa.rs panics or never converges on these inputs: an extension, "
+                          "graded against the Gotoh cost DP"})
+    if not args.skip_cpu:
+        ob.build()
+        idx = list(range(0, 100_000, 100_000 // 12))[:12]
+        ok = all(int(r4.score[p]) == ob.wfa_standard(b4.query(p), b4.db(p)) for p in idx)
+        m["parity"] = {"ok": bool(ok), "sample": "12 pairs spread over the batch vs oracle/wfa.c sao_wfa_standard (itself checked against the Gotoh cost DP in tests)"}
+        m["cpu_baseline"] = cpu_baseline_wfa(b4, 48)
+    out["config4"] = m
+    del b4
+    # ---- config5 (WFA half): 1 k pairs of 100 kbp --------------------------------------------------------
+    b5 = synth.random_pairs(1000, 100_000, 0.05, True, seed=synth.SEEDS["config5"])
+    m = measure(eng, b5, ALGO_WFA_STANDARD, steps=2, warmup=1, ctx=ctx, packed=False)
+    r5 = m.pop("result"); m.pop("timing"); m.pop("cells_all")
+    eng.align(b5, algo=ALGO_WFA_STANDARD, cigar=False)
+    wt = eng.timing()
+    m["roofline"] = roofline_wfa(peak, {"wavefront_cells": wt["wfa_cells"], "extended_bases": wt["wfa_extended"]}, m["ms_per_step"])
+    m.update({"unit": "GCUPS (equivalent cells n1*n2)", "dtype": DTYPES["config5"],
+              "workload": "gap-affine WFA (standard mode), 1000 synthetic pairs of 100 kbp at 5 % (BASELINE.json configs[4], WFA half); score only"})
+    if not args.skip_cpu:
+        pre = PairBatch.from_pairs([(b5.query(p)[:12000], b5.db(p)[:12000]) for p in range(3)])
+        rp = eng.align(pre, algo=ALGO_WFA_STANDARD, cigar=False)
+        t0 = time.perf_counter()
+        exp = [ob.wfa_standard(pre.query(p), pre.db(p)) for p in range(3)]
+        dt = time.perf_counter() - t0
+        m["parity"] = {"ok": bool([int(v) for v in rp.score] == exp), "sample": "12 kbp prefixes of the first 3 pairs vs oracle/wfa.c sao_wfa_standard"}
+        m["cpu_baseline"] = {"value": pre.cells / dt / 1e9, "unit": "GCUPS (equivalent cells)", "cores": 1, "kind": "port", "seconds": dt,
+                             "sample": "12 kbp prefixes of the first 3 pairs, oracle/wfa.c sao_wfa_standard"}
+    out["config5_wfa"] = m
+    # ---- config5 (NW half): the same 1 k pairs through the tiled long-pair path ----------------------------
+    m = measure(eng, b5, ALGO_NW_AFFINE, steps=2, warmup=1, ctx=ctx, packed=True)
+    r5n = m.pop("result"); tim = m.pop("timing"); cells = m.pop("cells_all")
+    m.update({"unit": "GCUPS", "dtype": DTYPES["config5nw"], "roofline": roofline_long(cells, tim, peak),
+              "pairs_fallback_literal_kernel": int(tim.get("pairs_fallback", 0)),
+              "workload": "affine NW score + status + CIGAR, 1000 synthetic pairs of 100 kbp at 5 % (BASELINE.json configs[4], NW half), "
+                          "tiled long-pair path (nw_long.cuh)"})
+    if not args.skip_cpu:
+        cb = cpu_baseline_long(b5)
+        q, d = b5.query(0)[:20000], b5.db(0)[:20000]
+        pre = PairBatch.from_pairs([(q, d)] + [(b5.query(p)[:2600], b5.db(p)[:2500]) for p in range(1, 5)])
+        rp = eng.align(pre)
+        small = pre.select(np.arange(1, 5))
+        ref = ob.affine_batch(small.residues, small.q_off, small.q_len, small.d_off, small.d_len, cigar_stride=5200, n_threads=4)
+        ok = (int(rp.score[0]) == ob.affine_score(q, d) and np.array_equal(ref.score, rp.score[1:]) and np.array_equal(ref.status, rp.status[1:])
+              and all(list(ref.cigar_pool[p, :ref.cigar_len[p]]) == rp.cigar_of(p + 1) for p in range(4)))
+        m["parity"] = {"ok": bool(ok), "sample": "20 kbp prefix of pair 0: score vs the oracle's score-only DP; 2.6 kbp prefixes of pairs 1-4: score, status, "
+                                                 "CIGAR vs oracle/nw_affine.c (100 kbp pairs are pinned in tests/test_gpu_affine.py)"}
+        m["cpu_baseline"] = cb
+    out["config5_nw"] = m
+    return out
 
 
 def main():
@@ -322,184 +649,92 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the one JSON line
+        # stdout carries the one JSON line; NCCL's log (NCCL_DEBUG) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")   # CPU-side barrier for the sharded block (no kernel waits on a GPU)
 
     numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank"
-    from sequencealigning_b200 import Engine
+    from sequencealigning_b200 import ALGO_NW_AFFINE, ALGO_WFA_STANDARD, Engine
     from sequencealigning_b200.build import build_all
     build_all()
     eng = Engine(local)
     batch = make_batch(args, rank)
-    cells = batch.cells
-    stream = torch.cuda.ExternalStream(eng.stream, device=local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident leg: `value` ------------------------------------------
-    from sequencealigning_b200 import ALGO_NW_AFFINE, ALGO_WFA_STANDARD
+    ctx = (torch, dist, world, local)
     algo = ALGO_WFA_STANDARD if args.workload in WFA_WORKLOADS else ALGO_NW_AFFINE
-    rb = eng.upload(batch)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # nvidia-smi start-up happens during warm-up, not in the timed region
         time.sleep(0.5)
-    for _ in range(args.warmup):
-        rb.align(algo=algo)
-    eng.synchronize()
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    launches = 0
-    reruns = 0
-    e0.record(stream)
-    for _ in range(args.steps):
-        rb.align(algo=algo)
-        t = eng.timing()
-        launches += t["kernel_launches"]
-        reruns = t["pairs_rerun"]
-    e1.record(stream)
-    e1.synchronize()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-        ct = torch.tensor([float(cells)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(ct, op=dist.ReduceOp.SUM)
-        cells_all = float(ct.item())
-    else:
-        cells_all = float(cells)
-    ms_step = ms_total / args.steps
-    gcups = cells_all / (ms_step * 1e-3) / 1e9
-    res_dev = rb.download()
-    rb.free()
-
-    # ---------------- end-to-end leg through the reference-facing call: `e2e` ----------------
-    e2e = None
-    clocks = None
-    if args.skip_e2e and rank == 0:
-        clocks = sampler.stop()
-    if not args.skip_e2e:
-        from sequencealigning_b200.engine import PinnedResult, pin_batch
-        cap = int(res_dev.cigar.size) + 1024
-        pres = PinnedResult(batch.n_pairs, cap)
-
-        def timed_e2e(host_batch):
-            for _ in range(2):
-                eng.align(host_batch, algo=algo, out=pres)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                r = eng.align(host_batch, algo=algo, out=pres)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / args.steps
-            tim = eng.timing()
-            if world > 1:
-                tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            assert np.array_equal(r.score, res_dev.score)
-            return {"value": cells_all / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3,
-                    "h2d_bytes_per_step": int(tim["h2d_bytes"]), "d2h_bytes_per_step": int(tim["d2h_bytes"]),
-                    "alignments_per_s": args.pairs * world / dt}
-
-        by_bytes = timed_e2e(pin_batch(batch))
-        clocks = sampler.stop() if rank == 0 else None
-        if args.workload in WFA_WORKLOADS:
-            e2e = by_bytes
-            e2e["input_format"] = "byte per residue (sa_batch_t.packing = 0)"
-        else:
-            # The product's input is what its packer writes (north star: "a packer that writes 2-bit
-            # DNA ... into pinned batches"): sa_batch_t.packing = 1, produced by sa_pack_2bit before
-            # the timed region, like FASTA parsing.  The byte-per-residue format is timed beside it.
-            t0 = time.perf_counter()
-            packed = batch.packed()
-            pack_s = time.perf_counter() - t0
-            e2e = timed_e2e(pin_batch(packed))
-            e2e["input_format"] = "2-bit packed residues (sa_batch_t.packing = 1), pinned"
-            e2e["packer_host_seconds_untimed"] = pack_s
-            e2e["byte_per_residue"] = by_bytes
-        e2e["api"] = "sa_align_batch (C ABI) with pinned host buffers; host wall clock, max over ranks"
+    m = measure(eng, batch, algo, args.steps, args.warmup, ctx, e2e=not args.skip_e2e, packed=args.workload not in WFA_WORKLOADS)
+    clocks = sampler.stop() if rank == 0 else None
+    res_dev, tim, cells_all = m.pop("result"), m.pop("timing"), m.pop("cells_all")
+    e2e = m.get("e2e")
+    if e2e is not None:
         e2e["host_binding"] = numa
+    gcups, ms_step = m["value"], m["ms_per_step"]
 
+    out = None
     if rank == 0:
         peak = int_peak()
-        step_issued = gcups * 1e9 * OPS_PER_CELL_ISSUED / world
-        tb_bytes = cells / 2.0
-        hbm_bytes = tb_bytes + batch.residues.size + batch.n_pairs * (24 + 17) + res_dev.cigar.size * 4
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        ipeak = peak["issue_lane_ops_per_s"]
-        roof = None
-        if args.workload not in WFA_WORKLOADS and args.workload != "config5nw":
-            pr = fill_kernel_probe(batch, local)
-            k_cups = pr["cells"] / (pr["ms"] * 1e-3)
-            roof = {
-                "bound": "int-issue (integer max-plus DP: neither HBM nor tensor cores bind; DESIGN.md 4.1)",
-                "kernel": "nw_affine_fill_s16<K,G> (150 bp: K=19 columns per lane, G=8 lanes per pair-of-pairs, single pass)",
-                "achieved": k_cups * OPS_PER_CELL_ISSUED / 1e12, "peak": ipeak / 1e12, "unit": "T lane-instr/s",
-                "frac": k_cups * OPS_PER_CELL_ISSUED / ipeak,
-                "lane_instr_per_cell": OPS_PER_CELL_ISSUED,
-                "launch": {"pairs": pr["pairs"], "cells": pr["cells"], "ms": pr["ms"], "gcups": k_cups / 1e9,
-                           "timed": "one fill launch alone, CUDA events on its stream, median of 7 after 3 warm-ups"},
-                "whole_step_frac": step_issued / ipeak,
-                # SURVEY.md 8d's algorithmic count (16 s32 ops per cell for score + 4-bit traceback); the packed
-                # u16x2 recurrence does that work in 8 issued instructions, so this ratio can pass 1
-                "s32_equivalent": {"ops_per_cell": OPS_PER_CELL_S32_EQUIV, "achieved": k_cups * OPS_PER_CELL_S32_EQUIV / 1e12,
-                                   "frac": k_cups * OPS_PER_CELL_S32_EQUIV / ipeak},
-                "traffic": (14133 + 325) * pr["pairs"] if args.length == 150 else None,
-                "traffic_detail": {"unit": "DRAM bytes per fill launch",
-                                   "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
-                                   "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14458 B per 150 bp pair: 96-bit rows of 19 four-bit cells, rows padded to the tile)"},
-                "per_gpu": True,
-                "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
-                        "/ fill-kernel time, i.e. the share of all issue slots doing recurrence work; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",
-                "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                        "bytes": "sequences + 0.5 B/cell traceback written + results, whole step"},
-            }
         out = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16x2 (packed pairs; exact integer)",
-            "data": "synthetic", "config": workload_config(args, world),
-            "alignments_per_s": args.pairs * world / (ms_step * 1e-3),
-            "gpu_launches": int(launches // max(args.steps, 1)), "pairs_rerun_per_step": int(reruns),
-            "clocks": clocks, "e2e": e2e,
-            "roofline": roof,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.workload],
+            "data": "synthetic", "config": workload_config(args, world), "alignments_per_s": m["alignments_per_s"],
+            "gpu_launches": m["gpu_launches"], "pairs_rerun_per_step": int(tim.get("pairs_rerun", 0)),
+            "clocks": clocks, "e2e": e2e, "roofline": None,
         }
         if args.workload == "config5nw":
-            out["roofline"] = {"bound": "int-issue", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
-                               "note": "literal 32-bit recurrences + DFS first-event bookkeeping, ~140 lane-instructions per cell "
-                                       "(nw_general.cuh); not the packed hot kernel, no roofline claimed"}
+            out["roofline"] = roofline_long(float(batch.cells), tim, peak)
             if not args.skip_cpu:
                 out["cpu_baseline"] = cpu_baseline_long(batch)
         elif args.workload in WFA_WORKLOADS:
-            out["roofline"] = {"bound": "latency (wavefront dependency chain)", "achieved": None, "peak": None, "unit": None,
-                               "frac": None, "traffic": None,
-                               "note": "WFA does O(s^2) work, not n1*n2: GCUPS here is equivalent cells; no roofline is claimed this round"}
+            out["roofline"] = {"bound": "latency (wavefront dependency chain)", "achieved": None, "peak": None, "unit": None, "frac": None,
+                               "traffic": None, "note": "WFA does O(s^2) work, not n1*n2: GCUPS here is equivalent cells"}
             if not args.skip_cpu:
                 out["cpu_baseline"] = cpu_baseline_wfa(batch, args.cpu_sample or (64 if args.workload == "config4" else 1))
-        elif not args.skip_cpu:
-            n_sample = args.cpu_sample or 20000
-            out["cpu_baseline"] = cpu_baseline(batch, n_sample, 1)
-            cores = os.cpu_count() or 1
-            allc = cpu_baseline(batch, n_sample * min(cores, 8), cores)
-            out["cpu_baseline"]["all_cores"] = {"value": allc["value"], "cores": cores, "unit": "GCUPS"}
+        else:
+            out["roofline"] = roofline_fill(batch, ms_step, gcups, world, local, res_dev, args, peak, hbm_peak)
+            if not args.skip_cpu:
+                out["parity"] = parity_affine(batch, res_dev)
+                n_sample = args.cpu_sample or 20000
+                out["cpu_baseline"] = cpu_baseline(batch, n_sample, 1)
+                cores = os.cpu_count() or 1
+                allc = cpu_baseline(batch, n_sample * min(cores, 8), cores)
+                out["cpu_baseline"]["all_cores"] = {"value": allc["value"], "cores": cores, "unit": "GCUPS"}
+        # the other BASELINE.json configs at their stated sizes (one GPU; rank 0's engine)
+        if args.configs == "all" and args.workload == "config2" and world == 1:
+            try:
+                out["configs"] = extra_configs(args, eng, ctx, peak)
+            except Exception as ex:   # an extra block must never cost the headline line
+                out["configs"] = {"error": f"{type(ex).__name__}: {ex}"}
+    del res_dev
+    eng.close()
+    torch.cuda.empty_cache()
+    # ---- config 3 from ONE host list through ONE multi-device call (rank 0 drives all GPUs) ----------------
+    if args.configs in ("all", "sharded") and args.workload == "config2":
+        if world > 1:
+            dist.barrier(group=gloo)     # every rank has released its GPU
+        if rank == 0:
+            try:
+                out["sharded"] = sharded_block(args, world)
+            except Exception as ex:
+                out["sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if world > 1:
+            dist.barrier(group=gloo)
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=gloo)
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -118,13 +118,21 @@ typedef struct {
   uint64_t cigar_used;     /* OUT: words written (or needed, on SA_E_CIGAR_CAPACITY)         */
 } sa_result_t;
 
-/* Kernel-time breakdown of the last call (device milliseconds from CUDA events). */
+/* Time breakdown of the last call: device milliseconds from CUDA events on the launching streams,
+ * except wall_ms.  On a multi-device engine: the slowest device's times, sums of the counters. */
 typedef struct {
-  double h2d_ms, fill_ms /* all kernels of the call */, walk_ms /* main fill kernel only */, d2h_ms, total_ms;
+  double kernels_ms;      /* first to last kernel of the call                                 */
+  double fill_ms;         /* packed fill kernels alone (nw_affine_fill_s16), summed over segments */
+  double long_fwd_ms;     /* tiled long-pair forward launches (nw_long_fwd), summed over waves */
+  double long_back_ms;    /* their classification + traceback kernels (nw_long_back)          */
+  double wall_ms;         /* host wall clock of sa_align_batch (copies included)              */
   uint64_t cells;         /* sum over pairs of n1*n2                                          */
   uint64_t kernel_launches;
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t pairs_rerun;   /* pairs re-filled without the panic-detection bonus                */
+  uint64_t pairs_fallback; /* long pairs handed from the tiled path to the literal kernel     */
+  uint64_t wfa_cells;     /* SA_ALGO_WFA_STANDARD: wavefront cells computed    */
+  uint64_t wfa_extended;  /* .. and residues passed by the extend step                        */
 } sa_timing_t;
 
 /* -- lifecycle ------------------------------------------------------------------------ */
@@ -224,6 +232,19 @@ sa_status_t sa_affine_count_cooptimal(sa_engine_t* e, const sa_scheme_t* scheme,
 /* Packer for packing = 1: appends n residues (A/C/G/T) to dst starting at residue index dst_pos.
  * SA_E_ARG at the first other byte.  Pure host code. */
 sa_status_t sa_pack_2bit(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_pos);
+/* The same for a whole buffer on n_threads host threads (0 = all): src[0, n) -> dst[0, (n+3)/4). */
+sa_status_t sa_pack_2bit_mt(const uint8_t* src, uint64_t n, uint8_t* dst, int n_threads);
+
+/* parse_fasta with the packer fused in (the north star's "parse.rs gains a packer"): as
+ * sa_parse_fasta, and `packed` (>= (out bytes + 3) / 4 bytes; pinned memory for the engine to
+ * stream from) receives the 2-bit codes of the WHOLE output buffer -- byte i of `out` at bits
+ * 2*(i&3) of packed[i>>2], header bytes and 'N' coding as 0 -- so the (seq_off, seq_len) of
+ * `index` address both formats.  *all_acgt = 1 when no record sequence holds an 'N': only then
+ * may a batch built on `packed` use packing = 1.  *out_len = bytes written to `out`.
+ * Chunk-parallel like sa_parse_fasta (SA_HOST_THREADS, default all cores, at most 32). */
+int64_t sa_parse_fasta_packed(const char* path, uint8_t* out, size_t out_cap, uint64_t* index, size_t index_cap,
+                              uint8_t* err_chars, size_t err_cap, size_t* n_err, uint8_t* packed, size_t packed_cap,
+                              int* all_acgt, uint64_t* out_len);
 
 /* The text the reference prints for one alignment (needleman_wunsch_affine.rs:283-286 and
  * Display :390-411): "alignment found\n\nseq1: ..\n      ..\nseq2: ..\n".  snprintf-style:

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
     "sa_affine_count_cooptimal", "sa_engine_create_multi", "sa_engine_device_count", "sa_last_shards", "sa_plan_shards",
+    "sa_pack_2bit_mt", "sa_parse_fasta_packed",
 ]
 
 
@@ -50,9 +51,10 @@ class Result(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [
-        ("h2d_ms", C.c_double), ("fill_ms", C.c_double), ("walk_ms", C.c_double), ("d2h_ms", C.c_double),
-        ("total_ms", C.c_double), ("cells", C.c_uint64), ("kernel_launches", C.c_uint64),
-        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("pairs_rerun", C.c_uint64),
+        ("kernels_ms", C.c_double), ("fill_ms", C.c_double), ("long_fwd_ms", C.c_double), ("long_back_ms", C.c_double),
+        ("wall_ms", C.c_double), ("cells", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("pairs_rerun", C.c_uint64), ("pairs_fallback", C.c_uint64),
+        ("wfa_cells", C.c_uint64), ("wfa_extended", C.c_uint64),
     ]
 
 
@@ -121,6 +123,11 @@ def lib() -> C.CDLL:
     l.sa_render_affine.restype = C.c_int64
     l.sa_pack_2bit.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     l.sa_pack_2bit.restype = C.c_int
+    l.sa_pack_2bit_mt.argtypes = [vp, C.c_uint64, vp, C.c_int]
+    l.sa_pack_2bit_mt.restype = C.c_int
+    l.sa_parse_fasta_packed.argtypes = [C.c_char_p, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t),
+                                        vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    l.sa_parse_fasta_packed.restype = C.c_int64
     l.sa_affine_all_alignments.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(Scheme), C.c_uint64,
                                            C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     l.sa_affine_all_alignments.restype = C.c_int64

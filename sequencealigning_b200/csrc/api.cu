@@ -87,7 +87,7 @@ sa_status_t sa_last_shards(const sa_engine_t* e, sa_shard_info_t* out, int cap, 
     out->h2d_bytes = e->timing.h2d_bytes;
     out->d2h_bytes = e->timing.d2h_bytes;
     out->kernel_launches = e->timing.kernel_launches;
-    out->device_ms = e->timing.fill_ms;
+    out->device_ms = e->timing.kernels_ms;
   }
   return SA_OK;
 }

@@ -471,7 +471,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   auto plan_fast = [&](const std::vector<uint32_t>& ids, uint64_t room) -> FastPlan {
     FastPlan fp_;
     const size_t nl = ids.size();
-    fp_.S = e->long_s ? e->long_s : (nl >= 64 ? 4u : (nl >= 16 ? 2u : 1u));
+    // (measured, 256 x 50 kbp: S = 2 is ~10 % faster than S = 4; S = 4 halves the kept column edges)
+    fp_.S = e->long_s ? e->long_s : (nl >= 16 ? 2u : 1u);
     fp_.R = e->long_r ? e->long_r : (nl >= 64 ? 1024u : (nl >= 16 ? 512u : 256u));
     // backward warps: two CTAs of four per SM (shared memory bound), no more than pairs
     fp_.back_warps = (uint32_t)std::min<uint64_t>(((uint64_t)nl + 3) / 4 * 4, (uint64_t)e->sm_count * 8);
@@ -482,16 +483,19 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       *col = (tc - 1) * ((uint64_t)b + 1);
       *ck = (((uint64_t)b - 1) / sa::kLongMr) * n1pad;
     };
-    // wider tiles (fewer kept column edges) when even one pair would not fit otherwise
+    // wider tiles (fewer kept column edges): to S = 4 when that lets all pairs share one wave,
+    // beyond when even one pair would not fit otherwise
     for (;;) {
-      uint64_t worst = 0;
+      uint64_t worst = 0, total = 0;
       for (uint32_t id : ids) {
         uint64_t r, c, k;
         edges_of(h_cols[id], h_rows[id], fp_.S, &r, &c, &k);
         worst = std::max(worst, (r + c + k) * 8);
+        total += (r + c + k) * 8;
       }
       const uint64_t back = (uint64_t)fp_.back_warps * fp_.S * 32 * sa::kLongMr * 8;
-      if (worst + back <= room || fp_.S >= 16 || e->long_s) break;
+      const bool fits = fp_.S < 4 ? total + back <= room : worst + back <= room;
+      if (fits || fp_.S >= 16 || e->long_s) break;
       fp_.S *= 2;
     }
     const uint64_t back = (uint64_t)fp_.back_warps * fp_.S * 32 * sa::kLongMr * 8;
@@ -888,7 +892,9 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     CUDA_TRY(e, cudaMemsetAsync(d_next, 0, (fq.waves.size() + 1) * 4, sx));
     const size_t smem_f = (size_t)sa::kLongWarps * sa::long_smem_per_warp(fq.R, fq.S > 1);
     const size_t smem_b = (size_t)sa::kLongWarps * sa::long_smem_per_warp(sa::kLongMr, true);
-    for (auto kv : {std::make_pair((const void*)sa::nw_long_fwd, smem_f), std::make_pair((const void*)sa::nw_long_back, smem_b)}) {
+    const bool minb5 = e->long_minb == 5;
+    const void* fwd_fn = minb5 ? (const void*)sa::nw_long_fwd<5> : (const void*)sa::nw_long_fwd<4>;
+    for (auto kv : {std::make_pair(fwd_fn, smem_f), std::make_pair((const void*)sa::nw_long_back, smem_b)}) {
       size_t& configured = e->smem_configured[kv.first];
       if (kv.second > configured) {
         CUDA_TRY(e, cudaFuncSetAttribute(kv.first, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -931,6 +937,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       lw.flag = d_flag + w.lo;
       lw.next_back = d_next + wv;
       const uint32_t ndiag = w.tr_max + w.tc_max - 1;
+      if (wv == 0) CUDA_TRY(e, cudaEventRecord(sl.ev_l0, sx));
       for (uint32_t d = 0; d < ndiag; ++d) {
         const uint32_t i_lo = d >= w.tc_max ? d - (w.tc_max - 1) : 0u, i_hi = std::min(d, w.tr_max - 1);
         const uint32_t tiles = i_hi - i_lo + 1;
@@ -944,16 +951,20 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           ly.col_off = lw.col_off + y0;
           ly.ck_off = lw.ck_off + y0;
           ly.end_h = lw.end_h + y0;
-          sa::nw_long_fwd<<<dim3((tiles + sa::kLongWarps - 1) / sa::kLongWarps, ny), 32 * sa::kLongWarps, smem_f, sx>>>(ly);
+          const dim3 grid((tiles + sa::kLongWarps - 1) / sa::kLongWarps, ny);
+          if (minb5) sa::nw_long_fwd<5><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
+          else sa::nw_long_fwd<4><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
           e->timing.kernel_launches++;
         }
       }
       CUDA_TRY(e, cudaGetLastError());
+      if (wv + 1 == fq.waves.size()) CUDA_TRY(e, cudaEventRecord(sl.ev_l1, sx));  // (several waves: the last one's split)
       sa::nw_long_classify<<<(cnt + 127) / 128, 128, 0, sx>>>(lw);
       sa::nw_long_back<<<(std::min(fq.back_warps, (cnt + 3) / 4 * 4) + sa::kLongWarps - 1) / sa::kLongWarps, 32 * sa::kLongWarps, smem_b, sx>>>(lw);
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches += 2;
     }
+    CUDA_TRY(e, cudaEventRecord(sl.ev_l2, sx));
     return SA_OK;
   };
   auto fast_runs_to_pool = [&](const FastPlan& fq, sa_engine::Slot& sl, cudaStream_t sx) -> sa_status_t {
@@ -1051,11 +1062,17 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaStreamSynchronize(e->stream));
       std::sort(ids.begin(), ids.end());
       if (getenv("SA_TRACE")) fprintf(stderr, "[sa trace]   %u long pair(s) handed to the literal kernel\n", n_fb);
+      e->timing.pairs_fallback += n_fb;
       fbp = plan_literal(ids, budget_re);
       if ((r = launch_literal(fbp, e->fb_lit, e->stream)) != SA_OK) return r;
     }
     float fms = 0;
-    if (cudaEventElapsedTime(&fms, sl.ev_f0, sl.ev_f1) == cudaSuccess) e->timing.walk_ms += fms;
+    if (cudaEventElapsedTime(&fms, sl.ev_f0, sl.ev_f1) == cudaSuccess) e->timing.fill_ms += fms;
+    if (!sg.fast.ids.empty()) {
+      if (cudaEventElapsedTime(&fms, sl.ev_l0, sl.ev_l1) == cudaSuccess) e->timing.long_fwd_ms += fms;
+      if (cudaEventElapsedTime(&fms, sl.ev_l1, sl.ev_l2) == cudaSuccess) e->timing.long_back_ms += fms;
+    }
+    cudaGetLastError();
     const uint64_t tiles_re = std::max<uint64_t>(1, std::min<uint64_t>(ctiles, std::max<uint64_t>(1, budget_re / tile_bytes)));
     const uint32_t sb = (cn + sa::kScanBlock - 1) / sa::kScanBlock;
     if (n_re) {
@@ -1322,7 +1339,10 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 8);
     if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4 + n * 4)) != SA_OK) return st;
     uint32_t* d_next = (uint32_t*)e->misc.p + 8;
+    unsigned long long* d_work = (unsigned long long*)((uint8_t*)e->misc.p + 64);
     CUDA_TRY(e, cudaMemsetAsync(d_next, 0, 4, e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(d_work, 0, 16, e->stream));
+    wp.work = d_work;
     wp.scratch = (int32_t*)e->wfa_scratch.p;
     wp.scratch_stride = stride;
     wp.width = width;
@@ -1348,6 +1368,7 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     sa::wfa_standard_kernel<<<blocks, warps_per_block * 32, smem, e->stream>>>(wp);
     CUDA_TRY(e, cudaGetLastError());
     e->timing.kernel_launches++;
+    if (out) CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 12, d_work, 16, cudaMemcpyDeviceToHost, e->stream));
   }
   CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->stream));
   if (out) {
@@ -1357,6 +1378,10 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     if (out->cigar_off) memset(out->cigar_off, 0, n * 8);
     e->timing.d2h_bytes += n * 5;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (!literal) {
+      memcpy(&e->timing.wfa_cells, e->h_count + 12, 8);
+      memcpy(&e->timing.wfa_extended, e->h_count + 14, 8);
+    }
   }
   return SA_OK;
 }
@@ -1440,8 +1465,8 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   for (cudaEvent_t* ev : {&e->ev_in, &e->ev_done, &e->ev_carry[0], &e->ev_carry[1], &e->slot[0].ev_count, &e->slot[1].ev_count,
                           &e->slot[0].ev_bdone, &e->slot[1].ev_bdone})
     CUDA_TRY(e, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
-  for (cudaEvent_t* ev : {&e->ev_t0, &e->ev_t1, &e->slot[0].ev_f0, &e->slot[0].ev_f1, &e->slot[1].ev_f0,
-                          &e->slot[1].ev_f1})
+  for (cudaEvent_t* ev : {&e->ev_t0, &e->ev_t1, &e->slot[0].ev_f0, &e->slot[0].ev_f1, &e->slot[1].ev_f0, &e->slot[1].ev_f1,
+                          &e->slot[0].ev_l0, &e->slot[0].ev_l1, &e->slot[0].ev_l2, &e->slot[1].ev_l0, &e->slot[1].ev_l1, &e->slot[1].ev_l2})
     CUDA_TRY(e, cudaEventCreate(ev));
   CUDA_TRY(e, cudaMallocHost((void**)&e->h_count, 64));
   if (const char* s = getenv("SA_FORCE_G")) e->force_g = atoi(s);
@@ -1450,6 +1475,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_LITERAL")) e->long_literal = atoi(s) != 0;
   if (const char* s = getenv("SA_LONG_S")) e->long_s = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_R")) e->long_r = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);
@@ -1482,7 +1508,8 @@ sa_status_t sd_destroy(sa_engine* e) {
       if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : {e->ev_in, e->ev_done, e->ev_carry[0], e->ev_carry[1], e->ev_t0, e->ev_t1, e->slot[0].ev_count,
                            e->slot[0].ev_f0, e->slot[0].ev_f1, e->slot[1].ev_count, e->slot[1].ev_f0,
-                           e->slot[1].ev_f1, e->slot[0].ev_bdone, e->slot[1].ev_bdone})
+                           e->slot[1].ev_f1, e->slot[0].ev_bdone, e->slot[1].ev_bdone, e->slot[0].ev_l0, e->slot[0].ev_l1,
+                           e->slot[0].ev_l2, e->slot[1].ev_l0, e->slot[1].ev_l1, e->slot[1].ev_l2})
       if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     cudaStreamDestroy(e->stream);
@@ -1685,6 +1712,7 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     return fail(e, SA_E_ARG, "null input array");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const uint64_t n = b->n_pairs;
+  const auto t_call = std::chrono::steady_clock::now();
   e->timing = sa_timing_t{};
   res->cigar_used = 0;
   bool not_impl = false;
@@ -1730,7 +1758,8 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     db.packing = b->packing;
     st = run_wfa(e, db, n, b->q_len, b->d_len, scheme, algo == SA_ALGO_WFA, b, res);
     float ms = 0;
-    if (st == SA_OK && cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.fill_ms = ms;
+    if (st == SA_OK && cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.kernels_ms = ms;
+    e->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     cudaGetLastError();
     return st;
   }
@@ -1787,9 +1816,9 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
   CUDA_TRY(e, cudaStreamSynchronize(e->s_out));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.fill_ms = ms;
+  if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.kernels_ms = ms;
   cudaGetLastError();
-  e->timing.total_ms = e->timing.fill_ms;
+  e->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
   return rc;
 }
 

@@ -82,6 +82,7 @@ struct sa_engine {
                                          // copies of other segments then get SMs as fill CTAs retire,
                                          // instead of queueing behind a whole fill
     cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
+    cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr, ev_l2 = nullptr;  // tiled long pairs: forward start / end, traceback end
   } slot[2];
   // scratch (grow-only)
   DevBuf tb2, end2, misc, block_sums, wfa_scratch, par_bytes, par_rows, par_in;
@@ -95,6 +96,7 @@ struct sa_engine {
   bool long_ckpt_always = false;  // SA_LONG_CKPT: checkpointed traceback for every long pair (tests)
   bool long_literal = false;      // SA_LONG_LITERAL: affine long pairs through the literal kernel only (tests)
   uint32_t long_s = 0, long_r = 0;  // SA_LONG_S / SA_LONG_R: tile shape of the tiled long-pair path (0 = auto)
+  uint32_t long_minb = 4;           // SA_LONG_MINB: register allocation of nw_long_fwd (4 or 5 CTAs per SM)
   LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;
   size_t tb_budget = 0;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <exception>
 #include <memory>
 #include <new>
 #include <sys/stat.h>
@@ -39,20 +40,91 @@ struct RecordSpan {
   uint64_t name_off, name_len, seq_off, seq_len;
 };
 
-}  // namespace
+// ---- 2-bit packer ---------------------------------------------------------------------------------
+// Two residues per table look-up: tab[b0 | b1 << 8] = code(b0) | code(b1) << 2, or 0xFF when either
+// byte is not A/C/G/T (A=0 C=1 G=2 T=3).  64 KB, built once; a look-up per two bytes does the
+// validation and the coding together.
+struct PackTable {
+  uint8_t strict[65536];   // 0xFF for any other byte
+  uint8_t lenient[65536];  // other bytes code as 0 (names, 'N': the caller knows whether it matters)
+  PackTable() {
+    int code[256];
+    for (int i = 0; i < 256; ++i) code[i] = -1;
+    code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3;
+    for (int b1 = 0; b1 < 256; ++b1)
+      for (int b0 = 0; b0 < 256; ++b0) {
+        const int c0 = code[b0], c1 = code[b1];
+        strict[b0 | (b1 << 8)] = (c0 < 0 || c1 < 0) ? 0xFF : (uint8_t)(c0 | (c1 << 2));
+        lenient[b0 | (b1 << 8)] = (uint8_t)((c0 < 0 ? 0 : c0) | ((c1 < 0 ? 0 : c1) << 2));
+      }
+  }
+};
+const PackTable& pack_table() {
+  static const PackTable t;
+  return t;
+}
 
-extern "C" {
+// packs src[0, n) to whole bytes at dst (n a multiple of 4 except for the last call of a buffer);
+// STRICT: returns false at the first byte that is not A/C/G/T
+template <bool STRICT>
+bool pack_run(const uint8_t* src, uint64_t n, uint8_t* dst) {
+  const uint8_t* tab = STRICT ? pack_table().strict : pack_table().lenient;
+  uint64_t k = 0;
+  for (; k + 8 <= n; k += 8) {
+    uint16_t w[4];
+    memcpy(w, src + k, 8);
+    const uint8_t a = tab[w[0]], b = tab[w[1]], c = tab[w[2]], d = tab[w[3]];
+    if (STRICT && ((a | b | c | d) & 0xF0)) return false;  // (valid entries are 0 .. 15)
+    dst[k >> 2] = (uint8_t)(a | (b << 4));
+    dst[(k >> 2) + 1] = (uint8_t)(c | (d << 4));
+  }
+  for (; k < n; k += 4) {
+    uint8_t v = 0;
+    for (uint64_t j = 0; j < 4 && k + j < n; ++j) {
+      const uint8_t t = tab[src[k + j] | ('A' << 8)];
+      if (STRICT && t == 0xFF) return false;
+      v |= (uint8_t)((t & 3) << (2 * j));
+    }
+    dst[k >> 2] = v;
+  }
+  return true;
+}
 
-int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t* index,
-                       size_t index_cap, uint8_t* err_chars, size_t err_cap, size_t* n_err) {
+// src[0, n) -> dst bytes [0, ceil(n / 4)), over `nt` threads on 4-residue boundaries
+template <bool STRICT>
+bool pack_parallel(const uint8_t* src, uint64_t n, uint8_t* dst, unsigned nt) {
+  if (n < ((uint64_t)1 << 20) || nt <= 1) return pack_run<STRICT>(src, n, dst);
+  std::vector<uint8_t> ok(nt, 1);
+  std::vector<std::thread> th;
+  const uint64_t per = ((n / nt) + 3) & ~(uint64_t)3;
+  for (unsigned k = 0; k < nt; ++k)
+    th.emplace_back([&, k] {
+      const uint64_t lo = std::min(n, per * k), hi = (k + 1 == nt) ? n : std::min(n, per * (k + 1));
+      if (lo < hi) ok[k] = pack_run<STRICT>(src + lo, hi - lo, dst + (lo >> 2)) ? 1 : 0;
+    });
+  for (auto& t : th) t.join();
+  for (unsigned k = 0; k < nt; ++k)
+    if (!ok[k]) return false;
+  return true;
+}
+
+unsigned host_threads() {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (const char* s = getenv("SA_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(s));
+  return std::max(1u, std::min(nt, 32u));
+}
+
+int64_t parse_impl(const char* path, uint8_t* out, size_t out_cap, uint64_t* index, size_t index_cap, uint8_t* err_chars,
+                   size_t err_cap, size_t* n_err, uint8_t* packed, size_t packed_cap, int* all_acgt, uint64_t* out_len) {
   if (n_err) *n_err = 0;
+  if (all_acgt) *all_acgt = 1;
+  if (out_len) *out_len = 0;
   if (!path) return SA_E_ARG;
   // parse.rs:55-60: anything but .fa/.fasta/.fna is FastaError(InvalidInput)
   if (!(has_ext(path, "fa") || has_ext(path, "fasta") || has_ext(path, "fna"))) return SA_E_ARG;
   const int fd = open(path, O_RDONLY);
   if (fd < 0) return SA_E_ARG;  // parse.rs:62 `read(path)?`
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = std::max(1u, std::min(nt, 16u));
+  unsigned nt = host_threads();
   // The whole file in one (uninitialised) buffer.  A regular file is read by all threads at once
   // (pread of disjoint ranges); anything else (pipe, /dev/stdin) by a plain read loop.
   std::unique_ptr<uint8_t[]> storage;
@@ -135,6 +207,7 @@ int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t*
     std::vector<RecordSpan> recs;     // offsets relative to the chunk's start
     std::vector<uint8_t> errs;        // first err_cap offending bytes, in order
     size_t nerr = 0;
+    bool has_n = false;               // a sequence holds an allowed byte that is not A/C/G/T ('N')
   };
   std::vector<Chunk> chunks(nt);
   auto work = [&](unsigned k) {
@@ -166,6 +239,7 @@ int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t*
       while (q < end && allowed(*q)) ++q;
       if (q > p) {
         if (have_rec) {
+          if (!ch.has_n && memchr(p, 'N', (size_t)(q - p))) ch.has_n = true;
           memmove(w, p, (size_t)(q - p));
           w += q - p;
           r.seq_len += (uint64_t)(q - p);
@@ -225,12 +299,59 @@ int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t*
     for (auto& t : th) t.join();
   }
   if (n_err) *n_err = nerr;
+  if (out_len) *out_len = cur;
+  const auto t_gather = std::chrono::steady_clock::now();
+  // The packer, fused into the parse: the 2-bit codes of the WHOLE output buffer (names and 'N'
+  // code as 0), so the record offsets of `index` address both formats.
+  if (packed && out) {
+    const uint64_t have = std::min<uint64_t>(cur, out_cap);
+    if ((have + 3) / 4 > packed_cap) return SA_E_ARG;
+    pack_parallel<false>(out, have, packed, nt);
+  }
+  if (all_acgt)
+    for (const Chunk& ch : chunks)
+      if (ch.has_n) *all_acgt = 0;
   if (trace)
-    fprintf(stderr, "[sa trace] parse_fasta %zu bytes, %u threads: parse %.1f ms, gather %.1f ms\n", size, nt,
+    fprintf(stderr, "[sa trace] parse_fasta %zu bytes, %u threads: parse %.1f ms, gather %.1f ms, pack %.1f ms\n", size, nt,
             std::chrono::duration<double, std::milli>(t_parse - t_read).count(),
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parse).count());
+            std::chrono::duration<double, std::milli>(t_gather - t_parse).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_gather).count());
   return nrec;
 }
+
+}  // namespace
+
+extern "C" {
+
+int64_t sa_parse_fasta(const char* path, uint8_t* out, size_t out_cap, uint64_t* index, size_t index_cap,
+                       uint8_t* err_chars, size_t err_cap, size_t* n_err) {
+  try {
+    return parse_impl(path, out, out_cap, index, index_cap, err_chars, err_cap, n_err, nullptr, 0, nullptr, nullptr);
+  } catch (const std::exception&) {
+    return SA_E_NOMEM;
+  }
+}
+
+int64_t sa_parse_fasta_packed(const char* path, uint8_t* out, size_t out_cap, uint64_t* index, size_t index_cap,
+                              uint8_t* err_chars, size_t err_cap, size_t* n_err, uint8_t* packed, size_t packed_cap,
+                              int* all_acgt, uint64_t* out_len) {
+  try {
+    return parse_impl(path, out, out_cap, index, index_cap, err_chars, err_cap, n_err, packed, packed_cap, all_acgt, out_len);
+  } catch (const std::exception&) {
+    return SA_E_NOMEM;
+  }
+}
+
+sa_status_t sa_pack_2bit_mt(const uint8_t* src, uint64_t n, uint8_t* dst, int n_threads) {
+  if (n && (!src || !dst)) return SA_E_ARG;
+  try {
+    const unsigned nt = n_threads > 0 ? (unsigned)n_threads : host_threads();
+    return pack_parallel<true>(src, n, dst, nt) ? SA_OK : SA_E_ARG;
+  } catch (const std::exception&) {
+    return SA_E_NOMEM;
+  }
+}
+
 
 // 2-bit packer for sa_batch_t.packing = 1: appends n residues (A, C, G, T only) to `dst`
 // starting at residue index dst_pos.  Returns SA_OK, or SA_E_ARG at the first other byte

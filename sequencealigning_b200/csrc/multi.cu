@@ -234,6 +234,7 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
   if (b->n_pairs && (!b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len)))
     return fail(e, SA_E_ARG, "null input array");
   const uint64_t n = b->n_pairs;
+  const auto t_call = std::chrono::steady_clock::now();
   e->timing = sa_timing_t{};
   e->err.clear();
   res->cigar_used = 0;
@@ -268,7 +269,7 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     si.h2d_bytes = c->timing.h2d_bytes;
     si.d2h_bytes = c->timing.d2h_bytes;
     si.kernel_launches = c->timing.kernel_launches;
-    si.device_ms = c->timing.fill_ms;
+    si.device_ms = c->timing.kernels_ms;
     si.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
 
@@ -448,10 +449,15 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     e->timing.h2d_bytes += t.h2d_bytes;
     e->timing.d2h_bytes += t.d2h_bytes;
     e->timing.pairs_rerun += t.pairs_rerun;
-    e->timing.walk_ms = std::max(e->timing.walk_ms, t.walk_ms);
+    e->timing.pairs_fallback += t.pairs_fallback;
+    e->timing.wfa_cells += t.wfa_cells;
+    e->timing.wfa_extended += t.wfa_extended;
+    e->timing.kernels_ms = std::max(e->timing.kernels_ms, t.kernels_ms);
     e->timing.fill_ms = std::max(e->timing.fill_ms, t.fill_ms);
+    e->timing.long_fwd_ms = std::max(e->timing.long_fwd_ms, t.long_fwd_ms);
+    e->timing.long_back_ms = std::max(e->timing.long_back_ms, t.long_back_ms);
   }
-  e->timing.total_ms = e->timing.fill_ms;
+  e->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
   return SA_OK;
 }
 

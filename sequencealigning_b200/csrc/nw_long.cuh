@@ -335,7 +335,9 @@ __device__ __forceinline__ uint32_t long_tc(uint32_t n1, uint32_t S) { return (n
 __device__ __forceinline__ uint32_t long_n1pad(uint32_t n1) { return (n1 + kLongStrip - 1) / kLongStrip * kLongStrip; }
 
 // Forward pass, one launch per tile anti-diagonal: grid (tiles / 4, pairs), 4 warps per CTA.
-__global__ void __launch_bounds__(32 * kLongWarps) nw_long_fwd(const LongParams p) {
+// MINB: resident CTAs per SM the register allocation is held to (4 -> 128 registers, 5 -> 102).
+template <int MINB>
+__global__ void __launch_bounds__(32 * kLongWarps, MINB) nw_long_fwd(const LongParams p) {
   extern __shared__ __align__(16) uint8_t long_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t k = blockIdx.y;

@@ -49,6 +49,7 @@ struct WfaParams {
   uint32_t packing;                // input format (see load_residue)
   const uint32_t* __restrict__ order;  // standard: hand-out order (longest pairs first), or nullptr
   int32_t s_step;                  // standard: gcd of the penalties -- only these scores can hold a wavefront
+  unsigned long long* __restrict__ work;  // standard: [0] wavefront cells computed, [1] residues passed by extend (or nullptr)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     const int32_t kend = n1 - n2;
     const int32_t koff = n2;  // array index = k + n2
     int32_t result = -1;
+    uint32_t w_cells = 0, w_ext = 0;  // this lane's share of the pair's work (SURVEY.md 8d units)
     // score 0
     if (lane < kWfRing) {
       lo_[lane] = 1;
@@ -229,8 +231,12 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
           if (dv > kWfNone && (dv > n1 || dv - k > n2 || dv < 0)) dv = kWfNone;
           if (mv > kWfNone && (mv > n1 || mv - k > n2)) mv = kWfNone;
           mv = max(mv, max(iv, dv));
-          if (mv > kWfNone)
+          ++w_cells;
+          if (mv > kWfNone) {
+            const int32_t before = mv;
             mv = wide ? wf_extend<8>(s1w, s2w, mv, mv - k, n1, n2) : wf_extend<2>(s1w, s2w, mv, mv - k, n1, n2);
+            w_ext += (uint32_t)(mv - before);
+          }
           Mc[k] = mv;
           Ic[k] = iv;
           Dc[k] = dv;
@@ -241,9 +247,17 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       __syncwarp();
       if (__any_sync(0xffffffffu, found)) result = s;
     }
+    if (p.work) {
+      w_cells = __reduce_add_sync(0xffffffffu, w_cells);
+      w_ext = __reduce_add_sync(0xffffffffu, w_ext);
+    }
     if (lane == 0) {
       p.score[id] = result;
       p.status[id] = 0;
+      if (p.work) {
+        atomicAdd(p.work, (unsigned long long)w_cells);
+        atomicAdd(p.work + 1, (unsigned long long)w_ext);
+      }
     }
     __syncwarp();
   }

@@ -92,7 +92,7 @@ class PairBatch:
             return self
         n = int(self.residues.size)
         out = np.zeros((n + 3) // 4 + 1, np.uint8)
-        rc = _capi.lib().sa_pack_2bit(self.residues.ctypes.data, n, out.ctypes.data, 0)
+        rc = _capi.lib().sa_pack_2bit_mt(self.residues.ctypes.data, n, out.ctypes.data, 0)
         if rc != 0:
             raise ValueError("2-bit packing needs A/C/G/T only")
         return PairBatch(out, self.q_off, self.q_len, self.d_off, self.d_len, 1)
@@ -396,6 +396,34 @@ def render_affine(seq1: bytes, seq2: bytes, cigar: Sequence[int]) -> str:
     buf = C.create_string_buffer(need + 1)
     l.sa_render_affine(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), buf, need + 1)
     return buf.value.decode("latin1")
+
+
+def parse_fasta_packed(path: str):
+    """sa_parse_fasta_packed: (records, err_chars, out, packed, index, all_acgt).  `out` is the parser's
+    output buffer (names and sequences), `packed` its 2-bit image, `index` the (name_off, name_len,
+    seq_off, seq_len) rows: a PairBatch built on `packed` with packing = 1 uses seq_off / seq_len as is."""
+    import os
+    l = _capi.lib()
+    if not os.path.isfile(path):
+        raise ValueError(f"FastaError: {path}")
+    size = os.path.getsize(path)
+    out = np.zeros(max(size, 1), np.uint8)
+    with open(path, "rb") as f:
+        idx_cap = f.read().count(b">") + 1 if size else 1
+    idx = np.zeros(4 * idx_cap, np.uint64)
+    err = np.zeros(max(size, 1), np.uint8)
+    packed = np.zeros((max(size, 1) + 3) // 4 + 1, np.uint8)
+    nerr = C.c_size_t()
+    acgt = C.c_int()
+    out_len = C.c_uint64()
+    n = l.sa_parse_fasta_packed(path.encode(), out.ctypes.data, out.size, idx.ctypes.data, idx_cap, err.ctypes.data, err.size,
+                                C.byref(nerr), packed.ctypes.data, packed.size, C.byref(acgt), C.byref(out_len))
+    if n < 0:
+        raise ValueError(f"FastaError: {path}")
+    raw = out.tobytes()
+    index = idx[: 4 * n].reshape(n, 4)
+    recs = [Record(seq=raw[int(so):int(so + sl)], name=raw[int(no):int(no + nl)]) for no, nl, so, sl in index]
+    return recs, err[: nerr.value].tobytes(), out[: out_len.value], packed[: (out_len.value + 3) // 4], index, bool(acgt.value)
 
 
 def parse_fasta(path: str):

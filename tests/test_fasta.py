@@ -106,3 +106,62 @@ def test_large_file_takes_the_parallel_path_and_agrees_with_the_oracle(tmp_path,
     assert a[1] == b[1]
     assert a[2] == b[2] and len(a[2]) > 100
     assert len(a[0]) > 30000
+
+
+def test_fused_parse_and_pack(tmp_path, oracle):
+    """sa_parse_fasta_packed: the same records as parse_fasta, plus the 2-bit image of the output
+    buffer; the record offsets address both formats; 'N' clears all_acgt (then the byte format is
+    what a batch must use)."""
+    import random
+    import numpy as np
+    from sequencealigning_b200.engine import PairBatch, parse_fasta, parse_fasta_packed
+    rng = random.Random(11)
+    parts = []
+    for i in range(40000):   # > 1 MB: the chunk-parallel path, pack slices on 4-residue boundaries
+        parts.append(b">read%d\n" % i)
+        parts.append(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 90))) + b"\n")
+    data = b"".join(parts)
+    assert len(data) > (1 << 20)
+    path = _write(tmp_path, "reads.fa", data)
+    recs, err, out, packed, index, all_acgt = parse_fasta_packed(path)
+    plain, err2 = parse_fasta(path)
+    assert [r.seq for r in recs] == [r.seq for r in plain] and [r.name for r in recs] == [r.name for r in plain]
+    assert err == err2 == b"" and all_acgt
+    # a batch on the packed image with the index's offsets decodes to the same sequences
+    so, sl = index[:, 2].copy(), index[:, 3].astype(np.uint32)
+    pb = PairBatch(packed, so, sl, so, sl, packing=1)
+    for r in list(range(0, len(recs), 997)) + [len(recs) - 1]:
+        assert pb.query(r) == recs[r].seq
+    # the image is the packer's output on the whole buffer (names code as 0)
+    codes = np.zeros(256, np.uint8)
+    codes[ord("C")], codes[ord("G")], codes[ord("T")] = 1, 2, 3
+    c = codes[out]
+    pad = np.concatenate([c, np.zeros((-len(c)) % 4, np.uint8)]).reshape(-1, 4)
+    expect = (pad[:, 0] | (pad[:, 1] << 2) | (pad[:, 2] << 4) | (pad[:, 3] << 6)).astype(np.uint8)
+    assert np.array_equal(packed, expect)
+    # an 'N' in a sequence: still parsed, but not packable
+    path_n = _write(tmp_path, "n.fa", b">a\nACGT\n>b\nACNT\n")
+    recs, err, out, packed, index, all_acgt = parse_fasta_packed(path_n)
+    assert [r.seq for r in recs] == [b"ACGT", b"ACNT"] and not all_acgt
+    # an 'N' in a header does not matter
+    assert parse_fasta_packed(_write(tmp_path, "h.fa", b">Nome\nACGT\n"))[5]
+
+
+def test_multithreaded_packer_matches_the_scalar_one():
+    import numpy as np
+    from sequencealigning_b200 import _capi
+    lib = _capi.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 3, 4, 5, 17, 4099, (1 << 21) + 3):
+        src = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+        a = np.zeros((n + 3) // 4 + 1, np.uint8)
+        b = np.zeros_like(a)
+        assert lib.sa_pack_2bit(src.ctypes.data, n, a.ctypes.data, 0) == 0
+        for threads in (1, 3, 0):
+            b[:] = 0
+            assert lib.sa_pack_2bit_mt(src.ctypes.data, n, b.ctypes.data, threads) == 0
+            assert np.array_equal(a, b), (n, threads)
+        if n > 4:
+            bad = src.copy()
+            bad[n // 2] = ord("N")
+            assert lib.sa_pack_2bit_mt(bad.ctypes.data, n, b.ctypes.data, 0) == -2

@@ -39,7 +39,7 @@ def main():
                 e1.record(st)
                 e1.synchronize()
                 times.append(e0.elapsed_time(e1))
-                fills.append(eng.timing()["walk_ms"])
+                fills.append(eng.timing()["fill_ms"])
             r = rb.download()
             rb.free()
         if ref is None:

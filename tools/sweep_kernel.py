@@ -38,7 +38,7 @@ def main():
                     e1.record(st)
                     e1.synchronize()
                     times.append(e0.elapsed_time(e1))
-                    fills.append(eng.timing()["walk_ms"])
+                    fills.append(eng.timing()["fill_ms"])
                 ms = min(times)
                 r = rb.download()
                 rb.free()
