@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SA_ABI_VERSION 2
+#define SA_ABI_VERSION 3
 
 typedef struct sa_engine sa_engine_t; /* opaque; one per process and device SET (sa_engine_create_multi) */
 
@@ -116,6 +116,14 @@ typedef struct {
                           skip traceback (score + status only)                               */
   uint64_t cigar_capacity; /* words available in `cigar`                                     */
   uint64_t cigar_used;     /* OUT: words written (or needed, on SA_E_CIGAR_CAPACITY)         */
+  uint32_t* end1;      /* optional (may be NULL): the cell the traceback STARTS from = the end of
+                          the alignment, as (residues of seq1, residues of seq2) consumed up to
+                          and including it.  Global modes: (n1, n2).  SA_MODE_LOCAL (linear NW):
+                          the first cell, in row-major order, that holds the matrix maximum
+                          (needleman_wunsch.rs:107-111, :256-272); the alignment covers
+                          seq1[end1 - I - M, end1) and seq2[end2 - D - M, end2), the residues
+                          the CIGAR's I+M and D+M columns consume                            */
+  uint32_t* end2;
 } sa_result_t;
 
 /* Time breakdown of the last call: device milliseconds from CUDA events on the launching streams,
@@ -251,6 +259,14 @@ int64_t sa_parse_fasta_packed(const char* path, uint8_t* out, size_t out_cap, ui
  * returns the bytes needed; SA_E_ARG if the CIGAR does not fit the sequences. */
 int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
                          const uint32_t* cigar, uint32_t cigar_len, char* buf, size_t cap);
+
+/* The text the reference's linear aligner prints for one hit (needleman_wunsch.rs:207/:211
+ * `println!("\nHit: {}\n", hit)`, Display for Hit :155-178, start_in_query/db :215-216):
+ * "\nHit: \nseq1: ..\n      ..\nseq2: ..\nstart in seq1: a\nstart in seq2: b\n\n\n\n".
+ * (end1, end2) = sa_result_t.end1/end2 of the pair.  snprintf-style; SA_E_ARG on a misfit. */
+int64_t sa_render_linear_hit(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                             const uint32_t* cigar, uint32_t cigar_len, uint32_t end1, uint32_t end2,
+                             char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

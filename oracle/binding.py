@@ -57,6 +57,8 @@ class _LinearResult(C.Structure):
         ("n_columns", C.c_uint32),
         ("start1", C.c_uint32),
         ("start2", C.c_uint32),
+        ("end1", C.c_uint32),
+        ("end2", C.c_uint32),
     ]
 
 
@@ -85,6 +87,12 @@ def lib() -> C.CDLL:
         _lib.sao_linear_matrices.restype = C.c_int
         _lib.sao_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         _lib.sao_linear_batch.restype = C.c_int
+        _lib.sao_linear_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.sao_linear_batch_ex.restype = C.c_int
+        _lib.sao_linear_print_hits.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p, C.c_size_t,
+                                               C.POINTER(C.c_uint64)]
+        _lib.sao_linear_print_hits.restype = C.c_int64
         _lib.sao_parse_fasta_mem.argtypes = [C.c_char_p, C.c_size_t, u8p, C.c_size_t, u64p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib.sao_parse_fasta_mem.restype = C.c_int64
         _lib.sao_parse_fasta_path.argtypes = [C.c_char_p, u8p, C.c_size_t, u64p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -224,6 +232,8 @@ class LinearResult:
     n_columns: int
     start1: int
     start2: int
+    end1: int = 0
+    end2: int = 0
 
 
 def linear_align(seq1: bytes, seq2: bytes, local: bool = False) -> LinearResult:
@@ -232,7 +242,7 @@ def linear_align(seq1: bytes, seq2: bytes, local: bool = False) -> LinearResult:
     rc = lib().sao_linear_align(seq1, len(seq1), seq2, len(seq2), int(local), C.byref(r), cig)
     if rc != 0:
         raise MemoryError("oracle allocation failed")
-    return LinearResult(r.status, r.score, r.n_hits, list(cig[: r.cigar_len]), r.n_columns, r.start1, r.start2)
+    return LinearResult(r.status, r.score, r.n_hits, list(cig[: r.cigar_len]), r.n_columns, r.start1, r.start2, r.end1, r.end2)
 
 
 def linear_matrices(seq1: bytes, seq2: bytes, local: bool = False):
@@ -245,19 +255,36 @@ def linear_matrices(seq1: bytes, seq2: bytes, local: bool = False):
     return s, mv, g
 
 
-def linear_batch(residues, q_off, q_len, d_off, d_len, cigar_stride: int = 0, n_threads: int = 1) -> BatchResult:
+def linear_batch(residues, q_off, q_len, d_off, d_len, cigar_stride: int = 0, n_threads: int = 1, local: bool = False) -> BatchResult:
     residues, q_off, q_len, d_off, d_len = _batch_args(residues, q_off, q_len, d_off, d_len)
     n = len(q_len)
     score = np.zeros(n, np.int32)
     status = np.zeros(n, np.uint8)
     clen = np.zeros(n, np.uint32)
+    end1 = np.zeros(n, np.uint32)
+    end2 = np.zeros(n, np.uint32)
     pool = np.zeros((n, cigar_stride), np.uint32) if cigar_stride else None
-    rc = lib().sao_linear_batch(
-        residues.ctypes.data, q_off.ctypes.data, q_len.ctypes.data, d_off.ctypes.data, d_len.ctypes.data, n,
-        score.ctypes.data, status.ctypes.data, clen.ctypes.data, pool.ctypes.data if pool is not None else None, cigar_stride, n_threads)
+    rc = lib().sao_linear_batch_ex(
+        residues.ctypes.data, q_off.ctypes.data, q_len.ctypes.data, d_off.ctypes.data, d_len.ctypes.data, n, int(local),
+        score.ctypes.data, status.ctypes.data, clen.ctypes.data, pool.ctypes.data if pool is not None else None, cigar_stride,
+        end1.ctypes.data, end2.ctypes.data, n_threads)
     if rc != 0:
         raise MemoryError("oracle batch failed")
-    return BatchResult(score, status, clen, pool)
+    out = BatchResult(score, status, clen, pool)
+    out.end1, out.end2 = end1, end2
+    return out
+
+
+def linear_print_hits(seq1: bytes, seq2: bytes, local: bool = False, max_hits: int = 1 << 20):
+    """The reference's stdout for the hits of one pair (needleman_wunsch.rs:106-116, :155-178, :205-254).
+    Returns (text, n_printed)."""
+    n = C.c_uint64()
+    need = lib().sao_linear_print_hits(seq1, len(seq1), seq2, len(seq2), int(local), max_hits, None, 0, C.byref(n))
+    if need < 0:
+        raise MemoryError("oracle allocation failed")
+    buf = C.create_string_buffer(need + 1)
+    lib().sao_linear_print_hits(seq1, len(seq1), seq2, len(seq2), int(local), max_hits, buf, need + 1, C.byref(n))
+    return buf.raw[:need].decode("latin1"), n.value
 
 
 @dataclass

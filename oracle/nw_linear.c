@@ -175,6 +175,8 @@ int sao_linear_align(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint
     }
   out->cigar_len = n;
   out->n_columns = cols;
+  out->end1 = si;
+  out->end2 = sj;
   free(cnt);
   lin_free(&t);
   return 0;
@@ -207,6 +209,8 @@ typedef struct {
   uint32_t cigar_stride;
   uint64_t lo, hi;
   int rc;
+  int local;
+  uint32_t *end1, *end2;
 } lin_job_t;
 
 static void* lin_worker(void* arg) {
@@ -226,7 +230,7 @@ static void* lin_worker(void* arg) {
       }
       cig = tmp;
     }
-    if (sao_linear_align(j->residues + j->q_off[p], n1, j->residues + j->d_off[p], n2, 0, &r,
+    if (sao_linear_align(j->residues + j->q_off[p], n1, j->residues + j->d_off[p], n2, j->local, &r,
                          cig) != 0) {
       j->rc = -1;
       break;
@@ -234,6 +238,8 @@ static void* lin_worker(void* arg) {
     j->score[p] = r.score;
     if (j->status) j->status[p] = (uint8_t)r.status;
     if (j->cigar_len) j->cigar_len[p] = r.cigar_len;
+    if (j->end1) j->end1[p] = r.end1;
+    if (j->end2) j->end2[p] = r.end2;
     if (j->cigar_pool) {
       uint32_t n = r.cigar_len < j->cigar_stride ? r.cigar_len : j->cigar_stride;
       memcpy(j->cigar_pool + (size_t)p * j->cigar_stride, cig, n * sizeof(uint32_t));
@@ -247,6 +253,14 @@ int sao_linear_batch(const uint8_t* residues, const uint64_t* q_off, const uint3
                      const uint64_t* d_off, const uint32_t* d_len, uint64_t n_pairs,
                      int32_t* score, uint8_t* status, uint32_t* cigar_len, uint32_t* cigar_pool,
                      uint32_t cigar_stride, int n_threads) {
+  return sao_linear_batch_ex(residues, q_off, q_len, d_off, d_len, n_pairs, 0, score, status, cigar_len,
+                             cigar_pool, cigar_stride, NULL, NULL, n_threads);
+}
+
+int sao_linear_batch_ex(const uint8_t* residues, const uint64_t* q_off, const uint32_t* q_len,
+                        const uint64_t* d_off, const uint32_t* d_len, uint64_t n_pairs, int local,
+                        int32_t* score, uint8_t* status, uint32_t* cigar_len, uint32_t* cigar_pool,
+                        uint32_t cigar_stride, uint32_t* end1, uint32_t* end2, int n_threads) {
   if (n_threads < 1) n_threads = 1;
   if ((uint64_t)n_threads > n_pairs) n_threads = n_pairs ? (int)n_pairs : 1;
   lin_job_t* jobs = (lin_job_t*)calloc((size_t)n_threads, sizeof(lin_job_t));
@@ -256,7 +270,7 @@ int sao_linear_batch(const uint8_t* residues, const uint64_t* q_off, const uint3
   for (int k = 0; k < n_threads; ++k) {
     jobs[k] = (lin_job_t){residues, q_off, d_off, q_len, d_len, score, status, cigar_len,
                           cigar_pool, cigar_stride, n_pairs * (uint64_t)k / (uint64_t)n_threads,
-                          n_pairs * (uint64_t)(k + 1) / (uint64_t)n_threads, 0};
+                          n_pairs * (uint64_t)(k + 1) / (uint64_t)n_threads, 0, local, end1, end2};
     if (n_threads == 1) lin_worker(&jobs[k]);
     else pthread_create(&th[k], NULL, lin_worker, &jobs[k]);
   }
@@ -267,4 +281,138 @@ int sao_linear_batch(const uint8_t* residues, const uint64_t* q_off, const uint3
   free(jobs);
   free(th);
   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The reference's stdout for the hits of one pair (:106-116, :155-178, :205-254), literally:
+ * an explicit-stack version of the recursion get_next, same visiting order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  char* buf;
+  size_t cap, len;
+} txt_t;
+
+static void txt_put(txt_t* t, const char* s, size_t n) {
+  for (size_t k = 0; k < n; ++k) {
+    if (t->buf && t->len + 1 < t->cap) t->buf[t->len] = s[k];
+    t->len++;
+  }
+}
+static void txt_str(txt_t* t, const char* s) { txt_put(t, s, strlen(s)); }
+static void txt_u(txt_t* t, uint32_t v) {
+  char tmp[16];
+  int n = 0;
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) txt_put(t, &tmp[--n], 1);
+}
+
+/* println!("\nHit: {}\n", hit) with Display for Hit (:155-178); q/d hold the columns in push
+ * order (end of the alignment first), the Display reverses them */
+static void print_hit(txt_t* t, const char* q, const char* d, size_t n, uint32_t s1, uint32_t s2) {
+  txt_str(t, "\nHit: ");
+  txt_str(t, "\nseq1: ");
+  for (size_t k = n; k-- > 0;) txt_put(t, &q[k], 1);
+  txt_str(t, "\n      ");
+  for (size_t k = n; k-- > 0;) txt_put(t, q[k] == d[k] ? "|" : " ", 1);
+  txt_str(t, "\nseq2: ");
+  for (size_t k = n; k-- > 0;) txt_put(t, &d[k], 1);
+  txt_str(t, "\n");
+  txt_str(t, "start in seq1: ");
+  txt_u(t, s1);
+  txt_str(t, "\nstart in seq2: ");
+  txt_u(t, s2);
+  txt_str(t, "\n\n"); /* writeln!(.."\n") of the Display */
+  txt_str(t, "\n\n"); /* the "\n" after {} and println's newline */
+}
+
+int64_t sao_linear_print_hits(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                              uint64_t max_hits, char* buf, size_t buf_cap, uint64_t* n_printed) {
+  lin_t t;
+  memset(&t, 0, sizeof(t));
+  if (lin_fill(&t, seq1, n1, seq2, n2, local) != 0) {
+    lin_free(&t);
+    return -1;
+  }
+  const size_t w = t.w;
+  txt_t out = {buf, buf_cap, 0};
+  uint64_t printed = 0;
+  /* start cells (:107-111) */
+  size_t n_starts = 0;
+  uint32_t* starts = (uint32_t*)malloc(2 * sizeof(uint32_t) * ((size_t)n1 + 1) * w);
+  const size_t depth = (size_t)n1 + n2 + 2;
+  char* q = (char*)malloc(depth);
+  char* d = (char*)malloc(depth);
+  /* frame: the cell and the index of the next move to try (0 Down, 1 Right, 2 Diag) */
+  uint32_t* fi = (uint32_t*)malloc(depth * sizeof(uint32_t));
+  uint32_t* fj = (uint32_t*)malloc(depth * sizeof(uint32_t));
+  uint8_t* fk = (uint8_t*)malloc(depth);
+  if (!starts || !q || !d || !fi || !fj || !fk) {
+    free(starts); free(q); free(d); free(fi); free(fj); free(fk);
+    lin_free(&t);
+    return -1;
+  }
+  if (!local) {
+    starts[0] = n1;
+    starts[1] = n2;
+    n_starts = 1;
+  } else {
+    int32_t best = INT32_MIN;
+    for (uint32_t i = 0; i <= n1; ++i)
+      for (uint32_t j = 0; j <= n2; ++j) {
+        const int32_t v = t.scores[(size_t)i * w + j];
+        if (v > best) {
+          best = v;
+          n_starts = 0;
+        }
+        if (v == best) {
+          starts[2 * n_starts] = i;
+          starts[2 * n_starts + 1] = j;
+          ++n_starts;
+        }
+      }
+  }
+  for (size_t s = 0; s < n_starts && printed < max_hits; ++s) {
+    uint32_t hs1 = 0, hs2 = 0; /* Hit::default() per start cell (:113) */
+    size_t sp = 0, cols = 0;
+    fi[0] = starts[2 * s];
+    fj[0] = starts[2 * s + 1];
+    fk[0] = 0;
+    sp = 1;
+    while (sp && printed < max_hits) {
+      const uint32_t i = fi[sp - 1], j = fj[sp - 1];
+      const uint8_t mv = t.moves[(size_t)i * w + j];
+      if (fk[sp - 1] == 0 && ((i == 0 && j == 0) || mv == 0)) { /* :206-213 */
+        print_hit(&out, q, d, cols, hs1, hs2);
+        ++printed;
+        --sp;
+        if (sp) --cols; /* the caller's hit.query.pop() / hit.db.pop() (:251-252) */
+        continue;
+      }
+      /* next stored move, in push order Down, Right, Diag (:92-100) */
+      int k = fk[sp - 1];
+      while (k < 3 && !(mv & (1u << k))) ++k;
+      if (k == 3) {
+        --sp;
+        if (sp) --cols;
+        continue;
+      }
+      fk[sp - 1] = (uint8_t)(k + 1);
+      hs1 = (i > 1 ? i : 1) - 1; /* :215-216 */
+      hs2 = (j > 1 ? j : 1) - 1;
+      uint32_t ni = i, nj = j;
+      if (k == 0) { q[cols] = (char)seq1[i - 1]; d[cols] = '-'; --ni; }
+      else if (k == 1) { q[cols] = '-'; d[cols] = (char)seq2[j - 1]; --nj; }
+      else { q[cols] = (char)seq1[i - 1]; d[cols] = (char)seq2[j - 1]; --ni; --nj; }
+      ++cols;
+      fi[sp] = ni;
+      fj[sp] = nj;
+      fk[sp] = 0;
+      ++sp;
+    }
+  }
+  if (out.buf && out.cap) out.buf[out.len < out.cap ? out.len : out.cap - 1] = 0;
+  if (n_printed) *n_printed = printed;
+  free(starts); free(q); free(d); free(fi); free(fj); free(fk);
+  lin_free(&t);
+  return (int64_t)out.len;
 }

@@ -114,6 +114,8 @@ typedef struct {
   uint32_t cigar_len;   /* canonical = FIRST printed hit: priority Down > Right > Diag        */
   uint32_t n_columns;
   uint32_t start1, start2; /* "start in seq1/seq2" lines of the first hit (:171-175)          */
+  uint32_t end1, end2;     /* the cell the first hit's recursion starts from: (n1, n2) in global
+                              mode, the first argmax cell in row-major order in local mode (:107-111) */
 } sao_linear_result_t;
 
 int sao_linear_align(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
@@ -125,6 +127,17 @@ int sao_linear_batch(const uint8_t* residues, const uint64_t* q_off, const uint3
                      const uint64_t* d_off, const uint32_t* d_len, uint64_t n_pairs,
                      int32_t* score, uint8_t* status, uint32_t* cigar_len, uint32_t* cigar_pool,
                      uint32_t cigar_stride, int n_threads);
+/* the same with the mode switch of n_w_align (:180) and the start cell of every pair (end1/end2 may be NULL) */
+int sao_linear_batch_ex(const uint8_t* residues, const uint64_t* q_off, const uint32_t* q_len,
+                        const uint64_t* d_off, const uint32_t* d_len, uint64_t n_pairs, int local,
+                        int32_t* score, uint8_t* status, uint32_t* cigar_len, uint32_t* cigar_pool,
+                        uint32_t cigar_stride, uint32_t* end1, uint32_t* end2, int n_threads);
+/* Literal recursion of backtrace / get_next (:106-116, :205-254) writing the reference's stdout for
+ * the hits of one pair -- "\nHit: {hit}\n\n" per hit, `Hit` as Display :155-178 -- in the order
+ * the reference prints them (start cells row-major, moves in stored order Down, Right, Diag).
+ * Stops after max_hits.  snprintf-style: returns the bytes the text needs; -1 on OOM. */
+int64_t sao_linear_print_hits(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                              uint64_t max_hits, char* buf, size_t buf_cap, uint64_t* n_printed);
 
 /* ------------------------------------------------------------------------------------- */
 /* parse_fasta, parse.rs:54-99.  Returns number of records (>=0), or -1 for FastaError

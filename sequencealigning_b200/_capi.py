@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
     "sa_affine_count_cooptimal", "sa_engine_create_multi", "sa_engine_device_count", "sa_last_shards", "sa_plan_shards",
-    "sa_pack_2bit_mt", "sa_parse_fasta_packed",
+    "sa_pack_2bit_mt", "sa_parse_fasta_packed", "sa_render_linear_hit",
 ]
 
 
@@ -46,6 +46,7 @@ class Result(C.Structure):
     _fields_ = [
         ("score", C.c_void_p), ("status", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar_len", C.c_void_p),
         ("cigar", C.c_void_p), ("cigar_capacity", C.c_uint64), ("cigar_used", C.c_uint64),
+        ("end1", C.c_void_p), ("end2", C.c_void_p),
     ]
 
 
@@ -121,6 +122,9 @@ def lib() -> C.CDLL:
     l.sa_parse_fasta.restype = C.c_int64
     l.sa_render_affine.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32, C.c_char_p, C.c_size_t]
     l.sa_render_affine.restype = C.c_int64
+    l.sa_render_linear_hit.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_char_p, C.c_size_t]
+    l.sa_render_linear_hit.restype = C.c_int64
     l.sa_pack_2bit.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     l.sa_pack_2bit.restype = C.c_int
     l.sa_pack_2bit_mt.argtypes = [vp, C.c_uint64, vp, C.c_int]

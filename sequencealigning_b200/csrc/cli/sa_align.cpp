@@ -172,8 +172,8 @@ int main(int argc, char** argv) {
   std::vector<int32_t> score(n);
   std::vector<uint8_t> status(n);
   std::vector<uint64_t> coff(n);
-  std::vector<uint32_t> clen(n), pool(64 * n + 1024);
-  sa_result_t res{score.data(), status.data(), coff.data(), clen.data(), pool.data(), pool.size(), 0};
+  std::vector<uint32_t> clen(n), pool(64 * n + 1024), end1(n), end2(n);
+  sa_result_t res{score.data(), status.data(), coff.data(), clen.data(), pool.data(), pool.size(), 0, end1.data(), end2.data()};
   const auto t0 = std::chrono::steady_clock::now();
   sa_status_t rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
   if (rc == SA_E_CIGAR_CAPACITY) {
@@ -215,8 +215,21 @@ int main(int argc, char** argv) {
         }
         continue;
       }
-      if (al == SA_ALGO_NW_LINEAR)  // needleman_wunsch.rs:196-200
+      if (al == SA_ALGO_NW_LINEAR) {
+        // needleman_wunsch.rs:193-201, then the FIRST hit of backtrace (:106-116, :205-213)
+        if (verbose) printf("search finished after %s\n", duration_debug(per_pair).c_str());
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
+        if (!omitted[p]) {
+          const int64_t need = sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                                    (uint32_t)D.seq.size(), pool.data() + coff[p], clen[p], end1[p], end2[p], nullptr, 0);
+          if (need < 0) { fprintf(stderr, "sa_render_linear_hit: the CIGAR does not fit the pair\n"); exit_code = 1; break; }
+          std::string text((size_t)need + 1, '\0');
+          sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
+                               pool.data() + coff[p], clen[p], end1[p], end2[p], &text[0], text.size());
+          fwrite(text.data(), 1, (size_t)need, stdout);
+        }
+        continue;
+      }
       const bool has_alignment = !omitted[p] && (clen[p] > 0 || (Q.seq.empty() && D.seq.empty()));
       if (all && al == SA_ALGO_NW_AFFINE) {
         // the reference's full output for the pair: every co-optimal alignment in DFS order,

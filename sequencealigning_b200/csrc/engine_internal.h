@@ -32,6 +32,7 @@ struct DeviceBatch {
   uint8_t* status = nullptr;
   uint32_t* cigar_len = nullptr;
   uint64_t* cigar_off = nullptr;
+  uint32_t *end1 = nullptr, *end2 = nullptr;  // local mode: start cell of the traceback (else unused)
   uint32_t* pool = nullptr;
   uint64_t pool_cap = 0;
   uint64_t* carry = nullptr;
@@ -51,6 +52,7 @@ struct sa_resident {
   uint64_t used = 0;  // CIGAR words of the last alignment
   bool aligned = false;
   bool want_cigar = false;
+  bool local = false;  // the last alignment ran in local mode (end cells live on the device)
   // segment plan of the last alignment (shapes do not change while the batch is resident):
   // opaque here, owned through the deleter
   void* plan = nullptr;
@@ -87,7 +89,7 @@ struct sa_engine {
   // scratch (grow-only)
   DevBuf tb2, end2, misc, block_sums, wfa_scratch, par_bytes, par_rows, par_in;
   // staging for sa_align_batch (grow-only)
-  DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry;
+  DevBuf b_res, b_qoff, b_doff, b_qlen, b_dlen, b_score, b_status, b_clen, b_coff, b_pool, b_carry, b_end1, b_end2;
   uint32_t* h_count = nullptr;  // pinned
   sa_timing_t timing = {};
   int sm_count = 0;

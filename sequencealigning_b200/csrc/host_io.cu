@@ -433,4 +433,52 @@ int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, 
   return (int64_t)s.size();
 }
 
+// The text the reference's linear aligner prints for one hit: println!("\nHit: {}\n", hit)
+// (needleman_wunsch.rs:207/:211) with Display for Hit (:155-178).  The alignment ends at cell
+// (end1, end2) and its CIGAR runs backwards from there (global mode: end = (n1, n2); local mode:
+// the start cell sa_result_t.end1/end2 name).  "start in seq1/seq2" are the coordinates of the last
+// cell the recursion left before it printed (:215-216: max(i,1)-1, max(j,1)-1), i.e. one step
+// after the alignment's first column; an empty hit prints 0 / 0 (Hit::default()).
+int64_t sa_render_linear_hit(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                             const uint32_t* cigar, uint32_t cigar_len, uint32_t end1, uint32_t end2,
+                             char* buf, size_t cap) {
+  if (end1 > n1 || end2 > n2) return SA_E_ARG;
+  uint64_t c1 = 0, c2 = 0;  // residues the alignment consumes
+  for (uint32_t k = 0; k < cigar_len; ++k) {
+    const uint32_t op = cigar[k] & 3u, len = cigar[k] >> 2;
+    if (op == SA_OP_M) { c1 += len; c2 += len; }
+    else if (op == SA_OP_I) c1 += len;
+    else if (op == SA_OP_D) c2 += len;
+    else return SA_E_ARG;
+  }
+  if (c1 > end1 || c2 > end2) return SA_E_ARG;
+  uint32_t i = (uint32_t)(end1 - c1), j = (uint32_t)(end2 - c2);  // the cell the hit was printed at
+  uint32_t s1 = 0, s2 = 0;
+  if (cigar_len) {  // the cell one move before it
+    const uint32_t op = cigar[0] & 3u;
+    const uint32_t pi = i + (op != SA_OP_D ? 1u : 0u), pj = j + (op != SA_OP_I ? 1u : 0u);
+    s1 = (pi > 1 ? pi : 1) - 1;
+    s2 = (pj > 1 ? pj : 1) - 1;
+  }
+  std::string r1, r2;
+  for (uint32_t k = 0; k < cigar_len; ++k) {
+    const uint32_t op = cigar[k] & 3u, len = cigar[k] >> 2;
+    for (uint32_t t = 0; t < len; ++t) {
+      r1.push_back(op == SA_OP_D ? '-' : (char)seq1[i++]);
+      r2.push_back(op == SA_OP_I ? '-' : (char)seq2[j++]);
+    }
+  }
+  std::string bars(r1.size(), ' ');
+  for (size_t k = 0; k < r1.size(); ++k)
+    if (r1[k] == r2[k]) bars[k] = '|';
+  std::string s = "\nHit: \nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\nstart in seq1: " + std::to_string(s1) +
+                  "\nstart in seq2: " + std::to_string(s2) + "\n\n\n\n";
+  if (buf && cap) {
+    const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
+}
+
 }  // extern "C"

@@ -242,7 +242,8 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
   mf.shards.assign(N, sa_shard_info_t{});
   for (int k = 0; k < N; ++k) mf.shards[k].device = e->children[k]->device;
   const bool is_wfa = algo == SA_ALGO_WFA || algo == SA_ALGO_WFA_STANDARD;
-  const bool want_cigar = !is_wfa && mode == SA_MODE_GLOBAL && res->cigar != nullptr && res->cigar_capacity > 0;
+  const bool local_ok = mode == SA_MODE_LOCAL && algo == SA_ALGO_NW_LINEAR;  // needleman_wunsch.rs:88-89
+  const bool want_cigar = !is_wfa && (mode == SA_MODE_GLOBAL || local_ok) && res->cigar != nullptr && res->cigar_capacity > 0;
 
   // ---- plan --------------------------------------------------------------------------------
   std::vector<uint64_t> begin(N + 1, 0), pw(N, 0);
@@ -312,6 +313,8 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
         sr.status = res->status ? res->status + p0 : nullptr;
         sr.cigar_off = res->cigar_off ? res->cigar_off + p0 : nullptr;
         sr.cigar_len = res->cigar_len ? res->cigar_len + p0 : nullptr;
+        sr.end1 = res->end1 ? res->end1 + p0 : nullptr;
+        sr.end2 = res->end2 ? res->end2 + p0 : nullptr;
         sr.cigar = want_cigar ? res->cigar : nullptr;
         sr.cigar_capacity = want_cigar ? lo[k + 1] : 0;
         sr.cigar_used = 0;
@@ -353,7 +356,7 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     std::vector<int32_t> part(n);
     lpt(b->q_len, b->d_len, n, N, part.data());
     struct Shard {
-      std::vector<uint32_t> idx, q_len, d_len, clen, pool;
+      std::vector<uint32_t> idx, q_len, d_len, clen, pool, end1, end2;
       std::vector<uint64_t> q_off, d_off, coff;
       std::vector<int32_t> score;
       std::vector<uint8_t> status;
@@ -376,6 +379,8 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
         try {
           s.q_off.resize(cnt); s.d_off.resize(cnt); s.q_len.resize(cnt); s.d_len.resize(cnt);
           s.score.resize(cnt); s.status.resize(cnt); s.coff.resize(cnt); s.clen.resize(cnt);
+          if (res->end1) s.end1.resize(cnt);
+          if (res->end2) s.end2.resize(cnt);
           uint64_t cells = 0, len = 0;
           for (size_t t = 0; t < cnt; ++t) {
             const uint32_t i = s.idx[t];
@@ -394,7 +399,8 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
           uint64_t cap = want_cigar ? (uint64_t)((unsigned __int128)res->cigar_capacity * len / std::max<uint64_t>(total_len, 1)) + 4096 : 0;
           for (int attempt = 0; attempt < 2; ++attempt) {
             if (want_cigar) s.pool.resize(cap);
-            sa_result_t sr{s.score.data(), s.status.data(), s.coff.data(), s.clen.data(), want_cigar ? s.pool.data() : nullptr, cap, 0};
+            sa_result_t sr{s.score.data(), s.status.data(), s.coff.data(), s.clen.data(), want_cigar ? s.pool.data() : nullptr, cap, 0,
+                           res->end1 ? s.end1.data() : nullptr, res->end2 ? s.end2.data() : nullptr};
             rc[k] = sd_align_batch(e->children[k], algo, mode, scheme, &sb, &sr, 0);
             s.pool_used = sr.cigar_used;
             if (rc[k] != SA_E_CIGAR_CAPACITY) break;
@@ -416,6 +422,8 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
         const uint32_t i = sh[k].idx[t];
         if (res->score) res->score[i] = sh[k].score[t];
         if (res->status) res->status[i] = sh[k].status[t];
+        if (res->end1) res->end1[i] = sh[k].end1[t];
+        if (res->end2) res->end2[i] = sh[k].end2[t];
         clen[i] = sh[k].clen[t];
       }
     std::vector<uint64_t> coff(n, 0);

@@ -128,6 +128,8 @@ class AlignResult:
     cigar_off: np.ndarray  # uint64
     cigar_len: np.ndarray  # uint32
     cigar: np.ndarray      # uint32 pool
+    end1: Optional[np.ndarray] = None  # uint32: cell the traceback starts from (global: n1, n2;
+    end2: Optional[np.ndarray] = None  # local: first row-major maximum, needleman_wunsch.rs:256-272)
 
     def cigar_of(self, p: int) -> List[int]:
         o, l = int(self.cigar_off[p]), int(self.cigar_len[p])
@@ -168,8 +170,9 @@ class PinnedResult:
     def __init__(self, n_pairs: int, cigar_capacity: int):
         self.n_pairs, self.cigar_capacity = n_pairs, cigar_capacity
         self._bufs = [PinnedBuffer(n_pairs, np.int32), PinnedBuffer(n_pairs, np.uint8), PinnedBuffer(n_pairs, np.uint64),
-                      PinnedBuffer(n_pairs, np.uint32), PinnedBuffer(max(cigar_capacity, 1), np.uint32)]
-        self.score, self.status, self.cigar_off, self.cigar_len, self.cigar = (b.array for b in self._bufs)
+                      PinnedBuffer(n_pairs, np.uint32), PinnedBuffer(max(cigar_capacity, 1), np.uint32),
+                      PinnedBuffer(n_pairs, np.uint32), PinnedBuffer(n_pairs, np.uint32)]
+        self.score, self.status, self.cigar_off, self.cigar_len, self.cigar, self.end1, self.end2 = (b.array for b in self._bufs)
 
     def free(self):
         for b in self._bufs:
@@ -273,9 +276,12 @@ class Engine:
         off = np.zeros(n, np.uint64)
         ln = np.zeros(n, np.uint32)
         pool = np.zeros(max(cigar_capacity, 0), np.uint32)
+        end1 = np.zeros(n, np.uint32)
+        end2 = np.zeros(n, np.uint32)
         res = _capi.Result(score.ctypes.data, status.ctypes.data, off.ctypes.data, ln.ctypes.data,
-                           pool.ctypes.data if cigar_capacity > 0 else None, max(cigar_capacity, 0), 0)
-        return res, (score, status, off, ln, pool)
+                           pool.ctypes.data if cigar_capacity > 0 else None, max(cigar_capacity, 0), 0,
+                           end1.ctypes.data, end2.ctypes.data)
+        return res, (score, status, off, ln, pool, end1, end2)
 
     def align(self, batch: PairBatch, algo: int = ALGO_NW_AFFINE, mode: int = MODE_GLOBAL, scheme=None,
               cigar: bool = True, cigar_capacity: Optional[int] = None, out: Optional["PinnedResult"] = None) -> AlignResult:
@@ -286,9 +292,9 @@ class Engine:
             cb = self._c_batch(batch)
             res = _capi.Result(out.score.ctypes.data, out.status.ctypes.data, out.cigar_off.ctypes.data,
                                out.cigar_len.ctypes.data, out.cigar.ctypes.data if cigar else None,
-                               out.cigar_capacity if cigar else 0, 0)
+                               out.cigar_capacity if cigar else 0, 0, out.end1.ctypes.data, out.end2.ctypes.data)
             self._check(self._lib.sa_align_batch(self._h, algo, mode, C.byref(sc) if sc else None, C.byref(cb), C.byref(res)))
-            return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)])
+            return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)], out.end1, out.end2)
         cap = 0
         if cigar:
             # 32 runs per pair covers read pairs; long pairs get a share of their length
@@ -304,8 +310,8 @@ class Engine:
                 continue
             self._check(rc)
             break
-        score, status, off, ln, pool = arrs
-        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)] if cap else pool)
+        score, status, off, ln, pool, end1, end2 = arrs
+        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)] if cap else pool, end1, end2)
 
     def all_alignments(self, seq1: bytes, seq2: bytes, scheme=None, max_alignments: int = 1 << 20):
         """Every co-optimal alignment of one pair as the reference prints them.
@@ -371,8 +377,8 @@ class ResidentBatch:
                 continue
             e._check(rc)
             break
-        score, status, off, ln, pool = arrs
-        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)])
+        score, status, off, ln, pool, end1, end2 = arrs
+        return AlignResult(score, status, off, ln, pool[: int(res.cigar_used)], end1, end2)
 
     def free(self):
         if self._h:
@@ -396,6 +402,20 @@ def render_affine(seq1: bytes, seq2: bytes, cigar: Sequence[int]) -> str:
     buf = C.create_string_buffer(need + 1)
     l.sa_render_affine(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), buf, need + 1)
     return buf.value.decode("latin1")
+
+
+def render_linear_hit(seq1: bytes, seq2: bytes, cigar: Sequence[int], end1: Optional[int] = None, end2: Optional[int] = None) -> str:
+    """Reference stdout for one hit of the linear aligner (needleman_wunsch.rs:155-178, :207-216)."""
+    l = _capi.lib()
+    end1 = len(seq1) if end1 is None else int(end1)
+    end2 = len(seq2) if end2 is None else int(end2)
+    arr = (C.c_uint32 * max(len(cigar), 1))(*cigar)
+    need = l.sa_render_linear_hit(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), end1, end2, None, 0)
+    if need < 0:
+        raise ValueError("CIGAR / end cell do not fit the sequences")
+    buf = C.create_string_buffer(need + 1)
+    l.sa_render_linear_hit(seq1, len(seq1), seq2, len(seq2), arr, len(cigar), end1, end2, buf, need + 1)
+    return buf.raw[:need].decode("latin1")
 
 
 def parse_fasta_packed(path: str):

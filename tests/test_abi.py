@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_capi.EXPORTED_SYMBOLS)
     for name in sorted(declared):
         assert hasattr(lib, name), f"libsa_engine.so does not export {name}"
-    assert lib.sa_abi_version() == 2
+    assert lib.sa_abi_version() == 3
 
 
 def test_no_oracle_in_the_product():
@@ -132,3 +132,21 @@ def test_pack_2bit(lib):
     assert pb.residues[0] == 0b11100100 and pb.residues[1] == 0b00011011   # A=0 C=1 G=2 T=3, little-endian pairs of bits
     with pytest.raises(ValueError):
         PairBatch.from_pairs([(b"ACGN", b"A")]).packed()
+
+
+def test_render_linear_hit_is_the_reference_text(lib, oracle):
+    """sa_render_linear_hit (pure host code): from (CIGAR, end cell) of the first hit to the text of
+    needleman_wunsch.rs:155-178/:207, against the oracle's literal printer, both modes."""
+    import random
+    from sequencealigning_b200 import render_linear_hit
+    from tests.util import mutate, random_seq
+    rng = random.Random(17)
+    for it in range(300):
+        q = random_seq(rng, rng.randint(0, 25), b"ACGT")
+        d = mutate(rng, q, 0.2, True, b"ACGT") if it % 2 else random_seq(rng, rng.randint(0, 25), b"ACGT")
+        for local in (False, True):
+            r = oracle.linear_align(q, d, local=local)
+            exp, n = oracle.linear_print_hits(q, d, local, 1)
+            assert n == 1 and render_linear_hit(q, d, r.cigar, r.end1, r.end2) == exp, (q, d, local)
+    with pytest.raises(ValueError):
+        render_linear_hit(b"AC", b"AC", [(3 << 2) | 0], 2, 2)  # consumes more than the end cell allows

@@ -80,3 +80,23 @@ def test_wfa_and_linear_algos(cli, tmp_path):
     assert "never converges" in r.stderr                      # ACGT vs ACGT (wfa.rs:189)
     r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear"], capture_output=True, text=True)
     assert r.stdout.count("Alignment between sequences") == 4 and "seq1: ACGT\n      ||||\nseq2: ACGT" in r.stdout
+
+
+@pytest.mark.gpu
+def test_linear_stdout_matches_reference_text(cli, tmp_path, oracle):
+    """needleman_wunsch.rs:193-201 header + the first hit (:205-213, Display :155-178), global and local mode."""
+    query = [(b"q1", b"ACGTACGT"), (b"q2", b"AAAA"), (b"q3", b"TTGACGTAA")]
+    db = [(b"d1", b"ACGGT"), (b"d2", b"CCC"), (b"d3", b"GGACGTCC")]
+    q, d = _fa(tmp_path / "q.fasta", query), _fa(tmp_path / "d.fna", db)
+    for mode, local in (("global", False), ("local", True)):
+        r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear", "-m", mode], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        exp = ""
+        for dn, ds in db:          # db-major, main.rs:61-62
+            for qn, qs in query:
+                exp += f"Alignment between sequences >{qn.decode()} and >{dn.decode()} found\n"
+                exp += oracle.linear_print_hits(qs, ds, local, 1)[0]
+        assert r.stdout == exp, mode
+    # the linear aligner has no semi-global mode (n_w_align takes `local: bool`, :180)
+    r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear", "-m", "semi-global"], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist in the reference" in r.stderr

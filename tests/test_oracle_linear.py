@@ -60,3 +60,42 @@ def test_cross_check_with_literal_model_global_and_local(oracle):
                 row1, row2, st1, st2 = o.hits[0]
                 assert r.cigar == L.columns_to_cigar(row1.encode(), row2.encode()), (q, d, local)
                 assert (r.start1, r.start2) == (st1, st2)
+
+
+def _hit_text(h):
+    """println!("\\nHit: {}\\n", hit) with Display for Hit (needleman_wunsch.rs:155-178, :207)."""
+    q, d, s1, s2 = h
+    bars = "".join("|" if a == b else " " for a, b in zip(q, d))
+    return f"\nHit: \nseq1: {q}\n      {bars}\nseq2: {d}\nstart in seq1: {s1}\nstart in seq2: {s2}\n\n\n\n"
+
+
+def test_hit_text_and_end_cells_against_the_literal_model(oracle):
+    """The oracle's printer (every hit, in the reference's order) and the start cell of the first
+    hit against the object-literal Python model, both modes."""
+    rng = random.Random(33)
+    for it in range(400):
+        alpha = b"ACGT" if it % 3 else b"AC"
+        q = random_seq(rng, rng.randint(0, 14), alpha)
+        d = mutate(rng, q, 0.25, True, alpha) if rng.random() < 0.5 else random_seq(rng, rng.randint(0, 14), alpha)
+        for local in (False, True):
+            o = L.linear_align(q, d, local=local, max_hits=200)
+            text, n = oracle.linear_print_hits(q, d, local, 200)
+            assert n == len(o.hits) and text == "".join(_hit_text(h) for h in o.hits), (q, d, local)
+            r = oracle.linear_align(q, d, local=local)
+            if not local:
+                assert (r.end1, r.end2) == (len(q), len(d))
+            else:  # the first maximum in row-major order (:256-272)
+                best = max(max(row) for row in o.scores)
+                cells = [(i, j) for i, row in enumerate(o.scores) for j, v in enumerate(row) if v == best]
+                assert (r.end1, r.end2) == cells[0] and r.score == best
+
+
+def test_local_batch_matches_single_calls(oracle):
+    from sequencealigning_b200 import PairBatch
+    from tests.util import random_pair_list
+    pairs = random_pair_list(9, 60, 0, 40)
+    b = PairBatch.from_pairs(pairs)
+    ref = oracle.linear_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=90, n_threads=3, local=True)
+    for p, (q, d) in enumerate(pairs):
+        r = oracle.linear_align(q, d, local=True)
+        assert (ref.score[p], ref.end1[p], ref.end2[p], ref.cigar(p)) == (r.score, r.end1, r.end2, r.cigar)
