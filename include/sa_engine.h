@@ -260,6 +260,17 @@ int64_t sa_parse_fasta_packed(const char* path, uint8_t* out, size_t out_cap, ui
 int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
                          const uint32_t* cigar, uint32_t cigar_len, char* buf, size_t cap);
 
+/* The reference's COMPLETE stdout for one pair under `-a wfa` (wfa_align, wfa.rs:23-42; SURVEY.md
+ * App. A.2), from a traced run of the literal kernel on the device: one `lo: .., hi: ..` line per
+ * created wavefront (:251); when the loop converges, `converged with score N: ` (:36), the `huhu`
+ * block with the converged element (:650, Debug :104-116), the `yeah / well shit / extend / open /
+ * huh` lines of rec_tr (:653-853) and the two prints of the (always empty) Alignment (:38-39).
+ * *status = SA_OK, SA_REF_PANIC (the text is what had been printed before the panic of
+ * :577/:603) or SA_REF_NO_CONVERGENCE (the first lines of a never-ending output).
+ * snprintf-style: returns the bytes needed, < 0 on error. */
+int64_t sa_wfa_reference_stdout(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                                char* buf, size_t cap, int32_t* status);
+
 /* The text the reference's linear aligner prints for one hit (needleman_wunsch.rs:207/:211
  * `println!("\nHit: {}\n", hit)`, Display for Hit :155-178, start_in_query/db :215-216):
  * "\nHit: \nseq1: ..\n      ..\nseq2: ..\nstart in seq1: a\nstart in seq2: b\n\n\n\n".

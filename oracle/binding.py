@@ -112,6 +112,8 @@ def _bind_wfa(l):  # filled in by oracle/wfa.c's section below
     l.sao_wfa_standard.restype = C.c_int64
     l.sao_wfa_literal_ex.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(_WfaResult), i32p, C.c_uint32, u32p, i32p]
     l.sao_wfa_literal_ex.restype = C.c_int
+    l.sao_wfa_print.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32)]
+    l.sao_wfa_print.restype = C.c_int64
     l.sao_wfa_literal_cap.argtypes = [C.c_uint32, C.c_uint32]
     l.sao_wfa_literal_cap.restype = C.c_uint32
     l.sao_wfa_literal_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -371,6 +373,19 @@ def wfa_literal_ex(seq1: bytes, seq2: bytes, max_score: Optional[int] = None):
     if r.status == OK:
         ce = (conv[0], "MDI"[conv[1]], tuple("MDI"[conv[3 + k]] for k in range(conv[2])))
     return WfaResult(r.status, r.printed_score, r.panic_line, r.n_wavefronts), lines, ce
+
+
+def wfa_print(seq1: bytes, seq2: bytes, max_score: Optional[int] = None):
+    """The reference's stdout for one pair under `-a wfa` (wfa.rs:23-42): (text, status)."""
+    if max_score is None:
+        max_score = wfa_literal_cap(len(seq1), len(seq2))
+    st = C.c_int32()
+    need = lib().sao_wfa_print(seq1, len(seq1), seq2, len(seq2), max_score, None, 0, C.byref(st))
+    if need < 0:
+        raise MemoryError("oracle allocation failed")
+    buf = C.create_string_buffer(need + 1)
+    lib().sao_wfa_print(seq1, len(seq1), seq2, len(seq2), max_score, buf, need + 1, C.byref(st))
+    return buf.raw[:need].decode("latin1"), st.value
 
 
 def wfa_literal_batch(residues, q_off, q_len, d_off, d_len):

@@ -602,3 +602,40 @@ def wfa_align(seq1: bytes, seq2: bytes, max_score: int = 4000) -> WfaOutcome:  #
         out.status = "PANIC"
         out.panic_site = e.site
         return out
+
+
+def wfa_stdout(seq1: bytes, seq2: bytes, max_score: int = 4000) -> Tuple[str, WfaOutcome]:
+    """What the reference writes to stdout for one pair under `-a wfa`, from the object model:
+    WaveFrontTensor::new :251, wfa_align :36-39, Ocean::traceback :634-651, rec_tr :653-853 (the
+    tensors it looks up are always None, see WfaOutcome / SURVEY B10), Debug :104-116, Display
+    :950-980.  On a panic: the text printed before it."""
+    o = wfa_align(seq1, seq2, max_score)
+    t = "".join(f"lo: {lo}, hi: {hi}\n" for lo, hi in o.lo_hi)
+    if o.status != "OK":
+        return t, o
+    offset, parents, state = o.converged
+    l = o.printed_score
+    diag = len(seq1) - len(seq2)
+    t += f"converged with score {l}: \n"
+    par = "[]" if not parents else "[\n" + "".join(f"    {p},\n" for p in parents) + "]"
+    t += f"huhu, diag: {diag}\nElement {{\n\tstate: {state}\n\toffset: {offset}\n\tparents: {par}\n}}\n\nscore: {l}\n"
+    if diag == 0 and offset == 0:
+        t += "ret\n"
+    else:
+        for d in (WFA_MISMATCH, WFA_GAP_EXTENSION, WFA_GAP_OPENING + WFA_GAP_EXTENSION):
+            if d > l:
+                t += "well shit\n"
+                continue
+            t += f"yeah, score: {l - d}\n"
+            assert (l - d) % 2 == 1  # an odd score never holds a wavefront: the looked-up tensor is None
+            if d == WFA_MISMATCH:
+                pass  # prints only after finding a parent element (:690)
+            elif d == WFA_GAP_EXTENSION:
+                if W_D in parents:
+                    t += "extend\n"  # :710-711, printed before the look-up
+            elif W_M in parents:
+                t += "open\n"  # :754-755
+        t += "huh\n"
+    t += "\n\n\n"  # println!("{}", t[0]): two writeln of empty strings + println
+    t += "Alignment {\n    seq1: [],\n    seq2: [],\n}\n"
+    return t, o

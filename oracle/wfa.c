@@ -22,6 +22,7 @@
  */
 #include "sa_oracle.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -406,6 +407,94 @@ int sao_wfa_literal_batch(const uint8_t* residues, const uint64_t* q_off, const 
     status[p] = (uint8_t)r.status;
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The reference's stdout for one pair under `-a wfa` (wfa_align :23-42).
+ *   :251      "lo: {}, hi: {}"                       per created wavefront
+ *   :36       "converged with score {}: "            wfs.len()
+ *   :650      "huhu, diag: {}\n{:#?}\nscore: {}"     diag = n1 - n2, Debug of the element :104-116
+ *   :662-665  "ret"                                   when diag == 0 && offset == 0
+ *   :667-678  per d in [4, 6, 8]: "well shit" when d > len, else "yeah, score: {len - d}";
+ *             wfs[len - d] is always a None tensor (len odd, penalties even), so the arms print
+ *             only what they print BEFORE looking into the tensor: "extend" when d == 6 and the
+ *             element's parents contain D (:710-711), "open" when d == 8 and they contain M (:754-755)
+ *   :851      "huh"
+ *   :38-39    Display (:950-980) and pretty Debug of the empty Alignment
+ * On a panic (status SAO_REF_PANIC) the text holds what had been printed before it.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  char* buf;
+  size_t cap, len;
+} wtxt_t;
+static void wput(wtxt_t* t, const char* s) {
+  for (; *s; ++s) {
+    if (t->buf && t->len + 1 < t->cap) t->buf[t->len] = *s;
+    t->len++;
+  }
+}
+static void wnum(wtxt_t* t, int64_t v) {
+  char tmp[32];
+  snprintf(tmp, sizeof(tmp), "%lld", (long long)v);
+  wput(t, tmp);
+}
+
+int64_t sao_wfa_print(const uint8_t* s1, uint32_t n1, const uint8_t* s2, uint32_t n2, uint32_t max_score,
+                      char* buf, size_t buf_cap, int32_t* status) {
+  const uint32_t cap = max_score + 8;
+  int32_t* lohi = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)cap);
+  if (!lohi) return -1;
+  uint32_t n_lohi = 0;
+  int32_t conv[6] = {0, 0, 0, 0, 0, 0};
+  wfa_result_t res;
+  if (sao_wfa_literal_ex(s1, n1, s2, n2, max_score, &res, lohi, cap, &n_lohi, conv)) {
+    free(lohi);
+    return -1;
+  }
+  if (status) *status = res.status;
+  wtxt_t t = {buf, buf_cap, 0};
+  for (uint32_t k = 0; k < n_lohi && k < cap; ++k) {
+    wput(&t, "lo: "); wnum(&t, lohi[2 * k]); wput(&t, ", hi: "); wnum(&t, lohi[2 * k + 1]); wput(&t, "\n");
+  }
+  free(lohi);
+  if (res.status == SAO_OK) {
+    static const char* names[3] = {"M", "D", "I"};
+    const int64_t len = res.printed_score, diag = (int64_t)n1 - (int64_t)n2;
+    wput(&t, "converged with score "); wnum(&t, len); wput(&t, ": \n");
+    wput(&t, "huhu, diag: "); wnum(&t, diag); wput(&t, "\n");
+    wput(&t, "Element {\n\tstate: "); wput(&t, names[conv[1]]); wput(&t, "\n\toffset: "); wnum(&t, conv[0]); wput(&t, "\n");
+    wput(&t, "\tparents: ");
+    if (conv[2] == 0) {
+      wput(&t, "[]\n");
+    } else {
+      wput(&t, "[\n");
+      for (int k = 0; k < conv[2]; ++k) { wput(&t, "    "); wput(&t, names[conv[3 + k]]); wput(&t, ",\n"); }
+      wput(&t, "]\n");
+    }
+    wput(&t, "}\n"); /* writeln!(f, "}}") */
+    wput(&t, "\nscore: "); wnum(&t, len); wput(&t, "\n");
+    int has_m = 0, has_d = 0;
+    for (int k = 0; k < conv[2]; ++k) {
+      if (conv[3 + k] == S_M) has_m = 1;
+      if (conv[3 + k] == S_D) has_d = 1;
+    }
+    if (diag == 0 && conv[0] == 0) {
+      wput(&t, "ret\n");
+    } else {
+      const int64_t ds[3] = {WFA_X, WFA_E, WFA_O + WFA_E};
+      for (int k = 0; k < 3; ++k) {
+        if (ds[k] > len) { wput(&t, "well shit\n"); continue; }
+        wput(&t, "yeah, score: "); wnum(&t, len - ds[k]); wput(&t, "\n");
+        if (k == 1 && has_d) wput(&t, "extend\n");
+        if (k == 2 && has_m) wput(&t, "open\n");
+      }
+      wput(&t, "huh\n");
+    }
+    wput(&t, "\n\n\n");
+    wput(&t, "Alignment {\n    seq1: [],\n    seq2: [],\n}\n");
+  }
+  if (t.buf && t.cap) t.buf[t.len < t.cap ? t.len : t.cap - 1] = 0;
+  return (int64_t)t.len;
 }
 
 /* ------------------------------------------------------------------------------------------ */

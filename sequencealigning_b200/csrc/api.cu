@@ -151,6 +151,20 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
   return r;
 }
 
+int64_t sa_wfa_reference_stdout(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                                char* buf, size_t cap, int32_t* status) {
+  if (!e) return SA_E_ARG;
+  sa_engine* t = is_multi(e) ? e->children[0] : e;
+  int64_t r;
+  try {
+    r = sd_wfa_stdout(t, seq1, n1, seq2, n2, buf, cap, status);
+  } catch (const std::exception& ex) {
+    r = fail(t, SA_E_NOMEM, "host allocation failed: %s", ex.what());
+  }
+  if (r < 0 && t != e) e->err = t->err;
+  return r;
+}
+
 void* sa_alloc_pinned(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {

@@ -2089,6 +2089,120 @@ sa_status_t sd_count_cooptimal(sa_engine* e, const sa_scheme_t* scheme, const sa
 // Every co-optimal alignment of one pair, in the order and text of the reference's traceback
 // (needleman_wunsch_affine.rs:246-329, Display :390-411): the device computes the parent sets,
 // the host walks them with the reference's LIFO stack.  snprintf-style return (bytes needed).
+// The reference's complete stdout for one pair under `-a wfa` (wfa.rs:23-42), from a traced run of the
+// literal kernel: the `lo: .., hi: ..` line of every created wavefront (:251), and -- when the loop
+// converges -- `converged with score` (:36), the `huhu` block with the converged element (:650,
+// Debug :104-116), the lines of rec_tr (:653-853) and the two prints of the empty Alignment (:38-39,
+// Display :950-980).  rec_tr looks at wfs[len - {4, 6, 8}]: len is odd, the penalties are even, so
+// those tensors are always None and the recursion never descends; what it prints before giving up
+// depends only on the converged element's parent list.  A pair on which the reference panics or
+// never converges yields the lines printed up to that point (never-ending output is cut at the
+// same wavefront bound the batched path reports REF_NO_CONVERGENCE at).
+int64_t sd_wfa_stdout(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
+                      char* buf, size_t cap, int32_t* status_out) {
+  if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
+  if (status_out) *status_out = SA_OK;
+  if (cudaSetDevice(e->device) != cudaSuccess) return fail(e, SA_E_CUDA, "cudaSetDevice failed");
+  sa_status_t st;
+  const int32_t x = 4, o = 2, ex = 6;  // wfa.rs:17-21
+  const uint64_t capw = std::min<uint64_t>(8ull * ((uint64_t)n1 + n2) + 64, 2048);
+  const uint32_t wcap = (uint32_t)(2 * (capw / 4) + 16);
+  const uint64_t stride = (uint64_t)sa::kLitRing * 3 * wcap;
+  const uint32_t trace_cap = (uint32_t)capw + 8;
+  const size_t trace_ints = 8 + 2 * (size_t)trace_cap;
+  if ((st = ensure(e, e->wfa_scratch, stride * 4)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_in, (size_t)n1 + n2 + 256)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_rows, trace_ints * 4 + 64)) != SA_OK) return st;
+  struct Meta {
+    uint64_t q_off, d_off;
+    uint32_t q_len, d_len;
+    int32_t score;
+    uint8_t status;
+  } meta{0, n1, n1, n2, 0, 0};
+  uint8_t* d_in = (uint8_t*)e->par_in.p;
+  cudaError_t err = cudaMemcpyAsync(d_in, &meta, sizeof(meta), cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && n1) err = cudaMemcpyAsync(d_in + 128, seq1, n1, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && n2) err = cudaMemcpyAsync(d_in + 128 + n1, seq2, n2, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) err = cudaMemsetAsync(e->par_rows.p, 0, 32, e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D failed: %s", cudaGetErrorString(err));
+  sa::WfaParams wp{};
+  wp.residues = d_in + 128;
+  wp.packing = 0;
+  wp.q_off = (const uint64_t*)(d_in + offsetof(Meta, q_off));
+  wp.d_off = (const uint64_t*)(d_in + offsetof(Meta, d_off));
+  wp.q_len = (const uint32_t*)(d_in + offsetof(Meta, q_len));
+  wp.d_len = (const uint32_t*)(d_in + offsetof(Meta, d_len));
+  wp.x = x;
+  wp.o = o;
+  wp.e = ex;
+  wp.score = (int32_t*)(d_in + offsetof(Meta, score));
+  wp.status = d_in + offsetof(Meta, status);
+  wp.scratch = (int32_t*)e->wfa_scratch.p;
+  wp.scratch_stride = stride;
+  wp.lit_wcap = wcap;
+  wp.pair_base = 0;
+  wp.n_launch_pairs = 1;
+  wp.trace = (int32_t*)e->par_rows.p;
+  wp.trace_cap = trace_cap;
+  sa::wfa_literal_kernel<<<1, 64, 0, e->stream>>>(wp);
+  if ((err = cudaGetLastError()) != cudaSuccess) return fail(e, SA_E_CUDA, "launch failed: %s", cudaGetErrorString(err));
+  e->timing.kernel_launches++;
+  std::vector<int32_t> tr(trace_ints);
+  Meta back{};
+  err = cudaMemcpyAsync(tr.data(), e->par_rows.p, trace_ints * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(&back, d_in, sizeof(back), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "literal WFA kernel failed: %s", cudaGetErrorString(err));
+  if (status_out) *status_out = back.status;
+  std::string t;
+  const uint32_t n_lines = std::min<uint32_t>((uint32_t)tr[0], trace_cap);
+  for (uint32_t k = 0; k < n_lines; ++k)
+    t += "lo: " + std::to_string(tr[8 + 2 * k]) + ", hi: " + std::to_string(tr[9 + 2 * k]) + "\n";
+  if (back.status == SA_OK) {
+    static const char* kState[3] = {"M", "D", "I"};  // `enum State` Debug names (:44-50)
+    const int32_t len = back.score, off = tr[1], state = tr[2], np = tr[3];
+    const int64_t diag = (int64_t)n1 - (int64_t)n2;  // :635
+    t += "converged with score " + std::to_string(len) + ": \n";                                          // :36
+    t += "huhu, diag: " + std::to_string(diag) + "\nElement {\n\tstate: " + kState[state] + "\n\toffset: " + std::to_string(off) + "\n";
+    if (np == 0) {
+      t += "\tparents: []\n";
+    } else {  // {:#?} of a non-empty Vec<State>
+      t += "\tparents: [\n";
+      for (int32_t k = 0; k < np; ++k) t += std::string("    ") + kState[tr[4 + k]] + ",\n";
+      t += "]\n";
+    }
+    t += "}\n\nscore: " + std::to_string(len) + "\n";                                                      // :650
+    bool has_m = false, has_d = false;
+    for (int32_t k = 0; k < np; ++k) {
+      has_m |= tr[4 + k] == 0;
+      has_d |= tr[4 + k] == 1;
+    }
+    if (diag == 0 && off == 0) {
+      t += "ret\n";  // :662-665
+    } else {
+      for (int32_t d : {x, ex, o + ex}) {  // :667-671
+        if (d > len) {
+          t += "well shit\n";
+          continue;
+        }
+        t += "yeah, score: " + std::to_string(len - d) + "\n";
+        if (d == x) continue;                      // mismatch arm: silent unless a parent element exists
+        if (d == ex && has_d) t += "extend\n";     // :710-711
+        if (d != ex && has_m) t += "open\n";       // :754-755
+      }
+      t += "huh\n";  // :851
+    }
+    t += "\n\n\n";                                     // println!("{}", t[0]): Display of the empty Alignment
+    t += "Alignment {\n    seq1: [],\n    seq2: [],\n}\n";  // println!("{:#?}", t[0])
+  }
+  if (buf && cap) {
+    const size_t n = t.size() < cap - 1 ? t.size() : cap - 1;
+    memcpy(buf, t.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)t.size();
+}
+
 int64_t sd_all_alignments(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
                           const sa_scheme_t* scheme, uint64_t max_alignments, char* buf, size_t cap,
                           uint64_t* n_printed, int32_t* panicked) {

@@ -50,6 +50,11 @@ struct WfaParams {
   const uint32_t* __restrict__ order;  // standard: hand-out order (longest pairs first), or nullptr
   int32_t s_step;                  // standard: gcd of the penalties -- only these scores can hold a wavefront
   unsigned long long* __restrict__ work;  // standard: [0] wavefront cells computed, [1] residues passed by extend (or nullptr)
+  int32_t* __restrict__ trace;     // literal, single-pair launches only (else nullptr): what the reference's stdout
+                                   // is made of -- [0] number of `lo: .., hi: ..` lines (wfa.rs:251), [1] offset,
+                                   // [2] state (0 M, 1 D, 2 I), [3] number of parents, [4..6] parents of the converged
+                                   // element (:634-651), [8 + 2k], [9 + 2k] = lo, hi of the k-th created wavefront
+  uint32_t trace_cap;              // lines the trace can hold
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -358,6 +363,40 @@ __global__ void __launch_bounds__(64) wfa_literal_kernel(const WfaParams p) {
           if (lit_x(off, diag) == tx && lit_y(off, diag) == ty) {
             status = kOk;
             score = len;  // printed `converged with score {wfs.len()}` (:31-36)
+            if (p.trace) {
+              // The element's parent list (get_parents :201-209) is a function of the source wavefronts
+              // of tensor s = len - 1, which are still in the ring and were final when s was created:
+              // recompute it here instead of carrying parents for every element.
+              const int32_t s = len - 1;
+              auto src = [&](int32_t back, int comp) -> const LitComp* {
+                if (s - back < 0 || !tensor_present[(s - back) % kLitRing]) return nullptr;
+                const LitComp* q = &ring[(s - back) % kLitRing][comp];
+                return q->present ? q : nullptr;
+              };
+              const LitComp *om = src(p.o + p.e, 2), *mm = src(p.x, 2), *ei = src(p.e, 0), *ed = src(p.e, 1);
+              int32_t np = 0, par[3] = {0, 0, 0};
+              const int32_t dsm = lit_get(om, diag + 1), dsd = lit_get(ed, diag + 1), dv = max(dsm, dsd);
+              const int32_t ism = lit_get(om, diag - 1), isi = lit_get(ei, diag - 1), ib = max(ism, isi);
+              const int32_t iv = ib != kWfNone ? ib + 1 : kWfNone;
+              if (s > 0 && c == 1) {          // D: sources in the order (M, D), :272-311
+                if (dsm != kWfNone && dsm == dv) par[np++] = 0;
+                if (dsd != kWfNone && dsd == dv) par[np++] = 1;
+              } else if (s > 0 && c == 0) {   // I: (M, I), compared before the increment, :313-352
+                if (ism != kWfNone && ism == ib) par[np++] = 0;
+                if (isi != kWfNone && isi == ib) par[np++] = 2;
+              } else if (s > 0) {             // M: (M, I, D) against the un-extended maximum, :353-398
+                const int32_t mb = lit_get(mm, diag);
+                const int32_t m0 = mb != kWfNone ? mb + 1 : kWfNone;
+                const int32_t mv = max(m0, max(iv, dv));
+                if (m0 != kWfNone && m0 == mv) par[np++] = 0;
+                if (iv != kWfNone && iv == mv) par[np++] = 2;
+                if (dv != kWfNone && dv == mv) par[np++] = 1;
+              }
+              p.trace[1] = off;
+              p.trace[2] = c == 2 ? 0 : (c == 1 ? 1 : 2);
+              p.trace[3] = np;
+              p.trace[4] = par[0]; p.trace[5] = par[1]; p.trace[6] = par[2];
+            }
             break;
           }
         }
@@ -402,6 +441,11 @@ __global__ void __launch_bounds__(64) wfa_literal_kernel(const WfaParams p) {
     if (!any) continue;  // the tensor is None (:238)
     hi += 1;
     lo -= 1;
+    if (p.trace) {  // println!("lo: {}, hi: {}", lo, hi) (:251)
+      const int32_t k = p.trace[0];
+      if ((uint32_t)k < p.trace_cap) { p.trace[8 + 2 * k] = lo; p.trace[9 + 2 * k] = hi; }
+      p.trace[0] = k + 1;
+    }
     if ((int64_t)hi - lo + 1 > wcap) {  // cannot happen below max_score; defensive
       status = kRefNoConv;
       break;

@@ -326,6 +326,16 @@ class Engine:
         self._check(self._lib.sa_affine_all_alignments(*args, buf, need + 1, C.byref(n), C.byref(pan)))
         return buf.value.decode("latin1"), n.value, bool(pan.value)
 
+    def wfa_reference_stdout(self, seq1: bytes, seq2: bytes):
+        """The reference's complete stdout for one pair under `-a wfa` (sa_wfa_reference_stdout).
+        Returns (text, status)."""
+        st = C.c_int32()
+        need = self._lib.sa_wfa_reference_stdout(self._h, seq1, len(seq1), seq2, len(seq2), None, 0, C.byref(st))
+        self._check(need)
+        buf = C.create_string_buffer(need + 1)
+        self._check(self._lib.sa_wfa_reference_stdout(self._h, seq1, len(seq1), seq2, len(seq2), buf, need + 1, C.byref(st)))
+        return buf.raw[:need].decode("latin1"), st.value
+
     # ---- device-resident path (benchmarks: inputs already in HBM) -------------------------
     def count_cooptimal(self, batch: PairBatch, scheme=None) -> np.ndarray:
         """Per pair, how many alignments the reference's traceback prints when nothing panics

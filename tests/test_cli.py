@@ -78,6 +78,8 @@ def test_wfa_and_linear_algos(cli, tmp_path):
     r = subprocess.run([cli, "-q", q, "-d", d, "-a", "wfa"], capture_output=True, text=True)
     assert "converged with score 25: \n" in r.stdout          # wfa.rs:36 on the reference's own test pair
     assert "never converges" in r.stderr                      # ACGT vs ACGT (wfa.rs:189)
+    r = subprocess.run([cli, "-q", q, "-d", d, "-a", "wfa-standard"], capture_output=True, text=True)
+    assert r.stdout.count("gap-affine cost") == 4 and ">r vs >e: gap-affine cost 0\n" in r.stdout
     r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear"], capture_output=True, text=True)
     assert r.stdout.count("Alignment between sequences") == 4 and "seq1: ACGT\n      ||||\nseq2: ACGT" in r.stdout
 
@@ -100,3 +102,21 @@ def test_linear_stdout_matches_reference_text(cli, tmp_path, oracle):
     # the linear aligner has no semi-global mode (n_w_align takes `local: bool`, :180)
     r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear", "-m", "semi-global"], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist in the reference" in r.stderr
+
+
+@pytest.mark.gpu
+def test_wfa_stdout_matches_reference_text(cli, tmp_path, oracle):
+    """`-a wfa`: wfa_align's complete stdout per pair, db-major, against the oracle's printer."""
+    query = [(b"q1", b"ACGT"), (b"q2", b"AAAATTTTCCCC"), (b"q3", b"GATTACA")]
+    db = [(b"d1", b"ACGA"), (b"d2", b"AAAATCTCC"), (b"d3", b"GCTTAGA"), (b"d4", b"ACGT")]
+    q, d = _fa(tmp_path / "q.fasta", query), _fa(tmp_path / "d.fna", db)
+    r = subprocess.run([cli, "-q", q, "-d", d, "-a", "wfa"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exp, bad = "", 0
+    for dn, ds in db:
+        for qn, qs in query:
+            text, st = oracle.wfa_print(qs, ds)
+            exp += text
+            bad += st != 0
+    assert r.stdout == exp
+    assert r.stderr.count("the reference") == bad and "huhu, diag: 0\nElement {\n\tstate: M" in r.stdout

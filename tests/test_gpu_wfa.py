@@ -14,6 +14,8 @@ import random
 import numpy as np
 import pytest
 
+from tests.util import mutate
+
 pytestmark = pytest.mark.gpu
 ST = {"OK": 0, "PANIC": 1, "NO_CONVERGENCE": 2}
 
@@ -133,3 +135,23 @@ def test_wfa_non_global_not_implemented(engine):
     from sequencealigning_b200 import ALGO_WFA, MODE_LOCAL, NOT_IMPLEMENTED
     r = engine.align(_batch([(b"ACGT", b"ACGA")]), algo=ALGO_WFA, mode=MODE_LOCAL)  # wfa.rs:26
     assert r.status[0] == NOT_IMPLEMENTED
+
+
+def test_reference_stdout_from_the_traced_literal_kernel(engine, oracle):
+    """sa_wfa_reference_stdout: the device run yields the lo/hi lines and the converged element, the text
+    is the reference's, byte for byte against the oracle's printer -- also where the
+    reference panics (text up to the panic) or never converges (the first lines of endless output)."""
+    import random
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wfa_golden.json")))["vectors"]
+    pairs = [(v["seq1"].encode(), v["seq2"].encode()) for v in vec[:150]] + [(b"ACGT", b"ACGA"), (b"A", b"C"), (b"A", b"A")]
+    rng = random.Random(12)
+    for _ in range(150):
+        a = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 40)))
+        pairs.append((a, mutate(rng, a, rng.choice([0.05, 0.2]), True, b"ACGT") or b"A"))
+    seen = set()
+    for a, b in pairs:
+        text, st = engine.wfa_reference_stdout(a, b)
+        exp, est = oracle.wfa_print(a, b)
+        assert (text, st) == (exp, est), (a, b)
+        seen.add(st)
+    assert seen == {0, 1, 2}

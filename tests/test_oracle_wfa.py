@@ -110,3 +110,45 @@ def test_standard_wfa_equals_gotoh_cost(oracle):
     assert oracle.wfa_gotoh_cost(b"ACGT", b"ACGT") == 0
     assert oracle.wfa_gotoh_cost(b"ACGT", b"AGT") == 8      # one gap of length 1: o + e
     assert oracle.wfa_gotoh_cost(b"ACGT", b"ACTT") == 4     # one mismatch
+
+
+SURVEY_A2 = ("lo: -1, hi: 1\nconverged with score 5: \nhuhu, diag: 0\nElement {\n\tstate: M\n\toffset: 3\n\tparents: [\n    M,\n]\n}\n"
+             "\nscore: 5\nyeah, score: 1\nwell shit\nwell shit\nhuh\n\n\n\nAlignment {\n    seq1: [],\n    seq2: [],\n}\n")
+
+
+def test_reference_stdout_text(oracle):
+    """The `-a wfa` stdout (wfa.rs:251, :36, :650, :104-116, :667-678, :851, :38-39):
+    the worked example, then the C printer against the object-literal Python model on the golden
+    corpus and random tiny pairs, all three outcomes."""
+    import json
+    import os
+    import random
+    from oracle import literal_model as L
+    text, st = oracle.wfa_print(b"ACGT", b"ACGA")
+    assert st == oracle.OK and text == SURVEY_A2
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wfa_golden.json")))["vectors"]
+    pairs = [(v["seq1"].encode(), v["seq2"].encode()) for v in vec]
+    rng = random.Random(3)
+    for _ in range(250):
+        a = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 12)))
+        b = bytearray(a)
+        for _ in range(rng.randint(0, 3)):
+            k = rng.randrange(len(b))
+            r = rng.random()
+            if r < 0.5:
+                b[k] = rng.choice(b"ACGT")
+            elif r < 0.75 and len(b) > 1:
+                del b[k]
+            else:
+                b.insert(k, rng.choice(b"ACGT"))
+        pairs.append((a, bytes(b)))
+    seen = set()
+    codes = {"OK": oracle.OK, "PANIC": oracle.REF_PANIC, "NO_CONVERGENCE": oracle.REF_NO_CONVERGENCE}
+    for a, b in pairs:
+        text, st = oracle.wfa_print(a, b)
+        exp, o = L.wfa_stdout(a, b, oracle.wfa_literal_cap(len(a), len(b)))
+        assert (text, st) == (exp, codes[o.status]), (a, b)
+        seen.add(st)
+        if st == oracle.OK:
+            seen.update(w for w in ("ret", "extend", "open") if f"\n{w}\n" in text)
+    assert {oracle.OK, oracle.REF_PANIC, oracle.REF_NO_CONVERGENCE, "open"} <= seen, seen
