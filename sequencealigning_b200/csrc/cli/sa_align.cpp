@@ -12,6 +12,7 @@
 //   * where the reference process would panic (nw_affine:299/:303, wfa.rs:577/:603) this tool
 //     reports it on stderr and goes on; with --strict it exits with status 101 like a Rust panic;
 //   * a-star (the reference's default algorithm) is not part of the GPU path.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,11 +22,30 @@
 
 #include "sa_engine.h"
 
+// A record as views into the parser's output buffer (names are copied: they are printed with %s).
+struct SeqView {
+  const char* p = nullptr;
+  size_t n = 0;
+  const char* data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+};
 struct Rec {
-  std::string name, seq;
+  std::string name;
+  SeqView seq;
+  uint64_t seq_off = 0;  // offset of the sequence in the file's output buffer (= in its 2-bit image, in residues)
 };
 
-static bool load_fasta(const char* what, const std::string& path, std::vector<Rec>& recs) {
+// One FASTA file through the fused parser + packer (sa_parse_fasta_packed): `out` receives names and
+// sequences, `packed` (pinned, the engine streams from it) their 2-bit image.
+struct Fasta {
+  std::vector<uint8_t> out;
+  std::vector<Rec> recs;
+  uint64_t out_len = 0;
+  bool all_acgt = true;
+};
+
+static size_t file_size(const std::string& path) {
   FILE* f = fopen(path.c_str(), "rb");
   size_t size = 0;
   if (f) {
@@ -33,15 +53,23 @@ static bool load_fasta(const char* what, const std::string& path, std::vector<Re
     size = (size_t)ftell(f);
     fclose(f);
   }
-  std::vector<uint8_t> out(size + 1), err(size + 1);
+  return size;
+}
+
+static bool load_fasta(const char* what, const std::string& path, Fasta& fa, uint8_t* packed, size_t packed_cap) {
+  const size_t size = file_size(path);
+  fa.out.resize(size + 1);
+  std::vector<uint8_t> err(size + 1);
   std::vector<uint64_t> index(4 * (size / 2 + 2));
   size_t nerr = 0;
-  const int64_t n = sa_parse_fasta(path.c_str(), out.data(), out.size(), index.data(), index.size() / 4,
-                                   err.data(), err.size(), &nerr);
+  int acgt = 1;
+  const int64_t n = sa_parse_fasta_packed(path.c_str(), fa.out.data(), fa.out.size(), index.data(), index.size() / 4, err.data(), err.size(),
+                                          &nerr, packed, packed_cap, &acgt, &fa.out_len);
   if (n < 0) {  // main.rs:24-28 / :44-48
     fprintf(stderr, "%s fasta could not be opened: invalid input parameter\naborting\n", what);
     return false;
   }
+  fa.all_acgt = acgt != 0;
   if (nerr) {  // main.rs:29-35: continue with the partial records
     std::string chars;
     for (size_t k = 0; k < nerr && k < err.size(); ++k) {
@@ -53,11 +81,12 @@ static bool load_fasta(const char* what, const std::string& path, std::vector<Re
     fprintf(stderr, "Invalid character '[%s]' detected in %s fasta; continuing by ignoring it\n", chars.c_str(),
             strcmp(what, "DB") == 0 ? "db" : "query");
   }
+  fa.recs.resize((size_t)n);
   for (int64_t r = 0; r < n; ++r) {
-    Rec rec;
-    rec.name.assign((const char*)out.data() + index[4 * r], index[4 * r + 1]);
-    rec.seq.assign((const char*)out.data() + index[4 * r + 2], index[4 * r + 3]);
-    recs.push_back(std::move(rec));
+    Rec& rec = fa.recs[(size_t)r];
+    rec.name.assign((const char*)fa.out.data() + index[4 * r], index[4 * r + 1]);
+    rec.seq = SeqView{(const char*)fa.out.data() + index[4 * r + 2], (size_t)index[4 * r + 3]};
+    rec.seq_off = index[4 * r + 2];
   }
   return true;
 }
@@ -74,6 +103,8 @@ static void usage() {
           "                                 needleman-wunsch-linear, wfa, wfa-standard]\n"
           "      --strict                   exit 101 where the reference would panic\n"
           "      --all                      needleman-wunsch: print EVERY co-optimal alignment, like the reference\n"
+          "      --timing                   wall time of parse+pack / align / print on stderr\n"
+          "      --no-output                align without printing the alignments\n"
           "      --device <N>               CUDA device [default: 0]\n"
           "      --devices <LIST>           several CUDA devices, e.g. 0,1,2,3: the pair list is sharded over them\n"
           "  -h, --help                     Print help\n  -V, --version                  Print version\n");
@@ -91,7 +122,7 @@ static std::string duration_debug(double seconds) {
 
 int main(int argc, char** argv) {
   std::string qpath, dpath, mode = "global", algo = "needleman-wunsch";
-  bool verbose = false, strict = false, all = false, algo_given = false;
+  bool verbose = false, strict = false, all = false, algo_given = false, timing = false, quiet = false;
   std::vector<int> devices;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -122,6 +153,8 @@ int main(int argc, char** argv) {
     else if (a == "-v" || a == "--verbose") verbose = true;
     else if (a == "--strict") strict = true;
     else if (a == "--all") all = true;
+    else if (a == "--timing") timing = true;   // phase times on stderr
+    else if (a == "--no-output") quiet = true;  // align, but print nothing (throughput measurements)
     else if (a == "-h" || a == "--help") { usage(); return 0; }
     else if (a == "-V" || a == "--version") { printf("sa_align 0.1.0 (ABI %d)\n", sa_abi_version()); return 0; }
     else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
@@ -143,23 +176,41 @@ int main(int argc, char** argv) {
   else if (algo == "a-star") { fprintf(stderr, "a-star is not part of the GPU path (see DESIGN.md); use the reference binary\n"); return 2; }
   else { fprintf(stderr, "error: invalid value '%s' for '--algo <ALGO>'\n", algo.c_str()); return 2; }
 
-  std::vector<Rec> db, query;
-  if (!load_fasta("DB", dpath, db)) return 0;       // the reference returns from main, status 0
-  if (!load_fasta("Query", qpath, query)) return 0;
+  // Both files through the fused parser + packer into ONE pinned 2-bit image: the query file's bytes at
+  // residue offset 0, the db file's behind them at a byte boundary (main.rs:22-59 loads the db first).
+  // Records with an 'N' cannot be 2-bit coded: then the byte images are concatenated (pinned) instead.
+  const auto t_start = std::chrono::steady_clock::now();
+  const size_t sq = file_size(qpath), sd = file_size(dpath);
+  const size_t q_bytes = (sq + 3) / 4 + 4, d_bytes = (sd + 3) / 4 + 4;
+  uint8_t* packed = (uint8_t*)sa_alloc_pinned(q_bytes + d_bytes);
+  if (!packed) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+  Fasta fdb, fq;
+  if (!load_fasta("DB", dpath, fdb, packed + q_bytes, d_bytes)) return 0;       // the reference returns from main, status 0
+  if (!load_fasta("Query", qpath, fq, packed, q_bytes)) return 0;
+  const std::vector<Rec>&db = fdb.recs, &query = fq.recs;
+  const bool two_bit = fdb.all_acgt && fq.all_acgt;
+  uint8_t* bytes = nullptr;
+  if (!two_bit) {
+    bytes = (uint8_t*)sa_alloc_pinned(fq.out_len + fdb.out_len + 1);
+    if (!bytes) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+    memcpy(bytes, fq.out.data(), fq.out_len);
+    memcpy(bytes + fq.out_len, fdb.out.data(), fdb.out_len);
+  }
+  const uint64_t d_base = two_bit ? 4 * (uint64_t)q_bytes : fq.out_len;  // where the db file's residues start
 
-  // pack: every record once, pairs in the db-major order of main.rs:61-62
-  std::string residues;
-  std::vector<uint64_t> off;
-  for (auto& r : query) { off.push_back(residues.size()); residues += r.seq; }
-  for (auto& r : db) { off.push_back(residues.size()); residues += r.seq; }
+  // pairs in the db-major order of main.rs:61-62, offsets and lengths in pinned memory
   const size_t nq = query.size(), nd = db.size(), n = nq * nd;
-  std::vector<uint64_t> q_off(n), d_off(n);
-  std::vector<uint32_t> q_len(n), d_len(n);
+  uint64_t* q_off = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
+  uint64_t* d_off = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
+  uint32_t* q_len = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  uint32_t* d_len = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  if (!q_off || !d_off || !q_len || !d_len) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
   for (size_t d = 0, p = 0; d < nd; ++d)
     for (size_t q = 0; q < nq; ++q, ++p) {
-      q_off[p] = off[q]; q_len[p] = (uint32_t)query[q].seq.size();
-      d_off[p] = off[nq + d]; d_len[p] = (uint32_t)db[d].seq.size();
+      q_off[p] = query[q].seq_off; q_len[p] = (uint32_t)query[q].seq.size();
+      d_off[p] = d_base + db[d].seq_off; d_len[p] = (uint32_t)db[d].seq.size();
     }
+  const auto t_parsed = std::chrono::steady_clock::now();
   sa_engine_t* eng = nullptr;
   const sa_status_t created = devices.size() == 1 ? sa_engine_create(devices[0], &eng)
                                                    : sa_engine_create_multi(devices.data(), (int)devices.size(), &eng);
@@ -168,18 +219,28 @@ int main(int argc, char** argv) {
     sa_engine_destroy(eng);
     return 1;
   }
-  sa_batch_t batch{(const uint8_t*)residues.data(), residues.size(), q_off.data(), q_len.data(), d_off.data(), d_len.data(), n, 0};
-  std::vector<int32_t> score(n);
-  std::vector<uint8_t> status(n);
-  std::vector<uint64_t> coff(n);
-  std::vector<uint32_t> clen(n), pool(64 * n + 1024), end1(n), end2(n);
-  sa_result_t res{score.data(), status.data(), coff.data(), clen.data(), pool.data(), pool.size(), 0, end1.data(), end2.data()};
+  sa_batch_t batch{two_bit ? packed : bytes, two_bit ? (uint64_t)(q_bytes + d_bytes) : fq.out_len + fdb.out_len, q_off, q_len, d_off, d_len, n,
+                   two_bit ? 1u : 0u};
+  // results in pinned memory as well (the engine streams them out segment by segment)
+  int32_t* score = (int32_t*)sa_alloc_pinned((n + 1) * 4);
+  uint8_t* status = (uint8_t*)sa_alloc_pinned(n + 1);
+  uint64_t* coff = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
+  uint32_t* clen = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  uint32_t* end1 = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  uint32_t* end2 = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  uint64_t pool_cap = 64 * (uint64_t)n + 1024;
+  uint32_t* pool = (uint32_t*)sa_alloc_pinned(pool_cap * 4);
+  if (!score || !status || !coff || !clen || !end1 || !end2 || !pool) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+  sa_result_t res{score, status, coff, clen, pool, pool_cap, 0, end1, end2};
   const auto t0 = std::chrono::steady_clock::now();
   sa_status_t rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
   if (rc == SA_E_CIGAR_CAPACITY) {
-    pool.resize(res.cigar_used + 16);
-    res.cigar = pool.data();
-    res.cigar_capacity = pool.size();
+    sa_free_pinned(pool);
+    pool_cap = res.cigar_used + 16;
+    pool = (uint32_t*)sa_alloc_pinned(pool_cap * 4);
+    if (!pool) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+    res.cigar = pool;
+    res.cigar_capacity = pool_cap;
     rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
   }
   const double per_pair = n ? std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (double)n : 0;
@@ -187,6 +248,27 @@ int main(int argc, char** argv) {
     fprintf(stderr, "sa_align_batch: %s\n", sa_last_error(eng));
     sa_engine_destroy(eng);
     return 1;
+  }
+  const auto t_aligned = std::chrono::steady_clock::now();
+  auto report_timing = [&]() {
+    if (!timing) return;
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    sa_timing_t tm{};
+    sa_last_timing(eng, &tm);
+    const auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr,
+            "timing: %zu pairs, %.3e cells | parse+pack %.1f ms (%.2f GB/s, %s) | engine create %.1f ms | sa_align_batch %.1f ms "
+            "(kernels %.1f ms, %.1f GCUPS end to end) | print %.1f ms | total %.1f ms\n",
+            n, (double)tm.cells, ms(t_start, t_parsed), (double)(sq + sd) / 1e6 / std::max(ms(t_start, t_parsed), 1e-6),
+            two_bit ? "2-bit" : "bytes", ms(t_parsed, t0), ms(t0, t_aligned), tm.kernels_ms,
+            (double)tm.cells / 1e6 / std::max(ms(t0, t_aligned), 1e-6), ms(t_aligned, t_end), ms(t_start, t_end));
+  };
+  if (quiet) {
+    report_timing();
+    sa_engine_destroy(eng);
+    return 0;
   }
   int exit_code = 0;
   // SA_ALIGNMENT_OMITTED is a flag on top of the status: report it, then treat the status as usual
@@ -235,11 +317,11 @@ int main(int argc, char** argv) {
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
         if (!omitted[p]) {
           const int64_t need = sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                                    (uint32_t)D.seq.size(), pool.data() + coff[p], clen[p], end1[p], end2[p], nullptr, 0);
+                                                    (uint32_t)D.seq.size(), pool + coff[p], clen[p], end1[p], end2[p], nullptr, 0);
           if (need < 0) { fprintf(stderr, "sa_render_linear_hit: the CIGAR does not fit the pair\n"); exit_code = 1; break; }
           std::string text((size_t)need + 1, '\0');
           sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
-                               pool.data() + coff[p], clen[p], end1[p], end2[p], &text[0], text.size());
+                               pool + coff[p], clen[p], end1[p], end2[p], &text[0], text.size());
           fwrite(text.data(), 1, (size_t)need, stdout);
         }
         continue;
@@ -269,10 +351,10 @@ int main(int argc, char** argv) {
       }
       if (has_alignment) {
         const int64_t need = sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                              (uint32_t)D.seq.size(), pool.data() + coff[p], clen[p], nullptr, 0);
+                                              (uint32_t)D.seq.size(), pool + coff[p], clen[p], nullptr, 0);
         std::string text((size_t)need + 1, '\0');
         sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
-                         pool.data() + coff[p], clen[p], &text[0], text.size());
+                         pool + coff[p], clen[p], &text[0], text.size());
         text.resize((size_t)need);
         fputs(text.c_str(), stdout);
       }
@@ -284,6 +366,8 @@ int main(int argc, char** argv) {
       }
       if (al == SA_ALGO_NW_AFFINE) printf("%s\n", duration_debug(per_pair).c_str());  // nw_affine:431
     }
+  fflush(stdout);
+  report_timing();
   sa_engine_destroy(eng);
   return exit_code;
 }

@@ -1336,7 +1336,12 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
       CUDA_TRY(e, cudaFuncSetAttribute(sa::wfa_standard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    const uint64_t stride = (uint64_t)sa::kWfRing * 3 * width + (nmax_sum + 32) / 4 + 8;
+    // all penalties share a factor (2 for the reference's 4/2/6): other scores stay empty
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    wp.s_step = std::max(1, gcd(gcd(x, o + ex), ex));
+    wp.ring_dm = std::max(x, o + ex) / wp.s_step + 1;
+    wp.ring_de = ex / wp.s_step + 1;
+    const uint64_t stride = (uint64_t)(wp.ring_dm + 2 * wp.ring_de) * width + (nmax_sum + 32) / 4 + 8;
     uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 8);
     if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4 + n * 4)) != SA_OK) return st;
     uint32_t* d_next = (uint32_t*)e->misc.p + 8;
@@ -1352,9 +1357,6 @@ sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h
     wp.pair_base = 0;
     wp.n_launch_pairs = (uint32_t)n;
     {
-      // all penalties share a factor (2 for the reference's 4/2/6): other scores stay empty
-      auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-      wp.s_step = std::max(1, gcd(gcd(x, o + ex), ex));
       // longest pairs first: one warp per pair, so the long ones must not start last
       std::vector<uint32_t> order(n);
       for (uint64_t p = 0; p < n; ++p) order[p] = (uint32_t)p;

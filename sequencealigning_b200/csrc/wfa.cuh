@@ -55,12 +55,13 @@ struct WfaParams {
                                    // [2] state (0 M, 1 D, 2 I), [3] number of parents, [4..6] parents of the converged
                                    // element (:634-651), [8 + 2k], [9 + 2k] = lo, hi of the k-th created wavefront
   uint32_t trace_cap;              // lines the trace can hold
+  int32_t ring_dm, ring_de;        // standard: ring depth of the M component (max(x, o+e) / s_step + 1) and of I / D (e / s_step + 1)
 };
 
 // ---------------------------------------------------------------------------------------------
 // STANDARD MODE
 // ---------------------------------------------------------------------------------------------
-constexpr int kWfRing = 16;  // >= max(x, o+e) + 1, power of two
+constexpr int kWfRing = 16;  // most scores the ring may have to keep: max(x, o+e) / s_step + 1 <= kWfRing
 
 // Extend along a diagonal on word-packed sequences: BITS = 8 (any byte alphabet, 4 residues per
 // comparison) or BITS = 2 (A/C/G/T codes, 16 residues per comparison).  `sa`, `sb` are 4-byte
@@ -92,7 +93,11 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
   uint32_t* sq = smem_w + (size_t)warp * (p.smem_seq_bytes >> 2);
-  int32_t* ring = p.scratch + (uint64_t)gwarp * p.scratch_stride;  // [kWfRing][3][width]
+  // The ring keeps only what the recurrences read: M of the last max(x, o+e) / s_step + 1 scores, I and D of
+  // the last e / s_step + 1 (13 arrays for the reference's 4 / 2 / 6 instead of 3 x 16): the live set of a warp
+  // is then small enough for the resident warps' rings to stay in L2.
+  int32_t* ring = p.scratch + (uint64_t)gwarp * p.scratch_stride;  // [ring_dm] M, then [ring_de] I, then [ring_de] D; width each
+  const int32_t DM = p.ring_dm, DE = p.ring_de;
   const int32_t W = (int32_t)p.width;
   // per-slot diagonal range, kept in shared memory (uniform per warp)
   __shared__ int32_t s_lo[4][kWfRing], s_hi[4][kWfRing];
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       s1w = sq;
       s2w = sq + w1;
     } else {
-      s1w = reinterpret_cast<uint32_t*>(ring + (size_t)kWfRing * 3 * W);
+      s1w = reinterpret_cast<uint32_t*>(ring + (size_t)(DM + 2 * DE) * W);
       s2w = s1w + w1;
     }
     __syncwarp();
@@ -168,9 +173,9 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     {
       const int32_t v0 = wide ? wf_extend<8>(s1w, s2w, 0, 0, n1, n2) : wf_extend<2>(s1w, s2w, 0, 0, n1, n2);
       if (lane == 0) {
-        ring[(0 * 3 + 0) * W + koff] = v0;
-        ring[(0 * 3 + 1) * W + koff] = kWfNone;
-        ring[(0 * 3 + 2) * W + koff] = kWfNone;
+        ring[koff] = v0;                                  // M, slot 0
+        ring[(size_t)DM * W + koff] = kWfNone;            // I, slot 0
+        ring[(size_t)(DM + DE) * W + koff] = kWfNone;     // D, slot 0
         lo_[0] = 0;
         hi_[0] = 0;
       }
@@ -178,10 +183,12 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     }
     __syncwarp();
     const int32_t max_s = 2 * p.o + p.e * (n1 + n2) + p.x + 8;
-    for (int32_t s = p.s_step; result < 0 && s <= max_s; s += p.s_step) {
-      const int slot = s & (kWfRing - 1);
-      const int sx = (s - p.x) & (kWfRing - 1), so = (s - p.o - p.e) & (kWfRing - 1),
-                se = (s - p.e) & (kWfRing - 1);
+    const int32_t step = p.s_step, bx = p.x / step, bo = (p.o + p.e) / step, be = p.e / step;  // look-backs in ring steps
+    for (int32_t s = step, t = 1; result < 0 && s <= max_s; s += step, ++t) {
+      // slot of score s: (s / step) mod depth; the range arrays follow the M ring
+      const int slot = t % DM, slot_e = t % DE;
+      const int sx = ((t - bx) % DM + DM) % DM, so = ((t - bo) % DM + DM) % DM, se = ((t - be) % DM + DM) % DM;
+      const int se_e = ((t - be) % DE + DE) % DE;
       const bool hx = s - p.x >= 0 && lo_[sx] <= hi_[sx];
       const bool ho = s - p.o - p.e >= 0 && lo_[so] <= hi_[so];
       const bool he = s - p.e >= 0 && lo_[se] <= hi_[se];
@@ -197,13 +204,13 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       }
       lo = max(lo, -n2);
       hi = min(hi, n1);
-      int32_t* Mc = ring + (slot * 3 + 0) * W + koff;
-      int32_t* Ic = ring + (slot * 3 + 1) * W + koff;
-      int32_t* Dc = ring + (slot * 3 + 2) * W + koff;
-      const int32_t* Mx = ring + (sx * 3 + 0) * W + koff;
-      const int32_t* Mo = ring + (so * 3 + 0) * W + koff;
-      const int32_t* Ie = ring + (se * 3 + 1) * W + koff;
-      const int32_t* De = ring + (se * 3 + 2) * W + koff;
+      int32_t* Mc = ring + (size_t)slot * W + koff;
+      int32_t* Ic = ring + (size_t)(DM + slot_e) * W + koff;
+      int32_t* Dc = ring + (size_t)(DM + DE + slot_e) * W + koff;
+      const int32_t* Mx = ring + (size_t)sx * W + koff;
+      const int32_t* Mo = ring + (size_t)so * W + koff;
+      const int32_t* Ie = ring + (size_t)(DM + se_e) * W + koff;
+      const int32_t* De = ring + (size_t)(DM + DE + se_e) * W + koff;
       const int32_t xlo = hx ? lo_[sx] : 1, xhi = hx ? hi_[sx] : 0;
       const int32_t olo = ho ? lo_[so] : 1, ohi = ho ? hi_[so] : 0;
       const int32_t elo = he ? lo_[se] : 1, ehi = he ? hi_[se] : 0;
