@@ -45,6 +45,13 @@ struct Fasta {
   bool all_acgt = true;
 };
 
+// Page-locked host memory when a CUDA device is there to lock it for (the engine then streams from / to it
+// asynchronously), plain memory otherwise (the FASTA errors of main.rs:24-48 must come out without a GPU too).
+static void* host_alloc(size_t bytes) {
+  void* p = sa_alloc_pinned(bytes);
+  return p ? p : malloc(bytes ? bytes : 1);
+}
+
 static size_t file_size(const std::string& path) {
   FILE* f = fopen(path.c_str(), "rb");
   size_t size = 0;
@@ -182,8 +189,8 @@ int main(int argc, char** argv) {
   const auto t_start = std::chrono::steady_clock::now();
   const size_t sq = file_size(qpath), sd = file_size(dpath);
   const size_t q_bytes = (sq + 3) / 4 + 4, d_bytes = (sd + 3) / 4 + 4;
-  uint8_t* packed = (uint8_t*)sa_alloc_pinned(q_bytes + d_bytes);
-  if (!packed) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+  uint8_t* packed = (uint8_t*)host_alloc(q_bytes + d_bytes);
+  if (!packed) { fprintf(stderr, "host allocation failed\n"); return 1; }
   Fasta fdb, fq;
   if (!load_fasta("DB", dpath, fdb, packed + q_bytes, d_bytes)) return 0;       // the reference returns from main, status 0
   if (!load_fasta("Query", qpath, fq, packed, q_bytes)) return 0;
@@ -191,8 +198,8 @@ int main(int argc, char** argv) {
   const bool two_bit = fdb.all_acgt && fq.all_acgt;
   uint8_t* bytes = nullptr;
   if (!two_bit) {
-    bytes = (uint8_t*)sa_alloc_pinned(fq.out_len + fdb.out_len + 1);
-    if (!bytes) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+    bytes = (uint8_t*)host_alloc(fq.out_len + fdb.out_len + 1);
+    if (!bytes) { fprintf(stderr, "host allocation failed\n"); return 1; }
     memcpy(bytes, fq.out.data(), fq.out_len);
     memcpy(bytes + fq.out_len, fdb.out.data(), fdb.out_len);
   }
@@ -200,11 +207,11 @@ int main(int argc, char** argv) {
 
   // pairs in the db-major order of main.rs:61-62, offsets and lengths in pinned memory
   const size_t nq = query.size(), nd = db.size(), n = nq * nd;
-  uint64_t* q_off = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
-  uint64_t* d_off = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
-  uint32_t* q_len = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
-  uint32_t* d_len = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
-  if (!q_off || !d_off || !q_len || !d_len) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+  uint64_t* q_off = (uint64_t*)host_alloc((n + 1) * 8);
+  uint64_t* d_off = (uint64_t*)host_alloc((n + 1) * 8);
+  uint32_t* q_len = (uint32_t*)host_alloc((n + 1) * 4);
+  uint32_t* d_len = (uint32_t*)host_alloc((n + 1) * 4);
+  if (!q_off || !d_off || !q_len || !d_len) { fprintf(stderr, "host allocation failed\n"); return 1; }
   for (size_t d = 0, p = 0; d < nd; ++d)
     for (size_t q = 0; q < nq; ++q, ++p) {
       q_off[p] = query[q].seq_off; q_len[p] = (uint32_t)query[q].seq.size();
@@ -222,23 +229,22 @@ int main(int argc, char** argv) {
   sa_batch_t batch{two_bit ? packed : bytes, two_bit ? (uint64_t)(q_bytes + d_bytes) : fq.out_len + fdb.out_len, q_off, q_len, d_off, d_len, n,
                    two_bit ? 1u : 0u};
   // results in pinned memory as well (the engine streams them out segment by segment)
-  int32_t* score = (int32_t*)sa_alloc_pinned((n + 1) * 4);
-  uint8_t* status = (uint8_t*)sa_alloc_pinned(n + 1);
-  uint64_t* coff = (uint64_t*)sa_alloc_pinned((n + 1) * 8);
-  uint32_t* clen = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
-  uint32_t* end1 = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
-  uint32_t* end2 = (uint32_t*)sa_alloc_pinned((n + 1) * 4);
+  int32_t* score = (int32_t*)host_alloc((n + 1) * 4);
+  uint8_t* status = (uint8_t*)host_alloc(n + 1);
+  uint64_t* coff = (uint64_t*)host_alloc((n + 1) * 8);
+  uint32_t* clen = (uint32_t*)host_alloc((n + 1) * 4);
+  uint32_t* end1 = (uint32_t*)host_alloc((n + 1) * 4);
+  uint32_t* end2 = (uint32_t*)host_alloc((n + 1) * 4);
   uint64_t pool_cap = 64 * (uint64_t)n + 1024;
-  uint32_t* pool = (uint32_t*)sa_alloc_pinned(pool_cap * 4);
-  if (!score || !status || !coff || !clen || !end1 || !end2 || !pool) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+  uint32_t* pool = (uint32_t*)host_alloc(pool_cap * 4);
+  if (!score || !status || !coff || !clen || !end1 || !end2 || !pool) { fprintf(stderr, "host allocation failed\n"); return 1; }
   sa_result_t res{score, status, coff, clen, pool, pool_cap, 0, end1, end2};
   const auto t0 = std::chrono::steady_clock::now();
   sa_status_t rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
   if (rc == SA_E_CIGAR_CAPACITY) {
-    sa_free_pinned(pool);
-    pool_cap = res.cigar_used + 16;
-    pool = (uint32_t*)sa_alloc_pinned(pool_cap * 4);
-    if (!pool) { fprintf(stderr, "sa_alloc_pinned failed\n"); return 1; }
+    pool_cap = res.cigar_used + 16;  // (the first pool is left to process exit)
+    pool = (uint32_t*)host_alloc(pool_cap * 4);
+    if (!pool) { fprintf(stderr, "host allocation failed\n"); return 1; }
     res.cigar = pool;
     res.cigar_capacity = pool_cap;
     rc = sa_align_batch(eng, al, m, nullptr, &batch, &res);
