@@ -186,6 +186,10 @@ sa_status_t sa_last_timing(const sa_engine_t* e, sa_timing_t* out);
 /* -- host helpers --------------------------------------------------------------------- */
 void* sa_alloc_pinned(size_t bytes);
 void sa_free_pinned(void* p);
+/* Page-locks memory the caller already owns (a parser's output, an mmap) so that sa_align_batch
+ * streams from / to it like from sa_alloc_pinned memory; undo with sa_host_unregister. */
+sa_status_t sa_host_register(void* p, size_t bytes);
+sa_status_t sa_host_unregister(void* p);
 
 /* How a multi-device call was sharded (one entry per device of the engine, in creation order). */
 typedef struct {

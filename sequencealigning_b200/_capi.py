@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
     "sa_affine_count_cooptimal", "sa_engine_create_multi", "sa_engine_device_count", "sa_last_shards", "sa_plan_shards",
-    "sa_pack_2bit_mt", "sa_parse_fasta_packed", "sa_render_linear_hit", "sa_wfa_reference_stdout",
+    "sa_pack_2bit_mt", "sa_parse_fasta_packed", "sa_render_linear_hit", "sa_wfa_reference_stdout", "sa_host_register", "sa_host_unregister",
 ]
 
 
@@ -116,6 +116,10 @@ def lib() -> C.CDLL:
     l.sa_alloc_pinned.restype = vp
     l.sa_free_pinned.argtypes = [vp]
     l.sa_free_pinned.restype = None
+    l.sa_host_register.argtypes = [vp, C.c_size_t]
+    l.sa_host_register.restype = C.c_int
+    l.sa_host_unregister.argtypes = [vp]
+    l.sa_host_unregister.restype = C.c_int
     l.sa_partition_lpt.argtypes = [vp, vp, C.c_uint64, C.c_int, vp]
     l.sa_partition_lpt.restype = C.c_int
     l.sa_parse_fasta.argtypes = [C.c_char_p, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]

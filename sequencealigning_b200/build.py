@@ -79,7 +79,7 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
     cli = os.path.join(CSRC, "cli", "sa_align.cpp")
     if os.path.exists(cli) and (force or _newer(CLI_PATH, deps + [LIB_PATH])):
         subprocess.run(
-            ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_PATH, cli, "-I", os.path.join(_ROOT, "include"),
+            ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", CLI_PATH, cli, "-I", os.path.join(_ROOT, "include"),
              "-L", LIB_DIR, "-lsa_engine", "-Wl,-rpath,$ORIGIN"],
             check=True,
         )

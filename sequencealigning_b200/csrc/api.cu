@@ -178,4 +178,22 @@ void sa_free_pinned(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+sa_status_t sa_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return SA_E_ARG;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return SA_E_CUDA;
+  }
+  return SA_OK;
+}
+
+sa_status_t sa_host_unregister(void* p) {
+  if (!p) return SA_E_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return SA_E_CUDA;
+  }
+  return SA_OK;
+}
+
 }  // extern "C"

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sa_engine.h"
@@ -45,11 +46,27 @@ struct Fasta {
   bool all_acgt = true;
 };
 
-// Page-locked host memory when a CUDA device is there to lock it for (the engine then streams from / to it
-// asynchronously), plain memory otherwise (the FASTA errors of main.rs:24-48 must come out without a GPU too).
+// Page-aligned plain memory: nothing here touches CUDA, so parsing runs while the engine (and the CUDA
+// context, ~1 s) comes up on another thread; the large buffers are page-locked afterwards in place
+// (sa_host_register), which is what lets sa_align_batch stream from / to them asynchronously.
 static void* host_alloc(size_t bytes) {
-  void* p = sa_alloc_pinned(bytes);
-  return p ? p : malloc(bytes ? bytes : 1);
+  const size_t rounded = (std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095;
+  return aligned_alloc(4096, rounded);
+}
+
+// One render call per text: the snprintf-style entry points write into a reused buffer and say how much they
+// needed; only a text that did not fit is rendered a second time.  Returns false when the call failed.
+template <class F>
+static bool emit_text(std::string& buf, F&& call) {
+  if (buf.size() < (1u << 16)) buf.resize(1u << 16);
+  int64_t need = call(&buf[0], buf.size());
+  if (need < 0) return false;
+  if ((size_t)need + 1 > buf.size()) {
+    buf.resize((size_t)need + 1);
+    need = call(&buf[0], buf.size());
+  }
+  fwrite(buf.data(), 1, (size_t)need, stdout);
+  return true;
 }
 
 static size_t file_size(const std::string& path) {
@@ -66,8 +83,17 @@ static size_t file_size(const std::string& path) {
 static bool load_fasta(const char* what, const std::string& path, Fasta& fa, uint8_t* packed, size_t packed_cap) {
   const size_t size = file_size(path);
   fa.out.resize(size + 1);
-  std::vector<uint8_t> err(size + 1);
-  std::vector<uint64_t> index(4 * (size / 2 + 2));
+  std::vector<uint8_t> err(4096);  // the first rejected bytes; the parser counts the rest
+  // one index row per '>' of the file (a scan at memory speed; the parser reads the page cache afterwards)
+  size_t n_gt = 0;
+  if (FILE* f = fopen(path.c_str(), "rb")) {
+    std::vector<char> chunk(1 << 22);
+    size_t got;
+    while ((got = fread(chunk.data(), 1, chunk.size(), f)) > 0)
+      for (const char* c = chunk.data(), *e = c + got; (c = (const char*)memchr(c, '>', (size_t)(e - c))) != nullptr; ++c) ++n_gt;
+    fclose(f);
+  }
+  std::vector<uint64_t> index(4 * (n_gt + 2));
   size_t nerr = 0;
   int acgt = 1;
   const int64_t n = sa_parse_fasta_packed(path.c_str(), fa.out.data(), fa.out.size(), index.data(), index.size() / 4, err.data(), err.size(),
@@ -112,6 +138,7 @@ static void usage() {
           "      --all                      needleman-wunsch: print EVERY co-optimal alignment, like the reference\n"
           "      --timing                   wall time of parse+pack / align / print on stderr\n"
           "      --no-output                align without printing the alignments\n"
+          "      --pageable                 leave the input buffers pageable (default: page-locked in place for >= 64 Ki pairs)\n"
           "      --device <N>               CUDA device [default: 0]\n"
           "      --devices <LIST>           several CUDA devices, e.g. 0,1,2,3: the pair list is sharded over them\n"
           "  -h, --help                     Print help\n  -V, --version                  Print version\n");
@@ -129,7 +156,7 @@ static std::string duration_debug(double seconds) {
 
 int main(int argc, char** argv) {
   std::string qpath, dpath, mode = "global", algo = "needleman-wunsch";
-  bool verbose = false, strict = false, all = false, algo_given = false, timing = false, quiet = false;
+  bool verbose = false, strict = false, all = false, algo_given = false, timing = false, quiet = false, pageable = false;
   std::vector<int> devices;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -161,6 +188,7 @@ int main(int argc, char** argv) {
     else if (a == "--strict") strict = true;
     else if (a == "--all") all = true;
     else if (a == "--timing") timing = true;   // phase times on stderr
+    else if (a == "--pageable") pageable = true;  // do not page-lock the inputs
     else if (a == "--no-output") quiet = true;  // align, but print nothing (throughput measurements)
     else if (a == "-h" || a == "--help") { usage(); return 0; }
     else if (a == "-V" || a == "--version") { printf("sa_align 0.1.0 (ABI %d)\n", sa_abi_version()); return 0; }
@@ -187,6 +215,17 @@ int main(int argc, char** argv) {
   // residue offset 0, the db file's behind them at a byte boundary (main.rs:22-59 loads the db first).
   // Records with an 'N' cannot be 2-bit coded: then the byte images are concatenated (pinned) instead.
   const auto t_start = std::chrono::steady_clock::now();
+  // the engine (CUDA context, streams, events) comes up while the FASTA files are parsed and packed
+  sa_engine_t* eng = nullptr;
+  sa_status_t created = SA_OK;
+  std::thread engine_thread([&] {
+    created = devices.size() == 1 ? sa_engine_create(devices[0], &eng)
+                                  : sa_engine_create_multi(devices.data(), (int)devices.size(), &eng);
+  });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{engine_thread};
   const size_t sq = file_size(qpath), sd = file_size(dpath);
   const size_t q_bytes = (sq + 3) / 4 + 4, d_bytes = (sd + 3) / 4 + 4;
   uint8_t* packed = (uint8_t*)host_alloc(q_bytes + d_bytes);
@@ -218,9 +257,7 @@ int main(int argc, char** argv) {
       d_off[p] = d_base + db[d].seq_off; d_len[p] = (uint32_t)db[d].seq.size();
     }
   const auto t_parsed = std::chrono::steady_clock::now();
-  sa_engine_t* eng = nullptr;
-  const sa_status_t created = devices.size() == 1 ? sa_engine_create(devices[0], &eng)
-                                                   : sa_engine_create_multi(devices.data(), (int)devices.size(), &eng);
+  engine_thread.join();
   if (created != SA_OK) {
     fprintf(stderr, "sa_engine_create: %s\n", sa_last_error(eng));
     sa_engine_destroy(eng);
@@ -228,14 +265,24 @@ int main(int argc, char** argv) {
   }
   sa_batch_t batch{two_bit ? packed : bytes, two_bit ? (uint64_t)(q_bytes + d_bytes) : fq.out_len + fdb.out_len, q_off, q_len, d_off, d_len, n,
                    two_bit ? 1u : 0u};
-  // results in pinned memory as well (the engine streams them out segment by segment)
+  const auto t_engine = std::chrono::steady_clock::now();
+  // page-lock the inputs in place (large batches only: locking costs about as much as one staged copy)
+  const bool pin = !pageable && n >= 65536;
+  if (pin) {
+    sa_host_register(two_bit ? (void*)packed : (void*)bytes, (size_t)batch.residues_len);
+    sa_host_register(q_off, (n + 1) * 8);
+    sa_host_register(d_off, (n + 1) * 8);
+    sa_host_register(q_len, (n + 1) * 4);
+    sa_host_register(d_len, (n + 1) * 4);
+  }
+  // results (pageable: a one-shot process would spend longer locking ~100 bytes per pair than the staged copy takes)
   int32_t* score = (int32_t*)host_alloc((n + 1) * 4);
   uint8_t* status = (uint8_t*)host_alloc(n + 1);
   uint64_t* coff = (uint64_t*)host_alloc((n + 1) * 8);
   uint32_t* clen = (uint32_t*)host_alloc((n + 1) * 4);
   uint32_t* end1 = (uint32_t*)host_alloc((n + 1) * 4);
   uint32_t* end2 = (uint32_t*)host_alloc((n + 1) * 4);
-  uint64_t pool_cap = 64 * (uint64_t)n + 1024;
+  uint64_t pool_cap = 24 * (uint64_t)n + 4096;
   uint32_t* pool = (uint32_t*)host_alloc(pool_cap * 4);
   if (!score || !status || !coff || !clen || !end1 || !end2 || !pool) { fprintf(stderr, "host allocation failed\n"); return 1; }
   sa_result_t res{score, status, coff, clen, pool, pool_cap, 0, end1, end2};
@@ -265,10 +312,11 @@ int main(int argc, char** argv) {
     sa_last_timing(eng, &tm);
     const auto t_end = std::chrono::steady_clock::now();
     fprintf(stderr,
-            "timing: %zu pairs, %.3e cells | parse+pack %.1f ms (%.2f GB/s, %s) | engine create %.1f ms | sa_align_batch %.1f ms "
+            "timing: %zu pairs, %.3e cells | parse+pack %.1f ms (%.2f GB/s, %s; engine start-up runs beside it) | "
+            "wait for the engine %.1f ms | page-lock + buffers %.1f ms | sa_align_batch %.1f ms "
             "(kernels %.1f ms, %.1f GCUPS end to end) | print %.1f ms | total %.1f ms\n",
             n, (double)tm.cells, ms(t_start, t_parsed), (double)(sq + sd) / 1e6 / std::max(ms(t_start, t_parsed), 1e-6),
-            two_bit ? "2-bit" : "bytes", ms(t_parsed, t0), ms(t0, t_aligned), tm.kernels_ms,
+            two_bit ? "2-bit" : "bytes", ms(t_parsed, t_engine), ms(t_engine, t0), ms(t0, t_aligned), tm.kernels_ms,
             (double)tm.cells / 1e6 / std::max(ms(t0, t_aligned), 1e-6), ms(t_aligned, t_end), ms(t_start, t_end));
   };
   if (quiet) {
@@ -283,6 +331,9 @@ int main(int argc, char** argv) {
     omitted[p] = (status[p] & SA_ALIGNMENT_OMITTED) ? 1 : 0;
     status[p] &= 0x7f;
   }
+  std::string text;  // reused render buffer
+  static char out_buf[1 << 20];
+  setvbuf(stdout, out_buf, _IOFBF, sizeof(out_buf));
   for (size_t d = 0, p = 0; d < nd && !exit_code; ++d)
     for (size_t q = 0; q < nq; ++q, ++p) {
       const Rec &Q = query[q], &D = db[d];
@@ -299,13 +350,14 @@ int main(int argc, char** argv) {
         // kernel: the `lo: .., hi: ..` lines, and after convergence the score, the `huhu` block, rec_tr's
         // lines and the empty Alignment.  Where the reference dies or loops: what it had printed by then.
         int32_t st = 0;
-        const int64_t need = sa_wfa_reference_stdout(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                                     (uint32_t)D.seq.size(), nullptr, 0, &st);
-        if (need < 0) { fprintf(stderr, "sa_wfa_reference_stdout: %s\n", sa_last_error(eng)); exit_code = 1; break; }
-        std::string text((size_t)need + 1, '\0');
-        sa_wfa_reference_stdout(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
-                                &text[0], text.size(), &st);
-        fwrite(text.data(), 1, (size_t)need, stdout);
+        if (!emit_text(text, [&](char* b, size_t c) {
+              return sa_wfa_reference_stdout(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                             (uint32_t)D.seq.size(), b, c, &st);
+            })) {
+          fprintf(stderr, "sa_wfa_reference_stdout: %s\n", sa_last_error(eng));
+          exit_code = 1;
+          break;
+        }
         if (st != SA_OK) {
           fprintf(stderr, "%s vs %s: the reference %s here\n", Q.name.c_str(), D.name.c_str(),
                   st == SA_REF_PANIC ? "panics in trim (wfa.rs:577/603)" : "never converges (wfa.rs:189)");
@@ -322,13 +374,14 @@ int main(int argc, char** argv) {
         if (verbose) printf("search finished after %s\n", duration_debug(per_pair).c_str());
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
         if (!omitted[p]) {
-          const int64_t need = sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                                    (uint32_t)D.seq.size(), pool + coff[p], clen[p], end1[p], end2[p], nullptr, 0);
-          if (need < 0) { fprintf(stderr, "sa_render_linear_hit: the CIGAR does not fit the pair\n"); exit_code = 1; break; }
-          std::string text((size_t)need + 1, '\0');
-          sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
-                               pool + coff[p], clen[p], end1[p], end2[p], &text[0], text.size());
-          fwrite(text.data(), 1, (size_t)need, stdout);
+          if (!emit_text(text, [&](char* b, size_t c) {
+                return sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                            (uint32_t)D.seq.size(), pool + coff[p], clen[p], end1[p], end2[p], b, c);
+              })) {
+            fprintf(stderr, "sa_render_linear_hit: the CIGAR does not fit the pair\n");
+            exit_code = 1;
+            break;
+          }
         }
         continue;
       }
@@ -355,15 +408,11 @@ int main(int argc, char** argv) {
         printf("%s\n", duration_debug(per_pair).c_str());
         continue;
       }
-      if (has_alignment) {
-        const int64_t need = sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                              (uint32_t)D.seq.size(), pool + coff[p], clen[p], nullptr, 0);
-        std::string text((size_t)need + 1, '\0');
-        sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
-                         pool + coff[p], clen[p], &text[0], text.size());
-        text.resize((size_t)need);
-        fputs(text.c_str(), stdout);
-      }
+      if (has_alignment)
+        emit_text(text, [&](char* b, size_t c) {
+          return sa_render_affine((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(),
+                                  pool + coff[p], clen[p], b, c);
+        });
       if (verbose) printf("score: %d\n", score[p]);
       if (status[p] == SA_REF_PANIC || status[p] == SA_REF_PANIC_EARLY) {
         fprintf(stderr, "%s vs %s: the reference panics here (index out of bounds, needleman_wunsch_affine.rs:299/303)%s\n",

@@ -122,7 +122,7 @@ struct Form {
   int K, G, regs;  // regs: registers per thread of the instantiation (cuobjdump -res-usage)
 };
 constexpr Form kForms[] = {{8, 1, 98},  {8, 2, 98},  {8, 4, 98},   {8, 8, 98},   {8, 16, 98},
-                           {8, 32, 98}, {13, 8, 104}, {13, 16, 104}, {16, 8, 116}, {16, 16, 116}, {19, 8, 142}, {19, 16, 142}};
+                           {8, 32, 98}, {13, 8, 100}, {13, 16, 100}, {16, 8, 115}, {16, 16, 115}, {19, 8, 134}, {19, 16, 134}};
 
 // Cost model for one shape class, in issue slots per pair:
 //   steps = passes x (rows + G - 1 ramp rows), 16 instructions per column + ~24 per row step,
@@ -206,6 +206,9 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     if (g.K == 13 && g.G == 16) return launch_fill_m<13, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 8) return launch_fill_m<16, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 16) return launch_fill_m<16, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    // K = 19 needs 134 registers (3 warps per scheduler); SA_FILL_MINB=16 selects the 128-register build (4 per scheduler)
+    if (g.K == 19 && g.G == 8 && e->fill_minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 16 && e->fill_minb == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
   }
@@ -1641,6 +1644,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_S")) e->long_s = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_R")) e->long_r = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_FILL_MINB")) e->fill_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);

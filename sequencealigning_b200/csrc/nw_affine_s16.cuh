@@ -111,6 +111,15 @@ struct AffineS16Params {
   uint32_t packing; // input format (see load_residue)
 };
 
+// min of two packed u16 pairs on whole 32-bit registers.  (__vminu2 takes its operands apart into 16-bit
+// halves; with a kernel parameter as one operand ptxas then rebuilds the packed constant with a PRMT
+// in front of every use: 12 of them per 19-column row step.)
+__device__ __forceinline__ uint32_t vmin_u16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 // max of two packed u16 pairs that also records, per half, whether the FIRST operand won or
 // tied: bit BIT of acc_lo (low half = pair A) / acc_hi (high half = pair B) is set when
 // a >= b.  ptxas folds the setp.eq pair into the predicate outputs of one VIMNMX.U16x2, and
@@ -176,7 +185,7 @@ struct StripCells {
       acc_b[w] = acc_b[w - 1] & zero;
     }
     const uint32_t hup = Hrow[c];
-    const uint32_t m = __vminu2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
+    const uint32_t m = vmin_u16x2(q[c] ^ d, pen2);  // 0 if equal, penalty otherwise (per half)
     const uint32_t M = hdiag + cm2 - m;           // M'[x][y]: one IADD3; no half leaves [0, 65535]
     if (CAP) {
       Mv[CAP ? c : 0] = M;
@@ -243,7 +252,7 @@ struct LinearCells {
                                              uint32_t& acc_a, uint32_t& acc_b) {
     constexpr int c = C;
     const uint32_t hup = Hrow[c];
-    const uint32_t m = __vminu2(q[c] ^ d, pen2);
+    const uint32_t m = vmin_u16x2(q[c] ^ d, pen2);
     const uint32_t diag = sdiag - m;
     const uint32_t down = hup - Gm[c];
     const uint32_t right = sl - gl;
@@ -432,7 +441,11 @@ __global__ void __launch_bounds__(32, MINB) nw_affine_fill_s16(const AffineS16Pa
   uint16_t* dp = reinterpret_cast<uint16_t*>(bnd + (SINGLE ? 0 : (size_t)p.smem_bnd_rows * NG));
 
   // ext2: the per-cell constant of the recurrence (affine: diagonal constant; linear: flag saving)
-  const uint32_t pen2 = p.pen2, open2 = p.open2, ext2 = (ALGO == kLinear) ? p.ext2 : p.cm2, zero = p.zero;
+  // pen2 as an opaque 32-bit register value.  Read straight from the parameter bank, ptxas
+  // keeps its two 16-bit halves in uniform registers and rebuilds the packed word (2 moves + PRMT) in front of
+  // most VIMNMX.U16x2 that use it -- 14 extra instructions per 19-column row step.
+  const uint32_t pen2 = p.pen2 + (n1t & p.zero);  // (n1t: a per-lane value from memory; p.zero: always 0, unknown to ptxas)
+  const uint32_t open2 = p.open2, ext2 = (ALGO == kLinear) ? p.ext2 : p.cm2, zero = p.zero;
 
   // ---- stage the db residues (one per row, read by every strip); they are widened to
   //      (byte << 8) per 16-bit half when read, so the XOR of two different residues is >= 256 >

@@ -184,11 +184,16 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
     __syncwarp();
     const int32_t max_s = 2 * p.o + p.e * (n1 + n2) + p.x + 8;
     const int32_t step = p.s_step, bx = p.x / step, bo = (p.o + p.e) / step, be = p.e / step;  // look-backs in ring steps
-    for (int32_t s = step, t = 1; result < 0 && s <= max_s; s += step, ++t) {
-      // slot of score s: (s / step) mod depth; the range arrays follow the M ring
-      const int slot = t % DM, slot_e = t % DE;
-      const int sx = ((t - bx) % DM + DM) % DM, so = ((t - bo) % DM + DM) % DM, se = ((t - be) % DM + DM) % DM;
-      const int se_e = ((t - be) % DE + DE) % DE;
+    int slot = 0, slot_e = 0;  // (s / step) mod depth, kept by increment-and-wrap (no division in the score loop)
+    for (int32_t s = step; result < 0 && s <= max_s; s += step) {
+      // slot of score s; the range arrays follow the M ring
+      slot = slot + 1 == DM ? 0 : slot + 1;
+      slot_e = slot_e + 1 == DE ? 0 : slot_e + 1;
+      int sx = slot - bx, so = slot - bo, se = slot - be, se_e = slot_e - be;  // look-backs are < depth
+      sx += sx < 0 ? DM : 0;
+      so += so < 0 ? DM : 0;
+      se += se < 0 ? DM : 0;
+      se_e += se_e < 0 ? DE : 0;
       const bool hx = s - p.x >= 0 && lo_[sx] <= hi_[sx];
       const bool ho = s - p.o - p.e >= 0 && lo_[so] <= hi_[so];
       const bool he = s - p.e >= 0 && lo_[se] <= hi_[se];
