@@ -1,7 +1,7 @@
 // engine.cu -- C ABI (include/sa_engine.h) over the CUDA kernels.  sm_100a only, no CPU path.
 //
 // Replaces the reference's per-pair dispatch loop (/root/reference/src/main.rs:61-79) with
-// batched launches.  The pair list is cut into SEGMENTS (up to 512 Ki pairs, fewer when the
+// batched launches.  The pair list is cut into SEGMENTS (up to 128 Ki pairs, fewer when the
 // packed traceback matrices would not fit the scratch budget).  Per segment:
 //     copy-in stream : offsets/lengths of the segment + the residue ranges it touches
 //     compute stream : fill (panic bonus on) -> classify/count walk -> [host reads the number of
@@ -209,7 +209,11 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     // K = 19 needs 134 registers (3 warps per scheduler); SA_FILL_MINB=16 selects the 128-register build (4 per scheduler)
     if (g.K == 19 && g.G == 8 && e->fill_minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 16 && e->fill_minb == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    // SA_ORMASK on the read-length forms: which tie-bit sets go to the alu pipe as LOP3 (development knob)
+    // measured (524 288 pairs x 150 bp, fill alone): 0x00 1928, 0x01 1949, 0x05 1882, 0x11 1926 (sweep units); the
+    // fma-heavy pipe is the busier one (80 % vs 71 %), one of the eight tie-bit sets as a LOP3 evens them out
+    if (g.K == 19 && g.G == 8 && e->ormask == 0xFF) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x01, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
   }
   return fail(e, SA_E_ARG, "no fill kernel for K %d G %d", g.K, g.G);

@@ -104,7 +104,7 @@ struct sa_engine {
   uint32_t fill_minb = 1;           // SA_FILL_MINB: 16 = the 128-register build of the K = 19 fill forms
   size_t tb_budget = 0;
   size_t budget_cached = 0;
-  uint32_t seg_pairs = 524288;
+  uint32_t seg_pairs = 131072;  // measured (1 M x 150 bp): 512 Ki 2672 / 256 Ki 2691 / 128 Ki 2696 GCUPS resident, e2e 1915 / 2126 / 2302
   std::map<const void*, size_t> smem_configured;  // kernel -> opted-in dynamic smem ON THIS DEVICE
   int sort_mode = 0;  // 0 auto, 1 always, 2 never (SA_SORT)
   bool seg_pairs_forced = false;
