@@ -640,6 +640,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line, the JSON: everything else a library prints there (NCCL's version banner
+    # goes to stdout whatever NCCL_DEBUG_FILE says) is sent to stderr by pointing fd 1 at fd 2 for the run.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        os.write(json_fd, (line + "\n").encode())
+
     import torch
     import torch.distributed as dist
 
@@ -731,7 +740,8 @@ def main():
         if world > 1:
             dist.barrier(group=gloo)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier(group=gloo)
         dist.destroy_process_group()

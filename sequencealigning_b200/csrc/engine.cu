@@ -1210,7 +1210,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   // Software pipeline over segments: A(0); then for each i: A(i+1) is queued BEFORE the host
   // waits for segment i's refill count, so the GPU never idles across the host round trip.
   // SA_TRACE=1: host-side timeline of the pipeline on stderr (developer aid)
-  static const bool trace = getenv("SA_TRACE") != nullptr;
+  const bool trace = getenv("SA_TRACE") != nullptr;
   const auto t_start = std::chrono::steady_clock::now();
   auto mark = [&](const char* what, uint64_t a) {
     if (trace)
@@ -2029,6 +2029,9 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
   if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.kernels_ms = ms;
   cudaGetLastError();
   e->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+  if (getenv("SA_TRACE"))
+    fprintf(stderr, "[sa trace] sd_align_batch on device %d: %llu pairs, wall %.3f ms, kernels %.3f ms, h2d %.1f MB, d2h %.1f MB\n", e->device,
+            (unsigned long long)n, e->timing.wall_ms, e->timing.kernels_ms, e->timing.h2d_bytes / 1e6, e->timing.d2h_bytes / 1e6);
   return rc;
 }
 

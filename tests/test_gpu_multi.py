@@ -135,3 +135,24 @@ def test_config3_shape_sharded(engine, oracle):
             r = multi.align(batch)
             assert np.array_equal(r.score, engine.align(batch, cigar=False).score)
             _oracle_check(oracle, b, r, f"{n} devices, packing {batch.packing}")
+
+
+@pytest.mark.parametrize("devices", _device_sets())
+def test_linear_local_mode_through_the_multi_engine(engine, devices):
+    """Local mode (needleman_wunsch.rs:88-89, :107-111) sharded: scores, end cells and CIGARs come back in input
+    order, both on the contiguous plan and on the LPT gather/scatter plan."""
+    import random
+    from sequencealigning_b200 import ALGO_NW_LINEAR, MODE_LOCAL, Engine
+    rng = random.Random(23)
+    many = _batch(random_pair_list(29, 3000, 0, 200, alphabet=b"ACGT", unrelated=0.4))
+    uneven = []
+    for n in [900, 20, 800, 35, 400, 50, 10, 3, 0, 1200, 60]:
+        q = random_seq(rng, n, b"ACGT")
+        uneven.append((random_seq(rng, 40, b"ACGT") + q, mutate(rng, q, 0.1, True, b"ACGT") + random_seq(rng, 25, b"ACGT")))
+    with Engine(devices=devices) as multi:
+        for b, contiguous in ((many, 1), (_batch(uneven), 0)):
+            single = engine.align(b, algo=ALGO_NW_LINEAR, mode=MODE_LOCAL)
+            r = multi.align(b, algo=ALGO_NW_LINEAR, mode=MODE_LOCAL)
+            assert all(s["contiguous"] == contiguous for s in multi.shards())
+            _same(single, r, f"local, devices {devices}")
+            assert np.array_equal(single.end1, r.end1) and np.array_equal(single.end2, r.end2)
