@@ -29,6 +29,7 @@ enum : uint8_t { kOk = 0, kRefPanic = 1, kRefNoConv = 2, kNotImpl = 3, kRefPanic
 #endif
 
 constexpr int32_t kWfNone = -(1 << 29);
+constexpr int32_t kWfLive = -(1 << 28);  // standard mode: offsets above this are real, everything below is "None"
 
 struct WfaParams {
   const uint8_t* __restrict__ residues;
@@ -220,6 +221,11 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
       const int32_t olo = ho ? lo_[so] : 1, ohi = ho ? hi_[so] : 0;
       const int32_t elo = he ? lo_[se] : 1, ehi = he ? hi_[se] : 0;
       bool found = false;
+      // Source windows as (first diagonal, width): ONE unsigned compare says whether a neighbour exists; an
+      // absent source matches nothing.  "None" is any value below kWfLive: kWfNone + (a few steps) stays far
+      // below it, so None + 1 needs no special case and the recurrences are plain max / add.
+      const int32_t oa = ho ? olo : (1 << 30), ea = he ? elo : (1 << 30), xa = hx ? xlo : (1 << 30);
+      const uint32_t ow = ho ? (uint32_t)(ohi - olo) : 0u, ew = he ? (uint32_t)(ehi - elo) : 0u, xw = hx ? (uint32_t)(xhi - xlo) : 0u;
       // kUnroll diagonals per lane per trip: all source loads of the trip are issued before
       // the first use, so one L2 round trip covers kUnroll cells instead of one
       constexpr int kUnroll = 8;
@@ -227,29 +233,30 @@ __global__ void __launch_bounds__(128) wfa_standard_kernel(const WfaParams p) {
         int32_t am[kUnroll], bi[kUnroll], ap[kUnroll], bd[kUnroll], mx[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-          const int32_t k = k0 + 32 * u;
-          am[u] = (k <= hi && k - 1 >= olo && k - 1 <= ohi) ? Mo[k - 1] : kWfNone;
-          bi[u] = (k <= hi && k - 1 >= elo && k - 1 <= ehi) ? Ie[k - 1] : kWfNone;
-          ap[u] = (k <= hi && k + 1 >= olo && k + 1 <= ohi) ? Mo[k + 1] : kWfNone;
-          bd[u] = (k <= hi && k + 1 >= elo && k + 1 <= ehi) ? De[k + 1] : kWfNone;
-          mx[u] = (k <= hi && k >= xlo && k <= xhi) ? Mx[k] : kWfNone;
+          const int32_t k = k0 + 32 * u;  // (k > hi: nothing matches or the values are never used)
+          am[u] = bi[u] = ap[u] = bd[u] = mx[u] = kWfNone;
+          if ((uint32_t)(k - 1 - oa) <= ow) am[u] = Mo[k - 1];
+          if ((uint32_t)(k - 1 - ea) <= ew) bi[u] = Ie[k - 1];
+          if ((uint32_t)(k + 1 - oa) <= ow) ap[u] = Mo[k + 1];
+          if ((uint32_t)(k + 1 - ea) <= ew) bd[u] = De[k + 1];
+          if ((uint32_t)(k - xa) <= xw) mx[u] = Mx[k];
         }
+        w_cells += (uint32_t)min(kUnroll, (hi - k0) / 32 + 1);
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const int32_t k = k0 + 32 * u;
           if (k > hi) break;
-          int32_t iv = kWfNone, dv, mv = kWfNone;
-          const int32_t best = max(am[u], bi[u]);  // insertion: consumes a seq1 residue: (k-1) -> k, v + 1
-          if (best > kWfNone) iv = best + 1;
-          dv = max(ap[u], bd[u]);                  // deletion: consumes a seq2 residue: (k+1) -> k, v unchanged
-          if (mx[u] > kWfNone) mv = mx[u] + 1;
-          // cells outside the matrix do not exist
-          if (iv > kWfNone && (iv > n1 || iv - k > n2 || iv - k < 0)) iv = kWfNone;
-          if (dv > kWfNone && (dv > n1 || dv - k > n2 || dv < 0)) dv = kWfNone;
-          if (mv > kWfNone && (mv > n1 || mv - k > n2)) mv = kWfNone;
+          // a cell of diagonal k exists for offsets up to min(n1, n2 + k); the lower ends hold by construction
+          // (an insertion keeps h = v - k, a deletion keeps v, and every source is inside the matrix)
+          const int32_t vmax = min(n1, n2 + k);
+          int32_t iv = max(am[u], bi[u]) + 1;  // insertion: consumes a seq1 residue: (k-1) -> k, v + 1
+          int32_t dv = max(ap[u], bd[u]);      // deletion: consumes a seq2 residue: (k+1) -> k, v unchanged
+          int32_t mv = mx[u] + 1;              // mismatch
+          iv = iv > vmax ? kWfNone : iv;
+          dv = dv > vmax ? kWfNone : dv;
+          mv = mv > vmax ? kWfNone : mv;
           mv = max(mv, max(iv, dv));
-          ++w_cells;
-          if (mv > kWfNone) {
+          if (mv > kWfLive) {
             const int32_t before = mv;
             mv = wide ? wf_extend<8>(s1w, s2w, mv, mv - k, n1, n2) : wf_extend<2>(s1w, s2w, mv, mv - k, n1, n2);
             w_ext += (uint32_t)(mv - before);
