@@ -28,14 +28,11 @@
 #include <vector>
 
 #include "engine_internal.h"
+#include "engine_util.h"
 #include "nw_affine_s16.cuh"
 #include "nw_walk.cuh"
-#include "wfa.cuh"
-#include "nw_parents.cuh"
 #include "nw_general.cuh"
 #include "nw_long.cuh"
-#include "nw_count.cuh"
-#include "nw_local.cuh"
 
 namespace sa_host {
 
@@ -54,32 +51,11 @@ sa_status_t fail(sa_engine* e, sa_status_t st, const char* fmt, ...) {
 namespace {
 
 using sa_host::fail;
-
-#define CUDA_TRY(e, call)                                                                   \
-  do {                                                                                      \
-    cudaError_t err__ = (call);                                                             \
-    if (err__ != cudaSuccess)                                                               \
-      return fail(e, SA_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
-                  __FILE__, __LINE__);                                                      \
-  } while (0)
-
-sa_status_t ensure(sa_engine* e, DevBuf& b, size_t bytes) {
-  if (b.cap >= bytes && b.p) return SA_OK;
-  if (b.p) {
-    CUDA_TRY(e, cudaDeviceSynchronize());
-    CUDA_TRY(e, cudaFree(b.p));
-  }
-  b.p = nullptr;
-  b.cap = 0;
-  bytes = std::max<size_t>(bytes, 256);
-  cudaError_t err = cudaMalloc(&b.p, bytes);
-  if (err != cudaSuccess) {
-    cudaGetLastError();
-    return fail(e, SA_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
-  }
-  b.cap = bytes;
-  return SA_OK;
-}
+using sa_host::ensure;
+using sa_host::view_end;
+using sa_host::view_in_bounds;
+using sa_host::run_wfa;
+using sa_host::run_linear_local;
 
 struct Geometry {
   int K = 8;  // columns per lane per row (8, 13, 16 or 19)
@@ -220,10 +196,6 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
 }
 
 uint32_t pack2(uint32_t v) { return v | (v << 16); }
-
-// end of a residue view, saturating: a garbage 64-bit offset must not wrap past the bounds check
-inline uint64_t view_end(uint64_t off, uint32_t len) { return off + len < off ? ~0ull : off + len; }
-inline bool view_in_bounds(uint64_t off, uint32_t len, uint64_t limit) { return off <= limit && len <= limit - off; }
 
 // Byte ranges of the residue buffer already resident on the device (sorted, disjoint).
 struct Coverage {
@@ -1265,297 +1237,6 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   return SA_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// WFA (score only).  literal = the reference's wfa_align as it really behaves (status per
-// pair); standard = textbook gap-affine WFA.  Inputs are uploaded in one piece: the kernels are
-// orders of magnitude cheaper per residue than the traceback DP, so there is nothing to hide.
-// ---------------------------------------------------------------------------------------------
-sa_status_t run_wfa(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h_q_len,
-                    const uint32_t* h_d_len, const sa_scheme_t* scheme, bool literal,
-                    const sa_batch_t* in, sa_result_t* out) {
-  sa_status_t st;
-  int32_t x = 4, o = 2, ex = 6;  // wfa.rs:17-21
-  if (scheme) {
-    x = scheme->mismatch;
-    o = scheme->gap_open;
-    ex = scheme->gap_ext;
-  }
-  if (x <= 0 || o < 0 || ex <= 0 || x >= sa::kWfRing || o + ex >= sa::kWfRing || (literal && (x > 8 || o + ex > 8)))
-    return fail(e, SA_E_UNSUPPORTED, "WFA penalties (x=%d, o=%d, e=%d) outside the kernel's ring", x, o, ex);
-  if (in) {
-    uint64_t max_end = 0;
-    for (uint64_t p = 0; p < n; ++p) {
-      max_end = std::max(max_end, std::max(view_end(in->q_off[p], h_q_len[p]), view_end(in->d_off[p], h_d_len[p])));
-      e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
-    }
-    if (max_end > (in->packing ? in->residues_len * 4 : in->residues_len))
-      return fail(e, SA_E_ARG, "a pair reaches past residues_len");
-    CUDA_TRY(e, cudaMemcpyAsync(db.residues, in->residues, in->residues_len, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(db.q_off, in->q_off, n * 8, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(db.d_off, in->d_off, n * 8, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(db.q_len, in->q_len, n * 4, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(db.d_len, in->d_len, n * 4, cudaMemcpyHostToDevice, e->stream));
-    e->timing.h2d_bytes += in->residues_len + n * 24;
-  }
-  uint32_t nmax_sum = 0;
-  for (uint64_t p = 0; p < n; ++p) nmax_sum = std::max<uint32_t>(nmax_sum, h_q_len[p] + h_d_len[p]);
-  sa::WfaParams wp{};
-  wp.residues = db.residues;
-  wp.packing = db.packing;
-  wp.q_off = db.q_off;
-  wp.q_len = db.q_len;
-  wp.d_off = db.d_off;
-  wp.d_len = db.d_len;
-  wp.x = x;
-  wp.o = o;
-  wp.e = ex;
-  wp.score = db.score;
-  wp.status = db.status;
-  CUDA_TRY(e, cudaMemsetAsync(db.cigar_len, 0, n * 4, e->stream));
-  CUDA_TRY(e, cudaMemsetAsync(db.cigar_off, 0, n * 8, e->stream));
-  CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, e->stream));
-  CUDA_TRY(e, cudaEventRecord(e->ev_t0, e->stream));
-  if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
-  if (literal) {
-    const uint64_t cap = std::min<uint64_t>(8ull * nmax_sum + 64, 2048);
-    const uint32_t wcap = (uint32_t)(2 * (cap / 4) + 16);
-    const uint64_t stride = (uint64_t)sa::kLitRing * 3 * wcap;
-    size_t budget = e->tb_budget ? e->tb_budget : (size_t)4 << 30;
-    const uint64_t chunk = std::max<uint64_t>(64, std::min<uint64_t>(n, budget / (stride * 4)));
-    if ((st = ensure(e, e->wfa_scratch, chunk * stride * 4)) != SA_OK) return st;
-    wp.scratch = (int32_t*)e->wfa_scratch.p;
-    wp.scratch_stride = stride;
-    wp.lit_wcap = wcap;
-    for (uint64_t base = 0; base < n; base += chunk) {
-      wp.pair_base = (uint32_t)base;
-      wp.n_launch_pairs = (uint32_t)std::min<uint64_t>(chunk, n - base);
-      sa::wfa_literal_kernel<<<(wp.n_launch_pairs + 63) / 64, 64, 0, e->stream>>>(wp);
-      CUDA_TRY(e, cudaGetLastError());
-      e->timing.kernel_launches++;
-    }
-  } else {
-    const uint32_t width = nmax_sum + 1;
-    const uint32_t warps_per_block = 4;
-    const uint32_t smem_seq = 6 * 1024;  // per warp: two 2-bit packed sequences of up to ~12 kbp stay on chip
-    const size_t smem = (size_t)warps_per_block * smem_seq;
-    size_t& configured = e->smem_configured[(const void*)sa::wfa_standard_kernel];
-    if (configured < smem) {
-      CUDA_TRY(e, cudaFuncSetAttribute(sa::wfa_standard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    // all penalties share a factor (2 for the reference's 4/2/6): other scores stay empty
-    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-    wp.s_step = std::max(1, gcd(gcd(x, o + ex), ex));
-    wp.ring_dm = std::max(x, o + ex) / wp.s_step + 1;
-    wp.ring_de = ex / wp.s_step + 1;
-    const uint64_t stride = (uint64_t)(wp.ring_dm + 2 * wp.ring_de) * width + (nmax_sum + 32) / 4 + 8;
-    uint32_t blocks = (uint32_t)std::min<uint64_t>((n + warps_per_block - 1) / warps_per_block, (uint64_t)e->sm_count * 8);
-    if ((st = ensure(e, e->wfa_scratch, (size_t)blocks * warps_per_block * stride * 4 + n * 4)) != SA_OK) return st;
-    uint32_t* d_next = (uint32_t*)e->misc.p + 8;
-    unsigned long long* d_work = (unsigned long long*)((uint8_t*)e->misc.p + 64);
-    CUDA_TRY(e, cudaMemsetAsync(d_next, 0, 4, e->stream));
-    CUDA_TRY(e, cudaMemsetAsync(d_work, 0, 16, e->stream));
-    wp.work = d_work;
-    wp.scratch = (int32_t*)e->wfa_scratch.p;
-    wp.scratch_stride = stride;
-    wp.width = width;
-    wp.next_pair = d_next;
-    wp.smem_seq_bytes = smem_seq;
-    wp.pair_base = 0;
-    wp.n_launch_pairs = (uint32_t)n;
-    {
-      // longest pairs first: one warp per pair, so the long ones must not start last
-      std::vector<uint32_t> order(n);
-      for (uint64_t p = 0; p < n; ++p) order[p] = (uint32_t)p;
-      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        return (uint64_t)h_q_len[a] + h_d_len[a] > (uint64_t)h_q_len[b] + h_d_len[b];
-      });
-      uint32_t* d_order = (uint32_t*)((int32_t*)e->wfa_scratch.p + (size_t)blocks * warps_per_block * stride);
-      CUDA_TRY(e, cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // `order` is a local
-      wp.order = d_order;
-    }
-    sa::wfa_standard_kernel<<<blocks, warps_per_block * 32, smem, e->stream>>>(wp);
-    CUDA_TRY(e, cudaGetLastError());
-    e->timing.kernel_launches++;
-    if (out) CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 12, d_work, 16, cudaMemcpyDeviceToHost, e->stream));
-  }
-  CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->stream));
-  if (out) {
-    if (out->score) CUDA_TRY(e, cudaMemcpyAsync(out->score, db.score, n * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (out->status) CUDA_TRY(e, cudaMemcpyAsync(out->status, db.status, n, cudaMemcpyDeviceToHost, e->stream));
-    if (out->cigar_len) memset(out->cigar_len, 0, n * 4);
-    if (out->cigar_off) memset(out->cigar_off, 0, n * 8);
-    e->timing.d2h_bytes += n * 5;
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    if (!literal) {
-      memcpy(&e->timing.wfa_cells, e->h_count + 12, 8);
-      memcpy(&e->timing.wfa_extended, e->h_count + 14, 8);
-    }
-  }
-  return SA_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Linear NW, LOCAL mode (needleman_wunsch.rs:88-89, :107-111, :256-272): nw_local.cuh, one warp
-// per pair.  Pairs go through in chunks that bound the CIGAR staging; per chunk: fill + argmax +
-// walk in one kernel, scan of the CIGAR lengths (offsets continue across chunks), gather.
-// ---------------------------------------------------------------------------------------------
-template <int K>
-sa_status_t launch_local(sa_engine* e, const sa::LocalParams& lp, uint32_t blocks, size_t smem, cudaStream_t sx) {
-  auto kern = sa::nw_linear_local_kernel<K>;
-  size_t& configured = e->smem_configured[(const void*)kern];
-  if (smem > configured) {
-    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)std::min(e->smem_optin, std::max<size_t>(smem, 48 * 1024))));
-    configured = std::max<size_t>(smem, 48 * 1024);
-  }
-  kern<<<blocks, 32 * sa::kLocalWarps, smem, sx>>>(lp);
-  CUDA_TRY(e, cudaGetLastError());
-  e->timing.kernel_launches++;
-  return SA_OK;
-}
-
-sa_status_t run_linear_local(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t* h_q_len,
-                             const uint32_t* h_d_len, const sa_scheme_t& sc, bool want_cigar,
-                             const sa_batch_t* in, sa_result_t* out, uint64_t* used_out) {
-  sa_status_t st;
-  *used_out = 0;
-  cudaStream_t sx = e->stream;
-  if (in) {
-    uint64_t max_end = 0;
-    for (uint64_t p = 0; p < n; ++p) {
-      max_end = std::max(max_end, std::max(view_end(in->q_off[p], h_q_len[p]), view_end(in->d_off[p], h_d_len[p])));
-      e->timing.cells += (uint64_t)h_q_len[p] * h_d_len[p];
-    }
-    if (max_end > (in->packing ? in->residues_len * 4 : in->residues_len))
-      return fail(e, SA_E_ARG, "a pair reaches past residues_len");
-    CUDA_TRY(e, cudaMemcpyAsync(db.residues, in->residues, in->residues_len, cudaMemcpyHostToDevice, sx));
-    CUDA_TRY(e, cudaMemcpyAsync(db.q_off, in->q_off, n * 8, cudaMemcpyHostToDevice, sx));
-    CUDA_TRY(e, cudaMemcpyAsync(db.d_off, in->d_off, n * 8, cudaMemcpyHostToDevice, sx));
-    CUDA_TRY(e, cudaMemcpyAsync(db.q_len, in->q_len, n * 4, cudaMemcpyHostToDevice, sx));
-    CUDA_TRY(e, cudaMemcpyAsync(db.d_len, in->d_len, n * 4, cudaMemcpyHostToDevice, sx));
-    e->timing.h2d_bytes += in->residues_len + n * 24;
-  }
-  if ((st = ensure(e, e->misc, 256)) != SA_OK) return st;
-  uint32_t* d_next = (uint32_t*)e->misc.p + 8;
-  CUDA_TRY(e, cudaMemsetAsync(db.carry, 0, 16, sx));
-  if (db.pool_base) {  // offsets continue from the slice's start (multi-device calls)
-    memcpy(e->h_count + 12, &db.pool_base, 8);
-    CUDA_TRY(e, cudaMemcpyAsync(db.carry, e->h_count + 12, 8, cudaMemcpyHostToDevice, sx));
-  }
-  CUDA_TRY(e, cudaEventRecord(e->ev_t0, sx));
-  const size_t budget = e->tb_budget ? e->tb_budget : (size_t)8 << 30;  // traceback scratch of the resident warps
-  const uint64_t stage_cap = (uint64_t)1 << 29;                          // CIGAR staging words per chunk (2 GB)
-  std::vector<uint64_t> runs_end;
-  for (uint64_t base = 0; base < n;) {
-    // chunk: as many pairs as the staging holds; shape maxima pick the kernel form
-    uint32_t n1max = 0, n2max = 0;
-    uint64_t words = 0, cnt = 0;
-    runs_end.clear();
-    while (base + cnt < n && cnt < (1u << 22)) {
-      const uint64_t p = base + cnt;
-      const uint64_t w = (uint64_t)h_q_len[p] + h_d_len[p];
-      if (cnt && words + w > stage_cap) break;
-      words += w;
-      runs_end.push_back(words);
-      n1max = std::max(n1max, h_q_len[p]);
-      n2max = std::max(n2max, h_d_len[p]);
-      ++cnt;
-    }
-    const int K = n2max <= 160 ? 5 : (n2max <= 256 ? 8 : 16);
-    const uint32_t wbytes = K == 16 ? 4 : 2;
-    const uint64_t ns = ((uint64_t)n2max + K - 1) / K;
-    const uint64_t tb_words = std::max<uint64_t>((uint64_t)n1max * ns, 1);
-    // the matrix of a pair stays in shared memory when four warps' worth leaves >= 2 blocks per SM
-    const bool in_smem = want_cigar && tb_words * wbytes * sa::kLocalWarps <= 96 * 1024;
-    const size_t smem = in_smem ? (size_t)tb_words * wbytes * sa::kLocalWarps : 0;
-    uint64_t warps = std::min<uint64_t>(cnt, (uint64_t)e->sm_count * 16);
-    if (in_smem) warps = std::min<uint64_t>(warps, (uint64_t)e->sm_count * sa::kLocalWarps * std::max<uint64_t>(1, (224 * 1024) / (smem + 1024)));
-    const uint64_t tb_stride = in_smem || !want_cigar ? 16 : ((tb_words * wbytes + 15) & ~(uint64_t)15);
-    bool omit = false;
-    if (!in_smem && want_cigar) {
-      if (tb_stride > budget) omit = true;  // not even one pair's matrix fits: score and end cell only
-      else warps = std::min<uint64_t>(warps, std::max<uint64_t>(1, budget / tb_stride));
-    }
-    const uint32_t blocks = (uint32_t)((warps + sa::kLocalWarps - 1) / sa::kLocalWarps);
-    const uint64_t gwarps = (uint64_t)blocks * sa::kLocalWarps;
-    const bool tb_on = want_cigar && !omit;
-    if ((st = ensure(e, e->tb2, (size_t)(gwarps * tb_stride))) != SA_OK) return st;
-    if ((st = ensure(e, e->par_rows, (size_t)(gwarps * ((uint64_t)n1max + 2) * 8))) != SA_OK) return st;
-    if (tb_on) {
-      if ((st = ensure(e, e->par_bytes, (size_t)(words * 4 + 256))) != SA_OK) return st;
-      if ((st = ensure(e, e->par_in, (size_t)(cnt * 8))) != SA_OK) return st;
-      CUDA_TRY(e, cudaMemcpyAsync(e->par_in.p, runs_end.data(), cnt * 8, cudaMemcpyHostToDevice, sx));
-    }
-    sa::LocalParams lp{};
-    lp.residues = db.residues;
-    lp.q_off = db.q_off;
-    lp.q_len = db.q_len;
-    lp.d_off = db.d_off;
-    lp.d_len = db.d_len;
-    lp.packing = db.packing;
-    lp.pair_base = (uint32_t)base;
-    lp.n_launch_pairs = (uint32_t)cnt;
-    lp.match = sc.match;
-    lp.mismatch = sc.mismatch;
-    lp.open = sc.gap_open;
-    lp.ext = sc.gap_ext;
-    lp.next_pair = d_next;
-    lp.smem_words = in_smem ? (uint32_t)tb_words : 0;
-    lp.tb = (uint8_t*)e->tb2.p;
-    lp.tb_stride = tb_stride;
-    lp.bnd = (int2*)e->par_rows.p;
-    lp.bnd_stride = (uint64_t)n1max + 2;
-    lp.runs = tb_on ? (uint32_t*)e->par_bytes.p : nullptr;
-    lp.runs_end = tb_on ? (const uint64_t*)e->par_in.p : nullptr;
-    lp.score = db.score;
-    lp.status = db.status;
-    lp.cigar_len = db.cigar_len;
-    lp.end1 = db.end1;
-    lp.end2 = db.end2;
-    lp.omit_flag = (want_cigar && omit) ? (uint32_t)SA_ALIGNMENT_OMITTED : 0u;
-    CUDA_TRY(e, cudaMemsetAsync(d_next, 0, 4, sx));
-    if (K == 5) st = launch_local<5>(e, lp, blocks, smem, sx);
-    else if (K == 8) st = launch_local<8>(e, lp, blocks, smem, sx);
-    else st = launch_local<16>(e, lp, blocks, smem, sx);
-    if (st != SA_OK) return st;
-    const uint32_t cn = (uint32_t)cnt;
-    const uint32_t sb = (cn + sa::kScanBlock - 1) / sa::kScanBlock;
-    if ((st = ensure(e, e->block_sums, (size_t)sb * 8)) != SA_OK) return st;
-    sa::scan_block_sums<<<sb, sa::kScanBlock, 0, sx>>>(db.cigar_len + base, (uint64_t*)e->block_sums.p, cn);
-    sa::scan_block_offsets<<<1, sa::kScanBlock, 0, sx>>>((uint64_t*)e->block_sums.p, sb, db.carry);
-    sa::scan_apply<<<sb, sa::kScanBlock, 0, sx>>>(db.cigar_len + base, (const uint64_t*)e->block_sums.p, db.cigar_off + base, cn);
-    e->timing.kernel_launches += 3;
-    if (tb_on) {
-      sa::local_runs_to_pool<<<(cn + 3) / 4, 128, 0, sx>>>((uint32_t)base, cn, (const uint32_t*)e->par_bytes.p, (const uint64_t*)e->par_in.p,
-                                                           db.cigar_len, db.cigar_off, db.pool, db.pool_cap);
-      e->timing.kernel_launches++;
-    }
-    CUDA_TRY(e, cudaGetLastError());
-    if (base + cnt < n) CUDA_TRY(e, cudaStreamSynchronize(sx));  // runs_end (a host vector) and the staging are reused
-    base += cnt;
-  }
-  CUDA_TRY(e, cudaEventRecord(e->ev_t1, sx));
-  CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 2, db.carry, 8, cudaMemcpyDeviceToHost, sx));
-  if (out) {
-    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-      if (!dst || !bytes) return cudaSuccess;
-      e->timing.d2h_bytes += bytes;
-      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sx);
-    };
-    CUDA_TRY(e, cp(out->score, db.score, n * 4));
-    CUDA_TRY(e, cp(out->status, db.status, n));
-    CUDA_TRY(e, cp(out->cigar_len, db.cigar_len, n * 4));
-    CUDA_TRY(e, cp(out->cigar_off, db.cigar_off, n * 8));
-    CUDA_TRY(e, cp(out->end1, db.end1, n * 4));
-    CUDA_TRY(e, cp(out->end2, db.end2, n * 4));
-  }
-  CUDA_TRY(e, cudaStreamSynchronize(sx));
-  memcpy(used_out, e->h_count + 2, 8);
-  return SA_OK;
-}
-
 sa_status_t resolve_scheme(sa_engine* e, const sa_scheme_t* scheme, Scheme2& s2) {
   s2.sc = sa_scheme_t{5, -4, -8, -6};  // nw_affine.rs:15-20
   if (scheme) s2.sc = *scheme;
@@ -2033,329 +1714,6 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     fprintf(stderr, "[sa trace] sd_align_batch on device %d: %llu pairs, wall %.3f ms, kernels %.3f ms, h2d %.1f MB, d2h %.1f MB\n", e->device,
             (unsigned long long)n, e->timing.wall_ms, e->timing.kernels_ms, e->timing.h2d_bytes / 1e6, e->timing.d2h_bytes / 1e6);
   return rc;
-}
-
-// Co-optimal alignment counts for a whole batch (nw_count.cuh), in chunks that bound the scratch.
-sa_status_t sd_count_cooptimal(sa_engine* e, const sa_scheme_t* scheme, const sa_batch_t* b, int64_t* counts) {
-  if (!e || !b) return SA_E_ARG;
-  if (b->packing > 1) return fail(e, SA_E_ARG, "packing %u (0 = bytes, 1 = 2-bit)", b->packing);
-  const uint64_t n = b->n_pairs;
-  if (n == 0) return SA_OK;
-  if (!counts || !b->q_off || !b->q_len || !b->d_off || !b->d_len || (!b->residues && b->residues_len))
-    return fail(e, SA_E_ARG, "null array");
-  if (n >= (1ull << 31)) return fail(e, SA_E_ARG, "n_pairs %llu too large", (unsigned long long)n);
-  CUDA_TRY(e, cudaSetDevice(e->device));
-  sa_scheme_t sc = sa_scheme_t{5, -4, -8, -6};  // nw_affine.rs:15-20
-  if (scheme) sc = *scheme;
-  const uint64_t limit = b->packing ? b->residues_len * 4 : b->residues_len;
-  uint32_t n1max = 0;
-  for (uint64_t i = 0; i < n; ++i) {
-    if ((b->q_len[i] && !view_in_bounds(b->q_off[i], b->q_len[i], limit)) || (b->d_len[i] && !view_in_bounds(b->d_off[i], b->d_len[i], limit)))
-      return fail(e, SA_E_ARG, "pair %llu reaches past residues_len", (unsigned long long)i);
-    n1max = std::max(n1max, b->q_len[i]);
-  }
-  sa_status_t st;
-  if ((st = ensure(e, e->b_res, b->residues_len)) != SA_OK) return st;
-  if ((st = ensure(e, e->b_qoff, n * 8)) != SA_OK) return st;
-  if ((st = ensure(e, e->b_doff, n * 8)) != SA_OK) return st;
-  if ((st = ensure(e, e->b_qlen, n * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->b_dlen, n * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->b_coff, n * 8)) != SA_OK) return st;  // the counts
-  cudaStream_t s = e->stream;
-  CUDA_TRY(e, cudaMemcpyAsync(e->b_res.p, b->residues, b->residues_len, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(e, cudaMemcpyAsync(e->b_qoff.p, b->q_off, n * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(e, cudaMemcpyAsync(e->b_doff.p, b->d_off, n * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(e, cudaMemcpyAsync(e->b_qlen.p, b->q_len, n * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(e, cudaMemcpyAsync(e->b_dlen.p, b->d_len, n * 4, cudaMemcpyHostToDevice, s));
-  // rolling rows: 36 bytes per column per pair in flight; at most ~1 GB of scratch
-  const uint64_t cols = (uint64_t)n1max + 1;
-  uint64_t chunk = std::max<uint64_t>(128, std::min<uint64_t>(n, ((uint64_t)1 << 30) / (36 * cols)));
-  chunk = std::min<uint64_t>(chunk, (uint64_t)1 << 20);
-  if ((st = ensure(e, e->par_rows, chunk * cols * 12)) != SA_OK) return st;
-  if ((st = ensure(e, e->par_bytes, chunk * cols * 24)) != SA_OK) return st;
-  sa::CountParams cp{};
-  cp.residues = (const uint8_t*)e->b_res.p;
-  cp.q_off = (const uint64_t*)e->b_qoff.p;
-  cp.q_len = (const uint32_t*)e->b_qlen.p;
-  cp.d_off = (const uint64_t*)e->b_doff.p;
-  cp.d_len = (const uint32_t*)e->b_dlen.p;
-  cp.packing = b->packing;
-  cp.match = sc.match;
-  cp.mismatch = sc.mismatch;
-  cp.open = sc.gap_open;
-  cp.ext = sc.gap_ext;
-  cp.rows = (int32_t*)e->par_rows.p;
-  cp.cnts = (int64_t*)e->par_bytes.p;
-  cp.cols = (uint32_t)cols;
-  cp.out = (int64_t*)e->b_coff.p;
-  for (uint64_t base = 0; base < n; base += chunk) {
-    cp.pair_base = (uint32_t)base;
-    cp.n_pairs = (uint32_t)std::min<uint64_t>(chunk, n - base);
-    sa::nw_affine_count_kernel<<<(cp.n_pairs + 127) / 128, 128, 0, s>>>(cp);
-    CUDA_TRY(e, cudaGetLastError());
-  }
-  CUDA_TRY(e, cudaMemcpyAsync(counts, e->b_coff.p, n * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(e, cudaStreamSynchronize(s));
-  return SA_OK;
-}
-
-// Every co-optimal alignment of one pair, in the order and text of the reference's traceback
-// (needleman_wunsch_affine.rs:246-329, Display :390-411): the device computes the parent sets,
-// the host walks them with the reference's LIFO stack.  snprintf-style return (bytes needed).
-// The reference's complete stdout for one pair under `-a wfa` (wfa.rs:23-42), from a traced run of the
-// literal kernel: the `lo: .., hi: ..` line of every created wavefront (:251), and -- when the loop
-// converges -- `converged with score` (:36), the `huhu` block with the converged element (:650,
-// Debug :104-116), the lines of rec_tr (:653-853) and the two prints of the empty Alignment (:38-39,
-// Display :950-980).  rec_tr looks at wfs[len - {4, 6, 8}]: len is odd, the penalties are even, so
-// those tensors are always None and the recursion never descends; what it prints before giving up
-// depends only on the converged element's parent list.  A pair on which the reference panics or
-// never converges yields the lines printed up to that point (never-ending output is cut at the
-// same wavefront bound the batched path reports REF_NO_CONVERGENCE at).
-int64_t sd_wfa_stdout(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
-                      char* buf, size_t cap, int32_t* status_out) {
-  if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
-  if (status_out) *status_out = SA_OK;
-  if (cudaSetDevice(e->device) != cudaSuccess) return fail(e, SA_E_CUDA, "cudaSetDevice failed");
-  sa_status_t st;
-  const int32_t x = 4, o = 2, ex = 6;  // wfa.rs:17-21
-  const uint64_t capw = std::min<uint64_t>(8ull * ((uint64_t)n1 + n2) + 64, 2048);
-  const uint32_t wcap = (uint32_t)(2 * (capw / 4) + 16);
-  const uint64_t stride = (uint64_t)sa::kLitRing * 3 * wcap;
-  const uint32_t trace_cap = (uint32_t)capw + 8;
-  const size_t trace_ints = 8 + 2 * (size_t)trace_cap;
-  if ((st = ensure(e, e->wfa_scratch, stride * 4)) != SA_OK) return st;
-  if ((st = ensure(e, e->par_in, (size_t)n1 + n2 + 256)) != SA_OK) return st;
-  if ((st = ensure(e, e->par_rows, trace_ints * 4 + 64)) != SA_OK) return st;
-  struct Meta {
-    uint64_t q_off, d_off;
-    uint32_t q_len, d_len;
-    int32_t score;
-    uint8_t status;
-  } meta{0, n1, n1, n2, 0, 0};
-  uint8_t* d_in = (uint8_t*)e->par_in.p;
-  cudaError_t err = cudaMemcpyAsync(d_in, &meta, sizeof(meta), cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess && n1) err = cudaMemcpyAsync(d_in + 128, seq1, n1, cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess && n2) err = cudaMemcpyAsync(d_in + 128 + n1, seq2, n2, cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess) err = cudaMemsetAsync(e->par_rows.p, 0, 32, e->stream);
-  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D failed: %s", cudaGetErrorString(err));
-  sa::WfaParams wp{};
-  wp.residues = d_in + 128;
-  wp.packing = 0;
-  wp.q_off = (const uint64_t*)(d_in + offsetof(Meta, q_off));
-  wp.d_off = (const uint64_t*)(d_in + offsetof(Meta, d_off));
-  wp.q_len = (const uint32_t*)(d_in + offsetof(Meta, q_len));
-  wp.d_len = (const uint32_t*)(d_in + offsetof(Meta, d_len));
-  wp.x = x;
-  wp.o = o;
-  wp.e = ex;
-  wp.score = (int32_t*)(d_in + offsetof(Meta, score));
-  wp.status = d_in + offsetof(Meta, status);
-  wp.scratch = (int32_t*)e->wfa_scratch.p;
-  wp.scratch_stride = stride;
-  wp.lit_wcap = wcap;
-  wp.pair_base = 0;
-  wp.n_launch_pairs = 1;
-  wp.trace = (int32_t*)e->par_rows.p;
-  wp.trace_cap = trace_cap;
-  sa::wfa_literal_kernel<<<1, 64, 0, e->stream>>>(wp);
-  if ((err = cudaGetLastError()) != cudaSuccess) return fail(e, SA_E_CUDA, "launch failed: %s", cudaGetErrorString(err));
-  e->timing.kernel_launches++;
-  std::vector<int32_t> tr(trace_ints);
-  Meta back{};
-  err = cudaMemcpyAsync(tr.data(), e->par_rows.p, trace_ints * 4, cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(&back, d_in, sizeof(back), cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "literal WFA kernel failed: %s", cudaGetErrorString(err));
-  if (status_out) *status_out = back.status;
-  std::string t;
-  const uint32_t n_lines = std::min<uint32_t>((uint32_t)tr[0], trace_cap);
-  for (uint32_t k = 0; k < n_lines; ++k)
-    t += "lo: " + std::to_string(tr[8 + 2 * k]) + ", hi: " + std::to_string(tr[9 + 2 * k]) + "\n";
-  if (back.status == SA_OK) {
-    static const char* kState[3] = {"M", "D", "I"};  // `enum State` Debug names (:44-50)
-    const int32_t len = back.score, off = tr[1], state = tr[2], np = tr[3];
-    const int64_t diag = (int64_t)n1 - (int64_t)n2;  // :635
-    t += "converged with score " + std::to_string(len) + ": \n";                                          // :36
-    t += "huhu, diag: " + std::to_string(diag) + "\nElement {\n\tstate: " + kState[state] + "\n\toffset: " + std::to_string(off) + "\n";
-    if (np == 0) {
-      t += "\tparents: []\n";
-    } else {  // {:#?} of a non-empty Vec<State>
-      t += "\tparents: [\n";
-      for (int32_t k = 0; k < np; ++k) t += std::string("    ") + kState[tr[4 + k]] + ",\n";
-      t += "]\n";
-    }
-    t += "}\n\nscore: " + std::to_string(len) + "\n";                                                      // :650
-    bool has_m = false, has_d = false;
-    for (int32_t k = 0; k < np; ++k) {
-      has_m |= tr[4 + k] == 0;
-      has_d |= tr[4 + k] == 1;
-    }
-    if (diag == 0 && off == 0) {
-      t += "ret\n";  // :662-665
-    } else {
-      for (int32_t d : {x, ex, o + ex}) {  // :667-671
-        if (d > len) {
-          t += "well shit\n";
-          continue;
-        }
-        t += "yeah, score: " + std::to_string(len - d) + "\n";
-        if (d == x) continue;                      // mismatch arm: silent unless a parent element exists
-        if (d == ex && has_d) t += "extend\n";     // :710-711
-        if (d != ex && has_m) t += "open\n";       // :754-755
-      }
-      t += "huh\n";  // :851
-    }
-    t += "\n\n\n";                                     // println!("{}", t[0]): Display of the empty Alignment
-    t += "Alignment {\n    seq1: [],\n    seq2: [],\n}\n";  // println!("{:#?}", t[0])
-  }
-  if (buf && cap) {
-    const size_t n = t.size() < cap - 1 ? t.size() : cap - 1;
-    memcpy(buf, t.data(), n);
-    buf[n] = 0;
-  }
-  return (int64_t)t.size();
-}
-
-int64_t sd_all_alignments(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
-                          const sa_scheme_t* scheme, uint64_t max_alignments, char* buf, size_t cap,
-                          uint64_t* n_printed, int32_t* panicked) {
-  if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
-  if (n_printed) *n_printed = 0;
-  if (panicked) *panicked = 0;
-  sa_scheme_t sc{5, -4, -8, -6};
-  if (scheme) sc = *scheme;
-  if (cudaSetDevice(e->device) != cudaSuccess) return fail(e, SA_E_CUDA, "cudaSetDevice failed");
-  const uint64_t cells = (uint64_t)n1 * n2;
-  if (cells > ((uint64_t)1 << 32)) return fail(e, SA_E_UNSUPPORTED, "pair too large for full parent sets");
-  sa_status_t st;
-  if ((st = ensure(e, e->par_bytes, cells + 16)) != SA_OK) return st;
-  if ((st = ensure(e, e->par_rows, (size_t)6 * (n1 + 1) * 4 + 64)) != SA_OK) return st;
-  if ((st = ensure(e, e->par_in, (size_t)n1 + n2 + 256)) != SA_OK) return st;
-  // layout of par_in: [meta 128 B][seq1][seq2]
-  struct Meta {
-    uint64_t q_off, d_off, par_off;
-    uint32_t q_len, d_len;
-    int32_t end[3];
-  } meta{0, n1, 0, n1, n2, {0, 0, 0}};
-  uint8_t* d_in = (uint8_t*)e->par_in.p;
-  cudaError_t err = cudaMemcpyAsync(d_in, &meta, sizeof(meta), cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess && n1) err = cudaMemcpyAsync(d_in + 128, seq1, n1, cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess && n2) err = cudaMemcpyAsync(d_in + 128 + n1, seq2, n2, cudaMemcpyHostToDevice, e->stream);
-  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D failed: %s", cudaGetErrorString(err));
-  sa::ParentsParams pp{};
-  pp.residues = d_in + 128;
-  pp.q_off = (const uint64_t*)(d_in + offsetof(Meta, q_off));
-  pp.d_off = (const uint64_t*)(d_in + offsetof(Meta, d_off));
-  pp.q_len = (const uint32_t*)(d_in + offsetof(Meta, q_len));
-  pp.d_len = (const uint32_t*)(d_in + offsetof(Meta, d_len));
-  pp.parents_off = (const uint64_t*)(d_in + offsetof(Meta, par_off));
-  pp.end_scores = (int32_t*)(d_in + offsetof(Meta, end));
-  pp.n_pairs = 1;
-  pp.packing = 0;
-  pp.match = sc.match;
-  pp.mismatch = sc.mismatch;
-  pp.open = sc.gap_open;
-  pp.ext = sc.gap_ext;
-  pp.parents = (uint8_t*)e->par_bytes.p;
-  pp.rows = (int32_t*)e->par_rows.p;
-  pp.row_stride = n1 + 1;
-  sa::nw_affine_parents_kernel<<<1, 64, 0, e->stream>>>(pp);
-  if ((err = cudaGetLastError()) != cudaSuccess) return fail(e, SA_E_CUDA, "launch failed: %s", cudaGetErrorString(err));
-  std::vector<uint8_t> par(cells);
-  int32_t end[3] = {0, 0, 0};
-  if (cells) err = cudaMemcpyAsync(par.data(), e->par_bytes.p, cells, cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(end, d_in + offsetof(Meta, end), 12, cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "parents kernel failed: %s", cudaGetErrorString(err));
-
-  // ---- the reference's traceback loop over the device-computed parent lists -------------------
-  enum { ST_M = 0, ST_D = 1, ST_I = 2 };
-  struct Col {
-    uint8_t c1, c2;
-    int64_t next;
-  };
-  struct Frame {
-    int st;
-    uint32_t x, y;
-    int64_t cols;
-  };
-  std::vector<Col> cols;
-  std::vector<Frame> stack;
-  std::string text;
-  const int32_t em = end[0], ei = end[1], ed = end[2];
-  const int32_t mx = std::max(std::max(ei, ed), em);  // :247-250
-  if (mx == ei) stack.push_back({ST_I, n2, n1, -1});  // push order I, M, D (:251-280)
-  if (mx == em) stack.push_back({ST_M, n2, n1, -1});
-  if (mx == ed) stack.push_back({ST_D, n2, n1, -1});
-  uint64_t printed = 0;
-  bool pan = false;
-  uint64_t needed = 0;  // bytes of the whole text; only the first cap - 1 are kept
-  const size_t keep = (buf && cap) ? cap - 1 : 0;
-  while (!stack.empty() && !pan) {
-    const Frame f = stack.back();
-    stack.pop_back();
-    // columns made after this frame was pushed belong to subtrees that are finished: drop them
-    cols.resize((size_t)(f.cols + 1));
-    if (f.x == 0 && f.y == 0) {  // :283-286
-      if (printed >= max_alignments) break;
-      std::string r1, r2;
-      for (int64_t k = f.cols; k >= 0; k = cols[k].next) {
-        r1.push_back((char)cols[k].c1);
-        r2.push_back((char)cols[k].c2);
-      }
-      std::string bars(r1.size(), ' ');
-      for (size_t k = 0; k < r1.size(); ++k)
-        if (r1[k] == r2[k]) bars[k] = '|';
-      const std::string piece = "alignment found\n\nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\n";
-      needed += piece.size();
-      if (text.size() < keep) text.append(piece, 0, keep - text.size());
-      ++printed;
-    }
-    // the popped cell's parent list, in push order
-    int pst[3], np = 0;
-    if (f.x >= 1 && f.y >= 1) {
-      const uint8_t b = par[(uint64_t)(f.x - 1) * n1 + (f.y - 1)];
-      if (f.st == ST_M) {
-        if (b & 1) pst[np++] = ST_M;
-        if (b & 2) pst[np++] = ST_I;
-        if (b & 4) pst[np++] = ST_D;
-      } else if (f.st == ST_I) {
-        if (b & 8) pst[np++] = ST_I;
-        if (b & 16) pst[np++] = ST_M;
-      } else {
-        if (b & 32) pst[np++] = ST_D;
-        if (b & 64) pst[np++] = ST_M;
-      }
-    } else if (f.x == 0 && f.y >= 1 && f.st == ST_D) {
-      pst[np++] = ST_D;  // boundary chain, parent d_scores[0][y-1] (:194-198)
-    } else if (f.y == 0 && f.x >= 1 && f.st == ST_I) {
-      pst[np++] = ST_I;  // parent i_scores[x-1][0] (:206-210)
-    }
-    for (int k = 0; k < np; ++k) {
-      // the loop body indexes seq1[y-1] (InM, InI) and seq2[x-1] (InM, InD): panic on 0-1
-      const bool bad = f.st == ST_M ? (f.x == 0 || f.y == 0) : (f.st == ST_D ? f.x == 0 : f.y == 0);
-      if (bad) {
-        pan = true;
-        break;
-      }
-      Col c;
-      c.next = f.cols;
-      uint32_t x = f.x, y = f.y;
-      if (f.st == ST_M) { c.c1 = seq1[y - 1]; c.c2 = seq2[x - 1]; --x; --y; }
-      else if (f.st == ST_D) { c.c1 = '-'; c.c2 = seq2[x - 1]; --x; }
-      else { c.c1 = seq1[y - 1]; c.c2 = '-'; --y; }
-      cols.push_back(c);
-      stack.push_back({pst[k], x, y, (int64_t)cols.size() - 1});
-    }
-  }
-  if (n_printed) *n_printed = printed;
-  if (panicked) *panicked = pan ? 1 : 0;
-  if (buf && cap) {
-    const size_t n = text.size() < cap - 1 ? text.size() : cap - 1;
-    memcpy(buf, text.data(), n);
-    buf[n] = 0;
-  }
-  return (int64_t)needed;
 }
 
 }  // namespace sa_host

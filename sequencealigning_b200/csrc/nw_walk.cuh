@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
 
 // Pool fill for the common case: the count pass left pair p's runs at the END of its temp slot
 // (tmp[kTmpRuns - len .. kTmpRuns)); copy them to pool[cigar_off[p] ..].
-__global__ void __launch_bounds__(256) cigar_gather(const uint32_t* __restrict__ tmp_runs,
+static __global__ void __launch_bounds__(256) cigar_gather(const uint32_t* __restrict__ tmp_runs,
                                                     const uint32_t* __restrict__ cigar_len,
                                                     const uint64_t* __restrict__ cigar_off,
                                                     uint32_t* __restrict__ pool, uint64_t pool_cap,
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) cigar_gather(const uint32_t* __restrict__
 // ---- exclusive scan of cigar_len -> cigar_off (three small kernels, no library) -------------
 constexpr int kScanBlock = 1024;
 
-__global__ void __launch_bounds__(kScanBlock) scan_block_sums(const uint32_t* __restrict__ len,
+static __global__ void __launch_bounds__(kScanBlock) scan_block_sums(const uint32_t* __restrict__ len,
                                                               uint64_t* __restrict__ block_sums,
                                                               uint32_t n) {
   __shared__ uint64_t warp_sums[32];
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_block_sums(const uint32_t* __
 }
 
 // single block: exclusive scan of block sums in place, starting from *carry; updates *carry
-__global__ void __launch_bounds__(kScanBlock) scan_block_offsets(uint64_t* __restrict__ block_sums,
+static __global__ void __launch_bounds__(kScanBlock) scan_block_offsets(uint64_t* __restrict__ block_sums,
                                                                  uint32_t n_blocks,
                                                                  uint64_t* __restrict__ carry) {
   __shared__ uint64_t sh[kScanBlock];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_block_offsets(uint64_t* __res
   if (threadIdx.x == 0) *carry = running;
 }
 
-__global__ void __launch_bounds__(kScanBlock) scan_apply(const uint32_t* __restrict__ len,
+static __global__ void __launch_bounds__(kScanBlock) scan_apply(const uint32_t* __restrict__ len,
                                                          const uint64_t* __restrict__ block_sums,
                                                          uint64_t* __restrict__ off, uint32_t n) {
   __shared__ uint64_t warp_sums[32];
