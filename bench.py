@@ -571,6 +571,35 @@ def extra_configs(args, eng, ctx, peak) -> dict:
     from oracle import binding as ob
     from sequencealigning_b200 import ALGO_NW_AFFINE, ALGO_WFA_STANDARD, PairBatch, synth
     out = {}
+    # ---- config1: linear NW, 1 query x 1 000 db records of ~150 bp (the reference's own CPU-sized case) --------
+    from sequencealigning_b200 import ALGO_NW_LINEAR, MODE_LOCAL
+    b1 = synth.config1(1000)
+    m = measure(eng, b1, ALGO_NW_LINEAR, steps=20, warmup=3, ctx=ctx, packed=True)
+    r1 = m.pop("result"); m.pop("timing"); m.pop("cells_all")
+    m.update({"unit": "GCUPS", "dtype": "u16x2 (two pairs per 32-bit register; exact integer)",
+              "workload": "linear-gap (single-matrix) NW score + first hit, 1 query x 1000 synthetic 150 bp db sequences at 5 % "
+                          "(BASELINE.json configs[0]); one sa_align_batch call on a live engine -- the sa_align CLI adds 1.3-3.8 s of "
+                          "CUDA context start-up per process (profiles/cli_bench_r02.json)"})
+    t0 = time.perf_counter()
+    eng.align(b1, algo=ALGO_NW_LINEAR, mode=MODE_LOCAL)
+    t0 = time.perf_counter()
+    rl = eng.align(b1, algo=ALGO_NW_LINEAR, mode=MODE_LOCAL)
+    m["local_mode"] = {"ms_per_call": (time.perf_counter() - t0) * 1e3, "note": "the same pairs with -m local (nw_local.cuh), host buffers, wall clock"}
+    if not args.skip_cpu:
+        ob.build()
+        t0 = time.perf_counter()
+        ref = ob.linear_batch(b1.residues, b1.q_off, b1.q_len, b1.d_off, b1.d_len, cigar_stride=320, n_threads=1)
+        dt = time.perf_counter() - t0
+        refl = ob.linear_batch(b1.residues, b1.q_off, b1.q_len, b1.d_off, b1.d_len, cigar_stride=320, n_threads=4, local=True)
+        ok = (np.array_equal(ref.score, r1.score) and np.array_equal(ref.cigar_len, r1.cigar_len)
+              and all(ref.cigar(p) == r1.cigar_of(p) for p in range(0, 1000, 10))
+              and np.array_equal(refl.score, rl.score) and np.array_equal(refl.end1, rl.end1) and np.array_equal(refl.end2, rl.end2)
+              and np.array_equal(refl.cigar_len, rl.cigar_len))
+        m["parity"] = {"ok": bool(ok), "sample": "all 1000 pairs vs oracle/nw_linear.c: score, CIGAR length (all), CIGAR words (every 10th); "
+                                                 "local mode: score, start cell, CIGAR length (all)"}
+        m["cpu_baseline"] = {"value": b1.cells / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": dt,
+                             "sample": "all 1000 pairs, oracle/nw_linear.c (the reference itself walks chars().nth() per cell, O(n) each)"}
+    out["config1"] = m
     # ---- config4: WFA, 100 k pairs of 1-10 kbp --------------------------------------------------------
     t0 = time.perf_counter()
     b4 = synth.config4(100_000)
