@@ -277,6 +277,9 @@ struct Segment {
   FastPlan fast;
   uint32_t n_long = 0;
   uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0;
+  // residue ranges to upload (merged intervals of the per-4096-pair extents): tighter than [qlo, qhi) and
+  // [dlo, dhi) when queries and db sequences live in separate regions of the buffer
+  std::vector<std::pair<uint64_t, uint64_t>> res_ranges;
   uint64_t cells = 0;  // sum of n1*n2 over the segment
   Geometry g;
 };
@@ -536,7 +539,17 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       sg.n1max = sg.n2max = 0;
       uint32_t n1m = 0, n2m = 0;
       uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0, cells = 0;
+      uint64_t bql = ~0ull, bqh = 0, bdl = ~0ull, bdh = 0;  // extents of the current block of 4096 pairs
       const bool ranges = in != nullptr;
+      sg.res_ranges.clear();
+      auto flush_block = [&] {
+        if (bql < bqh) sg.res_ranges.emplace_back(bql, bqh);
+        if (bdl < bdh) sg.res_ranges.emplace_back(bdl, bdh);
+        qlo = std::min(qlo, bql); qhi = std::max(qhi, bqh);
+        dlo = std::min(dlo, bdl); dhi = std::max(dhi, bdh);
+        bql = bdl = ~0ull;
+        bqh = bdh = 0;
+      };
       for (uint32_t i = 0; i < count; ++i) {
         const uint64_t p = base + i;
         const uint32_t ql = h_q_len[p], dl = h_d_len[p];
@@ -545,13 +558,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         if (ranges) {
           const uint64_t qo = in->q_off[p], dO = in->d_off[p];
           if (ql) {
-            qlo = std::min(qlo, qo);
-            qhi = std::max(qhi, view_end(qo, ql));
+            bql = std::min(bql, qo);
+            bqh = std::max(bqh, view_end(qo, ql));
           }
           if (dl) {
-            dlo = std::min(dlo, dO);
-            dhi = std::max(dhi, view_end(dO, dl));
+            bdl = std::min(bdl, dO);
+            bdh = std::max(bdh, view_end(dO, dl));
           }
+          if ((i & 4095u) == 4095u) flush_block();
         }
         const uint32_t a = linear ? dl : ql, b = linear ? ql : dl;
         if (is_long(a, b)) {
@@ -561,6 +575,19 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         real += c;
         n1m = std::max(n1m, a);
         n2m = std::max(n2m, b);
+      }
+      if (ranges) {
+        flush_block();
+        // merge: overlapping or closer than 64 KB (a copy has a fixed cost), so a record-ordered buffer is one interval
+        std::sort(sg.res_ranges.begin(), sg.res_ranges.end());
+        size_t w = 0;
+        for (size_t k = 0; k < sg.res_ranges.size(); ++k) {
+          if (w && sg.res_ranges[k].first <= sg.res_ranges[w - 1].second + 65536)
+            sg.res_ranges[w - 1].second = std::max(sg.res_ranges[w - 1].second, sg.res_ranges[k].second);
+          else
+            sg.res_ranges[w++] = sg.res_ranges[k];
+        }
+        sg.res_ranges.resize(w);
       }
       sg.n1max = n1m;
       sg.n2max = n2m;
@@ -714,8 +741,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     cp(db.d_len + sg.base, in->d_len + sg.base, (size_t)sg.n * 4);
     auto range = [&](uint64_t lo, uint64_t hi) { cp(db.residues + lo, in->residues + lo, hi - lo); };
     const int sh = in->packing ? 2 : 0;  // residue index -> byte index
-    if (sg.qlo < sg.qhi) cov.request(sg.qlo >> sh, (sg.qhi + (sh ? 3 : 0)) >> sh, range);
-    if (sg.dlo < sg.dhi) cov.request(sg.dlo >> sh, (sg.dhi + (sh ? 3 : 0)) >> sh, range);
+    for (const auto& r : sg.res_ranges) cov.request(r.first >> sh, (r.second + (sh ? 3 : 0)) >> sh, range);
     if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(err));
     CUDA_TRY(e, cudaEventRecord(e->ev_in, e->s_in));
     return SA_OK;

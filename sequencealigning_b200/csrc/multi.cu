@@ -251,13 +251,13 @@ sa_status_t md_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
   auto on_workers = [&](uint64_t nb, auto&& f) {
     // The planning pass of a 10 M pair list is worth spreading: block b on thread b % T.  The device workers
     // take the first N shares; with few devices extra threads take the rest, so that the pass costs the
-    // same (~0.7 ms per 10 M pairs on 8+ threads) whatever the number of devices.
+    // same (~1 ms per 10 M pairs on 8 threads, less on 16) whatever the number of devices.
     if (n < (1u << 18)) {
       for (uint64_t bl = 0; bl < nb; ++bl) f(bl);
       return;
     }
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int T = std::max(N, std::min(8, hw));
+    const int T = std::max(N, std::min(16, hw));
     auto share = [&, T](int k) {
       for (uint64_t bl = (uint64_t)k; bl < nb; bl += (uint64_t)T) f(bl);
     };
