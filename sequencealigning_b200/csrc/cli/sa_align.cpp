@@ -331,7 +331,7 @@ int main(int argc, char** argv) {
     omitted[p] = (status[p] & SA_ALIGNMENT_OMITTED) ? 1 : 0;
     status[p] &= 0x7f;
   }
-  std::string text;  // reused render buffer
+  std::string text, all_text;  // reused render buffers
   static char out_buf[1 << 20];
   setvbuf(stdout, out_buf, _IOFBF, sizeof(out_buf));
   for (size_t d = 0, p = 0; d < nd && !exit_code; ++d)
@@ -391,15 +391,16 @@ int main(int argc, char** argv) {
         // up to the point where it would panic
         uint64_t n_printed = 0;
         int32_t panicked = 0;
-        const int64_t need = sa_affine_all_alignments(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(),
-                                                      (const uint8_t*)D.seq.data(), (uint32_t)D.seq.size(), nullptr,
-                                                      ~0ull, nullptr, 0, &n_printed, &panicked);
-        if (need < 0) { fprintf(stderr, "sa_affine_all_alignments: %s\n", sa_last_error(eng)); exit_code = 1; break; }
-        std::string text((size_t)need + 1, '\0');
-        sa_affine_all_alignments(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
-                                 (uint32_t)D.seq.size(), nullptr, ~0ull, &text[0], text.size(), &n_printed, &panicked);
-        text.resize((size_t)need);
-        fputs(text.c_str(), stdout);
+        // one enumeration per pair: only a text beyond the reused buffer (1 MB to start with) is produced twice
+        if (all_text.size() < (1u << 20)) all_text.resize(1u << 20);
+        if (!emit_text(all_text, [&](char* b, size_t c) {
+              return sa_affine_all_alignments(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                              (uint32_t)D.seq.size(), nullptr, ~0ull, b, c, &n_printed, &panicked);
+            })) {
+          fprintf(stderr, "sa_affine_all_alignments: %s\n", sa_last_error(eng));
+          exit_code = 1;
+          break;
+        }
         if (panicked) {
           fprintf(stderr, "%s vs %s: the reference panics here (index out of bounds, needleman_wunsch_affine.rs:299/303) after %llu alignment(s)\n",
                   Q.name.c_str(), D.name.c_str(), (unsigned long long)n_printed);

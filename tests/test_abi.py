@@ -150,3 +150,12 @@ def test_render_linear_hit_is_the_reference_text(lib, oracle):
             assert n == 1 and render_linear_hit(q, d, r.cigar, r.end1, r.end2) == exp, (q, d, local)
     with pytest.raises(ValueError):
         render_linear_hit(b"AC", b"AC", [(3 << 2) | 0], 2, 2)  # consumes more than the end cell allows
+
+
+@pytest.mark.gpu
+def test_host_register_pins_caller_memory_in_place(lib):
+    """sa_host_register / sa_host_unregister: page-lock a buffer the caller already owns (the CLI's parser output)."""
+    buf = np.zeros(1 << 20, np.uint8)
+    assert lib.sa_host_register(buf.ctypes.data, buf.size) == 0
+    assert lib.sa_host_unregister(buf.ctypes.data) == 0
+    assert lib.sa_host_register(None, 16) == -2 and lib.sa_host_unregister(None) == -2
