@@ -6,7 +6,7 @@ Reference path under test: /root/reference/src/needleman_wunsch_affine.rs:169-33
 import numpy as np
 import pytest
 
-from tests.util import check_against_oracle, random_pair_list
+from tests.util import check_against_oracle, random_pair_list, rescore_cigars
 
 pytestmark = pytest.mark.gpu
 
@@ -570,3 +570,32 @@ def test_long_pairs_score_pinned_at_30_and_100_kbp(engine, oracle):
                 assert int(r.score[p]) == oracle.affine_score(b.query(p), b.db(p)), (length, p)
             assert r.status[p] in (0, 1) and r.cigar_len[p] > 0
             assert _cigar_score(b.query(p), b.db(p), r.cigar_of(p)) == int(r.score[p]), (length, p)
+
+
+def test_config2_full_size_properties(engine, oracle):
+    """BASELINE.json configs[1] at its full size (1 M x 150 bp): size-independent properties of every pair --
+    each CIGAR consumes exactly n1 query and n2 db residues, offsets are the scan of the lengths, every score is
+    the score its own CIGAR re-scores to under the reference's scheme (5 / -4 / -8 / -6 with the boundary gap's
+    extra extension, nw_affine.rs:15-20, :195, :207), 2-bit and byte input agree -- plus the oracle on a sample."""
+    from sequencealigning_b200 import REF_PANIC, REF_PANIC_EARLY, synth
+    b = synth.random_pairs(1_000_000, 150, 0.05, True, seed=synth.SEEDS["config2"])
+    r = engine.align(b)
+    n = b.n_pairs
+    assert set(np.unique(r.status)) <= {0, REF_PANIC, REF_PANIC_EARLY}
+    exp_off = np.zeros(n, np.uint64)
+    exp_off[1:] = np.cumsum(r.cigar_len[:-1], dtype=np.uint64)
+    assert np.array_equal(exp_off, r.cigar_off) and int(r.cigar_len.sum()) == r.cigar.size
+    has = r.cigar_len > 0
+    assert (has | (r.status == REF_PANIC_EARLY)).all()          # only an early panic prints nothing
+    op, ln = r.cigar & 3, (r.cigar >> 2).astype(np.int64)
+    starts = r.cigar_off[has].astype(np.int64)
+    use1 = np.add.reduceat(np.where(op != 2, ln, 0), starts)      # M and I consume the query
+    use2 = np.add.reduceat(np.where(op != 1, ln, 0), starts)      # M and D consume the db sequence
+    assert np.array_equal(use1, b.q_len[has].astype(np.int64)) and np.array_equal(use2, b.d_len[has].astype(np.int64))
+    score = rescore_cigars(b, r.cigar_off, r.cigar_len, r.cigar)
+    bad = np.nonzero(has & (score != r.score))[0]
+    assert bad.size == 0, (bad[:5], score[bad[:5]], r.score[bad[:5]])
+    rp = engine.align(b.packed())
+    assert np.array_equal(r.score, rp.score) and np.array_equal(r.status, rp.status) and np.array_equal(r.cigar, rp.cigar)
+    sub = b.select(np.arange(0, n, 997))
+    check_against_oracle(oracle, sub, engine.align(sub), what="every 997th pair of config 2")

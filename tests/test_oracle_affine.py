@@ -129,3 +129,19 @@ def test_sentinel_leak_at_long_lengths(oracle):
     assert m[1, 5600] == -32768 - 4          # sentinel + mismatch, not D[0][5599] - 4
     assert dd[0, 5599] < -32768
     assert oracle.affine_score(q, d) == oracle.affine_align(q, d).score
+
+
+def test_rescoring_helper_agrees_with_the_oracle(oracle):
+    """tests/util.rescore_cigars (used on the GPU at full BASELINE sizes) against the oracle's scores: the first
+    printed alignment of every pair re-scores to the reported score."""
+    from sequencealigning_b200 import PairBatch
+    from tests.util import random_pair_list, rescore_cigars
+    b = PairBatch.from_pairs(random_pair_list(5, 1500, 0, 120, alphabet=b"ACGT"))
+    stride = int((b.q_len.astype(np.int64) + b.d_len).max()) + 1
+    ref = oracle.affine_batch(b.residues, b.q_off, b.q_len, b.d_off, b.d_len, cigar_stride=stride, n_threads=4)
+    off = np.zeros(b.n_pairs, np.uint64)
+    off[1:] = np.cumsum(ref.cigar_len[:-1], dtype=np.uint64)
+    mask = np.arange(stride)[None, :] < ref.cigar_len[:, None]
+    score = rescore_cigars(b, off, ref.cigar_len, ref.cigar_pool[mask])
+    has = ref.cigar_len > 0
+    assert has.sum() > 1000 and np.array_equal(score[has], ref.score[has].astype(np.int64))
