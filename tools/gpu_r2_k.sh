@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_multi.py tests/test_gpu_linear.py -m gpu -x -q 2>&1 | tail -3
+for i in 1 2; do python bench.py --steps 20 --warmup 3 --skip-cpu --configs none 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), 'bytes', round(d['e2e']['byte_per_residue']['value'],1), 'launches', d['gpu_launches'], 'whole', round(d['roofline']['whole_step_frac'],4))"; done
+python bench.py --workload config3 --steps 10 --warmup 3 --skip-cpu --configs none 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('c3 value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3))"
+timeout 300 python tools/trace_e2e.py 2> gpurun_out/trace_e2e.err; grep -v "count of segment" gpurun_out/trace_e2e.err | tail -8
