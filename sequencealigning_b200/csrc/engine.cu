@@ -1702,6 +1702,9 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
     e->timing.d2h_bytes = 0;
     e->timing.cells = 0;
     sent = pool_base;
+    if (getenv("SA_TRACE"))
+      fprintf(stderr, "[sa trace] sd_align_batch: staging ready %.3f ms after entry\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
     if (local) {
       db.end1 = (uint32_t*)e->b_end1.p;
       db.end2 = (uint32_t*)e->b_end2.p;
@@ -1732,7 +1735,13 @@ sa_status_t sd_align_batch(sa_engine* e, sa_algo_t algo, sa_mode_t mode, const s
       e->timing.d2h_bytes += (used - sent) * 4;
     }
   }
+  if (getenv("SA_TRACE"))
+    fprintf(stderr, "[sa trace] sd_align_batch: pipeline returned %.3f ms after entry\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
   CUDA_TRY(e, cudaStreamSynchronize(e->s_out));
+  if (getenv("SA_TRACE"))
+    fprintf(stderr, "[sa trace] sd_align_batch: copy-out stream drained %.3f ms after entry\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->timing.kernels_ms = ms;

@@ -290,11 +290,16 @@ class Engine:
         if out is not None:
             sc = _scheme(scheme)
             cb = self._c_batch(batch)
+            # end cells: only local mode computes them; a global alignment ends at (n1, n2), which the caller
+            # already holds (asking the engine for them costs two n-element copies per call)
+            local = mode == MODE_LOCAL
             res = _capi.Result(out.score.ctypes.data, out.status.ctypes.data, out.cigar_off.ctypes.data,
                                out.cigar_len.ctypes.data, out.cigar.ctypes.data if cigar else None,
-                               out.cigar_capacity if cigar else 0, 0, out.end1.ctypes.data, out.end2.ctypes.data)
+                               out.cigar_capacity if cigar else 0, 0,
+                               out.end1.ctypes.data if local else None, out.end2.ctypes.data if local else None)
             self._check(self._lib.sa_align_batch(self._h, algo, mode, C.byref(sc) if sc else None, C.byref(cb), C.byref(res)))
-            return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)], out.end1, out.end2)
+            return AlignResult(out.score, out.status, out.cigar_off, out.cigar_len, out.cigar[: int(res.cigar_used)],
+                               out.end1 if local else batch.q_len, out.end2 if local else batch.d_len)
         cap = 0
         if cigar:
             # 32 runs per pair covers read pairs; long pairs get a share of their length
