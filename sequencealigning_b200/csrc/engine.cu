@@ -33,6 +33,7 @@
 #include "nw_walk.cuh"
 #include "nw_general.cuh"
 #include "nw_long.cuh"
+#include "nw_order.cuh"
 
 namespace sa_host {
 
@@ -260,6 +261,8 @@ struct Segment {
   uint32_t n = 0;
   uint32_t n1max = 0, n2max = 0;
   std::vector<uint32_t> order;  // launch index -> pair id, sorted by shape; empty = identity
+  bool dev_sort = false;        // one shape class whose rows differ a little: the DEVICE orders the pairs by rows (nw_order.cuh)
+  uint32_t n2min = 0;           // fewest rows among the packed-kernel pairs
   // A ragged (hence sorted) segment is launched as a few shape classes, each with its own
   // lane-group width, tile size and traceback stride; a uniform segment is one class.
   struct Sub {
@@ -371,7 +374,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   // most seg_pairs; when inputs stream from the host the first segment is small.
   const uint64_t seg_max = e->seg_pairs_forced ? e->seg_pairs
                                                 : std::min<uint64_t>(e->seg_pairs, std::max<uint64_t>(32768, (n + 1) / 2));
-  uint64_t seg_target = (in && !e->seg_pairs_forced) ? std::min<uint64_t>(seg_max, 65536) : seg_max;
+  uint64_t seg_target = (in && !e->seg_pairs_forced) ? std::min<uint64_t>(seg_max, e->seg_head) : seg_max;
 
   Coverage cov;
   // Scans the next segment on the host: extent, shape maxima, residue ranges, geometry.
@@ -539,7 +542,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       n_long = 0;
       real = 0;
       sg.n1max = sg.n2max = 0;
-      uint32_t n1m = 0, n2m = 0;
+      uint32_t n1m = 0, n2m = 0, n2lo = ~0u;
       uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0, cells = 0;
       uint64_t bql = ~0ull, bqh = 0, bdl = ~0ull, bdh = 0;  // extents of the current block of 4096 pairs
       const bool ranges = in != nullptr;
@@ -577,6 +580,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
         real += c;
         n1m = std::max(n1m, a);
         n2m = std::max(n2m, b);
+        n2lo = std::min(n2lo, b);
       }
       if (ranges) {
         flush_block();
@@ -593,6 +597,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       }
       sg.n1max = n1m;
       sg.n2max = n2m;
+      sg.n2min = n2lo == ~0u ? 0u : n2lo;
       sg.qlo = qlo; sg.qhi = qhi; sg.dlo = dlo; sg.dhi = dhi;
       sg.cells = cells;
     };
@@ -683,6 +688,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       if (sg.order.empty()) {
         sa_status_t rr = add_class(0, ns, sg.n1max, sg.n2max);
         if (rr != SA_OK) return rr;
+        // one class, identity order, rows not all alike: let the device order the pairs by rows
+        sg.dev_sort = e->sort_mode != 2 && !sg.subs.empty() && ns > 4 * sg.subs[0].g.ppt && sg.n2min < sg.n2max && sg.n2max < 11000;  // (bins in shared memory)
       } else {
         // (possibly) sorted by rows, then columns: cut where the rows have grown by more than a
         // quarter since the class began (at most 8 classes, at least 2048 pairs each)
@@ -1003,6 +1010,14 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       // pageable source: the copy is staged by the runtime before the call returns
       CUDA_TRY(e, cudaMemcpyAsync(sl.order.p, sg.order.data(), sg.order.size() * 4, cudaMemcpyHostToDevice, sx));
       d_order = (const uint32_t*)sl.order.p;
+    } else if (sg.dev_sort) {
+      const uint32_t nbins = sg.n2max + 2;
+      if ((r = ensure(e, sl.order, (size_t)cn * 4)) != SA_OK) return r;
+      sa::order_window<<<(cn + sa::kOrderWindow - 1) / sa::kOrderWindow, sa::kOrderWindow, (size_t)nbins * 4, sx>>>(
+          fp.d_len, (uint32_t)sg.base, cn, nbins, (uint32_t*)sl.order.p);
+      CUDA_TRY(e, cudaGetLastError());
+      e->timing.kernel_launches += 1;
+      d_order = (const uint32_t*)sl.order.p;
     }
     CUDA_TRY(e, cudaMemsetAsync(d_counts + k, 0, 4, sx));
     CUDA_TRY(e, cudaMemsetAsync(d_counts + 2 + k, 0, 4, sx));  // fallback queue of the tiled long-pair path
@@ -1149,7 +1164,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       wp.tmp_runs = nullptr;
       for (const Segment::Sub& sub : sg.subs) {
         set_geometry(sub.g);
-        wp.pair_ids = sg.order.empty() ? nullptr : (const uint32_t*)sl.order.p + sub.off;
+        wp.pair_ids = (sg.order.empty() && !sg.dev_sort) ? nullptr : (const uint32_t*)sl.order.p + sub.off;
         wp.pair_base = (uint32_t)sg.base + sub.off;
         wp.n_launch_pairs = sub.cnt;
         wp.tb = (const uint2*)sl.tb.p + sub.tb_off;
@@ -1357,6 +1372,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_S")) e->long_s = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_R")) e->long_r = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_SEG_HEAD")) e->seg_head = (uint32_t)std::max(1024, atoi(s));
   if (const char* s = getenv("SA_FILL_MINB")) e->fill_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;

@@ -106,6 +106,7 @@ struct sa_engine {
   size_t budget_cached = 0;
   uint32_t seg_pairs = 131072;  // measured (1 M x 150 bp): 512 Ki 2672 / 256 Ki 2691 / 128 Ki 2696 GCUPS resident, e2e 1915 / 2126 / 2302
   std::map<const void*, size_t> smem_configured;  // kernel -> opted-in dynamic smem ON THIS DEVICE
+  uint32_t seg_head = 65536;  // SA_SEG_HEAD: first segment of a call that streams from the host (sizes double from here)
   int sort_mode = 0;  // 0 auto, 1 always, 2 never (SA_SORT)
   bool seg_pairs_forced = false;
   // A multi-device engine (sa_engine_create_multi) owns no device itself: it shards a call over
