@@ -458,7 +458,7 @@ def roofline_fill(batch, ms_step, gcups, world, local, res_dev, args, peak, hbm_
                                    "per lane-op and the VIMNMX predicate outputs replace the compare/select ops, not because work is skipped"},
         "traffic": (14133 + 325) * pr["pairs"] if args.length == 150 else None,
         "traffic_detail": {"unit": "DRAM bytes per fill launch", "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
-                           "source": "profiles/ncu_fill_r01.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14458 B per 150 bp pair)"},
+                           "source": "profiles/ncu_fill_r02.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14459 B per 150 bp pair)"},
         "per_gpu": True,
         "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
                 "/ fill-kernel time; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",

@@ -186,11 +186,15 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     // K = 19 needs 134 registers (3 warps per scheduler); SA_FILL_MINB=16 selects the 128-register build (4 per scheduler)
     if (g.K == 19 && g.G == 8 && e->fill_minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
     if (g.K == 19 && g.G == 16 && e->fill_minb == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
-    // SA_ORMASK on the read-length forms: which tie-bit sets go to the alu pipe as LOP3 (development knob)
-    // measured (524 288 pairs x 150 bp, fill alone): 0x00 1928, 0x01 1949, 0x05 1882, 0x11 1926 (sweep units); the
-    // fma-heavy pipe is the busier one (80 % vs 71 %), one of the eight tie-bit sets as a LOP3 evens them out
+    // Which tie-bit sets go to the alu pipe as LOP3 instead of the fma-heavy pipe as VIADD (SA_ORMASK).  With every
+    // set a VIADD the fma-heavy pipe is the busier one (80 % vs 71 %, ncu); one of the eight sets of a cell pair as a
+    // LOP3 in EVERY column tips it the other way (alu 80 %, fma-heavy 74 %); in every second column the pipes are
+    // level.  Fill alone, 262 144 pairs x 150 bp after the row ordering: 0xFF (none) 3 102, 0x01 3 146, even columns
+    // 3 159, odd columns 3 190 GCUPS.  (K = 16: no difference between the variants.)
     if (g.K == 19 && g.G == 8 && e->ormask == 0xFF) return launch_fill_m<19, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x01, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && e->ormask == 0x1201) return launch_fill_m<19, 8, 0x1201, sa::kAffine, true>(e, p, g, n_tiles, stream);  // even columns
+    if (g.K == 19 && g.G == 8 && e->ormask == 0x01) return launch_fill_m<19, 8, 0x01, sa::kAffine, true>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8) return launch_fill_m<19, 8, 0x11201, sa::kAffine, true>(e, p, g, n_tiles, stream);  // odd columns
     if (g.K == 19 && g.G == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
   }
   return fail(e, SA_E_ARG, "no fill kernel for K %d G %d", g.K, g.G);

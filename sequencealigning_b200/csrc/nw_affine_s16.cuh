@@ -177,6 +177,11 @@ struct StripCells {
     constexpr int c = C;
     constexpr int w = c / 8;
     constexpr uint32_t sh = 4 * (c % 8);
+    // ORMASK bits 8-11 = period P, bits 12-15 = count N, bits 16-19 = offset O (P = 0: every column): the `or` selection of
+    // the low eight bits applies to the columns with (c + O) % P < N only, so the share of tie-bit sets that change pipe is adjustable in
+    // steps of one column
+    constexpr uint32_t OP = (ORMASK >> 8) & 15u, ON = (ORMASK >> 12) & 15u, OO = (ORMASK >> 16) & 15u;  // (.. + offset)
+    constexpr uint32_t OM = (OP != 0u && ((uint32_t)c + OO) % (OP ? OP : 1u) >= ON) ? 0u : (ORMASK & 0xFFu);
     // A new accumulator word starts from the previous one (AND 0): one dependency chain for all
     // tie-bit sets keeps ptxas from hoisting the VIMNMXs of later columns, whose predicates it
     // would otherwise have to spill (there are only seven predicate registers).
@@ -191,11 +196,11 @@ struct StripCells {
       Mv[CAP ? c : 0] = M;
       Ev[CAP ? c : 0] = E;
     }
-    const uint32_t t = vmax_tie<(1u << sh), (ORMASK >> 0) & 1, (ORMASK >> 1) & 1>(E, M, acc_a[w], acc_b[w]);     // I >= M
-    const uint32_t H = vmax_tie<(2u << sh), (ORMASK >> 2) & 1, (ORMASK >> 3) & 1>(F[c], t, acc_a[w], acc_b[w]);  // D >= max(I,M)
+    const uint32_t t = vmax_tie<(1u << sh), (OM >> 0) & 1, (OM >> 1) & 1>(E, M, acc_a[w], acc_b[w]);     // I >= M
+    const uint32_t H = vmax_tie<(2u << sh), (OM >> 2) & 1, (OM >> 3) & 1>(F[c], t, acc_a[w], acc_b[w]);  // D >= max(I,M)
     const uint32_t Mo = M - open2;
-    E = vmax_tie<(4u << sh), (ORMASK >> 4) & 1, (ORMASK >> 5) & 1>(Mo, E, acc_a[w], acc_b[w]);        // open ties/wins: I'[x][y+1]
-    F[c] = vmax_tie<(8u << sh), (ORMASK >> 6) & 1, (ORMASK >> 7) & 1>(Mo, F[c], acc_a[w], acc_b[w]);  // open ties/wins: D'[x+1][y]
+    E = vmax_tie<(4u << sh), (OM >> 4) & 1, (OM >> 5) & 1>(Mo, E, acc_a[w], acc_b[w]);        // open ties/wins: I'[x][y+1]
+    F[c] = vmax_tie<(8u << sh), (OM >> 6) & 1, (OM >> 7) & 1>(Mo, F[c], acc_a[w], acc_b[w]);  // open ties/wins: D'[x+1][y]
     Hrow[c] = H;
     StripCells<K, C + 1, ORMASK, CAP>::run(Hrow, F, q, d, hup, E, pen2, open2, cm2, zero, acc_a, acc_b, Mv, Ev);
   }
