@@ -264,6 +264,14 @@ int64_t sa_parse_fasta_packed(const char* path, uint8_t* out, size_t out_cap, ui
 int64_t sa_render_affine(const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
                          const uint32_t* cigar, uint32_t cigar_len, char* buf, size_t cap);
 
+/* EVERY hit the reference's linear aligner prints for one pair, in its order and text (needleman_wunsch.rs:106-116,
+ * :205-254): start cells = (n1, n2), or in local mode every cell holding the matrix maximum in row-major order
+ * (:256-272); per start cell the pre-order walk over the stored moves (Down, Right, Diag); a hit at (0, 0) or at a
+ * cell without moves, rendered as by sa_render_linear_hit.  The device fills the matrix (scores and move sets), the
+ * host walks it.  Stops after max_hits.  snprintf-style: returns the bytes needed, < 0 on error. */
+int64_t sa_linear_all_hits(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                           const sa_scheme_t* scheme, uint64_t max_hits, char* buf, size_t cap, uint64_t* n_printed);
+
 /* The reference's COMPLETE stdout for one pair under `-a wfa` (wfa_align, wfa.rs:23-42; SURVEY.md
  * App. A.2), from a traced run of the literal kernel on the device: one `lo: .., hi: ..` line per
  * created wavefront (:251); when the loop converges, `converged with score N: ` (:36), the `huhu`

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sa_engine_synchronize", "sa_engine_stream", "sa_last_timing", "sa_alloc_pinned", "sa_free_pinned",
     "sa_partition_lpt", "sa_parse_fasta", "sa_render_affine", "sa_pack_2bit", "sa_affine_all_alignments",
     "sa_affine_count_cooptimal", "sa_engine_create_multi", "sa_engine_device_count", "sa_last_shards", "sa_plan_shards",
-    "sa_pack_2bit_mt", "sa_parse_fasta_packed", "sa_render_linear_hit", "sa_wfa_reference_stdout", "sa_host_register", "sa_host_unregister",
+    "sa_pack_2bit_mt", "sa_parse_fasta_packed", "sa_render_linear_hit", "sa_wfa_reference_stdout", "sa_host_register", "sa_host_unregister", "sa_linear_all_hits",
 ]
 
 
@@ -131,6 +131,9 @@ def lib() -> C.CDLL:
     l.sa_render_linear_hit.restype = C.c_int64
     l.sa_wfa_reference_stdout.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32)]
     l.sa_wfa_reference_stdout.restype = C.c_int64
+    l.sa_linear_all_hits.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int, C.POINTER(Scheme), C.c_uint64,
+                                     C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    l.sa_linear_all_hits.restype = C.c_int64
     l.sa_pack_2bit.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
     l.sa_pack_2bit.restype = C.c_int
     l.sa_pack_2bit_mt.argtypes = [vp, C.c_uint64, vp, C.c_int]

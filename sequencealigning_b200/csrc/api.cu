@@ -151,6 +151,20 @@ int64_t sa_affine_all_alignments(sa_engine_t* e, const uint8_t* seq1, uint32_t n
   return r;
 }
 
+int64_t sa_linear_all_hits(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                           const sa_scheme_t* scheme, uint64_t max_hits, char* buf, size_t cap, uint64_t* n_printed) {
+  if (!e) return SA_E_ARG;
+  sa_engine* t = is_multi(e) ? e->children[0] : e;
+  int64_t r;
+  try {
+    r = sd_linear_all_hits(t, seq1, n1, seq2, n2, local, scheme, max_hits, buf, cap, n_printed);
+  } catch (const std::exception& ex) {
+    r = fail(t, SA_E_NOMEM, "host allocation failed: %s", ex.what());
+  }
+  if (r < 0 && t != e) e->err = t->err;
+  return r;
+}
+
 int64_t sa_wfa_reference_stdout(sa_engine_t* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2,
                                 char* buf, size_t cap, int32_t* status) {
   if (!e) return SA_E_ARG;

@@ -135,7 +135,7 @@ static void usage() {
           "  -a, --algo <ALGO>              algo [default: needleman-wunsch] [possible values: a-star, needleman-wunsch,\n"
           "                                 needleman-wunsch-linear, wfa, wfa-standard]\n"
           "      --strict                   exit 101 where the reference would panic\n"
-          "      --all                      needleman-wunsch: print EVERY co-optimal alignment, like the reference\n"
+          "      --all                      needleman-wunsch(-linear): print EVERY co-optimal alignment / hit, like the reference\n"
           "      --timing                   wall time of parse+pack / align / print on stderr\n"
           "      --no-output                align without printing the alignments\n"
           "      --pageable                 leave the input buffers pageable (default: page-locked in place for >= 64 Ki pairs)\n"
@@ -373,6 +373,19 @@ int main(int argc, char** argv) {
         // needleman_wunsch.rs:193-201, then the FIRST hit of backtrace (:106-116, :205-213)
         if (verbose) printf("search finished after %s\n", duration_debug(per_pair).c_str());
         printf("Alignment between sequences %s and %s found\n", Q.name.c_str(), D.name.c_str());
+        if (all) {  // every hit of every start cell, as the reference prints them (:106-116, :205-254)
+          uint64_t n_hits = 0;
+          if (all_text.size() < (1u << 20)) all_text.resize(1u << 20);
+          if (!emit_text(all_text, [&](char* b, size_t c) {
+                return sa_linear_all_hits(eng, (const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),
+                                          (uint32_t)D.seq.size(), m == SA_MODE_LOCAL, nullptr, ~0ull, b, c, &n_hits);
+              })) {
+            fprintf(stderr, "sa_linear_all_hits: %s\n", sa_last_error(eng));
+            exit_code = 1;
+            break;
+          }
+          continue;
+        }
         if (!omitted[p]) {
           if (!emit_text(text, [&](char* b, size_t c) {
                 return sa_render_linear_hit((const uint8_t*)Q.seq.data(), (uint32_t)Q.seq.size(), (const uint8_t*)D.seq.data(),

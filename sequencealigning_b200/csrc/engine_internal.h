@@ -139,6 +139,8 @@ int64_t sd_all_alignments(sa_engine* e, const uint8_t* seq1, uint32_t n1, const 
                           const sa_scheme_t* scheme, uint64_t max_alignments, char* buf, size_t cap,
                           uint64_t* n_printed, int32_t* panicked);
 
+int64_t sd_linear_all_hits(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                           const sa_scheme_t* scheme, uint64_t max_hits, char* buf, size_t cap, uint64_t* n_printed);
 int64_t sd_wfa_stdout(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, char* buf, size_t cap,
                       int32_t* status_out);
 

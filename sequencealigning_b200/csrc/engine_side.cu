@@ -6,7 +6,10 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
+#include <cstdint>
 #include <cstring>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -223,6 +226,130 @@ int64_t sd_all_alignments(sa_engine* e, const uint8_t* seq1, uint32_t n1, const 
     const size_t n = text.size() < cap - 1 ? text.size() : cap - 1;
     memcpy(buf, text.data(), n);
     buf[n] = 0;
+  }
+  return (int64_t)needed;
+}
+
+// EVERY hit the reference's linear aligner prints for one pair (needleman_wunsch.rs:106-116, :205-254), as its text:
+// the device fills the matrix (scores + move sets), the host finds the start cells -- (n1, n2) in global mode, every
+// cell holding the maximum in row-major order in local mode (:256-272) -- and walks the move sets in stored order
+// (Down, Right, Diag) with an explicit stack, printing a hit at (0, 0) or at a cell without moves.
+int64_t sd_linear_all_hits(sa_engine* e, const uint8_t* seq1, uint32_t n1, const uint8_t* seq2, uint32_t n2, int local,
+                           const sa_scheme_t* scheme, uint64_t max_hits, char* buf, size_t cap, uint64_t* n_printed) {
+  if (!e || (n1 && !seq1) || (n2 && !seq2)) return SA_E_ARG;
+  if (n_printed) *n_printed = 0;
+  sa_scheme_t sc{5, -4, -8, -6};  // needleman_wunsch.rs:181-186
+  if (scheme) sc = *scheme;
+  if (cudaSetDevice(e->device) != cudaSuccess) return fail(e, SA_E_CUDA, "cudaSetDevice failed");
+  const uint64_t w = (uint64_t)n2 + 1, cells = ((uint64_t)n1 + 1) * w;
+  if (cells > ((uint64_t)1 << 28)) return fail(e, SA_E_UNSUPPORTED, "pair too large for full move sets");
+  sa_status_t st;
+  if ((st = ensure(e, e->par_bytes, cells + 2 * w + 16)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_rows, cells * 4 + 64)) != SA_OK) return st;
+  if ((st = ensure(e, e->par_in, (size_t)n1 + n2 + 64)) != SA_OK) return st;
+  uint8_t* d_in = (uint8_t*)e->par_in.p;
+  cudaError_t err = cudaSuccess;
+  if (n1) err = cudaMemcpyAsync(d_in, seq1, n1, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && n2) err = cudaMemcpyAsync(d_in + n1, seq2, n2, cudaMemcpyHostToDevice, e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "H2D failed: %s", cudaGetErrorString(err));
+  sa::LinearMovesParams mp{};
+  mp.seq1 = d_in;
+  mp.seq2 = d_in + n1;
+  mp.n1 = n1;
+  mp.n2 = n2;
+  mp.match = sc.match;
+  mp.mismatch = sc.mismatch;
+  mp.open = sc.gap_open;
+  mp.ext = sc.gap_ext;
+  mp.local = local ? 1 : 0;
+  mp.scores = (int32_t*)e->par_rows.p;
+  mp.moves = (uint8_t*)e->par_bytes.p;
+  mp.gaps = (uint8_t*)e->par_bytes.p + cells;
+  sa::nw_linear_moves_kernel<<<1, 32, 0, e->stream>>>(mp);
+  if ((err = cudaGetLastError()) != cudaSuccess) return fail(e, SA_E_CUDA, "launch failed: %s", cudaGetErrorString(err));
+  e->timing.kernel_launches++;
+  std::vector<int32_t> scores(cells);
+  std::vector<uint8_t> moves(cells);
+  err = cudaMemcpyAsync(scores.data(), e->par_rows.p, cells * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(moves.data(), e->par_bytes.p, cells, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) return fail(e, SA_E_CUDA, "moves kernel failed: %s", cudaGetErrorString(err));
+
+  // start cells (:107-111)
+  std::vector<std::pair<uint32_t, uint32_t>> starts;
+  if (!local) {
+    starts.emplace_back(n1, n2);
+  } else {
+    int32_t best = INT32_MIN;
+    for (uint32_t i = 0; i <= n1; ++i)
+      for (uint32_t j = 0; j <= n2; ++j) {
+        const int32_t v = scores[(uint64_t)i * w + j];
+        if (v > best) {
+          best = v;
+          starts.clear();
+        }
+        if (v == best) starts.emplace_back(i, j);
+      }
+  }
+  std::string text;
+  uint64_t needed = 0, printed = 0;
+  const size_t keep = (buf && cap) ? cap - 1 : 0;
+  auto put = [&](const std::string& t) {
+    if (text.size() < keep) text.append(t, 0, std::min(t.size(), keep - text.size()));
+    needed += t.size();
+  };
+  struct Frame {
+    uint32_t i, j;
+    uint8_t next;  // index of the next move to try: 0 Down, 1 Right, 2 Diag
+  };
+  std::vector<Frame> stack;
+  std::string q, d;  // the hit's columns in push order (end of the alignment first)
+  for (size_t s = 0; s < starts.size() && printed < max_hits; ++s) {
+    uint32_t hs1 = 0, hs2 = 0;  // Hit::default() per start cell (:113)
+    q.clear();
+    d.clear();
+    stack.assign(1, Frame{starts[s].first, starts[s].second, 0});
+    while (!stack.empty() && printed < max_hits) {
+      Frame& f = stack.back();
+      const uint8_t mv = moves[(uint64_t)f.i * w + f.j];
+      if (f.next == 0 && ((f.i == 0 && f.j == 0) || mv == 0)) {  // :206-213
+        std::string r1(q.rbegin(), q.rend()), r2(d.rbegin(), d.rend()), bars(q.size(), ' ');
+        for (size_t k = 0; k < r1.size(); ++k)
+          if (r1[k] == r2[k]) bars[k] = '|';
+        put("\nHit: \nseq1: " + r1 + "\n      " + bars + "\nseq2: " + r2 + "\nstart in seq1: " + std::to_string(hs1) +
+            "\nstart in seq2: " + std::to_string(hs2) + "\n\n\n\n");
+        ++printed;
+        stack.pop_back();
+        if (!stack.empty()) {  // the caller's hit.query.pop() / hit.db.pop() (:251-252)
+          q.pop_back();
+          d.pop_back();
+        }
+        continue;
+      }
+      int k = f.next;
+      while (k < 3 && !(mv & (1u << k))) ++k;
+      if (k == 3) {
+        stack.pop_back();
+        if (!stack.empty()) {
+          q.pop_back();
+          d.pop_back();
+        }
+        continue;
+      }
+      f.next = (uint8_t)(k + 1);
+      hs1 = std::max(f.i, 1u) - 1;  // :215-216
+      hs2 = std::max(f.j, 1u) - 1;
+      uint32_t ni = f.i, nj = f.j;
+      if (k == 0) { q.push_back((char)seq1[f.i - 1]); d.push_back('-'); --ni; }
+      else if (k == 1) { q.push_back('-'); d.push_back((char)seq2[f.j - 1]); --nj; }
+      else { q.push_back((char)seq1[f.i - 1]); d.push_back((char)seq2[f.j - 1]); --ni; --nj; }
+      stack.push_back(Frame{ni, nj, 0});  // (invalidates f)
+    }
+  }
+  if (n_printed) *n_printed = printed;
+  if (buf && cap) {
+    memcpy(buf, text.data(), text.size());
+    buf[text.size()] = 0;
   }
   return (int64_t)needed;
 }

@@ -86,4 +86,58 @@ __global__ void __launch_bounds__(64) nw_affine_parents_kernel(const ParentsPara
   p.end_scores[3 * id + 2] = pd[n1];
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same service for the single-matrix ("linear") aligner: the reference prints EVERY hit of every start cell
+// (/root/reference/src/needleman_wunsch.rs:106-116, :205-254).  One thread runs the literal fill (:43-103) for one
+// pair and writes, per cell of the (n1+1) x (n2+1) matrix, the score and the move set in push order
+// (bit0 Down, bit1 Right, bit2 Diag; 0 = no moves); the host finds the start cells and walks the move sets.
+// Rows i walk seq1 (query), columns j walk seq2 (db) (:38).  On demand, one pair per call.
+// ---------------------------------------------------------------------------------------------
+struct LinearMovesParams {
+  const uint8_t* __restrict__ seq1;
+  const uint8_t* __restrict__ seq2;
+  uint32_t n1, n2;
+  int32_t match, mismatch, open, ext;
+  int32_t local;
+  int32_t* __restrict__ scores;  // [(n1+1) * (n2+1)]
+  uint8_t* __restrict__ moves;   // [(n1+1) * (n2+1)]
+  uint8_t* __restrict__ gaps;    // scratch: two rows of n2 + 1 flags
+};
+
+__global__ void nw_linear_moves_kernel(const LinearMovesParams p) {
+  if (blockIdx.x || threadIdx.x) return;
+  const uint32_t n1 = p.n1, n2 = p.n2, w = n2 + 1;
+  uint8_t* gprev = p.gaps;
+  uint8_t* gcur = p.gaps + w;
+  for (uint32_t j = 0; j <= n2; ++j) {  // row 0 (:44-54; scores[0][0] is initialised twice, :45-64)
+    p.scores[j] = p.local ? 0 : (int32_t)j * p.ext + p.open + (j == 0 ? p.open : 0);
+    p.moves[j] = p.local ? 0 : (uint8_t)(2u | (j == 0 ? 1u : 0u));
+    gprev[j] = p.local ? 0 : 1;
+  }
+  for (uint32_t i = 1; i <= n1; ++i) {
+    int32_t* row = p.scores + (uint64_t)i * w;
+    const int32_t* up = row - w;
+    uint8_t* mv = p.moves + (uint64_t)i * w;
+    row[0] = p.local ? 0 : (int32_t)i * p.ext + p.open;  // column 0 (:55-64)
+    mv[0] = p.local ? 0 : 1;
+    gcur[0] = p.local ? 0 : 1;
+    const uint8_t r1 = p.seq1[i - 1];
+    for (uint32_t j = 1; j <= n2; ++j) {  // :66-103
+      const int32_t diag = up[j - 1] + (r1 == p.seq2[j - 1] ? p.match : p.mismatch);
+      const int32_t down = up[j] + (gprev[j] ? p.ext : p.open);
+      const int32_t right = row[j - 1] + (gcur[j - 1] ? p.ext : p.open);
+      const int32_t mx = max(max(down, right), diag);
+      gcur[j] = (mx == down || mx == right) ? 1 : 0;  // :85-87, also when the score is then dropped
+      if (p.local && mx < 0) {                         // :88-89
+        row[j] = 0;
+        mv[j] = 0;
+      } else {
+        row[j] = mx;
+        mv[j] = (uint8_t)((mx == down ? 1u : 0u) | (mx == right ? 2u : 0u) | (mx == diag ? 4u : 0u));
+      }
+    }
+    uint8_t* t = gprev; gprev = gcur; gcur = t;
+  }
+}
+
 }  // namespace sa

@@ -331,6 +331,18 @@ class Engine:
         self._check(self._lib.sa_affine_all_alignments(*args, buf, need + 1, C.byref(n), C.byref(pan)))
         return buf.value.decode("latin1"), n.value, bool(pan.value)
 
+    def linear_all_hits(self, seq1: bytes, seq2: bytes, local: bool = False, scheme=None, max_hits: int = 1 << 20):
+        """Every hit the reference's linear aligner prints for one pair, as its text (sa_linear_all_hits).
+        Returns (text, n_printed)."""
+        sc = _scheme(scheme)
+        n = C.c_uint64()
+        args = (self._h, seq1, len(seq1), seq2, len(seq2), int(local), C.byref(sc) if sc else None, max_hits)
+        need = self._lib.sa_linear_all_hits(*args, None, 0, C.byref(n))
+        self._check(need)
+        buf = C.create_string_buffer(need + 1)
+        self._check(self._lib.sa_linear_all_hits(*args, buf, need + 1, C.byref(n)))
+        return buf.raw[:need].decode("latin1"), n.value
+
     def wfa_reference_stdout(self, seq1: bytes, seq2: bytes):
         """The reference's complete stdout for one pair under `-a wfa` (sa_wfa_reference_stdout).
         Returns (text, status)."""

@@ -99,6 +99,15 @@ def test_linear_stdout_matches_reference_text(cli, tmp_path, oracle):
                 exp += f"Alignment between sequences >{qn.decode()} and >{dn.decode()} found\n"
                 exp += oracle.linear_print_hits(qs, ds, local, 1)[0]
         assert r.stdout == exp, mode
+        # --all: every hit of every start cell = the reference's complete stdout (:106-116)
+        r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear", "-m", mode, "--all"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        exp = ""
+        for dn, ds in db:
+            for qn, qs in query:
+                exp += f"Alignment between sequences >{qn.decode()} and >{dn.decode()} found\n"
+                exp += oracle.linear_print_hits(qs, ds, local)[0]
+        assert r.stdout == exp, mode + " --all"
     # the linear aligner has no semi-global mode (n_w_align takes `local: bool`, :180)
     r = subprocess.run([cli, "-q", q, "-d", d, "-a", "needleman-wunsch-linear", "-m", "semi-global"], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist in the reference" in r.stderr

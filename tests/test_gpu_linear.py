@@ -166,3 +166,23 @@ def test_global_end_cells_and_hit_text(engine, oracle):
     for p, (q, d) in enumerate(pairs):
         exp, n = oracle.linear_print_hits(q, d, False, 1)
         assert render_linear_hit(q, d, r.cigar_of(p), r.end1[p], r.end2[p]) == exp, (q, d)
+
+
+def test_all_hits_text_matches_reference_order(engine, oracle):
+    """sa_linear_all_hits: EVERY hit of every start cell, in the reference's order and text
+    (needleman_wunsch.rs:106-116, :205-254), global and local, incl. the truncation by max_hits and the
+    snprintf-style sizing."""
+    pairs = random_pair_list(77, 40, 0, 14, alphabet=b"AC") + random_pair_list(78, 20, 0, 24, alphabet=b"ACGT") + [
+        (b"ACGT", b"AGT"), (b"", b"AC"), (b"AC", b""), (b"", b""), (b"AAAA", b"CCCC"), (b"AAAAAA", b"AAA"),
+        (b"ACGTTTTTTTTACGT", b"ACGTACGT")]
+    seen_many = 0
+    for q, d in pairs:
+        for local in (False, True):
+            exp, n = oracle.linear_print_hits(q, d, local, 500)
+            got, m = engine.linear_all_hits(q, d, local=local, max_hits=500)
+            assert (got, m) == (exp, n), (q, d, local)
+            seen_many += n > 1
+            if n > 2:
+                exp2, n2 = oracle.linear_print_hits(q, d, local, 2)
+                assert engine.linear_all_hits(q, d, local=local, max_hits=2) == (exp2, n2)
+    assert seen_many > 10
