@@ -373,6 +373,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
   wp.cigar_off = db.cigar_off;
   wp.pool = db.pool;
   wp.pool_cap = db.pool_cap;
+  wp.pf = e->walk_pf;
 
   // Segment size: at least two segments (alternate streams overlap each other's tails), at
   // most seg_pairs; when inputs stream from the host the first segment is small.
@@ -1035,10 +1036,18 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       fp.tb = (uint2*)sl.tb.p + sub.tb_off;
       fp.end = (uint32_t*)sl.end.p + sub.off;
       fp.row0 = pack2(row0_clean + (linear ? 0u : 1u));  // affine: panic bonus on
+      fp.rerun_ids = linear ? nullptr : (uint32_t*)sl.rerun_ids.p;  // the fill queues the pairs whose end cell carries the bonus
+      fp.rerun_count = linear ? nullptr : d_counts + k;
       if ((r = launch_fill_g(e, fp, sub.g, (sub.cnt + sub.g.ppt - 1) / sub.g.ppt, sl.fill_stream, s2.algo)) != SA_OK) return r;
     }
+    fp.rerun_ids = nullptr;
+    fp.rerun_count = nullptr;
     CUDA_TRY(e, cudaEventRecord(sl.ev_f1, sl.fill_stream));
     CUDA_TRY(e, cudaStreamWaitEvent(sx, sl.ev_f1, 0));
+    // the refill queue is complete when the fill is: its length goes to the host BEFORE the walks, so that stage B's
+    // refill (main stream) runs beside the classify + count walk of the untainted pairs instead of after it
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
+    CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));
     for (const Segment::Sub& sub : sg.subs) {
       set_geometry(sub.g);
       wp.pair_ids = d_order ? d_order + sub.off : nullptr;
@@ -1047,8 +1056,6 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       wp.n_launch_dev = nullptr;
       wp.tb = (const uint2*)sl.tb.p + sub.tb_off;
       wp.end = (const uint32_t*)sl.end.p + sub.off;
-      wp.rerun_ids = (uint32_t*)sl.rerun_ids.p;
-      wp.rerun_count = d_counts + k;
       wp.phase = 0;
       wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
       wp.tmp_base = (uint32_t)sg.base;
@@ -1061,9 +1068,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     }
     if (!sg.lit.ids.empty() && (r = launch_literal(sg.lit, sl.lit, sx)) != SA_OK) return r;
     if (!sg.fast.ids.empty() && (r = launch_fast(sg.fast, sl, d_counts + 2 + k, sx)) != SA_OK) return r;
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 6 + k, d_counts + 2 + k, 4, cudaMemcpyDeviceToHost, sx));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 4 + k, d_counts + k, 4, cudaMemcpyDeviceToHost, sx));
-    CUDA_TRY(e, cudaEventRecord(sl.ev_count, sx));
+    if (!sg.fast.ids.empty()) CUDA_TRY(e, cudaMemcpyAsync(e->h_count + 6 + k, d_counts + 2 + k, 4, cudaMemcpyDeviceToHost, sx));
+    CUDA_TRY(e, cudaEventRecord(sl.ev_w0, sx));  // walks (and long-pair kernels) of the segment done
     return SA_OK;
   };
   // Stage B: clean refill of the queued pairs, scan of the lengths, write walks, results out.
@@ -1074,9 +1080,10 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     const size_t tile_bytes = (size_t)g.tile_stride * 8;
     const uint32_t ctiles = (cn + g.ppt - 1) / g.ppt;
     sa_status_t r;
-    CUDA_TRY(e, cudaEventSynchronize(sl.ev_count));
+    // (the fallback count of tiled long pairs is only known after their kernels, at the end of stage A)
+    CUDA_TRY(e, cudaEventSynchronize(sg.fast.ids.empty() ? sl.ev_count : sl.ev_w0));
     if (getenv("SA_TRACE")) fprintf(stderr, "[sa trace]   count of segment at %llu arrived\n", (unsigned long long)sg.base);
-    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sl.ev_count, 0));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sg.fast.ids.empty() ? sl.ev_count : sl.ev_w0, 0));
     const uint32_t n_re = e->h_count[4 + k];
     e->timing.pairs_rerun += n_re;
     // tiled long pairs whose traceback can meet a dead end (provenance class 2): literal kernel, now
@@ -1135,8 +1142,6 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       wp.n_launch_dev = nullptr;
       wp.tb = (const uint2*)e->tb2.p;
       wp.end = (const uint32_t*)e->end2.p;
-      wp.rerun_ids = nullptr;
-      wp.rerun_count = nullptr;
       wp.phase = 1;
       wp.tmp_runs = want_cigar ? (uint32_t*)sl.tmp_runs.p : nullptr;
       wp.tmp_base = (uint32_t)sg.base;
@@ -1148,6 +1153,7 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
       CUDA_TRY(e, cudaGetLastError());
       e->timing.kernel_launches++;
     }
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, sl.ev_w0, 0));  // every length of the segment is known
     // offsets of this segment (continuing from the previous segments' total)
     sa::scan_block_sums<<<sb, sa::kScanBlock, 0, e->stream>>>(db.cigar_len + sg.base, (uint64_t*)e->block_sums.p, cn);
     sa::scan_block_offsets<<<1, sa::kScanBlock, 0, e->stream>>>((uint64_t*)e->block_sums.p, sb, db.carry);
@@ -1363,7 +1369,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
     CUDA_TRY(e, cudaStreamCreateWithPriority(&e->slot[k].fill_stream, cudaStreamNonBlocking, prio_least));
   }
   for (cudaEvent_t* ev : {&e->ev_in, &e->ev_done, &e->ev_carry[0], &e->ev_carry[1], &e->slot[0].ev_count, &e->slot[1].ev_count,
-                          &e->slot[0].ev_bdone, &e->slot[1].ev_bdone})
+                          &e->slot[0].ev_bdone, &e->slot[1].ev_bdone, &e->slot[0].ev_w0, &e->slot[1].ev_w0})
     CUDA_TRY(e, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   for (cudaEvent_t* ev : {&e->ev_t0, &e->ev_t1, &e->slot[0].ev_f0, &e->slot[0].ev_f1, &e->slot[1].ev_f0, &e->slot[1].ev_f1,
                           &e->slot[0].ev_l0, &e->slot[0].ev_l1, &e->slot[0].ev_l2, &e->slot[1].ev_l0, &e->slot[1].ev_l1, &e->slot[1].ev_l2})
@@ -1378,6 +1384,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_SEG_HEAD")) e->seg_head = (uint32_t)std::max(1024, atoi(s));
   if (const char* s = getenv("SA_FILL_MINB")) e->fill_minb = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_WALK_PF")) e->walk_pf = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;
   if (const char* s = getenv("SA_SORT")) e->sort_mode = atoi(s);
@@ -1411,7 +1418,7 @@ sa_status_t sd_destroy(sa_engine* e) {
     for (cudaEvent_t ev : {e->ev_in, e->ev_done, e->ev_carry[0], e->ev_carry[1], e->ev_t0, e->ev_t1, e->slot[0].ev_count,
                            e->slot[0].ev_f0, e->slot[0].ev_f1, e->slot[1].ev_count, e->slot[1].ev_f0,
                            e->slot[1].ev_f1, e->slot[0].ev_bdone, e->slot[1].ev_bdone, e->slot[0].ev_l0, e->slot[0].ev_l1,
-                           e->slot[0].ev_l2, e->slot[1].ev_l0, e->slot[1].ev_l1, e->slot[1].ev_l2})
+                           e->slot[0].ev_l2, e->slot[1].ev_l0, e->slot[1].ev_l1, e->slot[1].ev_l2, e->slot[0].ev_w0, e->slot[1].ev_w0})
       if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     cudaStreamDestroy(e->stream);

@@ -83,7 +83,7 @@ struct sa_engine {
     cudaStream_t fill_stream = nullptr;  // LOW priority: only the fill kernels.  The walks, scans and
                                          // copies of other segments then get SMs as fill CTAs retire,
                                          // instead of queueing behind a whole fill
-    cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr;
+    cudaEvent_t ev_count = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_bdone = nullptr, ev_w0 = nullptr;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr, ev_l2 = nullptr;  // tiled long pairs: forward start / end, traceback end
   } slot[2];
   // scratch (grow-only)
@@ -102,6 +102,7 @@ struct sa_engine {
   LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;
   uint32_t fill_minb = 1;           // SA_FILL_MINB: 16 = the 128-register build of the K = 19 fill forms
+  uint32_t walk_pf = 6;  // look-ahead of the traceback walks in steps (SA_WALK_PF; 0 = off)
   size_t tb_budget = 0;
   size_t budget_cached = 0;
   uint32_t seg_pairs = 131072;  // measured (1 M x 150 bp): 512 Ki 2672 / 256 Ki 2691 / 128 Ki 2696 GCUPS resident, e2e 1915 / 2126 / 2302

@@ -109,6 +109,10 @@ struct AffineS16Params {
   uint32_t zero;    // always 0; opaque to ptxas so that `or` bit-sets stay LOP3 (alu pipe)
   uint32_t step2;   // linear aligner: boundary step magnitude match - 2*ext, packed
   uint32_t packing; // input format (see load_residue)
+  // affine fill with the panic bonus on: a pair whose end cell carries the bonus (low bit of H') is queued
+  // here for the clean refill the moment its end cell is computed, so the refill does not wait for the walk
+  uint32_t* __restrict__ rerun_ids;
+  uint32_t* __restrict__ rerun_count;
 };
 
 // min of two packed u16 pairs on whole 32-bit registers.  (__vminu2 takes its operands apart into 16-bit
@@ -357,6 +361,7 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
             dw = (acc_a[c / 8] >> (4 * (c % 8) + 1)) & 1u;
           }
         p.end[la] = end_word(H, M, Ei, dw);
+        if (p.rerun_count && (H & 1u)) p.rerun_ids[atomicAdd(p.rerun_count, 1u)] = p.pair_ids ? p.pair_ids[la] : p.pair_base + la;
       }
       if (st.x == st.capx_b) {
         uint32_t H = 0, M = 0, Ei = 0, dw = 0;
@@ -367,6 +372,7 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
             dw = (acc_b[c / 8] >> (4 * (c % 8) + 1)) & 1u;
           }
         p.end[lb] = end_word(H, M, Ei, dw);
+        if (p.rerun_count && (H & 1u)) p.rerun_ids[atomicAdd(p.rerun_count, 1u)] = p.pair_ids ? p.pair_ids[lb] : p.pair_base + lb;
       }
     }
     if (ALGO == kLinear) if (st.x == st.capx_a || st.x == st.capx_b) {

@@ -59,9 +59,6 @@ struct WalkParams {
   const uint64_t* __restrict__ cigar_off;
   uint32_t* __restrict__ pool;
   uint64_t pool_cap;
-  // first pass only: pairs whose end cell carries the panic bonus are queued for a clean refill
-  uint32_t* __restrict__ rerun_ids;
-  uint32_t* __restrict__ rerun_count;
   int phase;  // 0: first fill (bonus on)  1: clean refill of queued pairs
   // The count pass already sees every run: it parks up to kTmpRuns of them per pair (back to
   // front, like the pool) so that the pool can be filled by a plain gather after the scan;
@@ -71,17 +68,64 @@ struct WalkParams {
   // decoding of the fill's end word: 2*score (+ taint bit) = H' - bias + diag2*(n1+n2)
   // (affine: diag2 = 2*ext; linear: diag2 = match)
   int32_t bias, diag2;
+  // Look-ahead of the walk, in steps (0 = off): every step also asks L2 for the word the walk reaches
+  // after pf more diagonal steps.  A step is one dependent read of a word nobody else has touched (a
+  // segment's traceback is GBs, far beyond L2), so without it a walk costs DRAM latency x path length;
+  // reads are mostly diagonal runs, so the guess is right except just after a gap.
+  uint32_t pf;
 };
 
 constexpr uint32_t kTmpRuns = 24;
 
-__device__ __forceinline__ uint32_t tb_nibble(const WalkParams& p, uint64_t tile_base, uint32_t grp,
-                                              uint32_t half, uint32_t x, uint32_t y) {
-  // strip and column-in-strip of column y-1; the reciprocal is exact for every y < 2^32 / k
-  const uint32_t s = __umulhi(y - 1, p.k_inv), c = (y - 1) - s * p.k;
-  const uint2 w = __ldg(&p.tb[tile_base + (((uint64_t)s * p.tb_rows + (x - 1)) * p.w + (c >> 3)) * p.ng + grp]);
-  return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
-}
+// Position of a walk inside its tile's traceback words.  The walks move one row and / or one column per step, so
+// the word index is kept incrementally (two predicated subtracts per step) instead of being rebuilt from (x, y)
+// with a division and three 64-bit multiplies in front of every dependent read.
+struct TbCursor {
+  const uint2* tile;     // the tile's words, offset by the lane group
+  uint32_t off;          // word 0 of (strip of column y-1, row x-1): ((s * tb_rows + (x - 1)) * w) * ng
+  uint32_t c;            // column y-1 inside its strip
+  uint32_t row_step;     // w * ng: one row up
+  uint32_t strip_step;   // tb_rows * w * ng: one strip to the left
+  uint32_t k, ng, pf, half;
+
+  __device__ __forceinline__ void init(const WalkParams& p, uint64_t tile_base, uint32_t grp, uint32_t half_, uint32_t x, uint32_t y) {
+    tile = p.tb + tile_base + grp;
+    k = p.k;
+    ng = p.ng;
+    half = half_;
+    pf = min(p.pf, p.k);  // the look-ahead crosses at most one strip edge
+    row_step = p.w * p.ng;
+    strip_step = p.tb_rows * row_step;
+    const uint32_t s = __umulhi(y - 1, p.k_inv);  // exact for every y < 2^32 / k
+    c = (y - 1) - s * p.k;
+    off = (s * p.tb_rows + (x - 1)) * row_step;
+  }
+  // one step to (x - dx, y - dy); leaving the matrix (x or y = 0) wraps harmlessly, nothing is read there
+  __device__ __forceinline__ void move(bool dx, bool dy) {
+    if (dx) off -= row_step;
+    if (dy) {
+      if (c == 0) {
+        c = k;
+        off -= strip_step;
+      }
+      --c;
+    }
+  }
+  __device__ __forceinline__ uint32_t nibble() const {
+    const uint2 w = __ldg(tile + off + (c >> 3) * ng);
+    return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
+  }
+  // ask L2 for the word the walk reaches after pf more diagonal steps from (x, y)
+  __device__ __forceinline__ void prefetch(uint32_t x, uint32_t y) const {
+    if (pf == 0 || x <= pf || y <= pf) return;
+    uint32_t o = off - pf * row_step, cp = c - pf;
+    if (c < pf) {
+      cp += k;
+      o -= strip_step;
+    }
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(tile + o + (cp >> 3) * ng));
+  }
+};
 
 // Next-state tables of the walk, 2 bits per nibble value (0 = M, 1 = I, 2 = D):
 //   from M: D if bit1, else I if bit0, else M      (:120-153 push M,I,D)
@@ -135,13 +179,10 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
     const int32_t taint = t2 & 1;
     if (p.phase == 0) {
       p.score[id] = (t2 - taint) / 2;
-      if (taint) {  // some co-optimal path starts with a gap: the reference panics somewhere.
-        const uint32_t slot = atomicAdd(p.rerun_count, 1u);
-        p.rerun_ids[slot] = id;
-        p.cigar_len[id] = 0;
-        p.status[id] = kRefPanic;  // refined by the clean refill
-        return;
-      }
+      // some co-optimal path starts with a gap: the reference panics somewhere.  The fill queued the pair for the
+      // clean refill (nw_affine_s16.cuh), whose walk (phase 1) owns its status, length and runs -- it may run
+      // beside this kernel, so nothing else is written here.
+      if (taint) return;
     }
   } else {
     // write pass: only pairs whose runs did not fit the temp slot; skip pairs that have no
@@ -155,6 +196,8 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   uint64_t wpos = 0;
   if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];  // runs are produced last-to-first
   uint32_t* tmp = (MODE == 0 && p.tmp_runs) ? p.tmp_runs + (uint64_t)(id - p.tmp_base) * kTmpRuns : nullptr;
+  TbCursor cur;
+  cur.init(p, tile_base, grp, half, x, y);  // (the end cell's own nibble is never read: its state comes from the end word)
   while (x > 0 && y > 0) {
     if (st != run_op) {
       if (MODE == 1 && run_len) {
@@ -173,8 +216,10 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
     //   D: '-' against seq2[x-1], go to (x-1,y), next state M if opening ties/wins else D
     x -= (st != 1u);
     y -= (st != 2u);
+    cur.move(st != 1u, st != 2u);
     if (x > 0 && y > 0) {
-      const uint32_t nb = tb_nibble(p, tile_base, grp, half, x, y);
+      const uint32_t nb = cur.nibble();
+      cur.prefetch(x, y);
       const uint32_t lut = st == 0 ? kLutM : (st == 1 ? kLutI : kLutD);
       st = (lut >> (2 * nb)) & 3u;
     }
@@ -230,6 +275,8 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
   uint64_t wpos = 0;
   if (MODE == 1) wpos = p.cigar_off[id] + p.cigar_len[id];
   uint32_t* tmp = (MODE == 0 && p.tmp_runs) ? p.tmp_runs + (uint64_t)(id - p.tmp_base) * kTmpRuns : nullptr;
+  TbCursor cur;
+  if (i > 0 && j > 0) cur.init(p, tile_base, grp, half, i, j);
   while (i > 0 || j > 0) {
     uint32_t op;
     if (i == 0) {
@@ -239,7 +286,8 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
       op = 1;
       --i;
     } else {
-      const uint32_t nb = tb_nibble(p, tile_base, grp, half, i, j);
+      const uint32_t nb = cur.nibble();
+      cur.prefetch(i, j);
       if ((nb & 3u) == 3u) {
         op = 1;
         --i;
@@ -251,6 +299,7 @@ __global__ void __launch_bounds__(128) nw_linear_walk(const WalkParams p) {
         --i;
         --j;
       }
+      cur.move(op != 2u, op != 1u);
     }
     if (op != run_op) {
       if (MODE == 1 && run_len) {
