@@ -25,16 +25,16 @@ def partition_lpt(q_len: np.ndarray, d_len: np.ndarray, n_parts: int) -> np.ndar
     return part
 
 
-def plan_shards(q_len: np.ndarray, d_len: np.ndarray, n_parts: int):
-    """sa_plan_shards: (begin[n_parts+1], part[n_pairs], contiguous) -- what a multi-device
+def plan_shards(q_len: np.ndarray, d_len: np.ndarray, n_parts: int, want_part: bool = True):
+    """sa_plan_shards: (begin[n_parts+1], part[n_pairs] or None, contiguous) -- what a multi-device
     sa_align_batch does with this pair list."""
     q_len = np.ascontiguousarray(q_len, np.uint32)
     d_len = np.ascontiguousarray(d_len, np.uint32)
     begin = np.zeros(n_parts + 1, np.uint64)
-    part = np.zeros(len(q_len), np.int32)
+    part = np.zeros(len(q_len), np.int32) if want_part else None
     contiguous = C.c_int()
     rc = _capi.lib().sa_plan_shards(q_len.ctypes.data, d_len.ctypes.data, len(q_len), n_parts, begin.ctypes.data,
-                                    part.ctypes.data, C.byref(contiguous))
+                                    part.ctypes.data if want_part else None, C.byref(contiguous))
     if rc != 0:
         raise ValueError(f"sa_plan_shards failed: {rc}")
     return begin, part, bool(contiguous.value)

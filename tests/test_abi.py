@@ -89,6 +89,25 @@ def test_plan_shards_contiguous_for_many_reads(lib):
     assert load.max() / load.mean() < 1.002 and np.diff(begin.astype(np.int64)).max() > 1.5 * np.diff(begin.astype(np.int64)).min()
 
 
+def test_plan_shards_sampled_for_very_large_lists(lib):
+    """Shards of >= 512 Ki pairs are planned from sampled block sums (1/16 of the pairs): the ranges stay
+    cell-balanced for random lengths, for a length-sorted list and for a periodic one (a db x query cross product)."""
+    from sequencealigning_b200.shard import plan_shards
+    rng = np.random.default_rng(7)
+    n = 2_300_000
+    q = rng.integers(100, 300, n).astype(np.uint32)
+    d = (q.astype(np.int64) + rng.integers(-8, 9, n)).astype(np.uint32)
+    periodic = (100 + (np.arange(n) % 4801) // 24).astype(np.uint32)
+    for name, (a, b) in {"random": (q, d), "sorted": (np.sort(q), np.sort(d)), "periodic": (periodic, periodic)}.items():
+        w = a.astype(np.float64) * b + 1
+        for parts in (2, 4):
+            begin, _, contiguous = plan_shards(a, b, parts, want_part=False)
+            assert contiguous, name
+            assert begin[0] == 0 and begin[-1] == n and (np.diff(begin.astype(np.int64)) > 0).all()
+            load = np.array([w[int(begin[k]):int(begin[k + 1])].sum() for k in range(parts)])
+            assert load.max() / load.mean() < 1.005, (name, parts, load)
+
+
 def test_plan_shards_lpt_for_few_uneven_pairs(lib):
     from sequencealigning_b200.shard import partition_lpt, plan_shards
     q = np.array([100_000, 10, 100_000, 20, 50_000, 30, 50_000, 40, 7, 9], np.uint32)

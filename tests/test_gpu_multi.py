@@ -156,3 +156,21 @@ def test_linear_local_mode_through_the_multi_engine(engine, devices):
             assert all(s["contiguous"] == contiguous for s in multi.shards())
             _same(single, r, f"local, devices {devices}")
             assert np.array_equal(single.end1, r.end1) and np.array_equal(single.end2, r.end2)
+
+
+def test_sampled_plan_of_a_very_large_list(engine):
+    """Shards of >= 512 Ki pairs are cut from sampled block sums (multi.cu plan_contiguous): same results as one
+    device, exact per-shard cell counts, balance within 1 %."""
+    from sequencealigning_b200 import Engine, synth
+    b = synth.random_pairs(1_100_000, 24, 0.1, True, seed=99)
+    single = engine.align(b)
+    with Engine(devices=[0, 0]) as multi:
+        r = multi.align(b)
+        shards = multi.shards()
+    assert np.array_equal(single.score, r.score) and np.array_equal(single.status, r.status)
+    assert np.array_equal(single.cigar_len, r.cigar_len)
+    for p in range(0, b.n_pairs, 997):   # (the pool of a multi-device call is one region per device)
+        assert single.cigar_of(p) == r.cigar_of(p), p
+    assert sum(s["pairs"] for s in shards) == b.n_pairs and sum(s["cells"] for s in shards) == b.cells
+    cells = np.array([s["cells"] for s in shards], np.float64)
+    assert cells.max() / cells.mean() < 1.01
