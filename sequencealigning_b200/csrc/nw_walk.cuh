@@ -75,7 +75,7 @@ struct WalkParams {
   uint32_t pf;
 };
 
-constexpr uint32_t kTmpRuns = 24;
+constexpr uint32_t kTmpRuns = 48;  // (a 150-250 bp read pair at 5 % has ~8-14 runs; beyond 48 the second walk does the work)
 
 // Position of a walk inside its tile's traceback words.  The walks move one row and / or one column per step, so
 // the word index is kept incrementally (two predicated subtracts per step) instead of being rebuilt from (x, y)

@@ -599,3 +599,28 @@ def test_config2_full_size_properties(engine, oracle):
     assert np.array_equal(r.score, rp.score) and np.array_equal(r.status, rp.status) and np.array_equal(r.cigar, rp.cigar)
     sub = b.select(np.arange(0, n, 997))
     check_against_oracle(oracle, sub, engine.align(sub), what="every 997th pair of config 2")
+
+
+def test_many_runs_take_the_second_walk(engine, oracle):
+    """Pairs with more CIGAR runs than the count walk parks per pair (kTmpRuns = 48, nw_walk.cuh) are walked a second
+    time after the scan; mixed with ordinary pairs, around the limit, through the refill as well."""
+    import random
+    from tests.util import random_seq
+    rng = random.Random(48)
+    pairs = random_pair_list(480, 400, 50, 200)
+    for period in (3, 4, 5, 6, 7, 9):           # every period-th base deleted: ~2 * n / period runs
+        for n in (150, 300, 600):
+            q = random_seq(rng, n, b"ACGT")
+            d = bytes(c for k, c in enumerate(q) if k % period != period - 1)
+            pairs.insert(rng.randrange(len(pairs)), (q, d))
+            pairs.insert(rng.randrange(len(pairs)), (d, q))
+    rng = random.Random(49)
+    for _ in range(400):                        # unrelated heads of unequal length: some co-optimal path starts with a gap
+        q = random_seq(rng, 200, b"ACGT")
+        d = bytes(c for k, c in enumerate(q) if k % 4 != 3)
+        pairs.append((random_seq(rng, rng.randrange(1, 12), b"ACGT") + q, random_seq(rng, rng.randrange(1, 12), b"ACGT") + d))
+    b = _batch(pairs)
+    r = engine.align(b)
+    check_against_oracle(oracle, b, r, what="many runs")
+    assert (r.cigar_len > 48).sum() >= 10
+    assert ((r.cigar_len > 48) & (r.status == 1)).sum() >= 1   # REF_PANIC pairs with long CIGARs (refill + second walk)
