@@ -183,9 +183,15 @@ sa_status_t launch_fill_g(sa_engine* e, const sa::AffineS16Params& p, const Geom
     if (g.K == 13 && g.G == 16) return launch_fill_m<13, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 8) return launch_fill_m<16, 8, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
     if (g.K == 16 && g.G == 16) return launch_fill_m<16, 16, 0x00, sa::kAffine, true>(e, p, g, n_tiles, stream);
-    // K = 19 needs 134 registers (3 warps per scheduler); SA_FILL_MINB=16 selects the 128-register build (4 per scheduler)
-    if (g.K == 19 && g.G == 8 && e->fill_minb == 16) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
-    if (g.K == 19 && g.G == 16 && e->fill_minb == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    // K = 19 wants ~147 registers (3 warps per scheduler); the 128-register build (4 per scheduler; its few spills are
+    // outside the steady-state rows) is the faster one for G = 8 since the steady-state rows lost the end-cell test
+    // (150 bp fill 3 190 -> 3 350 GCUPS) and the slower one for G = 16 (300 bp: 2 890 vs 2 930).  SA_FILL_MINB=1 / 16 force one.
+    const uint32_t minb = e->fill_minb ? e->fill_minb : (g.G == 8 ? 16u : 1u);
+    if (g.K == 19 && g.G == 8 && minb == 16 && e->ormask == 0xFF) return launch_fill_m<19, 8, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && minb == 16 && e->ormask == 0x1201) return launch_fill_m<19, 8, 0x1201, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && minb == 16 && e->ormask == 0x01) return launch_fill_m<19, 8, 0x01, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 8 && minb == 16) return launch_fill_m<19, 8, 0x11201, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
+    if (g.K == 19 && g.G == 16 && minb == 16) return launch_fill_m<19, 16, 0x00, sa::kAffine, true, 16>(e, p, g, n_tiles, stream);
     // Which tie-bit sets go to the alu pipe as LOP3 instead of the fma-heavy pipe as VIADD (SA_ORMASK).  With every
     // set a VIADD the fma-heavy pipe is the busier one (80 % vs 71 %, ncu); one of the eight sets of a cell pair as a
     // LOP3 in EVERY column tips it the other way (alu 80 %, fma-heavy 74 %); in every second column the pipes are

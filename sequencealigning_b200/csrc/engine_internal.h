@@ -101,7 +101,7 @@ struct sa_engine {
   uint32_t long_minb = 4;           // SA_LONG_MINB: register allocation of nw_long_fwd (4 or 5 CTAs per SM)
   LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;
-  uint32_t fill_minb = 1;           // SA_FILL_MINB: 16 = the 128-register build of the K = 19 fill forms
+  uint32_t fill_minb = 0;           // SA_FILL_MINB: 16 = the 128-register build of the K = 19 fill forms, 1 = the full one, 0 = per form
   uint32_t walk_pf = 6;  // look-ahead of the traceback walks in steps (SA_WALK_PF; 0 = off)
   size_t tb_budget = 0;
   size_t budget_cached = 0;

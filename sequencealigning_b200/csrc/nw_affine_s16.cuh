@@ -312,7 +312,9 @@ struct StripState {
 // pass, where the G lanes of a group are not all active yet / any more).  SINGLE = the launch
 // has one pass: the left edge of lane 0 is column 0 (a constant in V') and nothing is handed
 // to a next pass, so no boundary column exists at all.
-template <int K, int G, uint32_t ORMASK, bool CHECKED, int ALGO, bool SINGLE>
+// NOCAP = no lane of the warp computes a pair's end cell in this row (decided per warp for a whole run
+// of rows), so the row carries neither the two compares nor the branch over the end-cell copy.
+template <int K, int G, uint32_t ORMASK, bool CHECKED, int ALGO, bool SINGLE, bool NOCAP = false>
 __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Params& p, int j,
                                          uint32_t n2t, uint32_t pen2, uint32_t open2,
                                          uint32_t ext2, uint32_t zero, uint32_t la, uint32_t lb,
@@ -344,7 +346,7 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
       uint32_t sl = rh;
       LinearCells<K, 0>::run(st.Hrow, st.F, st.q, d, st.hd_prev, sl, E, pen2, open2, ext2 & 0xffffu,
                              ext2 & 0xffff0000u, acc_a[0], acc_b[0]);
-    } else if (st.x != st.capx_a && st.x != st.capx_b) {
+    } else if (NOCAP || (st.x != st.capx_a && st.x != st.capx_b)) {
       uint32_t Mv[1], Ev[1];
       StripCells<K, 0, ORMASK, false>::run(st.Hrow, st.F, st.q, d, st.hd_prev, E, pen2, open2, ext2,
                                            zero, acc_a, acc_b, Mv, Ev);
@@ -375,7 +377,7 @@ __device__ __forceinline__ void row_step(StripState<K>& st, const AffineS16Param
         if (p.rerun_count && (H & 1u)) p.rerun_ids[atomicAdd(p.rerun_count, 1u)] = p.pair_ids ? p.pair_ids[lb] : p.pair_base + lb;
       }
     }
-    if (ALGO == kLinear) if (st.x == st.capx_a || st.x == st.capx_b) {
+    if (ALGO == kLinear && !NOCAP) if (st.x == st.capx_a || st.x == st.capx_b) {
       // the linear aligner's end word is just S' (its walk needs no start state)
       if (st.x == st.capx_a) {
         uint32_t H = 0;
@@ -521,8 +523,16 @@ __global__ void __launch_bounds__(32, MINB) nw_affine_fill_s16(const AffineS16Pa
     // ramp-up: lanes j >= t are not active yet
     for (; t < (uint32_t)G && t <= n2t + G - 1; ++t)
       row_step<K, G, ORMASK, true, ALGO, SINGLE>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
-    // steady state: every lane is inside [1, n2t]
+    // steady state: every lane is inside [1, n2t].  Lane j computes row x in step x + j, so the first step in which
+    // any lane reaches an end cell is known up front; the steps before it (nearly all of them when the tile's
+    // pairs have about the same number of rows, which the segment's ordering by rows arranges) skip that test.
+    uint32_t t_cap = 0xffffffffu;
+    if (st.capx_a) t_cap = min(t_cap, st.capx_a + (uint32_t)j);
+    if (st.capx_b) t_cap = min(t_cap, st.capx_b + (uint32_t)j);
+    t_cap = min(__reduce_min_sync(0xffffffffu, t_cap), n2t + 1);
 #pragma unroll 2
+    for (; t < t_cap; ++t)
+      row_step<K, G, ORMASK, false, ALGO, SINGLE, true>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     for (; t <= n2t; ++t)
       row_step<K, G, ORMASK, false, ALGO, SINGLE>(st, p, j, n2t, pen2, open2, ext2, zero, la, lb, ca_, cb_);
     // ramp-down
