@@ -919,7 +919,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     const size_t smem_f = (size_t)sa::kLongWarps * sa::long_smem_per_warp(fq.R, fq.S > 1);
     const size_t smem_b = (size_t)sa::kLongWarps * sa::long_smem_per_warp(sa::kLongMr, true);
     const bool minb5 = e->long_minb == 5;
-    const void* fwd_fn = minb5 ? (const void*)sa::nw_long_fwd<5> : (const void*)sa::nw_long_fwd<4>;
+    const void* fwd_fn = minb5 ? (const void*)sa::nw_long_fwd<5> : e->long_cell == 2 ? (const void*)sa::nw_long_fwd<4, 2>
+                         : e->long_cell == 1 ? (const void*)sa::nw_long_fwd<4, 1> : (const void*)sa::nw_long_fwd<4>;
     for (auto kv : {std::make_pair(fwd_fn, smem_f), std::make_pair((const void*)sa::nw_long_back, smem_b)}) {
       size_t& configured = e->smem_configured[kv.first];
       if (kv.second > configured) {
@@ -979,6 +980,8 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
           ly.end_h = lw.end_h + y0;
           const dim3 grid((tiles + sa::kLongWarps - 1) / sa::kLongWarps, ny);
           if (minb5) sa::nw_long_fwd<5><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
+          else if (e->long_cell == 2) sa::nw_long_fwd<4, 2><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
+          else if (e->long_cell == 1) sa::nw_long_fwd<4, 1><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
           else sa::nw_long_fwd<4><<<grid, 32 * sa::kLongWarps, smem_f, sx>>>(ly);
           e->timing.kernel_launches++;
         }
@@ -1387,6 +1390,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_LITERAL")) e->long_literal = atoi(s) != 0;
   if (const char* s = getenv("SA_LONG_S")) e->long_s = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_R")) e->long_r = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_LONG_CELL")) e->long_cell = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_SEG_HEAD")) e->seg_head = (uint32_t)std::max(1024, atoi(s));
   if (const char* s = getenv("SA_FILL_MINB")) e->fill_minb = (uint32_t)std::max(0, atoi(s));

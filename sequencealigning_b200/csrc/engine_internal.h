@@ -98,6 +98,7 @@ struct sa_engine {
   bool long_ckpt_always = false;  // SA_LONG_CKPT: checkpointed traceback for every long pair (tests)
   bool long_literal = false;      // SA_LONG_LITERAL: affine long pairs through the literal kernel only (tests)
   uint32_t long_s = 0, long_r = 0;  // SA_LONG_S / SA_LONG_R: tile shape of the tiled long-pair path (0 = auto)
+  uint32_t long_cell = 2;           // SA_LONG_CELL: instruction mix of the score-only long-pair cell (nw_long.cuh long_cells)
   uint32_t long_minb = 4;           // SA_LONG_MINB: register allocation of nw_long_fwd (4 or 5 CTAs per SM)
   LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;

@@ -60,6 +60,7 @@ struct LongScheme {       // transformed units (all magnitudes > 0 except chain 
   int32_t ext4;           // -4*ext: what a fixed score gains per step of x + y
   int32_t chain;          // 4*(open + ext): D'[0][y] = I'[x][0] for all x, y >= 1 (:194-198, :206-210)
   int32_t sent;           // 4 * -32768
+  int32_t one;            // 1, as a value ptxas cannot see: multiplier of the adds that go to the fma pipe (IMAD)
 };
 
 __host__ __device__ inline LongScheme make_long_scheme(int match, int mismatch, int open, int ext) {
@@ -70,6 +71,7 @@ __host__ __device__ inline LongScheme make_long_scheme(int match, int mismatch, 
   s.ext4 = -4 * ext;
   s.chain = 4 * (open + ext);
   s.sent = 4 * -32768;
+  s.one = 1;
   return s;
 }
 
@@ -134,8 +136,20 @@ __device__ __forceinline__ int32_t long_max_tie(int32_t a, int32_t b, uint32_t& 
   return r;
 }
 
+// a + b as an IMAD (fma pipe) instead of an IADD3 (alu pipe, where every VIMNMX of the cell already sits)
+__device__ __forceinline__ int32_t fma_pipe_add(int32_t a, int32_t one, int32_t b) {
+  int32_t r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+  return r;
+}
+
 // TB: with tie bits, bonus off.  CAP: also keep M' and the incoming I' of column cap_c.
-template <bool TB, bool CAP>
+// CELL (score-only forward cell): 0 = LOP3, VIMNMX, IADD3, VIMNMX3, 2 x VIADDMNMX: 6 issue slots, but the fused
+// three-input ops hold the alu pipe for two slots each (int_peak: 3.2 against 6.4 per clock and SM): 9 alu slots per
+// cell.  1 = the two gap candidates from M - open computed once on the fma pipe: LOP3, VIMNMX, IADD3, VIMNMX3, IMAD,
+// 2 x VIMNMX: 7 issue slots, 7 alu.  2 = the diagonal add on the fma pipe as well: 8 issue slots, 6 alu.
+// Measured, 1 000 x 100 kbp: 0: 4 821 ms, 1: 4 912 ms, 2: 4 670 ms (the default).
+template <bool TB, bool CAP, int CELL = 0>
 __device__ __forceinline__ void long_cells(int32_t (&H)[kLongK], int32_t (&F)[kLongK], const uint32_t (&q)[kLongK],
                                            uint32_t d, int32_t hdiag, int32_t& E, const LongScheme& sc,
                                            uint32_t& acc0, uint32_t& acc1, int cap_c, int32_t& capM, int32_t& capE) {
@@ -143,7 +157,7 @@ __device__ __forceinline__ void long_cells(int32_t (&H)[kLongK], int32_t (&F)[kL
   for (int c = 0; c < kLongK; ++c) {
     const int32_t hup = H[c];
     const int32_t m = (int32_t)min(q[c] ^ d, (uint32_t)sc.pen);  // residues sit in bits 16+: unequal -> >= 65536 > pen
-    const int32_t M = hdiag + sc.cm - m;
+    const int32_t M = (!TB && CELL == 2) ? fma_pipe_add(hdiag, sc.one, sc.cm) - m : hdiag + sc.cm - m;
     if (CAP && c == cap_c) {
       capM = M;
       capE = E;
@@ -157,10 +171,16 @@ __device__ __forceinline__ void long_cells(int32_t (&H)[kLongK], int32_t (&F)[kL
       E = long_max_tie(Mo, E, acc, 4u << sh);                       // opening ties or wins: I'[x][y+1]
       F[c] = long_max_tie(Mo, F[c], acc, 8u << sh);                 // opening ties or wins: D'[x+1][y]
       H[c] = Hn;
-    } else {
+    } else if (CELL == 0) {
       const int32_t Hn = __vimax3_s32(F[c], E, M);
       E = __viaddmax_s32(M, -sc.open, E);
       F[c] = __viaddmax_s32(M, -sc.open, F[c]);
+      H[c] = Hn;
+    } else {
+      const int32_t Hn = __vimax3_s32(F[c], E, M);
+      const int32_t Mo = fma_pipe_add(M, sc.one, -sc.open);
+      E = max(Mo, E);
+      F[c] = max(Mo, F[c]);
       H[c] = Hn;
     }
     hdiag = hup;
@@ -175,7 +195,7 @@ __device__ __forceinline__ void long_cells(int32_t (&H)[kLongK], int32_t (&F)[kL
 // chunk ahead of the writes); right[0] is written only when write_corner.  tbs (TB): tie-bit
 // words [lane][tb_stride rows].  Returns the end-cell record when the strip holds (n2, n1):
 // forward: H'; TB: the start state of the traceback.
-template <bool TB>
+template <bool TB, int CELL = 0>
 __device__ __forceinline__ int32_t long_strip(const LongParams& p, uint32_t n1, uint32_t n2, uint64_t qo, uint64_t dof,
                                               uint32_t col0, uint32_t row0, uint32_t nrows, const int2* __restrict__ top,
                                               const int2* left, int2* bottom, int2* bottom2, int2* right, bool write_corner,
@@ -238,10 +258,10 @@ __device__ __forceinline__ int32_t long_strip(const LongParams& p, uint32_t n1, 
     int32_t E = re;
     uint32_t acc0 = 0, acc1 = 0;
     if (TB && decltype(cap_possible)::value && (int)xr == (cap_c >= 0 ? (int)nrows : -1)) {
-      long_cells<TB, true>(H, F, q, d, hd, E, sc, acc0, acc1, cap_c, capM, capE);
+      long_cells<TB, true, CELL>(H, F, q, d, hd, E, sc, acc0, acc1, cap_c, capM, capE);
       cap_bits = (int32_t)(((cap_c < 8 ? acc0 : acc1) >> (4 * (cap_c & 7))) & 15u);
     } else {
-      long_cells<TB, false>(H, F, q, d, hd, E, sc, acc0, acc1, -1, capM, capE);
+      long_cells<TB, false, CELL>(H, F, q, d, hd, E, sc, acc0, acc1, -1, capM, capE);
     }
     hd = rh;
     out_h = H[kLongK - 1];
@@ -336,7 +356,7 @@ __device__ __forceinline__ uint32_t long_n1pad(uint32_t n1) { return (n1 + kLong
 
 // Forward pass, one launch per tile anti-diagonal: grid (tiles / 4, pairs), 4 warps per CTA.
 // MINB: resident CTAs per SM the register allocation is held to (4 -> 128 registers, 5 -> 102).
-template <int MINB>
+template <int MINB, int CELL = 0>
 __global__ void __launch_bounds__(32 * kLongWarps, MINB) nw_long_fwd(const LongParams p) {
   extern __shared__ __align__(16) uint8_t long_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(32 * kLongWarps, MINB) nw_long_fwd(const LongP
     const bool last_strip = (s + 1 == p.S) || (col0 + kLongStrip >= n1);
     const int2* left = s ? tmpcol : (j ? coledge + (uint64_t)(j - 1) * (n2 + 1) + row0 : nullptr);
     int2* right = last_strip ? ((j + 1 < TC) ? coledge + (uint64_t)j * (n2 + 1) + row0 : nullptr) : tmpcol;
-    const int32_t r = long_strip<false>(p, n1, n2, qo, dof, col0, row0, nrows, i ? rowedge : nullptr, left, rowedge, ck,
+    const int32_t r = long_strip<false, CELL>(p, n1, n2, qo, dof, col0, row0, nrows, i ? rowedge : nullptr, left, rowedge, ck,
                                         right, /*write_corner=*/!last_strip || row0 == 0, nullptr, 0, lring, rring, panel);
     if (last_row == n2 && n1 > col0 && n1 <= col0 + kLongStrip) {
       const uint32_t owner = (n1 - 1 - col0) / kLongK;

@@ -81,21 +81,23 @@ constexpr uint32_t kTmpRuns = 48;  // (a 150-250 bp read pair at 5 % has ~8-14 r
 // the word index is kept incrementally (two predicated subtracts per step) instead of being rebuilt from (x, y)
 // with a division and three 64-bit multiplies in front of every dependent read.
 struct TbCursor {
-  const uint2* tile;     // the tile's words, offset by the lane group
+  const uint32_t* tile;  // the tile's words as 32-bit halves (pair A / pair B), offset by the lane group and the half
   uint32_t off;          // word 0 of (strip of column y-1, row x-1): ((s * tb_rows + (x - 1)) * w) * ng
   uint32_t c;            // column y-1 inside its strip
   uint32_t row_step;     // w * ng: one row up
   uint32_t strip_step;   // tb_rows * w * ng: one strip to the left
-  uint32_t k, ng, pf, half;
+  uint32_t k, ng;
+  uint32_t pf, pf_rows;  // look-ahead in steps (0xffffffff = off for the test below) and in words
 
-  __device__ __forceinline__ void init(const WalkParams& p, uint64_t tile_base, uint32_t grp, uint32_t half_, uint32_t x, uint32_t y) {
-    tile = p.tb + tile_base + grp;
+  __device__ __forceinline__ void init(const WalkParams& p, uint64_t tile_base, uint32_t grp, uint32_t half, uint32_t x, uint32_t y) {
+    tile = reinterpret_cast<const uint32_t*>(p.tb + tile_base + grp) + half;
     k = p.k;
     ng = p.ng;
-    half = half_;
-    pf = min(p.pf, p.k);  // the look-ahead crosses at most one strip edge
     row_step = p.w * p.ng;
     strip_step = p.tb_rows * row_step;
+    const uint32_t steps = min(p.pf, p.k);  // the look-ahead crosses at most one strip edge
+    pf = steps ? steps : 0xffffffffu;
+    pf_rows = steps * row_step;
     const uint32_t s = __umulhi(y - 1, p.k_inv);  // exact for every y < 2^32 / k
     c = (y - 1) - s * p.k;
     off = (s * p.tb_rows + (x - 1)) * row_step;
@@ -111,19 +113,27 @@ struct TbCursor {
       --c;
     }
   }
+  // the same with the step held in registers: row_dec = dx ? row_step : 0, dy = 0 / 1 (constant along a run)
+  __device__ __forceinline__ void move_run(uint32_t row_dec, uint32_t dy) {
+    off -= row_dec;
+    c -= dy;
+    if ((int32_t)c < 0) {
+      c += k;
+      off -= strip_step;
+    }
+  }
   __device__ __forceinline__ uint32_t nibble() const {
-    const uint2 w = __ldg(tile + off + (c >> 3) * ng);
-    return ((half ? w.y : w.x) >> (4 * (c & 7))) & 15u;
+    return (__ldg(tile + 2 * (off + (c >> 3) * ng)) >> (4 * (c & 7))) & 15u;
   }
   // ask L2 for the word the walk reaches after pf more diagonal steps from (x, y)
   __device__ __forceinline__ void prefetch(uint32_t x, uint32_t y) const {
-    if (pf == 0 || x <= pf || y <= pf) return;
-    uint32_t o = off - pf * row_step, cp = c - pf;
-    if (c < pf) {
+    if (min(x, y) <= pf) return;
+    uint32_t o = off - pf_rows, cp = c - pf;
+    if ((int32_t)cp < 0) {
       cp += k;
       o -= strip_step;
     }
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(tile + o + (cp >> 3) * ng));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(tile + 2 * (o + (cp >> 3) * ng)));
   }
 };
 
@@ -198,7 +208,13 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
   uint32_t* tmp = (MODE == 0 && p.tmp_runs) ? p.tmp_runs + (uint64_t)(id - p.tmp_base) * kTmpRuns : nullptr;
   TbCursor cur;
   cur.init(p, tile_base, grp, half, x, y);  // (the end cell's own nibble is never read: its state comes from the end word)
-  while (x > 0 && y > 0) {
+  // What a step does is fixed along a run (the state), so the per-state quantities -- the move, the next-state table --
+  // are set where the run changes and the common path is: count, move, test for the border, read, look up.
+  //   M: emit a diagonal column, go to (x-1,y-1), next state = its best state, priority D > I > M
+  //   I: seq1[y-1] against '-', go to (x,y-1), next state M if opening ties/wins else I
+  //   D: '-' against seq2[x-1], go to (x-1,y), next state M if opening ties/wins else D
+  uint32_t dx = 0, dy = 0, row_dec = 0, lut = 0;
+  for (;;) {  // (x > 0 and y > 0 here)
     if (st != run_op) {
       if (MODE == 1 && run_len) {
         --wpos;
@@ -208,21 +224,19 @@ __global__ void __launch_bounds__(128) nw_affine_walk(const WalkParams p) {
       run_op = st;
       run_len = 0;
       ++nruns;
+      dx = st != 1u;
+      dy = st != 2u;
+      row_dec = dx ? cur.row_step : 0u;
+      lut = st == 0 ? kLutM : (st == 1 ? kLutI : kLutD);
     }
     ++run_len;
-    // One step, the same instructions for every state (lanes of a warp are in different states):
-    //   M: emit a diagonal column, go to (x-1,y-1), next state = its best state, priority D > I > M
-    //   I: seq1[y-1] against '-', go to (x,y-1), next state M if opening ties/wins else I
-    //   D: '-' against seq2[x-1], go to (x-1,y), next state M if opening ties/wins else D
-    x -= (st != 1u);
-    y -= (st != 2u);
-    cur.move(st != 1u, st != 2u);
-    if (x > 0 && y > 0) {
-      const uint32_t nb = cur.nibble();
-      cur.prefetch(x, y);
-      const uint32_t lut = st == 0 ? kLutM : (st == 1 ? kLutI : kLutD);
-      st = (lut >> (2 * nb)) & 3u;
-    }
+    x -= dx;
+    y -= dy;
+    cur.move_run(row_dec, dy);
+    if (min(x, y) == 0) break;
+    const uint32_t nb = cur.nibble();
+    cur.prefetch(x, y);
+    st = (lut >> (2 * nb)) & 3u;
   }
   const bool complete = (x == 0 && y == 0);
   if (MODE == 0) {

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for i in 1 2; do python bench.py --steps 20 --warmup 3 --skip-cpu --configs none 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('value', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],3), 'probe', round(d['roofline']['launch']['gcups'],1), 'frac', round(d['roofline']['frac'],4), 'step frac', round(d['roofline']['whole_step_frac'],4))"; done
-python tools/local_bench.py 2>&1 | grep "global linear"
+python __graft_entry__.py --smoke 2>&1 | tail -1
+( time timeout 1500 python bench.py > gpurun_out/bench_r02_n1.json 2> gpurun_out/bench_r02_n1.err ) 2>&1 | tail -3
+python bench.py --workload config3 --steps 10 --warmup 3 --configs none > gpurun_out/bench_r02_c3.json 2>> gpurun_out/bench_r02_n1.err
+tail -c 300 gpurun_out/bench_r02_n1.err
+CMD="python bench.py --steps 2 --warmup 1 --skip-cpu --skip-e2e --configs none"
+$CMD > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv $CMD > gpurun_out/ncu_l.log 2>&1
