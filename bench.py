@@ -456,9 +456,9 @@ def roofline_fill(batch, ms_step, gcups, world, local, res_dev, args, peak, hbm_
                            "frac": k_cups * OPS_PER_CELL_S32_EQUIV / ipeak,
                            "note": "SURVEY 8d formula (16 s32-equivalent ops per cell / measured issue rate); above 1 because u16x2 does two cells "
                                    "per lane-op and the VIMNMX predicate outputs replace the compare/select ops, not because work is skipped"},
-        "traffic": (14133 + 325) * pr["pairs"] if args.length == 150 else None,
+        "traffic": (13920 + 365) * pr["pairs"] if args.length == 150 else None,
         "traffic_detail": {"unit": "DRAM bytes per fill launch", "algorithmic_bytes_per_launch": pr["cells"] / 2.0 + pr["residue_bytes"],
-                           "source": "profiles/ncu_fill_r02.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum = 14459 B per 150 bp pair)"},
+                           "source": "profiles/ncu_fill_r02_final.md (ncu --set full: dram__bytes_write.sum 1.392 GB + dram__bytes_read.sum 36.5 MB per 100 k pairs = 14285 B per 150 bp pair)"},
         "per_gpu": True,
         "note": "achieved = cells x 8 issued lane-instructions per cell (16 per packed pair of cells: 2 adds, 5 VIMNMX, 1 XOR, 8 tie-bit sets) "
                 "/ fill-kernel time; peak = measured issue rate, 32 lanes/clk/SMSP (" + peak["source"] + ")",

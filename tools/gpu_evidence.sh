@@ -1,4 +1,4 @@
-# round 2: the evidence run -- gpu tests, smoke, the default bench line, the reference arm, launch list, ncu captures
+# the evidence run (gpurun -- bash tools/gpu_evidence.sh) -- gpu tests, smoke, the default bench line, the reference arm, launch list, ncu captures
 mkdir -p gpurun_out
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5
 python __graft_entry__.py --smoke 2>&1 | tail -1
@@ -13,6 +13,5 @@ $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on 
 ncu --set full --clock-control none --import-source on -k regex:nw_affine_walk -s 0 -c 1 -o gpurun_out/walk_r02_final $CMD > gpurun_out/ncu_walk.log 2>&1
 CMD="python bench.py --workload config3 --steps 2 --warmup 1 --skip-cpu --skip-e2e --configs none --pairs 100000"
 $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:nw_affine_fill -s 0 -c 1 -o gpurun_out/fill250_r02_final $CMD > gpurun_out/ncu_fill250.log 2>&1
-timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_smoke.py > gpurun_out/sanitize_r02.txt 2>&1; echo "sanitizer rc $?" >> gpurun_out/sanitize_r02.txt; tail -3 gpurun_out/sanitize_r02.txt
 timeout 600 python tools/local_bench.py 2>&1 | tail -12 > gpurun_out/local_bench_r02.txt
 ls -la gpurun_out | tail -8
