@@ -54,6 +54,11 @@ namespace {
 using sa_host::fail;
 using sa_host::ensure;
 using sa_host::view_end;
+using sa_host::SegScanIn;
+using sa_host::SegScanOut;
+using sa_host::seg_scan;
+using sa_host::merge_ranges;
+using sa_host::kSegScanBlock;
 using sa_host::view_in_bounds;
 using sa_host::run_wfa;
 using sa_host::run_linear_local;
@@ -549,68 +554,27 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     // cells, and -- when streaming from the host -- the residue ranges to upload
     uint32_t n_long = 0;
     uint64_t real = 0;
+    // (seg_scan.h; SA_SCAN_THREADS > 1 splits the scan of a streamed call's first segments over threads)
     auto scan = [&](uint32_t count) {
-      n_long = 0;
-      real = 0;
-      sg.n1max = sg.n2max = 0;
-      uint32_t n1m = 0, n2m = 0, n2lo = ~0u;
-      uint64_t qlo = ~0ull, qhi = 0, dlo = ~0ull, dhi = 0, cells = 0;
-      uint64_t bql = ~0ull, bqh = 0, bdl = ~0ull, bdh = 0;  // extents of the current block of 4096 pairs
-      const bool ranges = in != nullptr;
-      sg.res_ranges.clear();
-      auto flush_block = [&] {
-        if (bql < bqh) sg.res_ranges.emplace_back(bql, bqh);
-        if (bdl < bdh) sg.res_ranges.emplace_back(bdl, bdh);
-        qlo = std::min(qlo, bql); qhi = std::max(qhi, bqh);
-        dlo = std::min(dlo, bdl); dhi = std::max(dhi, bdh);
-        bql = bdl = ~0ull;
-        bqh = bdh = 0;
-      };
-      for (uint32_t i = 0; i < count; ++i) {
-        const uint64_t p = base + i;
-        const uint32_t ql = h_q_len[p], dl = h_d_len[p];
-        const uint64_t c = (uint64_t)ql * dl;
-        cells += c;
-        if (ranges) {
-          const uint64_t qo = in->q_off[p], dO = in->d_off[p];
-          if (ql) {
-            bql = std::min(bql, qo);
-            bqh = std::max(bqh, view_end(qo, ql));
-          }
-          if (dl) {
-            bdl = std::min(bdl, dO);
-            bdh = std::max(bdh, view_end(dO, dl));
-          }
-          if ((i & 4095u) == 4095u) flush_block();
-        }
-        const uint32_t a = linear ? dl : ql, b = linear ? ql : dl;
-        if (is_long(a, b)) {
-          ++n_long;
-          continue;
-        }
-        real += c;
-        n1m = std::max(n1m, a);
-        n2m = std::max(n2m, b);
-        n2lo = std::min(n2lo, b);
-      }
-      if (ranges) {
-        flush_block();
-        // merge: overlapping or closer than 64 KB (a copy has a fixed cost), so a record-ordered buffer is one interval
-        std::sort(sg.res_ranges.begin(), sg.res_ranges.end());
-        size_t w = 0;
-        for (size_t k = 0; k < sg.res_ranges.size(); ++k) {
-          if (w && sg.res_ranges[k].first <= sg.res_ranges[w - 1].second + 65536)
-            sg.res_ranges[w - 1].second = std::max(sg.res_ranges[w - 1].second, sg.res_ranges[k].second);
-          else
-            sg.res_ranges[w++] = sg.res_ranges[k];
-        }
-        sg.res_ranges.resize(w);
-      }
-      sg.n1max = n1m;
-      sg.n2max = n2m;
-      sg.n2min = n2lo == ~0u ? 0u : n2lo;
-      sg.qlo = qlo; sg.qhi = qhi; sg.dlo = dlo; sg.dhi = dhi;
-      sg.cells = cells;
+      SegScanIn si;
+      si.q_len = h_q_len;
+      si.d_len = h_d_len;
+      si.q_off = in ? in->q_off : nullptr;
+      si.d_off = in ? in->d_off : nullptr;
+      si.linear = linear;
+      si.cols_lim = cols_lim;
+      si.rows_lim = rows_lim;
+      const int threads = (in && base < e->scan_mt_pairs && count >= 4 * kSegScanBlock) ? e->scan_threads : 1;
+      SegScanOut so = seg_scan(si, base, count, threads);
+      n_long = so.n_long;
+      real = so.real;
+      sg.res_ranges.swap(so.ranges);
+      if (in) merge_ranges(sg.res_ranges, 65536);
+      sg.n1max = so.n1max;
+      sg.n2max = so.n2max;
+      sg.n2min = so.n2min == ~0u ? 0u : so.n2min;
+      sg.qlo = so.qlo; sg.qhi = so.qhi; sg.dlo = so.dlo; sg.dhi = so.dhi;
+      sg.cells = so.cells;
     };
     scan(cn);
     sg.g = pick_geometry(sg.n1max, sg.n2max);
@@ -1394,6 +1358,7 @@ sa_status_t sd_create(int device_id, sa_engine** out) {
   if (const char* s = getenv("SA_LONG_MINB")) e->long_minb = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_SEG_HEAD")) e->seg_head = (uint32_t)std::max(1024, atoi(s));
   if (const char* s = getenv("SA_FILL_MINB")) e->fill_minb = (uint32_t)std::max(0, atoi(s));
+  if (const char* s = getenv("SA_SCAN_THREADS")) e->scan_threads = std::max(1, atoi(s));
   if (const char* s = getenv("SA_WALK_PF")) e->walk_pf = (uint32_t)std::max(0, atoi(s));
   if (const char* s = getenv("SA_ORMASK")) e->ormask = (uint32_t)strtoul(s, nullptr, 0);
   if (const char* s = getenv("SA_TB_BUDGET_MB")) e->tb_budget = (size_t)atoll(s) << 20;

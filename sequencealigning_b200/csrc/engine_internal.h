@@ -103,6 +103,9 @@ struct sa_engine {
   LitBufs fb_lit;                 // literal-kernel scratch for pairs the tiled path hands over
   uint32_t ormask = 0x00;
   uint32_t fill_minb = 0;           // SA_FILL_MINB: 16 = the 128-register build of the K = 19 fill forms, 1 = the full one, 0 = per form
+  int scan_threads = 1;             // SA_SCAN_THREADS: host threads for the scan of a streamed call's first segments (seg_scan.h);
+                                    // measured: 4 threads LOSE 3 % end to end (8.15 -> 8.40 ms: starting them costs more than the scan saves)
+  uint64_t scan_mt_pairs = 1u << 18;  // ... segments that start below this pair index
   uint32_t walk_pf = 6;  // look-ahead of the traceback walks in steps (SA_WALK_PF; 0 = off)
   size_t tb_budget = 0;
   size_t budget_cached = 0;

@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "engine_internal.h"
+#include "seg_scan.h"  // view_end / view_in_bounds, the host's pass over a segment
 
 #define CUDA_TRY(e, call)                                                                   \
   do {                                                                                      \
@@ -37,9 +38,6 @@ inline sa_status_t ensure(sa_engine* e, DevBuf& b, size_t bytes) {
   return SA_OK;
 }
 
-// end of a residue view, saturating: a garbage 64-bit offset must not wrap past the bounds check
-inline uint64_t view_end(uint64_t off, uint32_t len) { return off + len < off ? ~0ull : off + len; }
-inline bool view_in_bounds(uint64_t off, uint32_t len, uint64_t limit) { return off <= limit && len <= limit - off; }
 
 // ---- the other host paths (their own translation units) -------------------------------------------------
 // WFA, literal and standard mode (engine_wfa.cu)
