@@ -1075,6 +1075,12 @@ sa_status_t run_affine(sa_engine* e, DeviceBatch& db, uint64_t n, const uint32_t
     }
     float fms = 0;
     if (cudaEventElapsedTime(&fms, sl.ev_f0, sl.ev_f1) == cudaSuccess) e->timing.fill_ms += fms;
+    if (getenv("SA_TRACE")) {  // device-side timeline: when the segment's fill started and ended, from the call's first event
+      float t0 = 0, t1 = 0;
+      if (cudaEventElapsedTime(&t0, e->ev_t0, sl.ev_f0) == cudaSuccess && cudaEventElapsedTime(&t1, e->ev_t0, sl.ev_f1) == cudaSuccess)
+        fprintf(stderr, "[sa trace]   device: fill of segment at %llu (%u pairs) ran %.0f .. %.0f us\n", (unsigned long long)sg.base, sg.n,
+                t0 * 1e3, t1 * 1e3);
+    }
     if (!sg.fast.ids.empty()) {
       if (cudaEventElapsedTime(&fms, sl.ev_l0, sl.ev_l1) == cudaSuccess) e->timing.long_fwd_ms += fms;
       if (cudaEventElapsedTime(&fms, sl.ev_l1, sl.ev_l2) == cudaSuccess) e->timing.long_back_ms += fms;
